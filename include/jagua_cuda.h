@@ -1,0 +1,188 @@
+/* jagua_cuda.h — C ABI of the B200-native batched collision-query engine for jagua-rs's CDE.
+ *
+ * The reference (jagua-rs v0.6.4, pure Rust) has no FFI seam; the seam is the Rust API of
+ * `CDEngine` (jagua-rs/src/collision_detection/cd_engine.rs:33-342) plus the `HazardFilter`
+ * (hazards/filter.rs:7-9) and `HazardCollector` (hazards/collector.rs:7-42) traits. These entry
+ * points are what a `jagua-cuda-sys` crate would bind: plain pointers and
+ * sizes only. All functions return JG_OK (0) or a negative JgStatus; none of them aborts.
+ *
+ * Two layers:
+ *   jg_engine_*  device engine: owns HBM copies of one flattened layout (quadtree + hazards), the
+ *                item shapes and the filters, and resolves batches of queries with sm_100a kernels.
+ *   jg_cde_*     host-side mirror of CDEngine's update path (register / deregister / save /
+ *                restore and the quadtree maintenance behind them) that produces the flattened
+ *                layout blob. A Rust host keeps its own CDEngine and only needs jg_engine_*.
+ */
+#ifndef JAGUA_CUDA_H
+#define JAGUA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct JgEngine JgEngine;
+typedef struct JgCde JgCde;
+
+typedef enum JgStatus {
+    JG_OK = 0,
+    JG_ERR_CUDA = -1,         /* a CUDA runtime call failed; see jg_last_error */
+    JG_ERR_INVALID = -2,      /* bad argument / unknown id / malformed blob */
+    JG_ERR_NO_LAYOUT = -3,    /* query before any layout upload */
+    JG_ERR_CAPACITY = -4,     /* e.g. collector words too small for the layout's hazard slots */
+    JG_ERR_REFERENCE_PANIC = -5 /* host mirror reached a state where the reference would panic */
+} JgStatus;
+
+/* CDEConfig (cd_engine.rs:346-353) + SPSurrogateConfig's fail-fast counts (sp_surrogate.rs:120-131) */
+typedef struct JgConfig {
+    int32_t quadtree_depth; /* CDEConfig::quadtree_depth */
+    int32_t cd_threshold;   /* CDEConfig::cd_threshold (collect only, qt_node.rs:157) */
+    int32_t n_ff_poles;     /* SPSurrogateConfig::n_ff_poles */
+    int32_t n_ff_piers;     /* SPSurrogateConfig::n_ff_piers (ff_piers() = all piers uploaded) */
+} JgConfig;
+
+/* HazardEntity discriminants (hazards/hazard.rs:36-53) */
+enum { JG_HAZ_PLACED_ITEM = 0, JG_HAZ_EXTERIOR = 1, JG_HAZ_HOLE = 2, JG_HAZ_QZONE = 3 };
+
+/* detect verdict byte (one per query):
+ *   bit0  detect_surrogate_collision == true                (cd_engine.rs:204-223)
+ *   bit1  detect_poly_collision == true, evaluated only when bit0 == 0 (cd_engine.rs:160-197; the
+ *         two-stage order of lbf/src/opt/search.rs:44-57 and lbf/benches/ci_bench.rs:107-121)
+ *   bit7  the reference would hit `unreachable!` at cd_engine.rs:179 for this query (an Entire
+ *         hazard in the virtual root that the filter hides); bit1 is 0 then.                    */
+enum { JG_VERDICT_SURROGATE = 1, JG_VERDICT_POLY = 2, JG_VERDICT_REF_PANIC = 0x80 };
+
+/* query modes */
+enum {
+    JG_MODE_DEFAULT = 0,
+    JG_MODE_POLY_ONLY = 1 /* skip the surrogate stage (lbf/benches/quadtree_bench.rs:73-124) */
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* Device engine                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+
+/* CDEngine::new's device half: binds to CUDA device `device` and creates the engine's streams. */
+int jg_engine_create(int device, const JgConfig* cfg, JgEngine** out);
+void jg_engine_destroy(JgEngine* e);
+const char* jg_last_error(const JgEngine* e);
+
+/* Replaces the engine's layout (quadtree nodes, hazard entries, edges, hazard shapes) with the
+ * flattened blob produced by jg_cde_flatten (format: JgLayoutHeader in layout_soa.h). Mirrors the
+ * effect of CDEngine::{register_hazard, deregister_hazard_*, restore} (cd_engine.rs:59-149) on the
+ * data the queries read. `epoch` is returned by jg_engine_layout_epoch; queries issued after this
+ * call see the new layout, queries in flight finish on the old one. Host pointer. */
+int jg_layout_upload(JgEngine* e, const void* blob, size_t bytes, uint64_t epoch);
+/* Same, blob already in this device's memory (e.g. the receive buffer of an NCCL broadcast). */
+int jg_layout_upload_device(JgEngine* e, const void* d_blob, size_t bytes, uint64_t epoch);
+uint64_t jg_engine_layout_epoch(const JgEngine* e);
+
+/* An item's collision shape: SPolygon.vertices (x,y pairs, CCW, already centred), SPolygon.poi
+ * centre (simple_polygon.rs:24-37), SPSurrogate.poles (x,y,r) and piers (sx,sy,ex,ey)
+ * (sp_surrogate.rs:17-30). The first min(n_ff_poles, n_poles) poles and all piers are tested. */
+int jg_item_upload(JgEngine* e, int item_id, const float* verts_xy, int n_verts, const float* poi_xy,
+                   const float* poles_xyr, int n_poles, const float* piers, int n_piers);
+
+/* HazardFilter (hazards/filter.rs:7-76) as a bitset over hazard slot indices: bit set = the hazard
+ * is irrelevant. NoFilter = filter_id -1 in the query calls. */
+int jg_filter_upload(JgEngine* e, int filter_id, const uint32_t* bits, int words);
+
+/* detect_surrogate_collision + detect_poly_collision for n transformations of one item.
+ * transforms: n x (cos, sin, tx, ty) — the meaningful entries of `Transformation`
+ * (transformation.rs:11-13,131-139) composed on the host; out: n verdict bytes. HOST pointers
+ * (pinned memory from jg_host_alloc overlaps upload, kernels and download across chunks). */
+int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode,
+                    uint8_t* out);
+/* Same with DEVICE pointers; asynchronous on the engine's compute stream (jg_sync to wait). */
+int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int filter_id,
+                           int mode, uint8_t* d_out);
+
+/* collect_surrogate_collisions + collect_poly_collisions into one collector per query
+ * (cd_engine.rs:261-310; lbf/benches/ci_bench.rs:56-70). out_bits: n x words u32, bit = hazard slot
+ * index (an order-normalised BasicHazardCollector). words*32 must cover the layout's slot capacity. */
+int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode,
+                     uint32_t* out_bits, int words);
+int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int mode,
+                            uint32_t* d_out_bits, int words);
+
+int jg_sync(JgEngine* e);
+
+/* Counters since engine creation: [0] kernel launches, [1] queries resolved, [2] H2D bytes,
+ * [3] D2H bytes, [4] layout uploads, [5] survivors of the surrogate stage (detect). */
+int jg_engine_stats(const JgEngine* e, uint64_t out[8]);
+/* Device time (ms, CUDA events on the compute stream) of the kernels of the most recent
+ * *_batch_device call; valid after jg_sync. */
+float jg_engine_last_kernel_ms(JgEngine* e);
+/* CUDA-event stopwatch on the compute stream (the stream the *_device calls launch on):
+ * start records an event, stop records another, waits for it and returns the elapsed ms. */
+int jg_timer_start(JgEngine* e);
+int jg_timer_stop(JgEngine* e, float* ms);
+/* Chunk size (queries) and number of in-flight chunks used by the host-pointer batch calls. */
+int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams);
+/* Lanes per query (0 = choose from the item's vertex count, else 4, 8, 16 or 32) of the detect
+ * stage-2 and collect kernels. A tuning knob; results do not depend on it. */
+int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group);
+
+/* Memory helpers (pinned host / device) so callers can keep the C ABI free of CUDA headers. */
+int jg_host_alloc(size_t bytes, void** out);
+int jg_host_free(void* p);
+int jg_device_alloc(JgEngine* e, size_t bytes, void** out);
+int jg_device_free(JgEngine* e, void* p);
+int jg_memcpy_h2d(JgEngine* e, void* d_dst, const void* src, size_t bytes);
+int jg_memcpy_d2h(JgEngine* e, void* dst, const void* d_src, size_t bytes);
+
+/* DTransformation (rotation, tx, ty) -> (cos, sin, tx, ty) with the host libm's sinf/cosf, which is
+ * what f32::sin_cos lowers to (transformation.rs:131-139). The device never evaluates sin/cos. */
+void jg_compose_batch(const float* rot_tx_ty, int64_t n, float* out4, int n_threads);
+
+/* Non-FMA FP32 pipe peak of this device (independent FADD/FMUL chains), in Gflop/s: the roofline
+ * denominator for kernels compiled with -fmad=false. */
+int jg_fp32_nofma_peak(JgEngine* e, double* gflops, float* ms);
+/* Writes a buffer larger than L2 (bench hygiene between timed iterations). */
+int jg_flush_l2(JgEngine* e);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Host mirror of CDEngine's update path                                                       */
+/* ------------------------------------------------------------------------------------------ */
+
+/* CDEngine::new (cd_engine.rs:34-57) with no hazards yet; static hazards are registered next with
+ * dynamic = 0 (the Exterior must be among them before the first flatten). */
+int jg_cde_create(const float bbox4[4], const JgConfig* cfg, JgCde** out);
+void jg_cde_destroy(JgCde* c);
+const char* jg_cde_last_error(const JgCde* c);
+
+/* CDEngine::register_hazard (cd_engine.rs:59-69). shape = vertices (CCW) + poi centre; entity =
+ * (kind, id, quality, pk). Returns the HazKey (slot index | version << 32) through *hkey. */
+int jg_cde_register_hazard(JgCde* c, int kind, int64_t id, int64_t quality, uint64_t pk, const float* verts_xy,
+                           int n_verts, const float* poi_xy, int dynamic, uint64_t* hkey);
+/* CDEngine::deregister_hazard_by_key (cd_engine.rs:87-96) */
+int jg_cde_deregister_hazard(JgCde* c, uint64_t hkey);
+/* CDEngine::haz_key_from_pi_key (cd_engine.rs:333-341); *hkey = 0 when absent */
+int jg_cde_hkey_from_pk(const JgCde* c, uint64_t pk, uint64_t* hkey);
+/* CDEngine::save / restore (cd_engine.rs:98-149); snapshots are owned by the JgCde */
+int jg_cde_save(JgCde* c, int* snapshot_id);
+int jg_cde_restore(JgCde* c, int snapshot_id);
+/* number of slots of the hazard SlotMap (collector / filter bitsets must cover it) */
+int jg_cde_slot_capacity(const JgCde* c);
+int jg_cde_n_hazards(const JgCde* c);
+uint64_t jg_cde_hkey_exterior(const JgCde* c);
+/* HazKeyFilter::from_irrelevant_qzones (filter.rs:21-41): bit set iff InferiorQualityZone with
+ * quality < required_quality */
+int jg_cde_filter_qzones(const JgCde* c, int required_quality, uint32_t* bits, int words);
+
+/* Flattens quadtree + hazards into the SoA blob. Returns the byte size needed; writes it when
+ * cap >= size. */
+int64_t jg_cde_flatten(JgCde* c, void* buf, int64_t cap);
+/* flatten + jg_layout_upload in one call; bumps and returns the epoch */
+int jg_cde_sync_to_engine(JgCde* c, JgEngine* e, uint64_t* epoch);
+/* Canonical pre-order dump of the quadtree (u32 words) for tests: per node level, bbox bits,
+ * has_children, n_hazards, n_active_edges, then entries sorted (presence desc, slot asc) with
+ * ff_bbox and edges. Returns the word count; writes at most cap words. */
+int64_t jg_cde_tree_dump(const JgCde* c, uint32_t* out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAGUA_CUDA_H */

@@ -1,0 +1,438 @@
+"""jagua-rs_b200 — B200-native batched collision queries behind jagua-rs's CDEngine interface.
+
+Host-side mirror (Python over the C ABI in include/jagua_cuda.h) of the reference's Rust API for the
+collision-query path: `CDEngine` with `register_hazard`, `deregister_hazard_by_key`, `save`,
+`restore`, and batched versions of `detect_surrogate_collision` + `detect_poly_collision`
+(`detect_batch`) and `collect_surrogate_collisions` + `collect_poly_collisions` (`collect_batch`)
+— jagua-rs/src/collision_detection/cd_engine.rs:33-342.
+
+All compute runs in libjagua_cuda.so (hand-written sm_100a kernels). There is no CPU fallback: if the
+library is missing or no GPU is present, the query calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+HAZ_PLACED_ITEM, HAZ_EXTERIOR, HAZ_HOLE, HAZ_QZONE = 0, 1, 2, 3
+VERDICT_SURROGATE, VERDICT_POLY, VERDICT_REF_PANIC = 1, 2, 0x80
+MODE_DEFAULT, MODE_POLY_ONLY = 0, 1
+
+JG_OK, JG_ERR_CUDA, JG_ERR_INVALID, JG_ERR_NO_LAYOUT, JG_ERR_CAPACITY, JG_ERR_REFERENCE_PANIC = 0, -1, -2, -3, -4, -5
+
+
+class JgConfig(C.Structure):
+    _fields_ = [("quadtree_depth", C.c_int32), ("cd_threshold", C.c_int32), ("n_ff_poles", C.c_int32),
+                ("n_ff_piers", C.c_int32)]
+
+
+class JaguaCudaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"jagua_cuda error {code}: {msg}")
+        self.code = code
+
+
+_vp = C.c_void_p
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+# every symbol include/jagua_cuda.h declares: (restype, argtypes)
+C_ABI = {
+    "jg_engine_create": (C.c_int, [C.c_int, C.POINTER(JgConfig), C.POINTER(_vp)]),
+    "jg_engine_destroy": (None, [_vp]),
+    "jg_last_error": (C.c_char_p, [_vp]),
+    "jg_layout_upload": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64]),
+    "jg_layout_upload_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64]),
+    "jg_engine_layout_epoch": (C.c_uint64, [_vp]),
+    "jg_item_upload": (C.c_int, [_vp, C.c_int, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int]),
+    "jg_filter_upload": (C.c_int, [_vp, C.c_int, _u32p, C.c_int]),
+    "jg_detect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
+    "jg_detect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
+    "jg_collect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
+    "jg_collect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
+    "jg_sync": (C.c_int, [_vp]),
+    "jg_engine_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "jg_engine_last_kernel_ms": (C.c_float, [_vp]),
+    "jg_timer_start": (C.c_int, [_vp]),
+    "jg_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "jg_engine_set_batching": (C.c_int, [_vp, C.c_int64, C.c_int]),
+    "jg_engine_set_groups": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "jg_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "jg_host_free": (C.c_int, [_vp]),
+    "jg_device_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "jg_device_free": (C.c_int, [_vp, _vp]),
+    "jg_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "jg_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "jg_compose_batch": (None, [_f32p, C.c_int64, _f32p, C.c_int]),
+    "jg_fp32_nofma_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "jg_flush_l2": (C.c_int, [_vp]),
+    "jg_cde_create": (C.c_int, [_f32p, C.POINTER(JgConfig), C.POINTER(_vp)]),
+    "jg_cde_destroy": (None, [_vp]),
+    "jg_cde_last_error": (C.c_char_p, [_vp]),
+    "jg_cde_register_hazard": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64, _f32p, C.c_int, _f32p, C.c_int,
+                                         C.POINTER(C.c_uint64)]),
+    "jg_cde_deregister_hazard": (C.c_int, [_vp, C.c_uint64]),
+    "jg_cde_hkey_from_pk": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "jg_cde_save": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "jg_cde_restore": (C.c_int, [_vp, C.c_int]),
+    "jg_cde_slot_capacity": (C.c_int, [_vp]),
+    "jg_cde_n_hazards": (C.c_int, [_vp]),
+    "jg_cde_hkey_exterior": (C.c_uint64, [_vp]),
+    "jg_cde_filter_qzones": (C.c_int, [_vp, C.c_int, _u32p, C.c_int]),
+    "jg_cde_flatten": (C.c_int64, [_vp, _vp, C.c_int64]),
+    "jg_cde_sync_to_engine": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
+    "jg_cde_tree_dump": (C.c_int64, [_vp, _vp, C.c_int64]),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen libjagua_cuda.so (building it with nvcc when absent) and type every C-ABI symbol."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_build.LIB):
+        if not build_if_missing:
+            raise JaguaCudaError(JG_ERR_INVALID, f"{_build.LIB} is missing; run __graft_entry__.build()")
+        _build.build()
+    lib = C.CDLL(_build.LIB)
+    for name, (res, args) in C_ABI.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def compose(d_transfs, n_threads: int = 1) -> np.ndarray:
+    """DTransformation (rotation, tx, ty) -> (cos, sin, tx, ty) with the host libm
+    (geometry/transformation.rs:131-139 rot_transl_m; f32::sin_cos)."""
+    d = _f32(d_transfs).reshape(-1, 3)
+    out = np.empty((len(d), 4), np.float32)
+    load_library().jg_compose_batch(d, len(d), out, int(n_threads))
+    return out
+
+
+@dataclass
+class ItemShape:
+    """The part of an Item the CDE queries read: SPolygon vertices + poi centre + SPSurrogate
+    (entities/item.rs:12-53, geometry/primitives/simple_polygon.rs:24-37, fail_fast/sp_surrogate.rs:17-30)."""
+    verts: np.ndarray            # (V, 2) CCW, centred
+    poi: np.ndarray              # (x, y[, r])
+    poles: np.ndarray            # (P, 3) x, y, r
+    piers: np.ndarray = None     # (Q, 4)
+
+
+class PinnedBuffer:
+    """Page-locked host array (cudaHostAlloc) so that H2D/D2H copies overlap the kernels."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = _vp()
+        rc = self._lib.jg_host_alloc(max(self.nbytes, 1), C.byref(p))
+        if rc != JG_OK:
+            raise JaguaCudaError(rc, "cudaHostAlloc failed (no GPU?)")
+        self.ptr = p.value
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.jg_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceBuffer:
+    def __init__(self, cde: "CDEngine", nbytes: int):
+        self._cde = cde
+        self.nbytes = int(nbytes)
+        p = _vp()
+        cde._chk(cde._lib.jg_device_alloc(cde._eng, max(self.nbytes, 1), C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self._cde._chk(self._cde._lib.jg_memcpy_h2d(self._cde._eng, self.ptr, arr.ctypes.data, arr.nbytes))
+
+    def download(self, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        self._cde._chk(self._cde._lib.jg_memcpy_d2h(self._cde._eng, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr and self._cde._eng:
+            self._cde._lib.jg_device_free(self._cde._eng, self.ptr)
+        self.ptr = None
+
+
+class CDEngine:
+    """Mirror of jagua-rs's CDEngine (cd_engine.rs:22-342) whose queries run batched on one B200.
+
+    The update path (register / deregister / save / restore) runs in the C++ host mirror and the
+    flattened quadtree is re-uploaded lazily before the next query. `device=None` creates the host
+    half only (quadtree maintenance + flatten; usable without a GPU)."""
+
+    def __init__(self, bbox, quadtree_depth: int = 5, cd_threshold: int = 16, n_ff_poles: int = 2, n_ff_piers: int = 0,
+                 device: Optional[int] = 0):
+        self._lib = load_library()
+        self.config = JgConfig(int(quadtree_depth), int(cd_threshold), int(n_ff_poles), int(n_ff_piers))
+        self._cde = _vp()
+        self._eng = _vp()
+        b = _f32(bbox)
+        rc = self._lib.jg_cde_create(b, C.byref(self.config), C.byref(self._cde))
+        if rc != JG_OK:
+            raise JaguaCudaError(rc, "jg_cde_create: invalid bbox / config")
+        self._dirty = True
+        self.device = device
+        if device is not None:
+            rc = self._lib.jg_engine_create(int(device), C.byref(self.config), C.byref(self._eng))
+            if rc != JG_OK:
+                self._lib.jg_cde_destroy(self._cde)
+                self._cde = _vp()
+                raise JaguaCudaError(rc, "jg_engine_create failed: no usable CUDA device (this engine has no CPU fallback)")
+        self._items = {}
+        self._filters = {}
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_eng", None) and self._eng.value:
+            self._lib.jg_engine_destroy(self._eng)
+            self._eng = _vp()
+        if getattr(self, "_cde", None) and self._cde.value:
+            self._lib.jg_cde_destroy(self._cde)
+            self._cde = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int) -> int:
+        if rc < 0:
+            msg = self._lib.jg_last_error(self._eng).decode() if self._eng.value else ""
+            if not msg and self._cde.value:
+                msg = self._lib.jg_cde_last_error(self._cde).decode()
+            raise JaguaCudaError(rc, msg)
+        return rc
+
+    def _need_engine(self):
+        if not self._eng.value:
+            raise JaguaCudaError(JG_ERR_CUDA, "this CDEngine was created without a device; queries need a B200")
+
+    # -- update path (cd_engine.rs:59-149) -----------------------------------------------------
+    def register_hazard(self, kind: int, verts, poi, *, id: int = 0, quality: int = 0, pk: int = 0, dynamic: bool = True) -> int:
+        """CDEngine::register_hazard. Returns the HazKey (slot | version << 32)."""
+        v = _f32(verts).reshape(-1, 2)
+        key = C.c_uint64(0)
+        rc = self._lib.jg_cde_register_hazard(self._cde, int(kind), int(id), int(quality), int(pk), v, len(v),
+                                              _f32(poi)[:2].copy(), 1 if dynamic else 0, C.byref(key))
+        if rc < 0:
+            raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
+        self._dirty = True
+        return int(key.value)
+
+    def deregister_hazard_by_key(self, hkey: int):
+        rc = self._lib.jg_cde_deregister_hazard(self._cde, int(hkey))
+        if rc < 0:
+            raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
+        self._dirty = True
+
+    def haz_key_from_pi_key(self, pk: int) -> Optional[int]:
+        key = C.c_uint64(0)
+        self._lib.jg_cde_hkey_from_pk(self._cde, int(pk), C.byref(key))
+        return int(key.value) or None
+
+    def save(self) -> int:
+        sid = C.c_int(0)
+        self._lib.jg_cde_save(self._cde, C.byref(sid))
+        return sid.value
+
+    def restore(self, snapshot: int):
+        rc = self._lib.jg_cde_restore(self._cde, int(snapshot))
+        if rc < 0:
+            raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
+        self._dirty = True
+
+    def slot_capacity(self) -> int:
+        return self._lib.jg_cde_slot_capacity(self._cde)
+
+    def n_hazards(self) -> int:
+        return self._lib.jg_cde_n_hazards(self._cde)
+
+    def hkey_exterior(self) -> int:
+        return int(self._lib.jg_cde_hkey_exterior(self._cde))
+
+    def collector_words(self) -> int:
+        return max(1, (self.slot_capacity() + 31) // 32)
+
+    def filter_from_irrelevant_qzones(self, required_quality: int) -> np.ndarray:
+        """HazKeyFilter::from_irrelevant_qzones (hazards/filter.rs:21-41) as a slot bitset."""
+        bits = np.zeros(self.collector_words(), np.uint32)
+        self._lib.jg_cde_filter_qzones(self._cde, int(required_quality), bits, len(bits))
+        return bits
+
+    def filter_from_keys(self, hkeys: Sequence[int]) -> np.ndarray:
+        """HazKeyFilter::from_keys / `impl HazardFilter for HazKey` (filter.rs:43-76)."""
+        bits = np.zeros(self.collector_words(), np.uint32)
+        for k in hkeys:
+            s = int(k) & 0xFFFFFFFF
+            bits[s >> 5] |= np.uint32(1 << (s & 31))
+        return bits
+
+    def flatten(self) -> np.ndarray:
+        n = self._lib.jg_cde_flatten(self._cde, None, 0)
+        if n < 0:
+            raise JaguaCudaError(int(n), self._lib.jg_cde_last_error(self._cde).decode())
+        buf = np.zeros(n, np.uint8)
+        self._lib.jg_cde_flatten(self._cde, buf.ctypes.data, n)
+        return buf
+
+    def tree_dump(self) -> np.ndarray:
+        n = self._lib.jg_cde_tree_dump(self._cde, None, 0)
+        buf = np.zeros(n, np.uint32)
+        self._lib.jg_cde_tree_dump(self._cde, buf.ctypes.data, n)
+        return buf
+
+    # -- device residency ---------------------------------------------------------------------
+    def upload_item(self, item_id: int, shape: ItemShape):
+        self._need_engine()
+        v = _f32(shape.verts).reshape(-1, 2)
+        poles = _f32(shape.poles).reshape(-1, 3)
+        piers = _f32(shape.piers if shape.piers is not None else np.zeros((0, 4))).reshape(-1, 4)
+        self._chk(self._lib.jg_item_upload(self._eng, int(item_id), v, len(v), _f32(shape.poi)[:2].copy(),
+                                           poles if len(poles) else np.zeros((1, 3), np.float32), len(poles),
+                                           piers if len(piers) else np.zeros((1, 4), np.float32), len(piers)))
+        self._items[int(item_id)] = len(v)
+
+    def upload_filter(self, filter_id: int, bits: np.ndarray):
+        self._need_engine()
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        self._chk(self._lib.jg_filter_upload(self._eng, int(filter_id), bits, len(bits)))
+        self._filters[int(filter_id)] = len(bits)
+
+    def sync_layout(self, force: bool = False) -> int:
+        """Flatten the host quadtree and upload it if it changed since the last upload."""
+        self._need_engine()
+        if self._dirty or force:
+            ep = C.c_uint64(0)
+            self._chk(self._lib.jg_cde_sync_to_engine(self._cde, self._eng, C.byref(ep)))
+            self._dirty = False
+        return int(self._lib.jg_engine_layout_epoch(self._eng))
+
+    def upload_layout_blob(self, blob: np.ndarray, epoch: int = 0):
+        """jg_layout_upload of an externally produced blob (e.g. received from rank 0)."""
+        self._need_engine()
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._chk(self._lib.jg_layout_upload(self._eng, blob.ctypes.data, blob.nbytes, int(epoch)))
+        self._dirty = False
+
+    def upload_layout_device(self, d_ptr: int, nbytes: int, epoch: int = 0):
+        self._need_engine()
+        self._chk(self._lib.jg_layout_upload_device(self._eng, int(d_ptr), int(nbytes), int(epoch)))
+        self._dirty = False
+
+    # -- queries ----------------------------------------------------------------------------
+    def detect_batch(self, item_id: int, transforms, filter_id: int = -1, poly_only: bool = False,
+                     out: Optional[np.ndarray] = None) -> np.ndarray:
+        """detect_surrogate_collision then detect_poly_collision (cd_engine.rs:160-223) for every
+        (cos, sin, tx, ty) row. Host buffers in, verdict bytes out (see JG_VERDICT_* bits)."""
+        self.sync_layout()
+        t = transforms if isinstance(transforms, np.ndarray) and transforms.dtype == np.float32 and transforms.flags.c_contiguous else _f32(transforms)
+        n = t.size // 4
+        if out is None:
+            out = np.empty(n, np.uint8)
+        self._chk(self._lib.jg_detect_batch(self._eng, int(item_id), t.ctypes.data, n, int(filter_id),
+                                            MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data))
+        return out
+
+    def collect_batch(self, item_id: int, transforms, words: Optional[int] = None, poly_only: bool = False,
+                      out: Optional[np.ndarray] = None) -> np.ndarray:
+        """collect_surrogate_collisions + collect_poly_collisions (cd_engine.rs:261-310) into one
+        bitset over hazard slots per query."""
+        self.sync_layout()
+        t = transforms if isinstance(transforms, np.ndarray) and transforms.dtype == np.float32 and transforms.flags.c_contiguous else _f32(transforms)
+        n = t.size // 4
+        words = int(words or self.collector_words())
+        if out is None:
+            out = np.empty((n, words), np.uint32)
+        self._chk(self._lib.jg_collect_batch(self._eng, int(item_id), t.ctypes.data, n,
+                                             MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data, words))
+        return out
+
+    def detect_batch_device(self, item_id: int, d_transforms: int, n: int, d_out: int, filter_id: int = -1,
+                            poly_only: bool = False):
+        """Same as detect_batch with device pointers; asynchronous (call sync())."""
+        self.sync_layout()
+        self._chk(self._lib.jg_detect_batch_device(self._eng, int(item_id), int(d_transforms), int(n), int(filter_id),
+                                                   MODE_POLY_ONLY if poly_only else MODE_DEFAULT, int(d_out)))
+
+    def collect_batch_device(self, item_id: int, d_transforms: int, n: int, d_out_bits: int, words: int, poly_only: bool = False):
+        self.sync_layout()
+        self._chk(self._lib.jg_collect_batch_device(self._eng, int(item_id), int(d_transforms), int(n),
+                                                    MODE_POLY_ONLY if poly_only else MODE_DEFAULT, int(d_out_bits), int(words)))
+
+    def sync(self):
+        self._need_engine()
+        self._chk(self._lib.jg_sync(self._eng))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.jg_engine_last_kernel_ms(self._eng))
+
+    def timer_start(self):
+        self._chk(self._lib.jg_timer_start(self._eng))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        self._chk(self._lib.jg_timer_stop(self._eng, C.byref(ms)))
+        return float(ms.value)
+
+    def stats(self) -> dict:
+        a = (C.c_uint64 * 8)()
+        self._lib.jg_engine_stats(self._eng, a)
+        return dict(launches=int(a[0]), queries=int(a[1]), h2d_bytes=int(a[2]), d2h_bytes=int(a[3]),
+                    layout_uploads=int(a[4]), survivors=int(a[5]))
+
+    def set_batching(self, chunk_queries: int, n_streams: int):
+        self._chk(self._lib.jg_engine_set_batching(self._eng, int(chunk_queries), int(n_streams)))
+
+    def set_groups(self, detect_group: int = 0, collect_group: int = 0):
+        self._chk(self._lib.jg_engine_set_groups(self._eng, int(detect_group), int(collect_group)))
+
+    def fp32_nofma_peak(self):
+        g, ms = C.c_double(0), C.c_float(0)
+        self._chk(self._lib.jg_fp32_nofma_peak(self._eng, C.byref(g), C.byref(ms)))
+        return g.value, ms.value
+
+    def flush_l2(self):
+        self._chk(self._lib.jg_flush_l2(self._eng))
+
+
+from .workload import Workload, load_workload, build_engine, make_queries  # noqa: E402

@@ -1,0 +1,724 @@
+// C ABI of the device engine (include/jagua_cuda.h): HBM residency of layout / items / filters,
+// stream-overlapped batching of host buffers, kernel launches, counters.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/jagua_cuda.h"
+#include "cde_host.hpp"
+#include "launch.hpp"
+
+using namespace jg;
+
+namespace {
+
+struct ItemDev {
+    float2* verts = nullptr;
+    int n_verts = 0;
+    float poi_x = 0, poi_y = 0;
+    float4* poles = nullptr;
+    int n_poles = 0;
+    float4* piers = nullptr;
+    int n_piers = 0;
+};
+struct FilterDev {
+    uint32_t* bits = nullptr;
+    int words = 0;
+};
+// One in-flight chunk of a host-pointer batch: its own stream and staging buffers.
+struct ChunkCtx {
+    cudaStream_t st = nullptr;
+    float4* d_xf = nullptr;
+    uint8_t* d_out = nullptr;  // verdict bytes or collector words
+    size_t cap_q = 0, cap_out = 0;
+    SurvivorList sv{nullptr, nullptr, nullptr, nullptr};
+    size_t cap_sv = 0;
+};
+
+}  // namespace
+
+struct JgEngine {
+    int device = 0;
+    JgConfig cfg{};
+    int n_sms = 148;
+    std::string err;
+
+    void* d_blob = nullptr;
+    size_t blob_cap = 0;
+    JgLayoutHeader hdr{};
+    DevLayout L{};
+    bool has_layout = false;
+    uint64_t epoch = 0;
+
+    std::map<int, ItemDev> items;
+    std::map<int, FilterDev> filters;
+
+    cudaStream_t compute = nullptr;
+    ChunkCtx main_ctx;  // scratch of the *_device calls (compute stream)
+    std::vector<ChunkCtx> chunks;
+    int64_t chunk_queries = 1 << 18;
+    int detect_group = 0, collect_group = 0;  // 0 = auto
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;  // jg_timer_*
+    bool timing_valid = false;
+    uint32_t* d_flush = nullptr;
+    size_t flush_words = 0;
+
+    uint64_t stat_launches = 0, stat_queries = 0, stat_h2d = 0, stat_d2h = 0, stat_uploads = 0;
+};
+
+#define JG_CUDA(e, call)                                                                             \
+    do {                                                                                             \
+        cudaError_t _err = (call);                                                                   \
+        if (_err != cudaSuccess) {                                                                   \
+            (e)->err = std::string(#call) + ": " + cudaGetErrorString(_err);                         \
+            return JG_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+static int fail(JgEngine* e, int code, const char* msg) {
+    e->err = msg;
+    return code;
+}
+
+static int auto_group(int n_verts) {
+    // lanes per query in stage 2 / collect: enough lanes to cover the polygon in ~3 rounds
+    if (n_verts <= 12) return 4;
+    if (n_verts <= 48) return 8;
+    if (n_verts <= 128) return 16;
+    return 32;
+}
+
+static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bool own_xf) {
+    if (own_xf && c.cap_q < n_q) {
+        if (c.d_xf) cudaFree(c.d_xf);
+        JG_CUDA(e, cudaMalloc(&c.d_xf, n_q * sizeof(float4)));
+        c.cap_q = n_q;
+    }
+    if (out_bytes && c.cap_out < out_bytes) {
+        if (c.d_out) cudaFree(c.d_out);
+        JG_CUDA(e, cudaMalloc(&c.d_out, out_bytes));
+        c.cap_out = out_bytes;
+    }
+    if (c.cap_sv < n_q) {
+        if (c.sv.query) cudaFree(c.sv.query);
+        if (c.sv.vroot) cudaFree(c.sv.vroot);
+        if (c.sv.bbox) cudaFree(c.sv.bbox);
+        if (!c.sv.count) JG_CUDA(e, cudaMalloc(&c.sv.count, 64));
+        JG_CUDA(e, cudaMalloc(&c.sv.query, n_q * sizeof(int)));
+        JG_CUDA(e, cudaMalloc(&c.sv.vroot, n_q * sizeof(int)));
+        JG_CUDA(e, cudaMalloc(&c.sv.bbox, n_q * sizeof(float4)));
+        c.cap_sv = n_q;
+    }
+    return JG_OK;
+}
+
+static void free_ctx(ChunkCtx& c) {
+    if (c.d_xf) cudaFree(c.d_xf);
+    if (c.d_out) cudaFree(c.d_out);
+    if (c.sv.count) cudaFree(c.sv.count);
+    if (c.sv.query) cudaFree(c.sv.query);
+    if (c.sv.vroot) cudaFree(c.sv.vroot);
+    if (c.sv.bbox) cudaFree(c.sv.bbox);
+    c = ChunkCtx{};
+}
+
+static DevItem dev_item(const JgEngine* e, const ItemDev& it) {
+    DevItem d;
+    d.verts = it.verts;
+    d.n_verts = it.n_verts;
+    d.poi_x = it.poi_x;
+    d.poi_y = it.poi_y;
+    d.poles = it.poles;
+    d.n_poles = it.n_poles < e->cfg.n_ff_poles ? it.n_poles : e->cfg.n_ff_poles;
+    d.piers = it.piers;
+    d.n_piers = it.n_piers;
+    return d;
+}
+
+extern "C" {
+
+int jg_engine_create(int device, const JgConfig* cfg, JgEngine** out) {
+    if (!cfg || !out) return JG_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->quadtree_depth < 0 || cfg->quadtree_depth > JG_MAX_DEPTH || cfg->cd_threshold < 0 ||
+        cfg->n_ff_poles < 0 || cfg->n_ff_piers < 0)
+        return JG_ERR_INVALID;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return JG_ERR_CUDA;
+    JgEngine* e = new JgEngine();
+    e->device = device;
+    e->cfg = *cfg;
+    cudaError_t err = cudaSetDevice(device);
+    cudaDeviceProp prop;
+    if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, device);
+    if (err == cudaSuccess) {
+        e->n_sms = prop.multiProcessorCount;
+        err = cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking);
+    }
+    if (err == cudaSuccess) err = cudaEventCreate(&e->ev0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e->ev1);
+    if (err == cudaSuccess) err = cudaEventCreate(&e->tm0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e->tm1);
+    if (err != cudaSuccess) {
+        delete e;
+        return JG_ERR_CUDA;
+    }
+    e->main_ctx.st = e->compute;
+    e->chunks.resize(3);
+    for (ChunkCtx& c : e->chunks)
+        if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) {
+            delete e;
+            return JG_ERR_CUDA;
+        }
+    *out = e;
+    return JG_OK;
+}
+
+void jg_engine_destroy(JgEngine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : e->items) {
+        cudaFree(kv.second.verts);
+        cudaFree(kv.second.poles);
+        cudaFree(kv.second.piers);
+    }
+    for (auto& kv : e->filters) cudaFree(kv.second.bits);
+    for (ChunkCtx& c : e->chunks) {
+        cudaStream_t st = c.st;
+        free_ctx(c);
+        if (st) cudaStreamDestroy(st);
+    }
+    free_ctx(e->main_ctx);
+    if (e->d_blob) cudaFree(e->d_blob);
+    if (e->d_flush) cudaFree(e->d_flush);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->tm0) cudaEventDestroy(e->tm0);
+    if (e->tm1) cudaEventDestroy(e->tm1);
+    if (e->compute) cudaStreamDestroy(e->compute);
+    delete e;
+}
+
+const char* jg_last_error(const JgEngine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int jg_sync(JgEngine* e) {
+    if (!e) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
+    JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    return JG_OK;
+}
+
+static int validate_header(JgEngine* e, const JgLayoutHeader& h, size_t bytes) {
+    if (bytes < sizeof(JgLayoutHeader) || h.magic != JG_LAYOUT_MAGIC || h.version != JG_LAYOUT_VERSION)
+        return fail(e, JG_ERR_INVALID, "layout blob: bad magic / version");
+    if (h.total_bytes > bytes || h.n_nodes == 0) return fail(e, JG_ERR_INVALID, "layout blob: truncated");
+    if (h.root_level > JG_MAX_DEPTH) return fail(e, JG_ERR_INVALID, "layout blob: quadtree too deep");
+    struct {
+        uint32_t off, n, sz;
+    } secs[] = {{h.off_node_meta, h.n_nodes, 16},  {h.off_node_bbox, h.n_nodes, 16},    {h.off_node_nactive, h.n_nodes, 4},
+                {h.off_entry_meta, h.n_entries, 16}, {h.off_entry_ffbbox, h.n_entries, 16}, {h.off_edges, h.n_edges, 16},
+                {h.off_haz_meta, h.n_slots, 16},   {h.off_haz_bbox, h.n_slots, 16},     {h.off_haz_poi, h.n_slots, 16},
+                {h.off_haz_verts, h.n_haz_verts, 8}};
+    for (auto& s : secs)
+        if ((s.off & 15u) || (uint64_t)s.off + (uint64_t)s.n * s.sz > h.total_bytes)
+            return fail(e, JG_ERR_INVALID, "layout blob: section out of bounds / misaligned");
+    return JG_OK;
+}
+
+static void bind_layout(JgEngine* e, const JgLayoutHeader& h) {
+    const char* b = (const char*)e->d_blob;
+    e->hdr = h;
+    e->L.node_meta = (const int4*)(b + h.off_node_meta);
+    e->L.node_bbox = (const float4*)(b + h.off_node_bbox);
+    e->L.node_nactive = (const uint32_t*)(b + h.off_node_nactive);
+    e->L.entry_meta = (const int4*)(b + h.off_entry_meta);
+    e->L.entry_ff = (const float4*)(b + h.off_entry_ffbbox);
+    e->L.edges = (const float4*)(b + h.off_edges);
+    e->L.haz_meta = (const int4*)(b + h.off_haz_meta);
+    e->L.haz_bbox = (const float4*)(b + h.off_haz_bbox);
+    e->L.haz_poi = (const float4*)(b + h.off_haz_poi);
+    e->L.haz_verts = (const float2*)(b + h.off_haz_verts);
+    e->L.cde_bbox = Rect{h.cde_bbox[0], h.cde_bbox[1], h.cde_bbox[2], h.cde_bbox[3]};
+    e->L.n_nodes = (int)h.n_nodes;
+    e->L.n_slots = (int)h.n_slots;
+    e->L.cd_threshold = (int)h.cd_threshold;
+    e->L.exterior_slot = (int)h.exterior_slot;
+    e->has_layout = true;
+}
+
+static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t epoch, bool src_on_device) {
+    if (!e || !src) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    JgLayoutHeader h;
+    if (bytes < sizeof(h)) return fail(e, JG_ERR_INVALID, "layout blob: truncated");
+    if (src_on_device) JG_CUDA(e, cudaMemcpy(&h, src, sizeof(h), cudaMemcpyDeviceToHost));
+    else std::memcpy(&h, src, sizeof(h));
+    int rc = validate_header(e, h, bytes);
+    if (rc != JG_OK) return rc;
+    if (!src_on_device) {
+        // structural checks the kernels rely on: children blocks at 1 + 4k, indices in range
+        const int32_t* nm = (const int32_t*)((const char*)src + h.off_node_meta);
+        for (uint32_t i = 0; i < h.n_nodes; i++) {
+            const int32_t cb = nm[4 * i], eb = nm[4 * i + 1], cnt = nm[4 * i + 2], par = nm[4 * i + 3];
+            const uint32_t n_ent = (uint32_t)(cnt & 0xFFFF) + (uint32_t)((cnt >> 16) & 0xFFFF);
+            if (cb >= 0 && ((cb & 3) != 1 || (uint32_t)cb + 4 > h.n_nodes)) return fail(e, JG_ERR_INVALID, "layout blob: bad child block");
+            if (eb < 0 || (uint32_t)eb + n_ent > h.n_entries) return fail(e, JG_ERR_INVALID, "layout blob: bad entry range");
+            if (par >= (int32_t)h.n_nodes || (i > 0 && par < 0)) return fail(e, JG_ERR_INVALID, "layout blob: bad parent");
+        }
+        const int32_t* em = (const int32_t*)((const char*)src + h.off_entry_meta);
+        for (uint32_t i = 0; i < h.n_entries; i++) {
+            if (em[4 * i] < 0 || (uint32_t)em[4 * i] >= h.n_slots) return fail(e, JG_ERR_INVALID, "layout blob: bad hazard slot");
+            if (em[4 * i + 1] < 0 || em[4 * i + 2] < 0 || (uint32_t)em[4 * i + 1] + (uint32_t)em[4 * i + 2] > h.n_edges)
+                return fail(e, JG_ERR_INVALID, "layout blob: bad edge range");
+        }
+    }
+    rc = jg_sync(e);  // queries in flight finish on the old layout
+    if (rc != JG_OK) return rc;
+    if (e->blob_cap < h.total_bytes) {
+        if (e->d_blob) cudaFree(e->d_blob);
+        e->d_blob = nullptr;
+        e->blob_cap = 0;
+        const size_t cap = (size_t)h.total_bytes * 2 + 4096;
+        JG_CUDA(e, cudaMalloc(&e->d_blob, cap));
+        e->blob_cap = cap;
+    }
+    JG_CUDA(e, cudaMemcpyAsync(e->d_blob, src, h.total_bytes,
+                               src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->compute));
+    JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    bind_layout(e, h);
+    e->epoch = epoch;
+    e->stat_uploads++;
+    if (!src_on_device) e->stat_h2d += h.total_bytes;
+    return JG_OK;
+}
+
+int jg_layout_upload(JgEngine* e, const void* blob, size_t bytes, uint64_t epoch) {
+    return upload_common(e, blob, bytes, epoch, false);
+}
+int jg_layout_upload_device(JgEngine* e, const void* d_blob, size_t bytes, uint64_t epoch) {
+    return upload_common(e, d_blob, bytes, epoch, true);
+}
+uint64_t jg_engine_layout_epoch(const JgEngine* e) { return e ? e->epoch : 0; }
+
+int jg_item_upload(JgEngine* e, int item_id, const float* verts_xy, int n_verts, const float* poi_xy,
+                   const float* poles_xyr, int n_poles, const float* piers, int n_piers) {
+    if (!e || !verts_xy || n_verts < 3 || !poi_xy || n_poles < 0 || n_piers < 0) return JG_ERR_INVALID;
+    if (n_verts > 4096) return fail(e, JG_ERR_CAPACITY, "item has more than 4096 vertices");
+    JG_CUDA(e, cudaSetDevice(e->device));
+    int rc = jg_sync(e);
+    if (rc != JG_OK) return rc;
+    ItemDev& it = e->items[item_id];
+    cudaFree(it.verts);
+    cudaFree(it.poles);
+    cudaFree(it.piers);
+    it = ItemDev{};
+    it.n_verts = n_verts;
+    it.poi_x = poi_xy[0];
+    it.poi_y = poi_xy[1];
+    it.n_poles = n_poles;
+    it.n_piers = n_piers;
+    JG_CUDA(e, cudaMalloc(&it.verts, (size_t)n_verts * sizeof(float2)));
+    JG_CUDA(e, cudaMemcpy(it.verts, verts_xy, (size_t)n_verts * sizeof(float2), cudaMemcpyHostToDevice));
+    std::vector<float4> tmp;
+    if (n_poles) {
+        tmp.resize(n_poles);
+        for (int i = 0; i < n_poles; i++) tmp[i] = make_float4(poles_xyr[3 * i], poles_xyr[3 * i + 1], poles_xyr[3 * i + 2], 0.f);
+        JG_CUDA(e, cudaMalloc(&it.poles, (size_t)n_poles * sizeof(float4)));
+        JG_CUDA(e, cudaMemcpy(it.poles, tmp.data(), (size_t)n_poles * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    if (n_piers) {
+        JG_CUDA(e, cudaMalloc(&it.piers, (size_t)n_piers * sizeof(float4)));
+        JG_CUDA(e, cudaMemcpy(it.piers, piers, (size_t)n_piers * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    return JG_OK;
+}
+
+int jg_filter_upload(JgEngine* e, int filter_id, const uint32_t* bits, int words) {
+    if (!e || filter_id < 0 || !bits || words <= 0) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    int rc = jg_sync(e);
+    if (rc != JG_OK) return rc;
+    FilterDev& f = e->filters[filter_id];
+    cudaFree(f.bits);
+    f = FilterDev{};
+    JG_CUDA(e, cudaMalloc(&f.bits, (size_t)words * 4));
+    JG_CUDA(e, cudaMemcpy(f.bits, bits, (size_t)words * 4, cudaMemcpyHostToDevice));
+    f.words = words;
+    return JG_OK;
+}
+
+// resolves ids and checks the preconditions shared by all query calls
+static int query_prologue(JgEngine* e, int item_id, int filter_id, const ItemDev** it, const uint32_t** d_filt) {
+    if (!e) return JG_ERR_INVALID;
+    if (!e->has_layout) return fail(e, JG_ERR_NO_LAYOUT, "no layout uploaded");
+    auto f = e->items.find(item_id);
+    if (f == e->items.end()) return fail(e, JG_ERR_INVALID, "unknown item id");
+    *it = &f->second;
+    *d_filt = nullptr;
+    if (filter_id >= 0) {
+        auto g = e->filters.find(filter_id);
+        if (g == e->filters.end()) return fail(e, JG_ERR_INVALID, "unknown filter id");
+        if ((size_t)g->second.words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "filter bitset smaller than the hazard slot capacity");
+        *d_filt = g->second.bits;
+    }
+    return JG_OK;
+}
+
+int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int filter_id, int mode,
+                           uint8_t* d_out) {
+    const ItemDev* it;
+    const uint32_t* d_filt;
+    int rc = query_prologue(e, item_id, filter_id, &it, &d_filt);
+    if (rc != JG_OK) return rc;
+    if (n < 0 || n > 0x7FFFFFFF || (n > 0 && (!d_transforms || !d_out))) return JG_ERR_INVALID;
+    if (n == 0) return JG_OK;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    rc = ensure_ctx(e, e->main_ctx, (size_t)n, 0, false);
+    if (rc != JG_OK) return rc;
+    const int group = e->detect_group ? e->detect_group : auto_group(it->n_verts);
+    int launches = 0;
+    JG_CUDA(e, cudaEventRecord(e->ev0, e->compute));
+    JG_CUDA(e, launch_detect(e->L, dev_item(e, *it), (const float4*)d_transforms, n, d_filt, mode, d_out, e->main_ctx.sv,
+                             group, e->n_sms, e->compute, &launches));
+    JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
+    e->timing_valid = true;
+    e->stat_launches += launches;
+    e->stat_queries += (uint64_t)n;
+    return JG_OK;
+}
+
+int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int mode,
+                            uint32_t* d_out_bits, int words) {
+    const ItemDev* it;
+    const uint32_t* d_filt;
+    int rc = query_prologue(e, item_id, -1, &it, &d_filt);
+    if (rc != JG_OK) return rc;
+    if (n < 0 || words <= 0 || (n > 0 && (!d_transforms || !d_out_bits))) return JG_ERR_INVALID;
+    if ((size_t)words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "collector words do not cover the hazard slot capacity");
+    if (words > 1024) return fail(e, JG_ERR_CAPACITY, "collector wider than 1024 words");
+    if (n == 0) return JG_OK;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    const int group = e->collect_group ? e->collect_group : auto_group(it->n_verts);
+    int launches = 0;
+    JG_CUDA(e, cudaEventRecord(e->ev0, e->compute));
+    JG_CUDA(e, launch_collect(e->L, dev_item(e, *it), (const float4*)d_transforms, n, mode, d_out_bits, words, group,
+                              e->n_sms, e->compute, &launches));
+    JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
+    e->timing_valid = true;
+    e->stat_launches += launches;
+    e->stat_queries += (uint64_t)n;
+    return JG_OK;
+}
+
+// Host-pointer batches: split into chunks, each chunk on its own stream so the H2D copy of chunk
+// k+1 overlaps the kernels of chunk k and the D2H copy of chunk k-1.
+static int run_host_batch(JgEngine* e, const ItemDev* it, const uint32_t* d_filt, const float* transforms, int64_t n,
+                          int mode, bool collect, void* out, int words) {
+    JG_CUDA(e, cudaSetDevice(e->device));
+    const size_t out_per_q = collect ? (size_t)words * 4 : 1;
+    const int64_t chunk = e->chunk_queries;
+    const int group = collect ? (e->collect_group ? e->collect_group : auto_group(it->n_verts))
+                              : (e->detect_group ? e->detect_group : auto_group(it->n_verts));
+    const DevItem di = dev_item(e, *it);
+    int k = 0;
+    for (int64_t off = 0; off < n; off += chunk, k++) {
+        const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+        ChunkCtx& c = e->chunks[k % e->chunks.size()];
+        JG_CUDA(e, cudaStreamSynchronize(c.st));  // buffers of this slot are free again
+        int rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n) * out_per_q, true);
+        if (rc != JG_OK) return rc;
+        JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * off, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
+        int launches = 0;
+        if (collect) {
+            JG_CUDA(e, launch_collect(e->L, di, c.d_xf, m, mode, (uint32_t*)c.d_out, words, group, e->n_sms, c.st, &launches));
+        } else {
+            JG_CUDA(e, launch_detect(e->L, di, c.d_xf, m, d_filt, mode, c.d_out, c.sv, group, e->n_sms, c.st, &launches));
+        }
+        JG_CUDA(e, cudaMemcpyAsync((char*)out + (size_t)off * out_per_q, c.d_out, (size_t)m * out_per_q, cudaMemcpyDeviceToHost, c.st));
+        e->stat_launches += launches;
+        e->stat_h2d += (uint64_t)m * sizeof(float4);
+        e->stat_d2h += (uint64_t)m * out_per_q;
+    }
+    for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
+    e->stat_queries += (uint64_t)n;
+    return JG_OK;
+}
+
+int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode, uint8_t* out) {
+    const ItemDev* it;
+    const uint32_t* d_filt;
+    int rc = query_prologue(e, item_id, filter_id, &it, &d_filt);
+    if (rc != JG_OK) return rc;
+    if (n < 0 || (n > 0 && (!transforms || !out))) return JG_ERR_INVALID;
+    if (n == 0) return JG_OK;
+    return run_host_batch(e, it, d_filt, transforms, n, mode, false, out, 0);
+}
+
+int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words) {
+    const ItemDev* it;
+    const uint32_t* d_filt;
+    int rc = query_prologue(e, item_id, -1, &it, &d_filt);
+    if (rc != JG_OK) return rc;
+    if (n < 0 || words <= 0 || (n > 0 && (!transforms || !out_bits))) return JG_ERR_INVALID;
+    if ((size_t)words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "collector words do not cover the hazard slot capacity");
+    if (words > 1024) return fail(e, JG_ERR_CAPACITY, "collector wider than 1024 words");
+    if (n == 0) return JG_OK;
+    return run_host_batch(e, it, d_filt, transforms, n, mode, true, out_bits, words);
+}
+
+int jg_engine_stats(const JgEngine* e, uint64_t out[8]) {
+    if (!e || !out) return JG_ERR_INVALID;
+    std::memset(out, 0, 8 * sizeof(uint64_t));
+    out[0] = e->stat_launches;
+    out[1] = e->stat_queries;
+    out[2] = e->stat_h2d;
+    out[3] = e->stat_d2h;
+    out[4] = e->stat_uploads;
+    if (e->main_ctx.sv.count) {
+        int c = 0;
+        cudaSetDevice(e->device);
+        if (cudaMemcpy(&c, e->main_ctx.sv.count, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) out[5] = (uint64_t)c;
+    }
+    return JG_OK;
+}
+
+float jg_engine_last_kernel_ms(JgEngine* e) {
+    if (!e || !e->timing_valid) return -1.0f;
+    cudaSetDevice(e->device);
+    if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+int jg_timer_start(JgEngine* e) {
+    if (!e) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    JG_CUDA(e, cudaEventRecord(e->tm0, e->compute));
+    return JG_OK;
+}
+int jg_timer_stop(JgEngine* e, float* ms) {
+    if (!e || !ms) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    JG_CUDA(e, cudaEventRecord(e->tm1, e->compute));
+    JG_CUDA(e, cudaEventSynchronize(e->tm1));
+    JG_CUDA(e, cudaEventElapsedTime(ms, e->tm0, e->tm1));
+    return JG_OK;
+}
+
+int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams) {
+    if (!e || chunk_queries < 1 || chunk_queries > 0x7FFFFFFF || n_streams < 1 || n_streams > 16) return JG_ERR_INVALID;
+    int rc = jg_sync(e);
+    if (rc != JG_OK) return rc;
+    e->chunk_queries = chunk_queries;
+    while ((int)e->chunks.size() > n_streams) {
+        cudaStream_t st = e->chunks.back().st;
+        free_ctx(e->chunks.back());
+        cudaStreamDestroy(st);
+        e->chunks.pop_back();
+    }
+    while ((int)e->chunks.size() < n_streams) {
+        ChunkCtx c;
+        JG_CUDA(e, cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+        e->chunks.push_back(c);
+    }
+    for (ChunkCtx& c : e->chunks) {  // buffers are re-sized lazily
+        cudaStream_t st = c.st;
+        free_ctx(c);
+        c.st = st;
+    }
+    return JG_OK;
+}
+
+int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group) {
+    auto ok = [](int g) { return g == 0 || g == 4 || g == 8 || g == 16 || g == 32; };
+    if (!e || !ok(detect_group) || !ok(collect_group)) return JG_ERR_INVALID;
+    e->detect_group = detect_group;
+    e->collect_group = collect_group;
+    return JG_OK;
+}
+
+int jg_host_alloc(size_t bytes, void** out) {
+    if (!out) return JG_ERR_INVALID;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? JG_OK : JG_ERR_CUDA;
+}
+int jg_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? JG_OK : JG_ERR_CUDA; }
+int jg_device_alloc(JgEngine* e, size_t bytes, void** out) {
+    if (!e || !out) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    JG_CUDA(e, cudaMalloc(out, bytes ? bytes : 1));
+    return JG_OK;
+}
+int jg_device_free(JgEngine* e, void* p) {
+    if (!e) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    JG_CUDA(e, cudaFree(p));
+    return JG_OK;
+}
+int jg_memcpy_h2d(JgEngine* e, void* d_dst, const void* src, size_t bytes) {
+    if (!e) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    JG_CUDA(e, cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, e->compute));
+    JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    return JG_OK;
+}
+int jg_memcpy_d2h(JgEngine* e, void* dst, const void* d_src, size_t bytes) {
+    if (!e) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    JG_CUDA(e, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, e->compute));
+    JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    return JG_OK;
+}
+
+void jg_compose_batch(const float* rot_tx_ty, int64_t n, float* out4, int n_threads) {
+    auto work = [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; i++) {
+            const float r = rot_tx_ty[3 * i];
+            out4[4 * i + 0] = cosf(r);
+            out4[4 * i + 1] = sinf(r);
+            out4[4 * i + 2] = rot_tx_ty[3 * i + 1];
+            out4[4 * i + 3] = rot_tx_ty[3 * i + 2];
+        }
+    };
+    if (n_threads <= 1 || n < 4096) {
+        work(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int k = 0; k < n_threads; k++) th.emplace_back(work, n * k / n_threads, n * (k + 1) / n_threads);
+    for (auto& t : th) t.join();
+}
+
+int jg_fp32_nofma_peak(JgEngine* e, double* gflops, float* ms_out) {
+    if (!e || !gflops) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    const int blocks = e->n_sms * 8, iters = 1 << 15;
+    float* d = nullptr;
+    JG_CUDA(e, cudaMalloc(&d, (size_t)blocks * 256 * sizeof(float)));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        JG_CUDA(e, cudaEventRecord(e->ev0, e->compute));
+        JG_CUDA(e, launch_fp32_nofma(d, blocks, iters, e->compute));
+        JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
+        JG_CUDA(e, cudaEventSynchronize(e->ev1));
+        float ms = 0;
+        JG_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    e->timing_valid = false;
+    e->stat_launches += 5;
+    *gflops = (double)blocks * 256.0 * (double)iters * 8.0 / ((double)best * 1e-3) / 1e9;
+    if (ms_out) *ms_out = best;
+    return JG_OK;
+}
+
+int jg_flush_l2(JgEngine* e) {
+    if (!e) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    if (!e->d_flush) {
+        e->flush_words = (size_t)64 << 20;  // 256 MiB > 126 MB L2
+        JG_CUDA(e, cudaMalloc(&e->d_flush, e->flush_words * 4));
+    }
+    JG_CUDA(e, launch_fill(e->d_flush, e->flush_words, (uint32_t)e->stat_launches, e->n_sms, e->compute));
+    e->stat_launches++;
+    return JG_OK;
+}
+
+// ---- host mirror of CDEngine's update path ------------------------------------------------------------
+struct JgCdeBox {
+    HostCDE cde;
+    JgCdeBox(Rect r, JgConfig c) : cde(r, c) {}
+};
+
+int jg_cde_create(const float bbox4[4], const JgConfig* cfg, JgCde** out) {
+    if (!bbox4 || !cfg || !out) return JG_ERR_INVALID;
+    if (cfg->quadtree_depth < 0 || cfg->quadtree_depth > JG_MAX_DEPTH) return JG_ERR_INVALID;
+    if (!(bbox4[0] < bbox4[2] && bbox4[1] < bbox4[3])) return JG_ERR_INVALID;
+    *out = (JgCde*)new JgCdeBox(Rect{bbox4[0], bbox4[1], bbox4[2], bbox4[3]}, *cfg);
+    return JG_OK;
+}
+void jg_cde_destroy(JgCde* c) { delete (JgCdeBox*)c; }
+const char* jg_cde_last_error(const JgCde* c) { return c ? ((const JgCdeBox*)c)->cde.last_error.c_str() : "null cde"; }
+
+int jg_cde_register_hazard(JgCde* c, int kind, int64_t id, int64_t quality, uint64_t pk, const float* verts_xy,
+                           int n_verts, const float* poi_xy, int dynamic, uint64_t* hkey) {
+    if (!c || !verts_xy || n_verts < 3 || !poi_xy || kind < 0 || kind > 3) return JG_ERR_INVALID;
+    HostCDE& cde = ((JgCdeBox*)c)->cde;
+    HostHazard hz;
+    hz.kind = kind;
+    hz.id = id;
+    hz.quality = quality;
+    hz.pk = pk;
+    hz.dynamic = dynamic != 0;
+    hz.xy.assign(verts_xy, verts_xy + 2 * (size_t)n_verts);
+    hz.poi_x = poi_xy[0];
+    hz.poi_y = poi_xy[1];
+    cde.last_error.clear();
+    const uint64_t k = cde.register_hazard(std::move(hz));
+    if (hkey) *hkey = k;
+    return cde.last_error.empty() ? JG_OK : JG_ERR_REFERENCE_PANIC;
+}
+int jg_cde_deregister_hazard(JgCde* c, uint64_t hkey) {
+    if (!c) return JG_ERR_INVALID;
+    return ((JgCdeBox*)c)->cde.deregister_hazard(hkey) ? JG_OK : JG_ERR_INVALID;
+}
+int jg_cde_hkey_from_pk(const JgCde* c, uint64_t pk, uint64_t* hkey) {
+    if (!c || !hkey) return JG_ERR_INVALID;
+    *hkey = ((const JgCdeBox*)c)->cde.hkey_from_pk(pk);
+    return JG_OK;
+}
+int jg_cde_save(JgCde* c, int* snapshot_id) {
+    if (!c || !snapshot_id) return JG_ERR_INVALID;
+    *snapshot_id = ((JgCdeBox*)c)->cde.save();
+    return JG_OK;
+}
+int jg_cde_restore(JgCde* c, int snapshot_id) {
+    if (!c) return JG_ERR_INVALID;
+    return ((JgCdeBox*)c)->cde.restore(snapshot_id) ? JG_OK : JG_ERR_INVALID;
+}
+int jg_cde_slot_capacity(const JgCde* c) { return c ? ((const JgCdeBox*)c)->cde.slot_capacity() : 0; }
+int jg_cde_n_hazards(const JgCde* c) { return c ? ((const JgCdeBox*)c)->cde.n_hazards() : 0; }
+uint64_t jg_cde_hkey_exterior(const JgCde* c) { return c ? ((const JgCdeBox*)c)->cde.hkey_exterior() : 0; }
+int jg_cde_filter_qzones(const JgCde* c, int required_quality, uint32_t* bits, int words) {
+    if (!c || !bits || words <= 0) return JG_ERR_INVALID;
+    ((const JgCdeBox*)c)->cde.filter_qzones(required_quality, bits, words);
+    return JG_OK;
+}
+int64_t jg_cde_flatten(JgCde* c, void* buf, int64_t cap) {
+    if (!c) return JG_ERR_INVALID;
+    HostCDE& cde = ((JgCdeBox*)c)->cde;
+    if (cde.hkey_exterior() == 0) {
+        cde.last_error = "No exterior hazard registered in the CDE";  // cd_engine.rs:48
+        return JG_ERR_INVALID;
+    }
+    std::vector<uint8_t> blob = cde.flatten();
+    if (buf && cap >= (int64_t)blob.size()) std::memcpy(buf, blob.data(), blob.size());
+    return (int64_t)blob.size();
+}
+int jg_cde_sync_to_engine(JgCde* c, JgEngine* e, uint64_t* epoch) {
+    if (!c || !e) return JG_ERR_INVALID;
+    HostCDE& cde = ((JgCdeBox*)c)->cde;
+    if (cde.hkey_exterior() == 0) return fail(e, JG_ERR_INVALID, "No exterior hazard registered in the CDE");
+    std::vector<uint8_t> blob = cde.flatten();
+    int rc = jg_layout_upload(e, blob.data(), blob.size(), cde.epoch);
+    if (rc == JG_OK && epoch) *epoch = cde.epoch;
+    return rc;
+}
+int64_t jg_cde_tree_dump(const JgCde* c, uint32_t* out, int64_t cap) {
+    if (!c) return JG_ERR_INVALID;
+    std::vector<uint32_t> v = ((const JgCdeBox*)c)->cde.tree_dump();
+    if (out)
+        for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) out[i] = v[i];
+    return (int64_t)v.size();
+}
+
+}  // extern "C"

@@ -218,6 +218,35 @@ int orc_cde_finish(World* w) {
     return 0;
     ORC_CATCH(w, -1)
 }
+// Raw (de)registration of a hazard on the current layout's CDE (cd_engine.rs:59-96): shapes are taken
+// as-is. Used to rebuild a layout from a workload fixture with the same slot numbering.
+uint64_t orc_register_hazard_raw(World* w, int kind, int64_t id, int64_t quality, uint64_t pk, const float* xy,
+                                 int n, const float* poi_xyr, int dynamic) {
+    ORC_TRY(w)
+    HazardEntity e;
+    e.kind = (EntityKind)kind;
+    e.id = id;
+    e.quality = quality;
+    e.pk = pk;
+    return w->layout->cde.register_hazard({e, raw_polygon(xy, n, poi_xyr), dynamic != 0}).as_u64();
+    ORC_CATCH(w, 0)
+}
+int orc_deregister_hazard(World* w, uint64_t key) {
+    ORC_TRY(w)
+    w->layout->cde.deregister_hazard_by_key(HazKey::from_u64(key));
+    return 0;
+    ORC_CATCH(w, -1)
+}
+int orc_cde_save(World* w) {
+    w->snapshots.push_back(std::make_unique<CDESnapshot>(w->layout->cde.save()));
+    return (int)w->snapshots.size() - 1;
+}
+int orc_cde_restore(World* w, int snap) {
+    ORC_TRY(w)
+    w->layout->cde.restore(*w->snapshots.at(snap));
+    return 0;
+    ORC_CATCH(w, -1)
+}
 void orc_cde_bbox(World* w, float* out4) {
     Rect b = w->layout->cde.bbox();
     out4[0] = b.x_min;

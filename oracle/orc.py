@@ -66,6 +66,10 @@ def lib(count: bool = False):
         "orc_cde_add_static": (None, [vp, C.c_int, C.c_int64, C.c_int64, f32p, C.c_int, f32p]),
         "orc_cde_finish": (C.c_int, [vp]),
         "orc_cde_bbox": (None, [vp, f32p]),
+        "orc_register_hazard_raw": (C.c_uint64, [vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64, f32p, C.c_int, f32p, C.c_int]),
+        "orc_deregister_hazard": (C.c_int, [vp, C.c_uint64]),
+        "orc_cde_save": (C.c_int, [vp]),
+        "orc_cde_restore": (C.c_int, [vp, C.c_int]),
         "orc_place_item": (C.c_uint64, [vp, C.c_int, C.c_float, C.c_float, C.c_float]),
         "orc_remove_item": (C.c_int, [vp, C.c_uint64]),
         "orc_n_placed": (C.c_int, [vp]),
@@ -203,6 +207,22 @@ class OracleWorld:
             v = _f32(h["verts"]).reshape(-1, 2)
             self.L.orc_cde_add_static(self.w, int(h["kind"]), int(h["id"]), int(h["quality"]), v, len(v), _f32(h["poi"]))
         self._chk(self.L.orc_cde_finish(self.w))
+
+    def register_hazard_raw(self, kind, verts, poi, id=0, quality=0, pk=0, dynamic=True) -> int:
+        v = _f32(verts).reshape(-1, 2)
+        p = np.zeros(3, np.float32)
+        p[:len(np.ravel(poi))] = np.ravel(poi)[:3]
+        return self._chk(self.L.orc_register_hazard_raw(self.w, int(kind), int(id), int(quality), int(pk), v, len(v), p,
+                                                        1 if dynamic else 0), 0)
+
+    def deregister_hazard(self, key):
+        self._chk(self.L.orc_deregister_hazard(self.w, int(key)))
+
+    def cde_save(self) -> int:
+        return self.L.orc_cde_save(self.w)
+
+    def cde_restore(self, snap):
+        self._chk(self.L.orc_cde_restore(self.w, int(snap)))
 
     def cde_bbox(self) -> np.ndarray:
         b = np.zeros(4, np.float32)

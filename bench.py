@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — collision queries/s of the batched CDE on B200 (BASELINE.json config 2).
+
+A step = one pass of the hot path (detect_surrogate_collision + detect_poly_collision) over one
+1,048,576-query batch of the swim instance against the half-filled swim layout: 10 item types x
+~104,858 seeded (cos, sin, tx, ty) queries each (workloads/swim_half.npz, tools/make_workloads.py).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+value      queries/s, inputs resident in HBM, CUDA events on the engine's compute stream, L2 flushed
+           (untimed) before every step.
+e2e        queries/s through the public host-buffer API (CDEngine.detect_batch_async on pinned host
+           arrays + sync): H2D of the transforms and D2H of the verdicts inside the timed region.
+roofline   FP32 pipe without FMA (the kernels are compiled -fmad=false for bit-exactness): algorithmic
+           flops counted by the instrumented oracle (workloads/swim_half.flops.json) / device time,
+           against the peak measured live by jg_fp32_nofma_peak. The HBM view of the same step is
+           reported beside it (17 algorithmic bytes per query).
+cpu_baseline  the CPU restatement of the reference (oracle/, all host threads) on the same batch, and
+           a full-batch verdict comparison (mismatches must be 0).
+N > 1      one process per GPU (torchrun); the layout blob is flattened on rank 0 and broadcast over
+           NCCL, every rank resolves its own 1M-query batch (weak scaling), no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT,):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "collision queries/sec (swim, 1M placements, detect)"
+UNIT = "queries/s"
+WORKLOAD = "swim_half"
+TOTAL_QUERIES = 1 << 20
+ALG_BYTES_PER_QUERY = 17  # 16 B (cos, sin, tx, ty) in + 1 B verdict out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--queries", type=int, default=TOTAL_QUERIES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_oracle():
+    """CPU restatement of the reference (test infrastructure): only the cpu_baseline / --impl reference
+    legs come here."""
+    for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import orc
+    from helpers import oracle_world
+    orc.build()
+    return orc, oracle_world
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU implementation of the path on the host cores. The Rust
+    crate cannot be built in this image (no cargo), so this is the oracle port, all host threads."""
+    if rank != 0:
+        return
+    import jagua_rs_b200 as jg
+    orc, oracle_world = load_oracle()
+    wl = jg.load_workload(args.workload)
+    w = oracle_world(orc, wl)
+    sizes = jg.split_batch(args.queries, len(wl.items))
+    qs = [jg.make_queries(wl, i, n, seed=0) for i, n in enumerate(sizes)]
+    cores = os.cpu_count() or 1
+
+    def step():
+        for i, q in enumerate(qs):
+            w.detect_batch(i, q, nthreads=cores)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = args.queries * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {args.queries} uniform queries over the CDE bbox, 10 swim item types, "
+                                   "24 placed items + exterior, quadtree depth 5", "queries_per_step": args.queries},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"the full {args.queries}-query batch per step, std::thread static sharding"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import jagua_rs_b200 as jg
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = jg.load_workload(args.workload)
+    with open(os.path.join(ROOT, "workloads", f"{args.workload}.flops.json")) as f:
+        flops_info = json.load(f)
+
+    # ---- layout: built + flattened on rank 0, broadcast (NCCL) and uploaded from device memory elsewhere
+    t_b0 = time.perf_counter()
+    if world > 1:
+        import torch
+        if rank == 0:
+            cde = jg.build_engine(wl, device=local_rank)
+            blob = cde.flatten()
+            size = torch.tensor([blob.nbytes], dtype=torch.int64, device="cuda")
+        else:
+            cde = jg.CDEngine(wl.cde_bbox, wl.quadtree_depth, wl.cd_threshold, wl.n_ff_poles, wl.n_ff_piers, device=local_rank)
+            for i, it in enumerate(wl.items):
+                cde.upload_item(i, jg.ItemShape(it.verts, it.poi, it.poles, it.piers))
+            size = torch.zeros(1, dtype=torch.int64, device="cuda")
+        dist.broadcast(size, 0)
+        d_blob = torch.empty(int(size.item()), dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            d_blob.copy_(torch.from_numpy(blob))
+        dist.broadcast(d_blob, 0)
+        torch.cuda.synchronize()
+        cde.upload_layout_device(d_blob.data_ptr(), d_blob.numel(), epoch=1)
+    else:
+        cde = jg.build_engine(wl, device=local_rank)
+        cde.sync_layout()
+    layout_setup_ms = (time.perf_counter() - t_b0) * 1e3
+
+    # ---- inputs: every rank its own seeded batch (weak scaling); pinned host + device-resident copies
+    sizes = jg.split_batch(args.queries, len(wl.items))
+    n_items = len(wl.items)
+    host_t, host_out, dev_t, dev_out = [], [], [], []
+    for i, n in enumerate(sizes):
+        q = jg.make_queries(wl, i, n, seed=rank)
+        pt = jg.PinnedBuffer((n, 4), np.float32)
+        pt.array[:] = q
+        po = jg.PinnedBuffer((n,), np.uint8)
+        dt_ = jg.DeviceBuffer(cde, n * 16)
+        dt_.upload(q)
+        do = jg.DeviceBuffer(cde, n)
+        host_t.append(pt), host_out.append(po), dev_t.append(dt_), dev_out.append(do)
+
+    def step_device():
+        for i in range(n_items):
+            cde.detect_batch_device(i, dev_t[i].ptr, sizes[i], dev_out[i].ptr)
+
+    def step_e2e():
+        for i in range(n_items):
+            cde.detect_batch_async(i, host_t[i].array, host_out[i].array)
+        cde.sync()
+
+    def barrier():
+        cde.sync()
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    peak_gflops, _ = cde.fp32_nofma_peak()
+
+    # ---- value: device-resident, CUDA events, L2 flushed (untimed) before every step
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    cde.sync()
+    launches0 = cde.stats()["launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        cde.flush_l2()
+        cde.timer_start()
+        step_device()
+        dev_ms += cde.timer_stop()
+    barrier()
+    gpu_launches = cde.stats()["launches"] - launches0 - args.steps  # minus the untimed L2 flush fills
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(tt[0]), float(tt[1])
+
+    # verdicts of the last e2e step vs the device-resident path (same inputs -> identical)
+    same = all(np.array_equal(host_out[i].array, dev_out[i].download((sizes[i],), np.uint8)) for i in range(n_items))
+
+    if rank == 0:
+        total_q = args.queries * world
+        value = total_q * args.steps / (dev_ms * 1e-3)
+        e2e = total_q * args.steps / e2e_s
+        ms_per_step = dev_ms / args.steps
+        flops_per_q = flops_info["detect_flops_per_query"] if args.queries == flops_info["queries"] else None
+        roofline = None
+        if flops_per_q:
+            ach = flops_per_q * args.queries / (ms_per_step * 1e-3) / 1e12  # per GPU
+            roofline = {"bound": "fp32_nofma", "achieved": ach, "peak": peak_gflops / 1e3, "unit": "TFLOP/s",
+                        "frac": ach / (peak_gflops / 1e3), "traffic": None,
+                        "peak_source": "measured live: jg_fp32_nofma_peak (independent FADD/FMUL chains)",
+                        "flops_per_query": flops_per_q, "kernels": "k_detect_stage1 + k_detect_stage2 of all 10 item batches",
+                        "hbm": {"achieved": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9, "peak": 6555.2,
+                                "unit": "GB/s", "frac": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9 / 6555.2,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {args.queries} uniform queries per GPU over the CDE bbox, 10 swim item types, "
+                                       "24 placed items + exterior, quadtree depth 5, cd_threshold 16, 2 ff poles",
+                           "queries_per_step_per_gpu": args.queries, "l2": "flushed (256 MiB fill, untimed) before every timed step",
+                           "verdict_split": flops_info.get("verdicts")},
+                "clocks": clocks, "gpu_launches": int(gpu_launches),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 16 * args.queries, "d2h_bytes_per_step": args.queries,
+                        "ms_per_step": e2e_s / args.steps * 1e3, "same_verdicts_as_device_path": bool(same)},
+                "roofline": roofline, "layout_setup_ms": layout_setup_ms}
+        if world == 1 and not args.no_cpu_baseline:
+            orc, oracle_world = load_oracle()
+            w = oracle_world(orc, wl)
+            cores = os.cpu_count() or 1
+            qs = [host_t[i].array for i in range(n_items)]
+            exp = [w.detect_batch(i, qs[i], nthreads=cores) for i in range(n_items)]  # warm-up + checker
+            mism = int(sum((exp[i] != host_out[i].array).sum() for i in range(n_items)))
+            reps, t0 = 0, time.perf_counter()
+            while reps < 40 and time.perf_counter() - t0 < 10.0:
+                for i in range(n_items):
+                    w.detect_batch(i, qs[i], nthreads=cores)
+                reps += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": args.queries * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{reps} passes over the full {args.queries}-query batch ({dt:.1f} s), oracle/ C++ "
+                                              "restatement, std::thread static sharding",
+                                    "mismatches_vs_gpu": mism}
+        print(json.dumps(line))
+
+    cde.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -95,6 +95,10 @@ int jg_filter_upload(JgEngine* e, int filter_id, const uint32_t* bits, int words
  * (pinned memory from jg_host_alloc overlaps upload, kernels and download across chunks). */
 int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode,
                     uint8_t* out);
+/* Same, but returns once every chunk is enqueued; `transforms` and `out` must stay valid (and should
+ * be pinned) until jg_sync. Consecutive calls pipeline across the engine's chunk streams. */
+int jg_detect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode,
+                          uint8_t* out);
 /* Same with DEVICE pointers; asynchronous on the engine's compute stream (jg_sync to wait). */
 int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int filter_id,
                            int mode, uint8_t* d_out);
@@ -104,6 +108,8 @@ int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, 
  * index (an order-normalised BasicHazardCollector). words*32 must cover the layout's slot capacity. */
 int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode,
                      uint32_t* out_bits, int words);
+int jg_collect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode,
+                           uint32_t* out_bits, int words);
 int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int mode,
                             uint32_t* d_out_bits, int words);
 

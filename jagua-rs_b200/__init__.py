@@ -57,6 +57,8 @@ C_ABI = {
     "jg_item_upload": (C.c_int, [_vp, C.c_int, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int]),
     "jg_filter_upload": (C.c_int, [_vp, C.c_int, _u32p, C.c_int]),
     "jg_detect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
+    "jg_detect_batch_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
+    "jg_collect_batch_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
     "jg_detect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "jg_collect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
     "jg_collect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
@@ -387,6 +389,20 @@ class CDEngine:
                                              MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data, words))
         return out
 
+    def detect_batch_async(self, item_id: int, transforms: np.ndarray, out: np.ndarray, filter_id: int = -1, poly_only: bool = False):
+        """detect_batch without the final wait: `transforms` (float32, C-contiguous) and `out` must stay
+        alive — and should be pinned (PinnedBuffer) — until sync()."""
+        self.sync_layout()
+        assert transforms.dtype == np.float32 and transforms.flags.c_contiguous and out.dtype == np.uint8
+        self._chk(self._lib.jg_detect_batch_async(self._eng, int(item_id), transforms.ctypes.data, transforms.size // 4,
+                                                  int(filter_id), MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data))
+
+    def collect_batch_async(self, item_id: int, transforms: np.ndarray, out: np.ndarray, poly_only: bool = False):
+        self.sync_layout()
+        assert transforms.dtype == np.float32 and transforms.flags.c_contiguous and out.dtype == np.uint32 and out.ndim == 2
+        self._chk(self._lib.jg_collect_batch_async(self._eng, int(item_id), transforms.ctypes.data, transforms.size // 4,
+                                                   MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data, out.shape[1]))
+
     def detect_batch_device(self, item_id: int, d_transforms: int, n: int, d_out: int, filter_id: int = -1,
                             poly_only: bool = False):
         """Same as detect_batch with device pointers; asynchronous (call sync())."""
@@ -435,4 +451,4 @@ class CDEngine:
         self._chk(self._lib.jg_flush_l2(self._eng))
 
 
-from .workload import Workload, load_workload, build_engine, make_queries  # noqa: E402
+from .workload import Workload, load_workload, build_engine, make_queries, split_batch  # noqa: E402

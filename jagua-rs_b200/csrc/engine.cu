@@ -61,6 +61,7 @@ struct JgEngine {
     ChunkCtx main_ctx;  // scratch of the *_device calls (compute stream)
     std::vector<ChunkCtx> chunks;
     int64_t chunk_queries = 1 << 18;
+    uint64_t next_chunk = 0;
     int detect_group = 0, collect_group = 0;  // 0 = auto
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -421,17 +422,16 @@ int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms,
 // Host-pointer batches: split into chunks, each chunk on its own stream so the H2D copy of chunk
 // k+1 overlaps the kernels of chunk k and the D2H copy of chunk k-1.
 static int run_host_batch(JgEngine* e, const ItemDev* it, const uint32_t* d_filt, const float* transforms, int64_t n,
-                          int mode, bool collect, void* out, int words) {
+                          int mode, bool collect, void* out, int words, bool wait) {
     JG_CUDA(e, cudaSetDevice(e->device));
     const size_t out_per_q = collect ? (size_t)words * 4 : 1;
     const int64_t chunk = e->chunk_queries;
     const int group = collect ? (e->collect_group ? e->collect_group : auto_group(it->n_verts))
                               : (e->detect_group ? e->detect_group : auto_group(it->n_verts));
     const DevItem di = dev_item(e, *it);
-    int k = 0;
-    for (int64_t off = 0; off < n; off += chunk, k++) {
+    for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = (n - off) < chunk ? (n - off) : chunk;
-        ChunkCtx& c = e->chunks[k % e->chunks.size()];
+        ChunkCtx& c = e->chunks[e->next_chunk++ % e->chunks.size()];
         JG_CUDA(e, cudaStreamSynchronize(c.st));  // buffers of this slot are free again
         int rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n) * out_per_q, true);
         if (rc != JG_OK) return rc;
@@ -447,22 +447,32 @@ static int run_host_batch(JgEngine* e, const ItemDev* it, const uint32_t* d_filt
         e->stat_h2d += (uint64_t)m * sizeof(float4);
         e->stat_d2h += (uint64_t)m * out_per_q;
     }
-    for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
+    if (wait)
+        for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
     e->stat_queries += (uint64_t)n;
     return JG_OK;
 }
 
-int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode, uint8_t* out) {
+static int detect_host(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode, uint8_t* out,
+                       bool wait) {
     const ItemDev* it;
     const uint32_t* d_filt;
     int rc = query_prologue(e, item_id, filter_id, &it, &d_filt);
     if (rc != JG_OK) return rc;
     if (n < 0 || (n > 0 && (!transforms || !out))) return JG_ERR_INVALID;
     if (n == 0) return JG_OK;
-    return run_host_batch(e, it, d_filt, transforms, n, mode, false, out, 0);
+    return run_host_batch(e, it, d_filt, transforms, n, mode, false, out, 0, wait);
+}
+int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode, uint8_t* out) {
+    return detect_host(e, item_id, transforms, n, filter_id, mode, out, true);
+}
+int jg_detect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode,
+                          uint8_t* out) {
+    return detect_host(e, item_id, transforms, n, filter_id, mode, out, false);
 }
 
-int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words) {
+static int collect_host(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words,
+                        bool wait) {
     const ItemDev* it;
     const uint32_t* d_filt;
     int rc = query_prologue(e, item_id, -1, &it, &d_filt);
@@ -471,7 +481,14 @@ int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t 
     if ((size_t)words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "collector words do not cover the hazard slot capacity");
     if (words > 1024) return fail(e, JG_ERR_CAPACITY, "collector wider than 1024 words");
     if (n == 0) return JG_OK;
-    return run_host_batch(e, it, d_filt, transforms, n, mode, true, out_bits, words);
+    return run_host_batch(e, it, d_filt, transforms, n, mode, true, out_bits, words, wait);
+}
+int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words) {
+    return collect_host(e, item_id, transforms, n, mode, out_bits, words, true);
+}
+int jg_collect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits,
+                           int words) {
+    return collect_host(e, item_id, transforms, n, mode, out_bits, words, false);
 }
 
 int jg_engine_stats(const JgEngine* e, uint64_t out[8]) {

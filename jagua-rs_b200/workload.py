@@ -134,3 +134,9 @@ def make_queries(w: Workload, item_id: int, n: int, seed: int = 0) -> np.ndarray
     else:
         rot = np.asarray(it.rotations, np.float32)[rng.integers(0, len(it.rotations), n)]
     return compose(np.stack([rot, tx, ty], 1))
+
+
+def split_batch(total: int, n_items: int) -> List[int]:
+    """Per-item query counts of a `total`-query batch spread evenly over the item types."""
+    base, rem = divmod(int(total), int(n_items))
+    return [base + (1 if i < rem else 0) for i in range(n_items)]

@@ -99,6 +99,16 @@ int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n
  * be pinned) until jg_sync. Consecutive calls pipeline across the engine's chunk streams. */
 int jg_detect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode,
                           uint8_t* out);
+/* Multi-item batch: segment k = queries seg_offsets[k] .. seg_offsets[k+1] (seg_offsets[0] == 0) place
+ * item item_ids[k]; one launch sequence resolves all segments (the per-item calls are the 1-segment
+ * case). This is how a caller that samples several item types at once (sparrow, or lbf over its item
+ * list) amortises launches. Host pointers / async / device pointers as above. */
+int jg_detect_multi(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
+                    int filter_id, int mode, uint8_t* out);
+int jg_detect_multi_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
+                          const float* transforms, int filter_id, int mode, uint8_t* out);
+int jg_detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
+                           const float* d_transforms, int filter_id, int mode, uint8_t* d_out);
 /* Same with DEVICE pointers; asynchronous on the engine's compute stream (jg_sync to wait). */
 int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int filter_id,
                            int mode, uint8_t* d_out);

@@ -35,7 +35,8 @@ struct ChunkCtx {
     float4* d_xf = nullptr;
     uint8_t* d_out = nullptr;  // verdict bytes or collector words
     size_t cap_q = 0, cap_out = 0;
-    SurvivorList sv{nullptr, nullptr, nullptr, nullptr};
+    DetectCtl* ctl = nullptr;
+    Survivors sv{nullptr, nullptr, nullptr};
     size_t cap_sv = 0;
 };
 
@@ -110,7 +111,7 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
         if (c.sv.query) cudaFree(c.sv.query);
         if (c.sv.vroot) cudaFree(c.sv.vroot);
         if (c.sv.bbox) cudaFree(c.sv.bbox);
-        if (!c.sv.count) JG_CUDA(e, cudaMalloc(&c.sv.count, 64));
+        if (!c.ctl) JG_CUDA(e, cudaMalloc(&c.ctl, sizeof(DetectCtl)));
         JG_CUDA(e, cudaMalloc(&c.sv.query, n_q * sizeof(int)));
         JG_CUDA(e, cudaMalloc(&c.sv.vroot, n_q * sizeof(int)));
         JG_CUDA(e, cudaMalloc(&c.sv.bbox, n_q * sizeof(float4)));
@@ -122,7 +123,7 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
 static void free_ctx(ChunkCtx& c) {
     if (c.d_xf) cudaFree(c.d_xf);
     if (c.d_out) cudaFree(c.d_out);
-    if (c.sv.count) cudaFree(c.sv.count);
+    if (c.ctl) cudaFree(c.ctl);
     if (c.sv.query) cudaFree(c.sv.query);
     if (c.sv.vroot) cudaFree(c.sv.vroot);
     if (c.sv.bbox) cudaFree(c.sv.bbox);
@@ -356,39 +357,116 @@ int jg_filter_upload(JgEngine* e, int filter_id, const uint32_t* bits, int words
     return JG_OK;
 }
 
-// resolves ids and checks the preconditions shared by all query calls
-static int query_prologue(JgEngine* e, int item_id, int filter_id, const ItemDev** it, const uint32_t** d_filt) {
+// ---- queries ------------------------------------------------------------------------------------------
+static int check_ready(JgEngine* e) {
     if (!e) return JG_ERR_INVALID;
     if (!e->has_layout) return fail(e, JG_ERR_NO_LAYOUT, "no layout uploaded");
+    return JG_OK;
+}
+static int find_item(JgEngine* e, int item_id, const ItemDev** it) {
     auto f = e->items.find(item_id);
     if (f == e->items.end()) return fail(e, JG_ERR_INVALID, "unknown item id");
     *it = &f->second;
+    return JG_OK;
+}
+static int find_filter(JgEngine* e, int filter_id, const uint32_t** d_filt) {
     *d_filt = nullptr;
-    if (filter_id >= 0) {
-        auto g = e->filters.find(filter_id);
-        if (g == e->filters.end()) return fail(e, JG_ERR_INVALID, "unknown filter id");
-        if ((size_t)g->second.words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "filter bitset smaller than the hazard slot capacity");
-        *d_filt = g->second.bits;
+    if (filter_id < 0) return JG_OK;
+    auto g = e->filters.find(filter_id);
+    if (g == e->filters.end()) return fail(e, JG_ERR_INVALID, "unknown filter id");
+    if ((size_t)g->second.words * 32 < e->hdr.n_slots)
+        return fail(e, JG_ERR_CAPACITY, "filter bitset smaller than the hazard slot capacity");
+    *d_filt = g->second.bits;
+    return JG_OK;
+}
+
+// A detect batch is a sequence of segments (item_ids[k] for queries seg_offsets[k] .. seg_offsets[k+1]).
+// It is cut into launch pieces of at most `max_q` queries and JG_MAX_SEG segments; each piece gets a
+// SegTable with offsets relative to the piece.
+struct Piece {
+    int64_t off, m;
+    SegTable tab;
+};
+struct PieceCursor {
+    int64_t q = 0;
+    int seg = 0;
+};
+static bool next_piece(const JgEngine* e, int n_seg, const ItemDev* const* items, const int64_t* seg_offsets, int64_t max_q,
+                       PieceCursor& cur, Piece& p) {
+    const int64_t total = seg_offsets[n_seg];
+    while (cur.seg < n_seg && seg_offsets[cur.seg + 1] <= cur.q) cur.seg++;
+    if (cur.q >= total || cur.seg >= n_seg) return false;
+    p.off = cur.q;
+    p.tab.n_seg = 0;
+    int64_t covered = 0, edge_pairs = 0;
+    int sgi = cur.seg;
+    while (sgi < n_seg && p.tab.n_seg < JG_MAX_SEG && covered < max_q) {
+        const int64_t b = seg_offsets[sgi] > cur.q ? seg_offsets[sgi] : cur.q;
+        int64_t len = seg_offsets[sgi + 1] - b;
+        if (len <= 0) { sgi++; continue; }
+        const ItemDev& it = *items[sgi];
+        if (len > max_q - covered) len = max_q - covered;
+        // the flat (survivor, edge) index of k_s2_edges must fit an int
+        const int64_t room = (0x7FFFFFFFLL - edge_pairs) / it.n_verts;
+        if (len > room) len = room;
+        if (len <= 0) break;
+        SegDesc& sd = p.tab.seg[p.tab.n_seg++];
+        sd.begin = (int)covered;
+        sd.n_verts = it.n_verts;
+        sd.n_poles = it.n_poles < e->cfg.n_ff_poles ? it.n_poles : e->cfg.n_ff_poles;
+        sd.n_piers = it.n_piers;
+        sd.verts = it.verts;
+        sd.poles = it.poles;
+        sd.piers = it.piers;
+        sd.poi_x = it.poi_x;
+        sd.poi_y = it.poi_y;
+        covered += len;
+        edge_pairs += len * it.n_verts;
+        if (b + len < seg_offsets[sgi + 1]) break;  // segment cut: the rest goes to the next piece
+        sgi++;
+    }
+    p.m = covered;
+    p.tab.n_queries = (int)covered;
+    cur.q += covered;
+    return covered > 0;
+}
+
+static int resolve_segments(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
+                            std::vector<const ItemDev*>& items) {
+    if (n_seg <= 0 || !item_ids || !seg_offsets || seg_offsets[0] != 0) return fail(e, JG_ERR_INVALID, "bad segment table");
+    items.resize(n_seg);
+    for (int k = 0; k < n_seg; k++) {
+        if (seg_offsets[k + 1] < seg_offsets[k]) return fail(e, JG_ERR_INVALID, "segment offsets must be non-decreasing");
+        int rc = find_item(e, item_ids[k], &items[k]);
+        if (rc != JG_OK) return rc;
     }
     return JG_OK;
 }
 
-int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int filter_id, int mode,
-                           uint8_t* d_out) {
-    const ItemDev* it;
-    const uint32_t* d_filt;
-    int rc = query_prologue(e, item_id, filter_id, &it, &d_filt);
+static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
+                               const float* d_transforms, int filter_id, int mode, uint8_t* d_out) {
+    int rc = check_ready(e);
     if (rc != JG_OK) return rc;
-    if (n < 0 || n > 0x7FFFFFFF || (n > 0 && (!d_transforms || !d_out))) return JG_ERR_INVALID;
+    std::vector<const ItemDev*> items;
+    rc = resolve_segments(e, n_seg, item_ids, seg_offsets, items);
+    if (rc != JG_OK) return rc;
+    const uint32_t* d_filt;
+    rc = find_filter(e, filter_id, &d_filt);
+    if (rc != JG_OK) return rc;
+    const int64_t n = seg_offsets[n_seg];
+    if (n > 0 && (!d_transforms || !d_out)) return JG_ERR_INVALID;
     if (n == 0) return JG_OK;
     JG_CUDA(e, cudaSetDevice(e->device));
-    rc = ensure_ctx(e, e->main_ctx, (size_t)n, 0, false);
+    const int64_t max_q = 1 << 28;
+    rc = ensure_ctx(e, e->main_ctx, (size_t)(n < max_q ? n : max_q), 0, false);
     if (rc != JG_OK) return rc;
-    const int group = e->detect_group ? e->detect_group : auto_group(it->n_verts);
     int launches = 0;
     JG_CUDA(e, cudaEventRecord(e->ev0, e->compute));
-    JG_CUDA(e, launch_detect(e->L, dev_item(e, *it), (const float4*)d_transforms, n, d_filt, mode, d_out, e->main_ctx.sv,
-                             group, e->n_sms, e->compute, &launches));
+    PieceCursor cur;
+    Piece p;
+    while (next_piece(e, n_seg, items.data(), seg_offsets, max_q, cur, p))
+        JG_CUDA(e, launch_detect(e->L, p.tab, (const float4*)d_transforms + p.off, d_filt, mode, d_out + p.off, e->main_ctx.ctl,
+                                 e->main_ctx.sv, e->n_sms, e->compute, &launches));
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
     e->timing_valid = true;
     e->stat_launches += launches;
@@ -396,16 +474,90 @@ int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, 
     return JG_OK;
 }
 
+// Host-pointer batches: pieces of at most chunk_queries queries, piece k on stream k mod n_streams, so
+// the H2D copy of piece k+1 overlaps the kernels of piece k and the D2H copy of piece k-1.
+static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
+                             int filter_id, int mode, uint8_t* out, bool wait) {
+    int rc = check_ready(e);
+    if (rc != JG_OK) return rc;
+    std::vector<const ItemDev*> items;
+    rc = resolve_segments(e, n_seg, item_ids, seg_offsets, items);
+    if (rc != JG_OK) return rc;
+    const uint32_t* d_filt;
+    rc = find_filter(e, filter_id, &d_filt);
+    if (rc != JG_OK) return rc;
+    const int64_t n = seg_offsets[n_seg];
+    if (n > 0 && (!transforms || !out)) return JG_ERR_INVALID;
+    if (n == 0) return JG_OK;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    const int64_t chunk = e->chunk_queries;
+    PieceCursor cur;
+    Piece p;
+    while (next_piece(e, n_seg, items.data(), seg_offsets, chunk, cur, p)) {
+        ChunkCtx& c = e->chunks[e->next_chunk++ % e->chunks.size()];
+        JG_CUDA(e, cudaStreamSynchronize(c.st));  // buffers of this slot are free again
+        rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n), true);
+        if (rc != JG_OK) return rc;
+        JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * p.off, (size_t)p.m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
+        int launches = 0;
+        JG_CUDA(e, launch_detect(e->L, p.tab, c.d_xf, d_filt, mode, c.d_out, c.ctl, c.sv, e->n_sms, c.st, &launches));
+        JG_CUDA(e, cudaMemcpyAsync(out + p.off, c.d_out, (size_t)p.m, cudaMemcpyDeviceToHost, c.st));
+        e->stat_launches += launches;
+        e->stat_h2d += (uint64_t)p.m * sizeof(float4);
+        e->stat_d2h += (uint64_t)p.m;
+    }
+    if (wait)
+        for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
+    e->stat_queries += (uint64_t)n;
+    return JG_OK;
+}
+
+int jg_detect_multi(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
+                    int filter_id, int mode, uint8_t* out) {
+    return detect_multi_host(e, n_seg, item_ids, seg_offsets, transforms, filter_id, mode, out, true);
+}
+int jg_detect_multi_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
+                          int filter_id, int mode, uint8_t* out) {
+    return detect_multi_host(e, n_seg, item_ids, seg_offsets, transforms, filter_id, mode, out, false);
+}
+int jg_detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* d_transforms,
+                           int filter_id, int mode, uint8_t* d_out) {
+    return detect_multi_device(e, n_seg, item_ids, seg_offsets, d_transforms, filter_id, mode, d_out);
+}
+int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode, uint8_t* out) {
+    if (n < 0) return JG_ERR_INVALID;
+    const int64_t offs[2] = {0, n};
+    return detect_multi_host(e, 1, &item_id, offs, transforms, filter_id, mode, out, true);
+}
+int jg_detect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode,
+                          uint8_t* out) {
+    if (n < 0) return JG_ERR_INVALID;
+    const int64_t offs[2] = {0, n};
+    return detect_multi_host(e, 1, &item_id, offs, transforms, filter_id, mode, out, false);
+}
+int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int filter_id, int mode,
+                           uint8_t* d_out) {
+    if (n < 0) return JG_ERR_INVALID;
+    const int64_t offs[2] = {0, n};
+    return detect_multi_device(e, 1, &item_id, offs, d_transforms, filter_id, mode, d_out);
+}
+
+static int collect_checks(JgEngine* e, int item_id, int64_t n, const void* t, const void* out, int words, const ItemDev** it) {
+    int rc = check_ready(e);
+    if (rc != JG_OK) return rc;
+    rc = find_item(e, item_id, it);
+    if (rc != JG_OK) return rc;
+    if (n < 0 || words <= 0 || (n > 0 && (!t || !out))) return JG_ERR_INVALID;
+    if ((size_t)words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "collector words do not cover the hazard slot capacity");
+    if (words > 1024) return fail(e, JG_ERR_CAPACITY, "collector wider than 1024 words");
+    return JG_OK;
+}
+
 int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int mode,
                             uint32_t* d_out_bits, int words) {
     const ItemDev* it;
-    const uint32_t* d_filt;
-    int rc = query_prologue(e, item_id, -1, &it, &d_filt);
-    if (rc != JG_OK) return rc;
-    if (n < 0 || words <= 0 || (n > 0 && (!d_transforms || !d_out_bits))) return JG_ERR_INVALID;
-    if ((size_t)words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "collector words do not cover the hazard slot capacity");
-    if (words > 1024) return fail(e, JG_ERR_CAPACITY, "collector wider than 1024 words");
-    if (n == 0) return JG_OK;
+    int rc = collect_checks(e, item_id, n, d_transforms, d_out_bits, words, &it);
+    if (rc != JG_OK || n == 0) return rc;
     JG_CUDA(e, cudaSetDevice(e->device));
     const int group = e->collect_group ? e->collect_group : auto_group(it->n_verts);
     int launches = 0;
@@ -419,30 +571,26 @@ int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms,
     return JG_OK;
 }
 
-// Host-pointer batches: split into chunks, each chunk on its own stream so the H2D copy of chunk
-// k+1 overlaps the kernels of chunk k and the D2H copy of chunk k-1.
-static int run_host_batch(JgEngine* e, const ItemDev* it, const uint32_t* d_filt, const float* transforms, int64_t n,
-                          int mode, bool collect, void* out, int words, bool wait) {
+static int collect_host(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words,
+                        bool wait) {
+    const ItemDev* it;
+    int rc = collect_checks(e, item_id, n, transforms, out_bits, words, &it);
+    if (rc != JG_OK || n == 0) return rc;
     JG_CUDA(e, cudaSetDevice(e->device));
-    const size_t out_per_q = collect ? (size_t)words * 4 : 1;
+    const size_t out_per_q = (size_t)words * 4;
     const int64_t chunk = e->chunk_queries;
-    const int group = collect ? (e->collect_group ? e->collect_group : auto_group(it->n_verts))
-                              : (e->detect_group ? e->detect_group : auto_group(it->n_verts));
+    const int group = e->collect_group ? e->collect_group : auto_group(it->n_verts);
     const DevItem di = dev_item(e, *it);
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = (n - off) < chunk ? (n - off) : chunk;
         ChunkCtx& c = e->chunks[e->next_chunk++ % e->chunks.size()];
-        JG_CUDA(e, cudaStreamSynchronize(c.st));  // buffers of this slot are free again
-        int rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n) * out_per_q, true);
+        JG_CUDA(e, cudaStreamSynchronize(c.st));
+        rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n) * out_per_q, true);
         if (rc != JG_OK) return rc;
         JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * off, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
         int launches = 0;
-        if (collect) {
-            JG_CUDA(e, launch_collect(e->L, di, c.d_xf, m, mode, (uint32_t*)c.d_out, words, group, e->n_sms, c.st, &launches));
-        } else {
-            JG_CUDA(e, launch_detect(e->L, di, c.d_xf, m, d_filt, mode, c.d_out, c.sv, group, e->n_sms, c.st, &launches));
-        }
-        JG_CUDA(e, cudaMemcpyAsync((char*)out + (size_t)off * out_per_q, c.d_out, (size_t)m * out_per_q, cudaMemcpyDeviceToHost, c.st));
+        JG_CUDA(e, launch_collect(e->L, di, c.d_xf, m, mode, (uint32_t*)c.d_out, words, group, e->n_sms, c.st, &launches));
+        JG_CUDA(e, cudaMemcpyAsync((char*)out_bits + (size_t)off * out_per_q, c.d_out, (size_t)m * out_per_q, cudaMemcpyDeviceToHost, c.st));
         e->stat_launches += launches;
         e->stat_h2d += (uint64_t)m * sizeof(float4);
         e->stat_d2h += (uint64_t)m * out_per_q;
@@ -451,37 +599,6 @@ static int run_host_batch(JgEngine* e, const ItemDev* it, const uint32_t* d_filt
         for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
     e->stat_queries += (uint64_t)n;
     return JG_OK;
-}
-
-static int detect_host(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode, uint8_t* out,
-                       bool wait) {
-    const ItemDev* it;
-    const uint32_t* d_filt;
-    int rc = query_prologue(e, item_id, filter_id, &it, &d_filt);
-    if (rc != JG_OK) return rc;
-    if (n < 0 || (n > 0 && (!transforms || !out))) return JG_ERR_INVALID;
-    if (n == 0) return JG_OK;
-    return run_host_batch(e, it, d_filt, transforms, n, mode, false, out, 0, wait);
-}
-int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode, uint8_t* out) {
-    return detect_host(e, item_id, transforms, n, filter_id, mode, out, true);
-}
-int jg_detect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode,
-                          uint8_t* out) {
-    return detect_host(e, item_id, transforms, n, filter_id, mode, out, false);
-}
-
-static int collect_host(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words,
-                        bool wait) {
-    const ItemDev* it;
-    const uint32_t* d_filt;
-    int rc = query_prologue(e, item_id, -1, &it, &d_filt);
-    if (rc != JG_OK) return rc;
-    if (n < 0 || words <= 0 || (n > 0 && (!transforms || !out_bits))) return JG_ERR_INVALID;
-    if ((size_t)words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "collector words do not cover the hazard slot capacity");
-    if (words > 1024) return fail(e, JG_ERR_CAPACITY, "collector wider than 1024 words");
-    if (n == 0) return JG_OK;
-    return run_host_batch(e, it, d_filt, transforms, n, mode, true, out_bits, words, wait);
 }
 int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words) {
     return collect_host(e, item_id, transforms, n, mode, out_bits, words, true);
@@ -499,10 +616,11 @@ int jg_engine_stats(const JgEngine* e, uint64_t out[8]) {
     out[2] = e->stat_h2d;
     out[3] = e->stat_d2h;
     out[4] = e->stat_uploads;
-    if (e->main_ctx.sv.count) {
-        int c = 0;
+    if (e->main_ctx.ctl) {  // survivors of the last *_device detect sequence (sum over its segments)
+        DetectCtl c;
         cudaSetDevice(e->device);
-        if (cudaMemcpy(&c, e->main_ctx.sv.count, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) out[5] = (uint64_t)c;
+        if (cudaMemcpy(&c, e->main_ctx.ctl, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int k = 0; k < JG_MAX_SEG; k++) out[5] += (uint64_t)c.n_surv[k];
     }
     return JG_OK;
 }

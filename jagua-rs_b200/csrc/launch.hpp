@@ -1,4 +1,4 @@
-// Host-visible launch interface of kernels.cu (kept free of kernel bodies so engine.cu stays small).
+// Host-visible launch interface of kernels.cu / detect.cu (kept free of kernel bodies so engine.cu stays small).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -9,18 +9,40 @@
 
 namespace jg {
 
-// Queries that passed the surrogate stage and the bbox test, appended by stage 1 in arbitrary order
-// (results are written by query index, so the order is never observable).
-struct SurvivorList {
-    int* count;
-    int* query;     // query index within the batch
-    int* vroot;     // virtual-root node of the transformed bbox
-    float4* bbox;   // transformed bbox
+#define JG_MAX_SEG 32
+
+// One segment of a detect batch: the queries [begin, next segment's begin) all place the same item.
+struct SegDesc {
+    int begin;
+    int n_verts, n_poles, n_piers;
+    const float2* verts;
+    const float4* poles;  // (x, y, r, 0); only the first n_ff poles are counted in n_poles
+    const float4* piers;
+    float poi_x, poi_y;
+};
+struct SegTable {
+    int n_seg;
+    int n_queries;
+    SegDesc seg[JG_MAX_SEG];
 };
 
-cudaError_t launch_detect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, const uint32_t* d_filt,
-                          int mode, uint8_t* d_out, const SurvivorList& sv, int group, int n_sms, cudaStream_t st,
-                          int* n_launches);
+// Work counters of one detect launch sequence (device memory, zeroed by launch_detect).
+struct DetectCtl {
+    int s1_next;             // next unclaimed query (k_s1_poles)
+    int s2_next;             // next unclaimed (survivor, edge) pair (k_s2_edges)
+    int n_surv[JG_MAX_SEG];  // survivors of the surrogate stage, per segment
+};
+
+// Queries that passed the surrogate stage, per segment: slot = seg.begin + position. Appended in
+// arbitrary order (results are written by query index, so the order is never observable).
+struct Survivors {
+    int* query;    // query index within the batch
+    int* vroot;    // virtual-root node of the transformed bbox, -1 = bbox not inside the CDE bbox
+    float4* bbox;  // transformed bbox
+};
+
+cudaError_t launch_detect(const DevLayout& L, const SegTable& tab, const float4* d_xf, const uint32_t* d_filt, int mode,
+                          uint8_t* d_out, DetectCtl* ctl, const Survivors& sv, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,
                            uint32_t* d_out_bits, int words, int group, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_fp32_nofma(float* d_out, int blocks, int iters, cudaStream_t st);

@@ -59,6 +59,9 @@ C_ABI = {
     "jg_detect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "jg_detect_batch_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "jg_collect_batch_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
+    "jg_detect_multi": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_detect_multi_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_detect_multi_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "jg_detect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "jg_collect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
     "jg_collect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
@@ -402,6 +405,35 @@ class CDEngine:
         assert transforms.dtype == np.float32 and transforms.flags.c_contiguous and out.dtype == np.uint32 and out.ndim == 2
         self._chk(self._lib.jg_collect_batch_async(self._eng, int(item_id), transforms.ctypes.data, transforms.size // 4,
                                                    MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data, out.shape[1]))
+
+    @staticmethod
+    def _segments(item_ids, seg_offsets):
+        ids = np.ascontiguousarray(item_ids, dtype=np.int32)
+        offs = np.ascontiguousarray(seg_offsets, dtype=np.int64)
+        assert len(offs) == len(ids) + 1 and offs[0] == 0
+        return ids, offs
+
+    def detect_multi(self, item_ids, seg_offsets, transforms: np.ndarray, filter_id: int = -1, poly_only: bool = False,
+                     out: Optional[np.ndarray] = None, wait: bool = True) -> np.ndarray:
+        """detect for a batch of segments: queries seg_offsets[k]..seg_offsets[k+1] place item item_ids[k].
+        One launch sequence for all segments. With wait=False the call returns after enqueueing
+        (transforms / out must stay alive, ideally pinned, until sync())."""
+        self.sync_layout()
+        ids, offs = self._segments(item_ids, seg_offsets)
+        t = transforms if isinstance(transforms, np.ndarray) and transforms.dtype == np.float32 and transforms.flags.c_contiguous else _f32(transforms)
+        assert t.size // 4 == int(offs[-1])
+        if out is None:
+            out = np.empty(int(offs[-1]), np.uint8)
+        fn = self._lib.jg_detect_multi if wait else self._lib.jg_detect_multi_async
+        self._chk(fn(self._eng, len(ids), ids.ctypes.data, offs.ctypes.data, t.ctypes.data, int(filter_id),
+                     MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data))
+        return out
+
+    def detect_multi_device(self, item_ids, seg_offsets, d_transforms: int, d_out: int, filter_id: int = -1, poly_only: bool = False):
+        self.sync_layout()
+        ids, offs = self._segments(item_ids, seg_offsets)
+        self._chk(self._lib.jg_detect_multi_device(self._eng, len(ids), ids.ctypes.data, offs.ctypes.data, int(d_transforms),
+                                                   int(filter_id), MODE_POLY_ONLY if poly_only else MODE_DEFAULT, int(d_out)))
 
     def detect_batch_device(self, item_id: int, d_transforms: int, n: int, d_out: int, filter_id: int = -1,
                             poly_only: bool = False):

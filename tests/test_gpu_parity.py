@@ -77,3 +77,48 @@ def test_group_size_does_not_change_results(jg, engines, group):
             assert np.array_equal(cde.collect_batch(item_id, t, words), w.collect_batch(item_id, t, words))
     finally:
         cde.set_groups(0, 0)
+
+
+@pytest.mark.parametrize("name", ["swim_half", "baldacci1_bin", "gardeyn1c_half", "shirts_full_d10"])
+def test_multi_segment_batch_matches_oracle(jg, engines, name):
+    """All item types in one launch sequence (jg_detect_multi), ragged and empty segments included."""
+    wl, cde, w = engines(name)
+    rng = np.random.default_rng(3)
+    ids = list(range(len(wl.items))) + [0, 0]
+    sizes = [int(x) for x in rng.integers(0, 3000, len(ids))]
+    sizes[1] = 0      # empty segment
+    sizes[-1] = 1     # single query
+    ts = [jg.make_queries(wl, i, n, seed=21 + k) for k, (i, n) in enumerate(zip(ids, sizes))]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    t = np.concatenate(ts)
+    exp = np.concatenate([w.detect_batch(i, q) for i, q in zip(ids, ts)])
+    got = cde.detect_multi(ids, offs, t)
+    assert np.array_equal(got, exp), f"{(got != exp).sum()} mismatches"
+    got2 = cde.detect_multi(ids, offs, t, poly_only=True)
+    exp2 = np.concatenate([w.detect_batch(i, q, poly_only=True) for i, q in zip(ids, ts)])
+    assert np.array_equal(got2, exp2)
+
+
+def test_many_segments_and_small_chunks(jg, engines):
+    """More segments than one launch holds (JG_MAX_SEG = 32) and chunks that cut segments."""
+    wl, cde, w = engines("swim_half")
+    ids = [k % len(wl.items) for k in range(75)]
+    sizes = [37 + 13 * (k % 7) for k in range(75)]
+    ts = [jg.make_queries(wl, i, n, seed=100 + k) for k, (i, n) in enumerate(zip(ids, sizes))]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    t = np.concatenate(ts)
+    exp = np.concatenate([w.detect_batch(i, q) for i, q in zip(ids, ts)])
+    assert np.array_equal(cde.detect_multi(ids, offs, t), exp)
+    cde.set_batching(1000, 2)
+    try:
+        assert np.array_equal(cde.detect_multi(ids, offs, t), exp)
+        one = jg.make_queries(wl, 3, 5000, seed=5)
+        assert np.array_equal(cde.detect_batch(3, one), w.detect_batch(3, one))
+    finally:
+        cde.set_batching(1 << 18, 3)
+
+
+def test_empty_batch(jg, engines):
+    wl, cde, w = engines("swim_half")
+    assert len(cde.detect_batch(0, np.zeros((0, 4), np.float32))) == 0
+    assert cde.collect_batch(0, np.zeros((0, 4), np.float32)).shape[0] == 0

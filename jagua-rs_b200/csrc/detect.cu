@@ -234,7 +234,7 @@ k_s2_edges(const DevLayout L, const __grid_constant__ SegTable gtab, const float
     WarpFeed feed;
     feed.init();
     bool active = false;
-    int q = 0;
+    int q = 0, seg_hint = 0;
     Seg sg{0, 0, 0, 0};
     Walk w;
     w.start(0);
@@ -243,9 +243,11 @@ k_s2_edges(const DevLayout L, const __grid_constant__ SegTable gtab, const float
         if (idle == 0xFFFFFFFFu && feed.dry && feed.next >= feed.end) break;
         if (__popc(idle) >= REFILL_MIN || idle == 0xFFFFFFFFu) {
             const int idx = feed.take<S2_CHUNK>(!active, lane, &ctl->s2_next, total);
+            int k = 0x7FFFFFFF;
             if (idx >= 0) {
-                int k = 0;
-                for (int j = 1; j < tab.n_seg; j++) k += (idx >= cum[j]) ? 1 : 0;
+                // indices handed to a warp only grow, so the segment found last time is a lower bound
+                k = seg_hint;
+                while (k + 1 < tab.n_seg && idx >= cum[k + 1]) k++;
                 const SegDesc& sd = tab.seg[k];
                 const int r = idx - cum[k];
                 const int si = r / sd.n_verts, e = r - si * sd.n_verts;
@@ -262,6 +264,8 @@ k_s2_edges(const DevLayout L, const __grid_constant__ SegTable gtab, const float
                     active = true;
                 }
             }
+            const int kmin = __reduce_min_sync(0xFFFFFFFFu, k);
+            if (kmin != 0x7FFFFFFF) seg_hint = kmin;
         }
         if (active) {
             const int r = walk_step<Seg, FILT>(L, w, sg, filt);

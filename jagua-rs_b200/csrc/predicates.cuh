@@ -118,6 +118,29 @@ JG_HD bool rect_seg(const Rect& r, const Seg& e) {
     return !(all_pos || all_neg);
 }
 
+// fl(a / d) in [0, 1] for finite a and d != 0, WITHOUT the division whenever the answer is already
+// determined. Exact, not approximate (round-to-nearest-even, denormals kept):
+//   * |a| > |d|  ->  |a/d| >= 1/(1 - 2^-24) > 1 + 2^-24, which rounds to >= 1 + 2^-23: the quotient is
+//     > 1 (or < -1); conversely a/d <= 1 rounds to <= 1 by monotonicity.
+//   * a == 0 or equal signs, |a| <= |d|  ->  0 <= a/d <= 1, and -0 compares >= 0 like the reference's
+//     `(0.0..=1.0).contains(&t)`.
+//   * opposite signs  ->  negative, unless the quotient underflows to -0 (|a/d| <= 2^-150), which again
+//     compares >= 0. That needs |a| < |d| * 1e-30 by a wide margin; only then is the division performed.
+JG_HD bool unit_quotient(float a, float d) {
+    const float aa = fabsf(a), ad = fabsf(d);
+    if (!(ad <= 3.402823466e+38f)) {  // infinite / NaN divisor (coordinates overflowed): no shortcut
+        const float q = a / d;
+        return q >= 0.0f && q <= 1.0f;
+    }
+    if (!(aa <= ad)) return false;  // also NaN / infinite numerators
+    if (a == 0.0f || (a < 0.0f) == (d < 0.0f)) return true;
+    if (aa < ad * 1e-30f) {
+        const float q = a / d;
+        return q >= 0.0f && q <= 1.0f;
+    }
+    return false;
+}
+
 // primitives/edge.rs:180-228 edge_intersection(e1, e2, false): range reject with strict '>',
 // then t,u by IEEE division, hit iff both in [0,1]; parallel (denominator == 0) is "no".
 JG_HD bool seg_seg(const Seg& e1, const Seg& e2) {
@@ -130,8 +153,7 @@ JG_HD bool seg_seg(const Seg& e1, const Seg& e2) {
     const float denom = (x2 - x1) * (y4 - y3) - (y2 - y1) * (x4 - x3);  // t_denom == u_denom
     const float u_nom = (x2 - x4) * (y2 - y1) - (y2 - y4) * (x2 - x1);
     if (denom == 0.0f) return false;
-    const float t = t_nom / denom, u = u_nom / denom;
-    return t >= 0.0f && t <= 1.0f && u >= 0.0f && u <= 1.0f;
+    return unit_quotient(t_nom, denom) && unit_quotient(u_nom, denom);  // t, u in [0, 1]
 }
 
 // collision_detection/quadtree/qt_traits.rs:144-177 edge_intersection_half: same t,u without the
@@ -143,9 +165,9 @@ JG_HD int seg_seg_half(const Seg& e1, const Seg& e2) {
     const float denom = (x2 - x1) * (y4 - y3) - (y2 - y1) * (x4 - x3);
     const float u_nom = (x2 - x4) * (y2 - y1) - (y2 - y4) * (x2 - x1);
     if (denom == 0.0f) return 0;
-    const float t = t_nom / denom, u = u_nom / denom;
-    if (t >= 0.0f && t <= 1.0f && u >= 0.0f && u <= 1.0f) return u > 0.5f ? 1 : (u < 0.5f ? 2 : 3);
-    return 0;
+    if (!(unit_quotient(t_nom, denom) && unit_quotient(u_nom, denom))) return 0;
+    const float u = u_nom / denom;  // the half is decided on the rounded quotient, as in the reference
+    return u > 0.5f ? 1 : (u < 0.5f ? 2 : 3);
 }
 
 // primitives/rect.rs:141-151 quadrants(): child i = from_diagonal_corners(corner_i, centroid),
@@ -205,17 +227,23 @@ JG_HD bool circ_rect(const Circ& c, const Rect& r) {
     const float ny = fmaxf(r.y_min, fminf(c.cy, r.y_max));
     return (nx - c.cx) * (nx - c.cx) + (ny - c.cy) * (ny - c.cy) <= c.r * c.r;
 }
-// primitives/circle.rs:109-113 via edge.rs:63-87 closest_point_on_edge + :153-159 sq_distance_to
+// primitives/circle.rs:109-113 via edge.rs:63-87 closest_point_on_edge + :153-159 sq_distance_to.
+// param = dot / len_sq is only divided out when it is used (0 < dot <= len_sq): dot <= 0 gives a
+// quotient <= +0 whose three possible treatments (param < 0, or param = +-0 in the interpolation) all
+// yield the start point; dot > len_sq > 0 gives a rounded quotient > 1 (see unit_quotient); len_sq == 0
+// is the reference's param = -1.
 JG_HD bool circ_seg(const Circ& c, const Seg& e) {
     const float a = c.cx - e.sx, b = c.cy - e.sy, cc = e.ex - e.sx, d = e.ey - e.sy;
     const float dot = a * cc + b * d;
     const float len_sq = cc * cc + d * d;
-    float param = -1.0f;
-    if (len_sq != 0.0f) param = dot / len_sq;
     float xx, yy;
-    if (param < 0.0f) { xx = e.sx; yy = e.sy; }
-    else if (param > 1.0f) { xx = e.ex; yy = e.ey; }
-    else { xx = e.sx + param * cc; yy = e.sy + param * d; }
+    if (len_sq == 0.0f || !(dot > 0.0f)) { xx = e.sx; yy = e.sy; }
+    else if (dot > len_sq) { xx = e.ex; yy = e.ey; }
+    else {
+        const float param = dot / len_sq;
+        xx = e.sx + param * cc;
+        yy = e.sy + param * d;
+    }
     const float dx = c.cx - xx, dy = c.cy - yy;
     return dx * dx + dy * dy <= c.r * c.r;
 }

@@ -35,8 +35,7 @@ struct ChunkCtx {
     float4* d_xf = nullptr;
     uint8_t* d_out = nullptr;  // verdict bytes or collector words
     size_t cap_q = 0, cap_out = 0;
-    DetectCtl* ctl = nullptr;
-    Survivors sv{nullptr, nullptr, nullptr};
+    DetectScratch sc{nullptr, nullptr, nullptr, nullptr, {nullptr, nullptr, nullptr}};
     size_t cap_sv = 0;
 };
 
@@ -108,25 +107,26 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
         c.cap_out = out_bytes;
     }
     if (c.cap_sv < n_q) {
-        if (c.sv.query) cudaFree(c.sv.query);
-        if (c.sv.vroot) cudaFree(c.sv.vroot);
-        if (c.sv.bbox) cudaFree(c.sv.bbox);
-        if (!c.ctl) JG_CUDA(e, cudaMalloc(&c.ctl, sizeof(DetectCtl)));
-        JG_CUDA(e, cudaMalloc(&c.sv.query, n_q * sizeof(int)));
-        JG_CUDA(e, cudaMalloc(&c.sv.vroot, n_q * sizeof(int)));
-        JG_CUDA(e, cudaMalloc(&c.sv.bbox, n_q * sizeof(float4)));
+        cudaFree(c.sc.keys), cudaFree(c.sc.order), cudaFree(c.sc.sv.entry), cudaFree(c.sc.sv.vroot), cudaFree(c.sc.sv.bbox);
+        c.sc.keys = c.sc.order = c.sc.sv.entry = c.sc.sv.vroot = nullptr;
+        c.sc.sv.bbox = nullptr;
+        c.cap_sv = 0;
+        if (!c.sc.ctl) JG_CUDA(e, cudaMalloc(&c.sc.ctl, sizeof(DetectCtl)));
+        if (!c.sc.hist) JG_CUDA(e, cudaMalloc(&c.sc.hist, detect_bin_words(JG_MAX_SEG) * sizeof(int)));
+        JG_CUDA(e, cudaMalloc(&c.sc.keys, n_q * sizeof(int)));
+        JG_CUDA(e, cudaMalloc(&c.sc.order, n_q * sizeof(int)));
+        JG_CUDA(e, cudaMalloc(&c.sc.sv.entry, n_q * sizeof(int)));
+        JG_CUDA(e, cudaMalloc(&c.sc.sv.vroot, n_q * sizeof(int)));
+        JG_CUDA(e, cudaMalloc(&c.sc.sv.bbox, n_q * sizeof(float4)));
         c.cap_sv = n_q;
     }
     return JG_OK;
 }
 
 static void free_ctx(ChunkCtx& c) {
-    if (c.d_xf) cudaFree(c.d_xf);
-    if (c.d_out) cudaFree(c.d_out);
-    if (c.ctl) cudaFree(c.ctl);
-    if (c.sv.query) cudaFree(c.sv.query);
-    if (c.sv.vroot) cudaFree(c.sv.vroot);
-    if (c.sv.bbox) cudaFree(c.sv.bbox);
+    cudaFree(c.d_xf), cudaFree(c.d_out);
+    cudaFree(c.sc.ctl), cudaFree(c.sc.keys), cudaFree(c.sc.order), cudaFree(c.sc.hist);
+    cudaFree(c.sc.sv.entry), cudaFree(c.sc.sv.vroot), cudaFree(c.sc.sv.bbox);
     c = ChunkCtx{};
 }
 
@@ -457,7 +457,7 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
     if (n > 0 && (!d_transforms || !d_out)) return JG_ERR_INVALID;
     if (n == 0) return JG_OK;
     JG_CUDA(e, cudaSetDevice(e->device));
-    const int64_t max_q = 1 << 28;
+    const int64_t max_q = JG_MAX_LAUNCH_QUERIES;
     rc = ensure_ctx(e, e->main_ctx, (size_t)(n < max_q ? n : max_q), 0, false);
     if (rc != JG_OK) return rc;
     int launches = 0;
@@ -465,8 +465,8 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
     PieceCursor cur;
     Piece p;
     while (next_piece(e, n_seg, items.data(), seg_offsets, max_q, cur, p))
-        JG_CUDA(e, launch_detect(e->L, p.tab, (const float4*)d_transforms + p.off, d_filt, mode, d_out + p.off, e->main_ctx.ctl,
-                                 e->main_ctx.sv, e->n_sms, e->compute, &launches));
+        JG_CUDA(e, launch_detect(e->L, p.tab, (const float4*)d_transforms + p.off, d_filt, mode, d_out + p.off, e->main_ctx.sc,
+                                 e->n_sms, e->compute, &launches));
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
     e->timing_valid = true;
     e->stat_launches += launches;
@@ -500,7 +500,7 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
         if (rc != JG_OK) return rc;
         JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * p.off, (size_t)p.m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
         int launches = 0;
-        JG_CUDA(e, launch_detect(e->L, p.tab, c.d_xf, d_filt, mode, c.d_out, c.ctl, c.sv, e->n_sms, c.st, &launches));
+        JG_CUDA(e, launch_detect(e->L, p.tab, c.d_xf, d_filt, mode, c.d_out, c.sc, e->n_sms, c.st, &launches));
         JG_CUDA(e, cudaMemcpyAsync(out + p.off, c.d_out, (size_t)p.m, cudaMemcpyDeviceToHost, c.st));
         e->stat_launches += launches;
         e->stat_h2d += (uint64_t)p.m * sizeof(float4);
@@ -616,11 +616,10 @@ int jg_engine_stats(const JgEngine* e, uint64_t out[8]) {
     out[2] = e->stat_h2d;
     out[3] = e->stat_d2h;
     out[4] = e->stat_uploads;
-    if (e->main_ctx.ctl) {  // survivors of the last *_device detect sequence (sum over its segments)
+    if (e->main_ctx.sc.ctl) {  // survivors of the last *_device detect launch sequence
         DetectCtl c;
         cudaSetDevice(e->device);
-        if (cudaMemcpy(&c, e->main_ctx.ctl, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess)
-            for (int k = 0; k < JG_MAX_SEG; k++) out[5] += (uint64_t)c.n_surv[k];
+        if (cudaMemcpy(&c, e->main_ctx.sc.ctl, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) out[5] = (uint64_t)c.n_surv;
     }
     return JG_OK;
 }
@@ -650,7 +649,7 @@ int jg_timer_stop(JgEngine* e, float* ms) {
 }
 
 int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams) {
-    if (!e || chunk_queries < 1 || chunk_queries > 0x7FFFFFFF || n_streams < 1 || n_streams > 16) return JG_ERR_INVALID;
+    if (!e || chunk_queries < 1 || chunk_queries > JG_MAX_LAUNCH_QUERIES || n_streams < 1 || n_streams > 16) return JG_ERR_INVALID;
     int rc = jg_sync(e);
     if (rc != JG_OK) return rc;
     e->chunk_queries = chunk_queries;

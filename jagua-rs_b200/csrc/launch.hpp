@@ -28,21 +28,33 @@ struct SegTable {
 
 // Work counters of one detect launch sequence (device memory, zeroed by launch_detect).
 struct DetectCtl {
-    int s1_next;             // next unclaimed query (k_s1_poles)
-    int s2_next;             // next unclaimed (survivor, edge) pair (k_s2_edges)
-    int n_surv[JG_MAX_SEG];  // survivors of the surrogate stage, per segment
+    int s1_next;  // next unclaimed position of the sorted query order (k_s1_poles)
+    int s2_next;  // next unclaimed survivor (k_s2_edges)
+    int n_surv;   // survivors of the surrogate stage
+    int pad;
 };
 
-// Queries that passed the surrogate stage, per segment: slot = seg.begin + position. Appended in
-// arbitrary order (results are written by query index, so the order is never observable).
+// Queries that passed the surrogate stage. Appended in warp-sized bursts in arbitrary order (results are
+// written by query index, so the order is never observable).
 struct Survivors {
-    int* query;    // query index within the batch
+    int* entry;    // query index within the batch (low 26 bits) | segment (high 6 bits)
     int* vroot;    // virtual-root node of the transformed bbox, -1 = bbox not inside the CDE bbox
     float4* bbox;  // transformed bbox
 };
+#define JG_MAX_LAUNCH_QUERIES (1 << 26)
+
+// Device scratch of one detect launch sequence (sized for the largest batch piece seen so far).
+struct DetectScratch {
+    DetectCtl* ctl;
+    int* keys;   // bin key per query
+    int* order;  // queries sorted by bin
+    int* hist;   // bin counters / cursors, detect_bin_words(n_seg) ints
+    Survivors sv;
+};
+size_t detect_bin_words(int n_seg);
 
 cudaError_t launch_detect(const DevLayout& L, const SegTable& tab, const float4* d_xf, const uint32_t* d_filt, int mode,
-                          uint8_t* d_out, DetectCtl* ctl, const Survivors& sv, int n_sms, cudaStream_t st, int* n_launches);
+                          uint8_t* d_out, const DetectScratch& sc, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,
                            uint32_t* d_out_bits, int words, int group, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_fp32_nofma(float* d_out, int blocks, int iters, cudaStream_t st);

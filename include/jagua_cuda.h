@@ -126,7 +126,8 @@ int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms,
 int jg_sync(JgEngine* e);
 
 /* Counters since engine creation: [0] kernel launches, [1] queries resolved, [2] H2D bytes,
- * [3] D2H bytes, [4] layout uploads, [5] survivors of the surrogate stage (detect). */
+ * [3] D2H bytes, [4] layout uploads, [5] survivors of the surrogate stage and [6] work items that
+ * took the register-only fallback walk in the most recent *_device detect call. */
 int jg_engine_stats(const JgEngine* e, uint64_t out[8]);
 /* Device time (ms, CUDA events on the compute stream) of the kernels of the most recent
  * *_batch_device call; valid after jg_sync. */

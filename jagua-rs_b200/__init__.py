@@ -466,7 +466,7 @@ class CDEngine:
         a = (C.c_uint64 * 8)()
         self._lib.jg_engine_stats(self._eng, a)
         return dict(launches=int(a[0]), queries=int(a[1]), h2d_bytes=int(a[2]), d2h_bytes=int(a[3]),
-                    layout_uploads=int(a[4]), survivors=int(a[5]))
+                    layout_uploads=int(a[4]), survivors=int(a[5]), fallbacks=int(a[6]))
 
     def set_batching(self, chunk_queries: int, n_streams: int):
         self._chk(self._lib.jg_engine_set_batching(self._eng, int(chunk_queries), int(n_streams)))

@@ -1,24 +1,33 @@
 // detect pipeline (sm_100a): detect_surrogate_collision + detect_poly_collision for a batch made of up
-// to JG_MAX_SEG segments (one segment = one item's queries). One launch sequence per batch:
+// to JG_MAX_SEG segments (one segment = one item's queries). Two persistent kernels per batch:
 //
-//   k_bin_count / k_bin_scan / k_bin_scatter
-//                counting sort of the queries by (segment, rotation octant, Morton cell of the translation
-//                on a 32x32 grid over the CDE bbox). Purely a scheduling device: queries that sit next to
-//                each other in this order are the same item in almost the same pose, so the lanes of a
-//                warp walk the same quadtree nodes and take the same branches. Results never depend on it.
-//   k_s1_poles   persistent warps, one lane = one query (in sorted order); lanes REFILL from a shared work
-//                counter when their query is decided. Surrogate stage (cd_engine.rs:204-223): poles then
-//                piers, each walk from the ROOT. Undecided queries are appended to the survivor list in
-//                warp-sized bursts, which keeps the list spatially sorted.
-//   k_s2_edges   persistent warps, one lane = one survivor: transformed bbox (simple_polygon.rs:226-253),
-//                `bbox.relation_to(shape.bbox) != Surrounding -> collision` (cd_engine.rs:161-163), virtual
-//                root (cd_engine.rs:314-327), then the edges IN ORDER with QTNode::collides
-//                (qt_node.rs:99-147) and the reference's early exit at the first colliding edge.
-//   k_s3_contain one lane per survivor without an edge hit: the `unreachable!` of cd_engine.rs:179 (bit 7) or
-//                detect_containment_collision over the virtual root's relevant Partial entries.
+//   k_s1_surr   surrogate stage (cd_engine.rs:204-223). A warp takes 32 consecutive queries; lane = query.
+//               Poles (then piers) are resolved one entity index at a time, all 32 queries together.
+//   k_s2_poly   polygon stage (cd_engine.rs:160-197) for the survivors of stage 1. A warp takes a GROUP of
+//               up to 8 survivors; their transformed bboxes, virtual roots (cd_engine.rs:314-327) and the
+//               flat list of all their edges are set up once, then the edges are resolved together; the
+//               containment tests (cd_engine.rs:174-193) of the survivors without an edge hit follow.
 //
-// Every predicate is the reference's arithmetic (predicates.cuh); the order in which lanes pick up queries
-// is never observable because each query's verdict is computed by one lane exactly as the CPU would.
+// Both kernels run QTNode::collides (qt_node.rs:99-147) as a WAVEFRONT instead of a per-lane recursion:
+// the unit of work is a pair (entity, node). Pairs live on two per-warp LIFO stacks in shared memory
+// ("inner": the node has children and the quadrant test decides which are entered; "leaf": the node's
+// Partial hazards are tested edge by edge). Every step pops up to 32 pairs of ONE kind, so all lanes run
+// the same predicate, and pushes the surviving (entity, child) pairs with ballot-compacted stores. A
+// collision verdict is an OR over the visited nodes, so the visiting order is free; pairs of an
+// already-decided query are dropped when popped.
+//
+// Two exact shortcuts keep most entities off the stacks (proofs in DESIGN.md §4):
+//   * seg_chain   an edge whose endpoints lie inside a node and strictly on one side of both bisectors gets
+//                 exactly that quadrant from Edge::collides_with_quadrants (qt_traits.rs:19-106: the other
+//                 three are range-rejected, the fourth holds an endpoint) -> 4 compares instead of the test.
+//   * circ_chain  a circle whose centre is inside the node and further than r(1+1e-5) from both bisectors
+//                 collides with exactly the centre's quadrant (circle.rs:115-128 in f32, margin >> rounding).
+//   The children's hazard summary ("kind": none / partial / entire, per filter; k_node_kinds) is read from
+//   the parent's pair, so an Entire child (qt_node.rs:108) decides the query without being pushed.
+//
+// Node arrays (meta, bbox, kind) are staged into shared memory once per CTA when they fit; entries, hazard
+// edges and hazard shapes are read through L1. If a stack could overflow (never seen; the capacity follows
+// the tree depth) the warp falls back to the register-only walk of kernels.cuh for that work item.
 #include "kernels.cuh"
 #include "launch.hpp"
 
@@ -26,402 +35,649 @@ namespace jg {
 
 #define S_THREADS 256
 #define S_WARPS (S_THREADS / 32)
-#define S1_CHUNK 128  // sorted queries fetched per atomic by a warp
-#define S2_CHUNK 64   // survivors fetched per atomic by a warp
-#define REFILL_MIN 8  // refill once this many lanes of a warp are idle (or none is active)
-#define BIN_CELLS 1024
-#define BIN_ROT 8
+#define LEAF_CAP 160  // a leaf step runs as soon as 32 pairs wait; one inner step adds at most 128
+#define FULL 0xFFFFFFFFu
+#define S2_MAX_GROUP 8
 
-// One node visit of QTNode::collides. Returns 0 = walk continues, 1 = hit, 2 = walk finished, no hit.
-template <class Ent, bool FILT>
-__device__ __forceinline__ int walk_step(const DevLayout& L, Walk& w, const Ent& ent, const uint32_t* filt) {
-    const int4 m = __ldg(&L.node_meta[w.node]);
+enum : int { KIND_NONE = 0, KIND_INNER = 1, KIND_ENTIRE = 2, KIND_LEAF = 3 };
+enum : int { CH_DEAD = 0, CH_HIT = 1, CH_LEAF = 2, CH_INNER = 3 };
+
+// ---- per-filter node summary ------------------------------------------------------------------------
+// kinds[i + 3] = what QTHazardVec::strongest (qt_hazard_vec.rs:60-63) yields at node i under the filter:
+// none / Entire / Partial with children (KIND_INNER) / Partial without children (KIND_LEAF). The +3 offset
+// makes the four kinds of a child block (first child = 1 + 4k) one aligned 32-bit word.
+__global__ void k_node_kinds(const DevLayout L, const uint32_t* __restrict__ filt, uint8_t* __restrict__ kinds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n_nodes) return;
+    const int4 m = L.node_meta[i];
     const int n_entire = m.z & 0xFFFF, n_partial = (m.z >> 16) & 0xFFFF;
-    int first_partial = 0, kind;
-    if (!FILT) {
-        kind = n_entire ? 2 : (n_partial ? 1 : 0);
+    int kind = KIND_NONE;
+    if (!filt) {
+        kind = n_entire ? KIND_ENTIRE : (n_partial ? KIND_INNER : KIND_NONE);
     } else {
-        kind = 0;
-        for (int i = 0; i < n_entire; i++)
-            if (!filt_bit(filt, __ldg(&L.entry_meta[m.y + i]).x)) { kind = 2; break; }
-        if (kind == 0)
-            for (int i = 0; i < n_partial; i++)
-                if (!filt_bit(filt, __ldg(&L.entry_meta[m.y + n_entire + i]).x)) { kind = 1; first_partial = i; break; }
+        for (int j = 0; j < n_entire && kind == KIND_NONE; j++)
+            if (!filt_bit(filt, L.entry_meta[m.y + j].x)) kind = KIND_ENTIRE;
+        for (int j = 0; j < n_partial && kind == KIND_NONE; j++)
+            if (!filt_bit(filt, L.entry_meta[m.y + n_entire + j].x)) kind = KIND_INNER;
     }
-    if (kind == 2) return 1;
-    if (kind == 1) {
-        if (m.x >= 0) {
-            const unsigned mask = ent_quadrants(ent, ld_rect(&L.node_bbox[w.node]));
-            if (mask) { w.descend(m.x, mask); return 0; }
-        } else {
-            const int e0 = m.y + n_entire;
-            for (int i = first_partial; i < n_partial; i++) {
-                const int4 em = __ldg(&L.entry_meta[e0 + i]);
-                if (FILT && filt_bit(filt, em.x)) continue;
-                if (!ent_rect(ent, ld_rect(&L.entry_ff[e0 + i]))) continue;
-                for (int k = 0; k < em.z; k++)
-                    if (ent_seg(ent, ld_seg(&L.edges[em.y + k]))) return 1;
-            }
-        }
-    }
-    return w.next(L) ? 0 : 2;
+    if (kind == KIND_INNER && m.x < 0) kind = KIND_LEAF;
+    kinds[i + 3] = (uint8_t)kind;
 }
 
-// Warp-level work distribution: the warp owns a range [next, end) of work indices fetched CHUNK at a
-// time from a global counter; idle lanes take consecutive indices from it.
-struct WarpFeed {
-    int next, end;
-    bool dry;  // the global counter is exhausted
-    __device__ __forceinline__ void init() { next = end = 0; dry = false; }
-    __device__ __forceinline__ bool finished() const { return dry && next >= end; }
-    // gives lane `lane` an index (or -1). `want` = this lane is idle. Warp-uniform control flow.
-    template <int CHUNK>
-    __device__ __forceinline__ int take(bool want, int lane, int* counter, int total) {
-        const unsigned need = __ballot_sync(0xFFFFFFFFu, want);
-        if (next >= end && !dry) {
-            int b = 0;
-            if (lane == 0) b = atomicAdd(counter, CHUNK);
-            b = __shfl_sync(0xFFFFFFFFu, b, 0);
-            next = b;
-            end = b + CHUNK < total ? b + CHUNK : total;
-            if (b >= total) { dry = true; next = end = 0; }
-        }
-        const int avail = end - next;
-        const int rank = __popc(need & ((1u << lane) - 1u));
-        const int cnt = __popc(need);
-        const int idx = (want && rank < avail) ? next + rank : -1;
-        next += cnt < avail ? cnt : avail;
-        return idx;
-    }
+// ---- node arrays: shared memory when they fit, else the HBM copies ----------------------------------
+struct NodeView {
+    const int4* meta;
+    const float4* bbox;
+    const uint8_t* kind;  // kind[i + 3]
+    __device__ __forceinline__ int kind_of(int node) const { return kind[node + 3]; }
+    __device__ __forceinline__ uint32_t child_kinds(int child_base) const { return *(const uint32_t*)(kind + child_base + 3); }
 };
+
+__host__ __device__ inline size_t kinds_bytes(int n_nodes) { return ((size_t)n_nodes + 3 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t node_smem_bytes(int n_nodes) { return (size_t)n_nodes * 32 + kinds_bytes(n_nodes); }
+
+// carves [SegTable][node arrays] from the front of dynamic shared memory and fills them (whole CTA);
+// returns the first free byte (16-byte aligned)
+__device__ __forceinline__ unsigned char* stage_common(unsigned char* smem, const SegTable& gtab, const DevLayout& L,
+                                                       const uint8_t* g_kinds, int nodes_in_smem, const SegTable*& tab,
+                                                       NodeView& nv) {
+    SegTable* t = (SegTable*)smem;
+    for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
+    tab = t;
+    unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
+    if (nodes_in_smem) {
+        const int n = L.n_nodes;
+        int4* s_meta = (int4*)p;
+        float4* s_bbox = (float4*)(p + (size_t)n * 16);
+        uint4* s_kind = (uint4*)(p + (size_t)n * 32);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            s_meta[i] = __ldg(&L.node_meta[i]);
+            s_bbox[i] = __ldg(&L.node_bbox[i]);
+        }
+        const int kw = (int)(kinds_bytes(n) / 16);
+        for (int i = threadIdx.x; i < kw; i += blockDim.x) s_kind[i] = __ldg((const uint4*)g_kinds + i);
+        nv.meta = s_meta;
+        nv.bbox = s_bbox;
+        nv.kind = (const uint8_t*)s_kind;
+        p += node_smem_bytes(n);
+    } else {
+        nv.meta = L.node_meta;
+        nv.bbox = L.node_bbox;
+        nv.kind = g_kinds;
+    }
+    __syncthreads();
+    return p;
+}
+
+// ---- warp stacks ----------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// every lane may push one value; order among lanes is kept
+__device__ __forceinline__ void wpush(uint32_t* buf, int& n, bool want, uint32_t val) {
+    const unsigned b = __ballot_sync(FULL, want);
+    if (want) buf[n + __popc(b & lanemask_lt())] = val;
+    n += __popc(b);
+}
+
+// ---- the exact shortcuts ----------------------------------------------------------------------------
+// Descends from `node` (kind `kind`) while Edge::collides_with_quadrants provably flags exactly one child.
+// Precondition: both endpoints inside bbox(node), inclusive. Returns CH_*; `node` = where it stopped.
+__device__ __forceinline__ int seg_chain(const NodeView& nv, int& node, int kind, const Seg& s) {
+    for (;;) {
+        if (kind == KIND_ENTIRE) return CH_HIT;   // qt_node.rs:108
+        if (kind == KIND_NONE) return CH_DEAD;    // qt_node.rs:105
+        if (kind == KIND_LEAF) return CH_LEAF;    // qt_node.rs:128-143
+        const float4 b = nv.bbox[node];
+        const float mx = (b.x + b.z) / 2.0f, my = (b.y + b.w) / 2.0f;  // rect.rs:248-253 centroid
+        const bool xr = s.sx > mx && s.ex > mx, xl = s.sx < mx && s.ex < mx;
+        const bool yu = s.sy > my && s.ey > my, yd = s.sy < my && s.ey < my;
+        if (!((xr || xl) && (yu || yd))) return CH_INNER;
+        const int q = yu ? (xr ? 0 : 1) : (xl ? 2 : 3);  // NE, NW, SW, SE (rect.rs:141-161)
+        node = nv.meta[node].x + q;
+        kind = nv.kind_of(node);
+    }
+}
+// Same for a circle, from the root. The margin 1e-5 covers the <= 3 roundings of circle.rs:115-128.
+__device__ __forceinline__ int circ_chain(const NodeView& nv, int& node, const Circ& c) {
+    node = 0;
+    int kind = nv.kind_of(0);
+    const float rk = c.r * 1.00001f;
+    bool ok = c.r > 1e-15f && c.r < 1e15f;
+    {
+        const float4 b = nv.bbox[0];
+        ok = ok && c.cx >= b.x && c.cx <= b.z && c.cy >= b.y && c.cy <= b.w;
+    }
+    for (;;) {
+        if (kind == KIND_ENTIRE) return CH_HIT;
+        if (kind == KIND_NONE) return CH_DEAD;
+        if (kind == KIND_LEAF) return CH_LEAF;
+        const float4 b = nv.bbox[node];
+        const float mx = (b.x + b.z) / 2.0f, my = (b.y + b.w) / 2.0f;
+        const float dx = c.cx - mx, dy = c.cy - my;
+        if (!(ok && fabsf(dx) > rk && fabsf(dy) > rk)) return CH_INNER;
+        const int q = dy > 0.0f ? (dx > 0.0f ? 0 : 1) : (dx < 0.0f ? 2 : 3);
+        node = nv.meta[node].x + q;
+        kind = nv.kind_of(node);
+    }
+}
+
+// QTHazPartial::collides_with (qt_partial_hazard.rs:67-72) over the relevant Partial entries of a node
+// without children (qt_node.rs:128-143)
+template <class Ent, bool FILT>
+__device__ __forceinline__ bool leaf_collides(const DevLayout& L, const int4 m, const Ent& ent, const uint32_t* filt) {
+    const int n_entire = m.z & 0xFFFF, n_partial = (m.z >> 16) & 0xFFFF;
+    const int e0 = m.y + n_entire;
+    for (int i = 0; i < n_partial; i++) {
+        const int4 em = __ldg(&L.entry_meta[e0 + i]);
+        if (FILT && filt_bit(filt, em.x)) continue;
+        if (!ent_rect(ent, ld_rect(&L.entry_ff[e0 + i]))) continue;
+        for (int k = 0; k < em.z; k++)
+            if (ent_seg(ent, ld_seg(&L.edges[em.y + k]))) return true;
+    }
+    return false;
+}
+
+// visit of an inner pair: which children are entered (pin), which are leaves to test (plf), or a hit
+template <class Ent>
+__device__ __forceinline__ bool inner_visit(const NodeView& nv, int node, const Ent& ent, int& child_base, unsigned& pin,
+                                            unsigned& plf) {
+    const unsigned mask = ent_quadrants(ent, ld_rect_any(&nv.bbox[node]));
+    child_base = nv.meta[node].x;
+    const uint32_t ck = nv.child_kinds(child_base);
+    bool hit = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (!((mask >> q) & 1u)) continue;
+        const int kq = (ck >> (8 * q)) & 0xFF;
+        hit = hit || kq == KIND_ENTIRE;
+        if (kq == KIND_INNER) pin |= 1u << q;
+        if (kq == KIND_LEAF) plf |= 1u << q;
+    }
+    return hit;
+}
 
 __device__ __forceinline__ int seg_of_query(const SegTable& tab, int q) {
     int k = 0;
     for (int j = 1; j < tab.n_seg; j++) k += (q >= tab.seg[j].begin) ? 1 : 0;
     return k;
 }
-
-// ---- spatial binning ------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned morton5(unsigned x, unsigned y) {
-    unsigned r = 0;
-#pragma unroll
-    for (int b = 0; b < 5; b++) r |= (((x >> b) & 1u) << (2 * b)) | (((y >> b) & 1u) << (2 * b + 1));
-    return r;
-}
-
-__global__ void __launch_bounds__(S_THREADS)
-k_bin_count(const __grid_constant__ SegTable tab, const DevLayout L, const float4* __restrict__ xforms, int* __restrict__ keys,
-            int* __restrict__ hist) {
-    const int n = tab.n_queries;
-    const float sx = 32.0f / (L.cde_bbox.x_max - L.cde_bbox.x_min), sy = 32.0f / (L.cde_bbox.y_max - L.cde_bbox.y_min);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        const float4 t = __ldg(&xforms[q]);
-        int k = 0;
-        for (int j = 1; j < tab.n_seg; j++) k += (q >= tab.seg[j].begin) ? 1 : 0;
-        const int cx = min(31, max(0, (int)((t.z - L.cde_bbox.x_min) * sx)));
-        const int cy = min(31, max(0, (int)((t.w - L.cde_bbox.y_min) * sy)));
-        const int rot = (t.x < 0.0f ? 1 : 0) | (t.y < 0.0f ? 2 : 0) | (fabsf(t.x) < fabsf(t.y) ? 4 : 0);
-        const int key = ((k * BIN_ROT + rot) * BIN_CELLS) + (int)morton5((unsigned)cx, (unsigned)cy);
-        keys[q] = key;
-        atomicAdd(&hist[key], 1);
-    }
-}
-
-// exclusive scan of hist[0 .. n_bins) in place, one CTA
-__global__ void __launch_bounds__(1024) k_bin_scan(int* __restrict__ hist, int n_bins) {
-    __shared__ int part[1024];
-    const int per = (n_bins + 1023) / 1024;
-    const int b0 = min(n_bins, (int)threadIdx.x * per), b1 = min(n_bins, b0 + per);
-    int s = 0;
-    for (int i = b0; i < b1; i++) s += hist[i];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
-        const int v = (int)threadIdx.x >= off ? part[threadIdx.x - off] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    int run = part[threadIdx.x] - s;
-    for (int i = b0; i < b1; i++) {
-        const int c = hist[i];
-        hist[i] = run;
-        run += c;
-    }
-}
-
-__global__ void __launch_bounds__(S_THREADS)
-k_bin_scatter(int n, const int* __restrict__ keys, int* __restrict__ cursor, int* __restrict__ order) {
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
-        order[atomicAdd(&cursor[keys[q]], 1)] = q;
-}
-
-// ---------------------------------------------------------------------------------------------
 // survivor entries: query index in the low 26 bits, segment in the high 6
 __device__ __forceinline__ int sv_pack(int q, int k) { return q | (k << 26); }
 
+// edge e of the item under xf (simple_polygon.rs:86-93 edge_iter over the transformed vertices)
+__device__ __forceinline__ Seg item_edge(const SegDesc& sd, const Xf& xf, int e) {
+    const float2 a = __ldg(&sd.verts[e]);
+    const float2 b = __ldg(&sd.verts[e == sd.n_verts - 1 ? 0 : e + 1]);
+    Seg sg;
+    xf_point(xf, a.x, a.y, sg.sx, sg.sy);
+    xf_point(xf, b.x, b.y, sg.ex, sg.ey);
+    return sg;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 1: surrogate
+// ---------------------------------------------------------------------------------------------------
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
-k_s1_poles(const DevLayout L, const __grid_constant__ SegTable gtab, const float4* __restrict__ xforms,
-           const int* __restrict__ order, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
-           DetectCtl* __restrict__ ctl, Survivors sv) {
-    __shared__ SegTable tab;
-    __shared__ int burst[S_WARPS][64];
-    for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)&tab)[i] = ((const int*)&gtab)[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+k_s1_surr(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_t* __restrict__ g_kinds, int nodes_in_smem,
+          int cap_in, const float4* __restrict__ xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
+          DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SegTable* tabp;
+    NodeView nv;
+    unsigned char* p = stage_common(smem, gtab, L, g_kinds, nodes_in_smem, tabp, nv);
+    const SegTable& tab = *tabp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t per_warp = 32 * sizeof(float4) + ((size_t)cap_in + LEAF_CAP + 4) * sizeof(uint32_t);
+    unsigned char* wp = p + (size_t)warp * per_warp;
+    float4* s_ent = (float4*)wp;                      // entity of each lane's query for the current round
+    uint32_t* s_inner = (uint32_t*)(wp + 32 * sizeof(float4));
+    uint32_t* s_leaf = s_inner + cap_in;
+    unsigned* s_hit = (unsigned*)(s_leaf + LEAF_CAP);  // bit = lane whose query is decided
     const int n = tab.n_queries;
-    int* wb = burst[threadIdx.x >> 5];
-    int n_burst = 0;  // warp-uniform
-
-    WarpFeed feed;
-    feed.init();
-    bool active = false;
-    int q = 0, k = 0, ent_i = 0, n_ent = 0;
-    Xf xf{1, 0, 0, 0};
-    Circ c{0, 0, 0};
-    Seg s{0, 0, 0, 0};
-    bool is_circ = true;
-    Walk w;
-    w.start(0);
 
     for (;;) {
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
-        if (idle == 0xFFFFFFFFu && feed.finished()) break;
-        if (__popc(idle) >= REFILL_MIN || idle == 0xFFFFFFFFu) {
-            const int i = feed.take<S1_CHUNK>(!active, lane, &ctl->s1_next, n);
-            if (i >= 0) {
-                q = __ldg(&order[i]);
-                k = seg_of_query(tab, q);
-                const float4 t4 = __ldg(&xforms[q]);
-                xf = Xf{t4.x, t4.y, t4.z, t4.w};
-                ent_i = -1;
-                n_ent = tab.seg[k].n_poles + tab.seg[k].n_piers;
-                active = true;
-                w.depth = -1;  // "entity finished": pick the first one below
-            }
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->s1_next, 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) break;
+        const int q = base + lane;
+        const bool valid = q < n;
+        Xf xf{1.0f, 0.0f, 0.0f, 0.0f};
+        int k = 0, n_poles = 0, n_ent = 0;
+        if (valid) {
+            const float4 t4 = __ldg(&xforms[q]);
+            xf = Xf{t4.x, t4.y, t4.z, t4.w};
+            k = seg_of_query(tab, q);
+            n_poles = tab.seg[k].n_poles;
+            n_ent = n_poles + tab.seg[k].n_piers;
         }
-        bool survived = false;
-        if (active) {
-            int r = 2;
-            if (w.depth >= 0) r = is_circ ? walk_step<Circ, FILT>(L, w, c, filt) : walk_step<Seg, FILT>(L, w, s, filt);
-            if (r == 1) {  // cd_engine.rs:212,218: first colliding pole / pier decides
-                out[q] = JG_VERDICT_SURROGATE;
-                active = false;
-            } else if (r == 2) {
-                ent_i++;
-                if (ent_i < n_ent) {
-                    const SegDesc& sd = tab.seg[k];
-                    if (ent_i < sd.n_poles) {  // circle.rs:79-85: centre transformed, radius unchanged
-                        const float4 pl = __ldg(&sd.poles[ent_i]);
-                        xf_point(xf, pl.x, pl.y, c.cx, c.cy);
-                        c.r = pl.z;
-                        is_circ = true;
-                    } else {  // edge.rs:126-134
-                        const float4 pr = __ldg(&sd.piers[ent_i - sd.n_poles]);
-                        xf_point(xf, pr.x, pr.y, s.sx, s.sy);
-                        xf_point(xf, pr.z, pr.w, s.ex, s.ey);
-                        is_circ = false;
-                    }
-                    w.start(0);  // surrogate walks start at the ROOT (cd_engine.rs:212)
-                } else {
-                    active = false;  // no surrogate collision
-                    survived = true;
+        bool hit = false;
+        const int max_ent = __reduce_max_sync(FULL, n_ent);
+        for (int j = 0; j < max_ent; j++) {
+            // cd_engine.rs:210-221: poles in order, then piers; the first colliding one decides
+            const bool act = valid && !hit && j < n_ent;
+            if (!__any_sync(FULL, act)) break;
+            const bool is_seg = act && j >= n_poles;
+            const unsigned segmask = __ballot_sync(FULL, is_seg);
+            int code = CH_DEAD, node = 0;
+            if (act) {
+                const SegDesc& sd = tab.seg[k];
+                if (!is_seg) {  // circle.rs:79-85: centre transformed, radius unchanged
+                    const float4 pl = __ldg(&sd.poles[j]);
+                    Circ c;
+                    xf_point(xf, pl.x, pl.y, c.cx, c.cy);
+                    c.r = pl.z;
+                    s_ent[lane] = make_float4(c.cx, c.cy, c.r, 0.0f);
+                    code = circ_chain(nv, node, c);
+                } else {  // edge.rs:126-134
+                    const float4 pr = __ldg(&sd.piers[j - n_poles]);
+                    Seg s;
+                    xf_point(xf, pr.x, pr.y, s.sx, s.sy);
+                    xf_point(xf, pr.z, pr.w, s.ex, s.ey);
+                    s_ent[lane] = make_float4(s.sx, s.sy, s.ex, s.ey);
+                    const int kr = nv.kind_of(0);  // no shortcut: a pier may leave the root's bbox
+                    code = kr == KIND_ENTIRE ? CH_HIT : kr == KIND_INNER ? CH_INNER : kr == KIND_LEAF ? CH_LEAF : CH_DEAD;
                 }
             }
-        }
-        // survivors leave in bursts of >= 32 consecutive list slots per warp
-        const unsigned sm = __ballot_sync(0xFFFFFFFFu, survived);
-        if (sm) {
-            if (survived) wb[n_burst + __popc(sm & ((1u << lane) - 1u))] = sv_pack(q, k);
-            n_burst += __popc(sm);
-            __syncwarp();
-            if (n_burst >= 32) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&ctl->n_surv, n_burst);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                for (int j = lane; j < n_burst; j += 32) sv.entry[base + j] = wb[j];
-                n_burst = 0;
+            hit = hit || code == CH_HIT;
+            if (lane == 0) *s_hit = 0u;
+            int n_in = 0, n_lf = 0;
+            wpush(s_inner, n_in, code == CH_INNER, ((uint32_t)node << 5) | (uint32_t)lane);
+            wpush(s_leaf, n_lf, code == CH_LEAF, ((uint32_t)node << 5) | (uint32_t)lane);
+            bool overflow = false;
+            for (;;) {
                 __syncwarp();
+                const unsigned hm = *(volatile unsigned*)s_hit;
+                bool lanehit = false;
+                int slot = 0;
+                if (n_lf >= 32 || (n_in == 0 && n_lf > 0)) {
+                    const int cnt = n_lf < 32 ? n_lf : 32;
+                    n_lf -= cnt;
+                    if (lane < cnt) {
+                        const uint32_t pr = s_leaf[n_lf + lane];
+                        slot = pr & 31;
+                        if (!((hm >> slot) & 1u)) {
+                            const int4 m = nv.meta[pr >> 5];
+                            const float4 e4 = s_ent[slot];
+                            lanehit = ((segmask >> slot) & 1u)
+                                          ? leaf_collides<Seg, FILT>(L, m, Seg{e4.x, e4.y, e4.z, e4.w}, filt)
+                                          : leaf_collides<Circ, FILT>(L, m, Circ{e4.x, e4.y, e4.z}, filt);
+                        }
+                    }
+                } else if (n_in > 0) {
+                    const int cnt = n_in < 32 ? n_in : 32;
+                    if (n_in + 3 * cnt > cap_in) { overflow = true; break; }
+                    n_in -= cnt;
+                    unsigned pin = 0, plf = 0;
+                    int cb = 0;
+                    if (lane < cnt) {
+                        const uint32_t pr = s_inner[n_in + lane];
+                        slot = pr & 31;
+                        if (!((hm >> slot) & 1u)) {
+                            const float4 e4 = s_ent[slot];
+                            lanehit = ((segmask >> slot) & 1u)
+                                          ? inner_visit<Seg>(nv, pr >> 5, Seg{e4.x, e4.y, e4.z, e4.w}, cb, pin, plf)
+                                          : inner_visit<Circ>(nv, pr >> 5, Circ{e4.x, e4.y, e4.z}, cb, pin, plf);
+                            if (lanehit) pin = plf = 0;
+                        }
+                    }
+                    __syncwarp();  // all pops done before the pushes overwrite the popped range
+#pragma unroll
+                    for (int qd = 0; qd < 4; qd++) {
+                        const uint32_t v = ((uint32_t)(cb + qd) << 5) | (uint32_t)slot;
+                        wpush(s_inner, n_in, (pin >> qd) & 1u, v);
+                        wpush(s_leaf, n_lf, (plf >> qd) & 1u, v);
+                    }
+                } else {
+                    break;
+                }
+                if (__any_sync(FULL, lanehit)) {
+                    if (lanehit) atomicOr(s_hit, 1u << slot);
+                }
             }
+            __syncwarp();
+            if (overflow) {  // register-only walk of this round's entity (kernels.cuh), never seen in practice
+                if (lane == 0) atomicAdd(&ctl->fallbacks, 1);
+                if (act && !hit) {
+                    const float4 e4 = s_ent[lane];
+                    hit = is_seg ? qt_collides<Seg, FILT>(L, 0, Seg{e4.x, e4.y, e4.z, e4.w}, filt)
+                                 : qt_collides<Circ, FILT>(L, 0, Circ{e4.x, e4.y, e4.z}, filt);
+                }
+            } else {
+                hit = hit || ((*(volatile unsigned*)s_hit >> lane) & 1u);
+            }
+            __syncwarp();
         }
-    }
-    if (n_burst > 0) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->n_surv, n_burst);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        for (int j = lane; j < n_burst; j += 32) sv.entry[base + j] = wb[j];
+        if (valid) out[q] = hit ? (uint8_t)JG_VERDICT_SURROGATE : (uint8_t)0;
+        // survivors keep the query order inside the warp's 32
+        const unsigned sm = __ballot_sync(FULL, valid && !hit);
+        if (sm) {
+            int sb = 0;
+            if (lane == 0) sb = atomicAdd(&ctl->n_surv, __popc(sm));
+            sb = __shfl_sync(FULL, sb, 0);
+            if (valid && !hit) sv_entry[sb + __popc(sm & lanemask_lt())] = sv_pack(q, k);
+        }
     }
 }
 
 // JG_MODE_POLY_ONLY: no surrogate stage, every query is a survivor (lbf/benches/quadtree_bench.rs:73-124)
 __global__ void __launch_bounds__(S_THREADS)
-k_s1_all_survive(const __grid_constant__ SegTable tab, const int* __restrict__ order, DetectCtl* __restrict__ ctl, Survivors sv) {
+k_s1_all_survive(const __grid_constant__ SegTable tab, DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
     const int n = tab.n_queries;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int q = order[i];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         int k = 0;
         for (int j = 1; j < tab.n_seg; j++) k += (q >= tab.seg[j].begin) ? 1 : 0;
-        sv.entry[i] = sv_pack(q, k);
+        sv_entry[q] = sv_pack(q, k);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->n_surv = n;
 }
 
-// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------
+// stage 2: polygon
+// ---------------------------------------------------------------------------------------------------
+struct S2Slots {  // per-warp state of the survivors of the current group
+    float4 xf[S2_MAX_GROUP];
+    float4 bb[S2_MAX_GROUP];
+    int q[S2_MAX_GROUP];
+    int seg[S2_MAX_GROUP];
+    int vroot[S2_MAX_GROUP];
+    int vk[S2_MAX_GROUP];
+    int ebeg[S2_MAX_GROUP + 1];  // flat edge index ranges of the slots
+    unsigned hit;                // bit = slot with a colliding edge
+    int pad[2];
+};
+
+// CDEngine::get_virtual_root (cd_engine.rs:314-327) on the staged node arrays
+__device__ __forceinline__ int virtual_root_nv(const NodeView& nv, const Rect& bb) {
+    int node = 0;
+    for (;;) {
+        const int cb = nv.meta[node].x;
+        if (cb < 0) return node;
+        int nxt = -1;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (nxt < 0 && rect_relation(ld_rect_any(&nv.bbox[cb + i]), bb) == REL_SURROUNDING) nxt = cb + i;
+        if (nxt < 0) return node;
+        node = nxt;
+    }
+}
+
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
-k_s2_edges(const DevLayout L, const __grid_constant__ SegTable gtab, const float4* __restrict__ xforms,
-           const uint32_t* __restrict__ filt, uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, Survivors sv) {
-    __shared__ SegTable tab;
-    for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)&tab)[i] = ((const int*)&gtab)[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+k_s2_poly(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_t* __restrict__ g_kinds, int nodes_in_smem,
+          int cap_in, int gbits, const float4* __restrict__ xforms, const uint32_t* __restrict__ filt,
+          uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, const int* __restrict__ sv_entry) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SegTable* tabp;
+    NodeView nv;
+    unsigned char* p = stage_common(smem, gtab, L, g_kinds, nodes_in_smem, tabp, nv);
+    const SegTable& tab = *tabp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t per_warp = sizeof(S2Slots) + ((size_t)cap_in + LEAF_CAP) * sizeof(uint32_t);
+    unsigned char* wp = p + (size_t)warp * per_warp;
+    S2Slots& W = *(S2Slots*)wp;
+    uint32_t* s_inner = (uint32_t*)(wp + sizeof(S2Slots));
+    uint32_t* s_leaf = s_inner + cap_in;
+    const int G = 1 << gbits;
+    const int ebits = 12 + gbits;  // pair = node << ebits | edge << gbits | slot
+    const uint32_t emask = (1u << ebits) - 1u;
     const int total = ctl->n_surv;
 
-    WarpFeed feed;
-    feed.init();
-    bool active = false;
-    int q = 0, k = 0, e = 0, vroot = 0;
-    Xf xf{1, 0, 0, 0};
-    Seg sg{0, 0, 0, 0};
-    Walk w;
-    w.start(0);
     for (;;) {
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
-        if (idle == 0xFFFFFFFFu && feed.finished()) break;
-        if (__popc(idle) >= REFILL_MIN || idle == 0xFFFFFFFFu) {
-            const int slot = feed.take<S2_CHUNK>(!active, lane, &ctl->s2_next, total);
-            if (slot >= 0) {
-                const int ent = sv.entry[slot];
-                q = ent & 0x3FFFFFF;
-                k = (unsigned)ent >> 26;
-                const SegDesc& sd = tab.seg[k];
-                const float4 t4 = __ldg(&xforms[q]);
-                xf = Xf{t4.x, t4.y, t4.z, t4.w};
-                // SPolygon::transform_from + generate_bounding_box
-                float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
-                for (int j = 0; j < sd.n_verts; j++) {
-                    const float2 v = __ldg(&sd.verts[j]);
-                    float x, y;
-                    xf_point(xf, v.x, v.y, x, y);
-                    x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
-                }
-                const Rect bb{x0, y0, x1, y1};
-                if (rect_relation(L.cde_bbox, bb) != REL_SURROUNDING) {
-                    out[q] = JG_VERDICT_POLY;  // cd_engine.rs:161-163
-                    sv.vroot[slot] = -1;
-                } else {
-                    vroot = virtual_root(L, bb);
-                    sv.vroot[slot] = vroot;
-                    sv.bbox[slot] = make_float4(x0, y0, x1, y1);
-                    e = -1;
-                    w.depth = -1;  // "edge finished": take edge 0 below
-                    active = true;
-                }
+        int gbase = 0;
+        if (lane == 0) gbase = atomicAdd(&ctl->s2_next, G);
+        gbase = __shfl_sync(FULL, gbase, 0);
+        if (gbase >= total) break;
+        const int ng = (total - gbase) < G ? (total - gbase) : G;
+        if (lane < ng) {
+            const int ent = sv_entry[gbase + lane];
+            const int q = ent & 0x3FFFFFF;
+            W.q[lane] = q;
+            W.seg[lane] = (int)((unsigned)ent >> 26);
+            W.xf[lane] = __ldg(&xforms[q]);
+        }
+        __syncwarp();
+        // SPolygon::transform_from + generate_bounding_box (simple_polygon.rs:226-253, 122-133): min/max folds
+        // are exact in any order, so lanes fold strided vertices and a butterfly joins them
+        for (int s = 0; s < ng; s++) {
+            const SegDesc& sd = tab.seg[W.seg[s]];
+            const float4 t4 = W.xf[s];
+            const Xf xf{t4.x, t4.y, t4.z, t4.w};
+            float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
+            for (int j = lane; j < sd.n_verts; j += 32) {
+                const float2 v = __ldg(&sd.verts[j]);
+                float x, y;
+                xf_point(xf, v.x, v.y, x, y);
+                x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o));
+                y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o));
+                x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
+                y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
+            }
+            if (lane == 0) W.bb[s] = make_float4(x0, y0, x1, y1);
+        }
+        __syncwarp();
+        // lane s classifies survivor s
+        int verdict = -1, nE = 0;
+        if (lane < ng) {
+            const float4 b4 = W.bb[lane];
+            const Rect bb{b4.x, b4.y, b4.z, b4.w};
+            if (rect_relation(L.cde_bbox, bb) != REL_SURROUNDING) {
+                verdict = JG_VERDICT_POLY;  // cd_engine.rs:161-163
+            } else {
+                const int vroot = virtual_root_nv(nv, bb);
+                const int vk = nv.kind_of(vroot);
+                W.vroot[lane] = vroot;
+                W.vk[lane] = vk;
+                if (vk == KIND_ENTIRE) verdict = JG_VERDICT_POLY;  // every edge sees it (qt_node.rs:108)
+                else if (vk != KIND_NONE) nE = tab.seg[W.seg[lane]].n_verts;
             }
         }
-        if (active) {
-            int r = 2;
-            if (w.depth >= 0) r = walk_step<Seg, FILT>(L, w, sg, filt);
-            if (r == 1) {  // cd_engine.rs:169-172: first colliding edge decides
-                out[q] = JG_VERDICT_POLY;
-                active = false;
-            } else if (r == 2) {
-                const SegDesc& sd = tab.seg[k];
-                e++;
-                if (e < sd.n_verts) {
-                    const float2 a = __ldg(&sd.verts[e]);
-                    const float2 b = __ldg(&sd.verts[e == sd.n_verts - 1 ? 0 : e + 1]);  // simple_polygon.rs:86-93
-                    xf_point(xf, a.x, a.y, sg.sx, sg.sy);
-                    xf_point(xf, b.x, b.y, sg.ex, sg.ey);
-                    w.start(vroot);
-                } else {
-                    out[q] = 0;  // no edge hit: k_s3_contain decides
-                    active = false;
+        int incl = nE;
+#pragma unroll
+        for (int o = 1; o < S2_MAX_GROUP; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int E = __shfl_sync(FULL, incl, S2_MAX_GROUP - 1);
+        if (lane < S2_MAX_GROUP) W.ebeg[lane + 1] = incl;
+        if (lane == 0) {
+            W.ebeg[0] = 0;
+            W.hit = 0u;
+        }
+        const unsigned need = __ballot_sync(FULL, nE > 0);
+
+        int n_in = 0, n_lf = 0, f_next = 0;
+        bool overflow = false;
+        for (;;) {
+            __syncwarp();
+            const unsigned hm = *(volatile unsigned*)&W.hit;
+            if ((hm & need) == need) break;  // every survivor with edges has a colliding one
+            bool lanehit = false;
+            int slot = 0;
+            if (n_lf >= 32 || (n_lf > 0 && n_in == 0 && f_next >= E)) {
+                const int cnt = n_lf < 32 ? n_lf : 32;
+                n_lf -= cnt;
+                if (lane < cnt) {
+                    const uint32_t pr = s_leaf[n_lf + lane];
+                    slot = pr & (G - 1);
+                    if (!((hm >> slot) & 1u)) {
+                        const float4 t4 = W.xf[slot];
+                        const Seg sg = item_edge(tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, (pr & emask) >> gbits);
+                        lanehit = leaf_collides<Seg, FILT>(L, nv.meta[pr >> ebits], sg, filt);
+                    }
                 }
+            } else if (n_in < 32 && f_next < E) {
+                // next 32 edges of the group: shortcut descent from the virtual root
+                const int f = f_next + lane;
+                f_next += 32;
+                int code = CH_DEAD, node = 0;
+                uint32_t ent = 0;
+                if (f < E) {
+                    for (int j = 1; j < G; j++) slot += (W.ebeg[j] <= f) ? 1 : 0;
+                    if (!((hm >> slot) & 1u)) {
+                        const int e = f - W.ebeg[slot];
+                        const float4 t4 = W.xf[slot];
+                        const Seg sg = item_edge(tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, e);
+                        node = W.vroot[slot];
+                        code = seg_chain(nv, node, W.vk[slot], sg);
+                        ent = ((uint32_t)e << gbits) | (uint32_t)slot;
+                        lanehit = code == CH_HIT;
+                    }
+                }
+                wpush(s_inner, n_in, code == CH_INNER, ((uint32_t)node << ebits) | ent);
+                wpush(s_leaf, n_lf, code == CH_LEAF, ((uint32_t)node << ebits) | ent);
+            } else if (n_in > 0) {
+                const int cnt = n_in < 32 ? n_in : 32;
+                if (n_in + 3 * cnt > cap_in) { overflow = true; break; }
+                n_in -= cnt;
+                unsigned pin = 0, plf = 0;
+                int cb = 0;
+                uint32_t ent = 0;
+                if (lane < cnt) {
+                    const uint32_t pr = s_inner[n_in + lane];
+                    ent = pr & emask;
+                    slot = ent & (G - 1);
+                    if (!((hm >> slot) & 1u)) {
+                        const float4 t4 = W.xf[slot];
+                        const Seg sg = item_edge(tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, ent >> gbits);
+                        lanehit = inner_visit<Seg>(nv, pr >> ebits, sg, cb, pin, plf);
+                        if (lanehit) pin = plf = 0;
+                    }
+                }
+                __syncwarp();  // all pops done before the pushes overwrite the popped range
+#pragma unroll
+                for (int qd = 0; qd < 4; qd++) {
+                    const uint32_t v = ((uint32_t)(cb + qd) << ebits) | ent;
+                    wpush(s_inner, n_in, (pin >> qd) & 1u, v);
+                    wpush(s_leaf, n_lf, (plf >> qd) & 1u, v);
+                }
+            } else {
+                break;
+            }
+            if (__any_sync(FULL, lanehit)) {
+                if (lanehit) atomicOr(&W.hit, 1u << slot);
             }
         }
+        __syncwarp();
+        unsigned hm = *(volatile unsigned*)&W.hit;
+        if (overflow) {  // register-only walks (kernels.cuh) for the undecided survivors; never seen in practice
+            if (lane == 0) atomicAdd(&ctl->fallbacks, 1);
+            for (int s = 0; s < ng; s++) {
+                if (!((need >> s) & 1u) || ((hm >> s) & 1u)) continue;
+                const SegDesc& sd = tab.seg[W.seg[s]];
+                const float4 t4 = W.xf[s];
+                bool h = false;
+                for (int e = lane; e < sd.n_verts && !h; e += 32)
+                    h = qt_collides<Seg, FILT>(L, W.vroot[s], item_edge(sd, Xf{t4.x, t4.y, t4.z, t4.w}, e), filt);
+                if (__any_sync(FULL, h)) hm |= 1u << s;
+            }
+        }
+        // cd_engine.rs:174-193: survivors without an edge hit -> `unreachable!` or containment tests
+        for (int s = 0; s < ng; s++) {
+            if (__shfl_sync(FULL, verdict, s) >= 0) continue;
+            int v = 0;
+            if ((hm >> s) & 1u) {
+                v = JG_VERDICT_POLY;
+            } else {
+                const int4 m = nv.meta[W.vroot[s]];
+                const int n_entire = m.z & 0xFFFF, n_partial = (m.z >> 16) & 0xFFFF;
+                if (n_entire > 0) {
+                    v = JG_VERDICT_REF_PANIC;  // cd_engine.rs:179, reachable only under a filter
+                } else {
+                    const SegDesc& sd = tab.seg[W.seg[s]];
+                    const float4 t4 = W.xf[s], b4 = W.bb[s];
+                    bool c = false;
+                    for (int j = lane; j < n_partial && !c; j += 32) {
+                        const int hs = __ldg(&L.entry_meta[m.y + j]).x;
+                        if (FILT && filt_bit(filt, hs)) continue;
+                        c = containment_collision(L, sd.verts, sd.n_verts, sd.poi_x, sd.poi_y, Xf{t4.x, t4.y, t4.z, t4.w},
+                                                  Rect{b4.x, b4.y, b4.z, b4.w}, hs);
+                    }
+                    if (__any_sync(FULL, c)) v = JG_VERDICT_POLY;
+                }
+            }
+            if (lane == s) verdict = v;
+        }
+        if (lane < ng) out[W.q[lane]] = (uint8_t)verdict;
+        __syncwarp();
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-template <bool FILT>
-__global__ void __launch_bounds__(S_THREADS)
-k_s3_contain(const DevLayout L, const __grid_constant__ SegTable tab, const float4* __restrict__ xforms,
-             const uint32_t* __restrict__ filt, uint8_t* __restrict__ out, const DetectCtl* __restrict__ ctl, Survivors sv) {
-    const int ns = ctl->n_surv;
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < ns; slot += gridDim.x * blockDim.x) {
-        const int vroot = sv.vroot[slot];
-        if (vroot < 0) continue;
-        const int ent = sv.entry[slot];
-        const int q = ent & 0x3FFFFFF;
-        if (out[q] != 0) continue;
-        const SegDesc& sd = tab.seg[(unsigned)ent >> 26];
-        const int4 m = __ldg(&L.node_meta[vroot]);
-        const int n_entire = m.z & 0xFFFF, n_partial = (m.z >> 16) & 0xFFFF;
-        if (n_entire > 0) {  // cd_engine.rs:179 `unreachable!` (only reachable under a filter)
-            out[q] = JG_VERDICT_REF_PANIC;
-            continue;
-        }
-        const float4 t4 = __ldg(&xforms[q]);
-        const Xf xf{t4.x, t4.y, t4.z, t4.w};
-        const float4 b4 = sv.bbox[slot];
-        const Rect sb{b4.x, b4.y, b4.z, b4.w};
-        bool c = false;
-        for (int j = 0; j < n_partial && !c; j++) {
-            const int hs = __ldg(&L.entry_meta[m.y + j]).x;
-            if (FILT && filt_bit(filt, hs)) continue;
-            c = containment_collision(L, sd.verts, sd.n_verts, sd.poi_x, sd.poi_y, xf, sb, hs);
-        }
-        if (c) out[q] = JG_VERDICT_POLY;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------
 static int g_occ[8];
+static size_t g_occ_smem[8];
 template <class K>
-static int persistent_grid(K kernel, int slot, int n_sms) {
-    if (g_occ[slot] == 0) {
+static int persistent_grid(K kernel, int slot, int n_sms, size_t smem) {
+    if (g_occ[slot] == 0 || g_occ_smem[slot] != smem) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int b = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, S_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, S_THREADS, smem);
         g_occ[slot] = b < 1 ? 1 : b;
+        g_occ_smem[slot] = smem;
     }
     return n_sms * g_occ[slot];
 }
 
-size_t detect_bin_words(int n_seg) { return (size_t)n_seg * BIN_ROT * BIN_CELLS; }
+size_t detect_kinds_bytes(int n_nodes) { return kinds_bytes(n_nodes); }
 
-cudaError_t launch_detect(const DevLayout& L, const SegTable& tab, const float4* d_xf, const uint32_t* d_filt, int mode,
-                          uint8_t* d_out, const DetectScratch& sc, int n_sms, cudaStream_t st, int* n_launches) {
+cudaError_t launch_node_kinds(const DevLayout& L, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st) {
+    cudaMemsetAsync(d_kinds, 0, kinds_bytes(L.n_nodes), st);
+    k_node_kinds<<<(L.n_nodes + 255) / 256, 256, 0, st>>>(L, d_filt, d_kinds);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const float4* d_xf,
+                          const uint32_t* d_filt, const uint8_t* d_kinds, int mode, uint8_t* d_out, const DetectScratch& sc,
+                          int n_sms, cudaStream_t st, int* n_launches) {
     const int n = tab.n_queries;
-    const int n_bins = (int)detect_bin_words(tab.n_seg);
     cudaMemsetAsync(sc.ctl, 0, sizeof(DetectCtl), st);
-    cudaMemsetAsync(sc.hist, 0, (size_t)n_bins * sizeof(int), st);
-    const int want = (n + S_THREADS - 1) / S_THREADS;
-    const int gs = want < n_sms * 8 ? want : n_sms * 8;
-    k_bin_count<<<gs, S_THREADS, 0, st>>>(tab, L, d_xf, sc.keys, sc.hist);
-    k_bin_scan<<<1, 1024, 0, st>>>(sc.hist, n_bins);
-    k_bin_scatter<<<gs, S_THREADS, 0, st>>>(n, sc.keys, sc.hist, sc.order);
+    const size_t common = ((sizeof(SegTable) + 15) & ~(size_t)15) + (plan.nodes_in_smem ? node_smem_bytes(L.n_nodes) : 0);
+    const size_t smem1 = common + S_WARPS * (32 * sizeof(float4) + ((size_t)plan.cap_in + LEAF_CAP + 4) * sizeof(uint32_t));
+    const size_t smem2 = common + S_WARPS * (sizeof(S2Slots) + ((size_t)plan.cap_in + LEAF_CAP) * sizeof(uint32_t));
+    const int want1 = (n + S_THREADS - 1) / S_THREADS;                               // 32 queries per warp batch
+    const int want2 = (n + S_WARPS * (1 << plan.gbits) - 1) / (S_WARPS * (1 << plan.gbits));  // upper bound
     if (mode & JG_MODE_POLY_ONLY) {
-        k_s1_all_survive<<<gs, S_THREADS, 0, st>>>(tab, sc.order, sc.ctl, sc.sv);
+        const int gs = want1 < n_sms * 8 ? want1 : n_sms * 8;
+        k_s1_all_survive<<<gs, S_THREADS, 0, st>>>(tab, sc.ctl, sc.sv_entry);
     } else if (d_filt) {
-        const int g = persistent_grid(k_s1_poles<true>, 0, n_sms);
-        k_s1_poles<true><<<want < g ? want : g, S_THREADS, 0, st>>>(L, tab, d_xf, sc.order, d_filt, d_out, sc.ctl, sc.sv);
+        const int g = persistent_grid(k_s1_surr<true>, 0, n_sms, smem1);
+        k_s1_surr<true><<<want1 < g ? want1 : g, S_THREADS, smem1, st>>>(L, tab, d_kinds, plan.nodes_in_smem, plan.cap_in, d_xf,
+                                                                       d_filt, d_out, sc.ctl, sc.sv_entry);
     } else {
-        const int g = persistent_grid(k_s1_poles<false>, 1, n_sms);
-        k_s1_poles<false><<<want < g ? want : g, S_THREADS, 0, st>>>(L, tab, d_xf, sc.order, d_filt, d_out, sc.ctl, sc.sv);
+        const int g = persistent_grid(k_s1_surr<false>, 1, n_sms, smem1);
+        k_s1_surr<false><<<want1 < g ? want1 : g, S_THREADS, smem1, st>>>(L, tab, d_kinds, plan.nodes_in_smem, plan.cap_in, d_xf,
+                                                                        d_filt, d_out, sc.ctl, sc.sv_entry);
     }
     if (d_filt) {
-        const int g = persistent_grid(k_s2_edges<true>, 2, n_sms);
-        k_s2_edges<true><<<want < g ? want : g, S_THREADS, 0, st>>>(L, tab, d_xf, d_filt, d_out, sc.ctl, sc.sv);
-        k_s3_contain<true><<<gs, S_THREADS, 0, st>>>(L, tab, d_xf, d_filt, d_out, sc.ctl, sc.sv);
+        const int g = persistent_grid(k_s2_poly<true>, 2, n_sms, smem2);
+        k_s2_poly<true><<<want2 < g ? want2 : g, S_THREADS, smem2, st>>>(L, tab, d_kinds, plan.nodes_in_smem, plan.cap_in,
+                                                                       plan.gbits, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
     } else {
-        const int g = persistent_grid(k_s2_edges<false>, 3, n_sms);
-        k_s2_edges<false><<<want < g ? want : g, S_THREADS, 0, st>>>(L, tab, d_xf, d_filt, d_out, sc.ctl, sc.sv);
-        k_s3_contain<false><<<gs, S_THREADS, 0, st>>>(L, tab, d_xf, d_filt, d_out, sc.ctl, sc.sv);
+        const int g = persistent_grid(k_s2_poly<false>, 3, n_sms, smem2);
+        k_s2_poly<false><<<want2 < g ? want2 : g, S_THREADS, smem2, st>>>(L, tab, d_kinds, plan.nodes_in_smem, plan.cap_in,
+                                                                        plan.gbits, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
     }
-    if (n_launches) *n_launches += 6;
+    if (n_launches) *n_launches += 2;
     return cudaGetLastError();
+}
+
+// Chooses where the node arrays live and how the stacks are sized for a layout.
+DetectPlan make_detect_plan(int n_nodes, int depth) {
+    DetectPlan p;
+    p.cap_in = 96 * (depth > 0 ? depth : 1) + 128;
+    // pair word of stage 2: node << (12 + gbits); shrink the group when the tree has many nodes
+    p.gbits = 3;
+    while (p.gbits > 0 && ((uint64_t)n_nodes >> (32 - 12 - p.gbits)) != 0) p.gbits--;
+    p.nodes_in_smem = node_smem_bytes(n_nodes) <= 72 * 1024 ? 1 : 0;
+    return p;
 }
 
 }  // namespace jg

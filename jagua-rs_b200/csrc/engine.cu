@@ -28,6 +28,9 @@ struct ItemDev {
 struct FilterDev {
     uint32_t* bits = nullptr;
     int words = 0;
+    uint8_t* kinds = nullptr;  // node summary under this filter (k_node_kinds), valid for kinds_version
+    size_t kinds_cap = 0;
+    uint64_t kinds_version = 0;
 };
 // One in-flight chunk of a host-pointer batch: its own stream and staging buffers.
 struct ChunkCtx {
@@ -35,7 +38,7 @@ struct ChunkCtx {
     float4* d_xf = nullptr;
     uint8_t* d_out = nullptr;  // verdict bytes or collector words
     size_t cap_q = 0, cap_out = 0;
-    DetectScratch sc{nullptr, nullptr, nullptr, nullptr, {nullptr, nullptr, nullptr}};
+    DetectScratch sc{nullptr, nullptr};
     size_t cap_sv = 0;
 };
 
@@ -53,6 +56,10 @@ struct JgEngine {
     DevLayout L{};
     bool has_layout = false;
     uint64_t epoch = 0;
+    uint64_t layout_version = 0;  // bumped by every upload; per-filter node summaries are keyed on it
+    DetectPlan plan{0, 0, 0};
+    uint8_t* d_kinds = nullptr;   // node summary under NoFilter
+    size_t kinds_cap = 0;
 
     std::map<int, ItemDev> items;
     std::map<int, FilterDev> filters;
@@ -107,17 +114,14 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
         c.cap_out = out_bytes;
     }
     if (c.cap_sv < n_q) {
-        cudaFree(c.sc.keys), cudaFree(c.sc.order), cudaFree(c.sc.sv.entry), cudaFree(c.sc.sv.vroot), cudaFree(c.sc.sv.bbox);
-        c.sc.keys = c.sc.order = c.sc.sv.entry = c.sc.sv.vroot = nullptr;
-        c.sc.sv.bbox = nullptr;
+        cudaFree(c.sc.sv_entry);
+        c.sc.sv_entry = nullptr;
         c.cap_sv = 0;
-        if (!c.sc.ctl) JG_CUDA(e, cudaMalloc(&c.sc.ctl, sizeof(DetectCtl)));
-        if (!c.sc.hist) JG_CUDA(e, cudaMalloc(&c.sc.hist, detect_bin_words(JG_MAX_SEG) * sizeof(int)));
-        JG_CUDA(e, cudaMalloc(&c.sc.keys, n_q * sizeof(int)));
-        JG_CUDA(e, cudaMalloc(&c.sc.order, n_q * sizeof(int)));
-        JG_CUDA(e, cudaMalloc(&c.sc.sv.entry, n_q * sizeof(int)));
-        JG_CUDA(e, cudaMalloc(&c.sc.sv.vroot, n_q * sizeof(int)));
-        JG_CUDA(e, cudaMalloc(&c.sc.sv.bbox, n_q * sizeof(float4)));
+        if (!c.sc.ctl) {
+            JG_CUDA(e, cudaMalloc(&c.sc.ctl, sizeof(DetectCtl)));
+            JG_CUDA(e, cudaMemset(c.sc.ctl, 0, sizeof(DetectCtl)));
+        }
+        JG_CUDA(e, cudaMalloc(&c.sc.sv_entry, n_q * sizeof(int)));
         c.cap_sv = n_q;
     }
     return JG_OK;
@@ -125,8 +129,7 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
 
 static void free_ctx(ChunkCtx& c) {
     cudaFree(c.d_xf), cudaFree(c.d_out);
-    cudaFree(c.sc.ctl), cudaFree(c.sc.keys), cudaFree(c.sc.order), cudaFree(c.sc.hist);
-    cudaFree(c.sc.sv.entry), cudaFree(c.sc.sv.vroot), cudaFree(c.sc.sv.bbox);
+    cudaFree(c.sc.ctl), cudaFree(c.sc.sv_entry);
     c = ChunkCtx{};
 }
 
@@ -191,7 +194,8 @@ void jg_engine_destroy(JgEngine* e) {
         cudaFree(kv.second.poles);
         cudaFree(kv.second.piers);
     }
-    for (auto& kv : e->filters) cudaFree(kv.second.bits);
+    for (auto& kv : e->filters) cudaFree(kv.second.bits), cudaFree(kv.second.kinds);
+    if (e->d_kinds) cudaFree(e->d_kinds);
     for (ChunkCtx& c : e->chunks) {
         cudaStream_t st = c.st;
         free_ctx(c);
@@ -223,6 +227,7 @@ static int validate_header(JgEngine* e, const JgLayoutHeader& h, size_t bytes) {
         return fail(e, JG_ERR_INVALID, "layout blob: bad magic / version");
     if (h.total_bytes > bytes || h.n_nodes == 0) return fail(e, JG_ERR_INVALID, "layout blob: truncated");
     if (h.root_level > JG_MAX_DEPTH) return fail(e, JG_ERR_INVALID, "layout blob: quadtree too deep");
+    if (h.n_nodes > JG_MAX_NODES) return fail(e, JG_ERR_CAPACITY, "layout blob: more than 2^20 quadtree nodes");
     struct {
         uint32_t off, n, sz;
     } secs[] = {{h.off_node_meta, h.n_nodes, 16},  {h.off_node_bbox, h.n_nodes, 16},    {h.off_node_nactive, h.n_nodes, 4},
@@ -275,6 +280,13 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
             if (eb < 0 || (uint32_t)eb + n_ent > h.n_entries) return fail(e, JG_ERR_INVALID, "layout blob: bad entry range");
             if (par >= (int32_t)h.n_nodes || (i > 0 && par < 0)) return fail(e, JG_ERR_INVALID, "layout blob: bad parent");
         }
+        // the shortcut descents of detect.cu assume finite, non-empty node boxes
+        const float* nb = (const float*)((const char*)src + h.off_node_bbox);
+        for (uint32_t i = 0; i < h.n_nodes; i++) {
+            const float x0 = nb[4 * i], y0 = nb[4 * i + 1], x1 = nb[4 * i + 2], y1 = nb[4 * i + 3];
+            if (!(std::fabs(x0) < 1e30f && std::fabs(y0) < 1e30f && std::fabs(x1) < 1e30f && std::fabs(y1) < 1e30f && x0 <= x1 && y0 <= y1))
+                return fail(e, JG_ERR_INVALID, "layout blob: node bbox not finite");
+        }
         const int32_t* em = (const int32_t*)((const char*)src + h.off_entry_meta);
         for (uint32_t i = 0; i < h.n_entries; i++) {
             if (em[4 * i] < 0 || (uint32_t)em[4 * i] >= h.n_slots) return fail(e, JG_ERR_INVALID, "layout blob: bad hazard slot");
@@ -296,6 +308,19 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
                                src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->compute));
     JG_CUDA(e, cudaStreamSynchronize(e->compute));
     bind_layout(e, h);
+    e->layout_version++;
+    e->plan = make_detect_plan((int)h.n_nodes, (int)h.root_level);
+    if (e->kinds_cap < detect_kinds_bytes((int)h.n_nodes)) {
+        if (e->d_kinds) cudaFree(e->d_kinds);
+        e->d_kinds = nullptr;
+        e->kinds_cap = 0;
+        const size_t cap = detect_kinds_bytes((int)h.n_nodes) * 2;
+        JG_CUDA(e, cudaMalloc(&e->d_kinds, cap));
+        e->kinds_cap = cap;
+    }
+    JG_CUDA(e, launch_node_kinds(e->L, nullptr, e->d_kinds, e->compute));
+    JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    e->stat_launches++;
     e->epoch = epoch;
     e->stat_uploads++;
     if (!src_on_device) e->stat_h2d += h.total_bytes;
@@ -350,6 +375,7 @@ int jg_filter_upload(JgEngine* e, int filter_id, const uint32_t* bits, int words
     if (rc != JG_OK) return rc;
     FilterDev& f = e->filters[filter_id];
     cudaFree(f.bits);
+    cudaFree(f.kinds);
     f = FilterDev{};
     JG_CUDA(e, cudaMalloc(&f.bits, (size_t)words * 4));
     JG_CUDA(e, cudaMemcpy(f.bits, bits, (size_t)words * 4, cudaMemcpyHostToDevice));
@@ -369,14 +395,32 @@ static int find_item(JgEngine* e, int item_id, const ItemDev** it) {
     *it = &f->second;
     return JG_OK;
 }
-static int find_filter(JgEngine* e, int filter_id, const uint32_t** d_filt) {
+static int find_filter(JgEngine* e, int filter_id, const uint32_t** d_filt, const uint8_t** d_kinds) {
     *d_filt = nullptr;
+    *d_kinds = e->d_kinds;
     if (filter_id < 0) return JG_OK;
     auto g = e->filters.find(filter_id);
     if (g == e->filters.end()) return fail(e, JG_ERR_INVALID, "unknown filter id");
-    if ((size_t)g->second.words * 32 < e->hdr.n_slots)
+    FilterDev& f = g->second;
+    if ((size_t)f.words * 32 < e->hdr.n_slots)
         return fail(e, JG_ERR_CAPACITY, "filter bitset smaller than the hazard slot capacity");
-    *d_filt = g->second.bits;
+    if (f.kinds_version != e->layout_version) {  // node summary of this filter for the current layout
+        JG_CUDA(e, cudaSetDevice(e->device));
+        const size_t need = detect_kinds_bytes((int)e->hdr.n_nodes);
+        if (f.kinds_cap < need) {
+            cudaFree(f.kinds);
+            f.kinds = nullptr;
+            f.kinds_cap = 0;
+            JG_CUDA(e, cudaMalloc(&f.kinds, need * 2));
+            f.kinds_cap = need * 2;
+        }
+        JG_CUDA(e, launch_node_kinds(e->L, f.bits, f.kinds, e->compute));
+        JG_CUDA(e, cudaStreamSynchronize(e->compute));
+        e->stat_launches++;
+        f.kinds_version = e->layout_version;
+    }
+    *d_filt = f.bits;
+    *d_kinds = f.kinds;
     return JG_OK;
 }
 
@@ -451,7 +495,8 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
     rc = resolve_segments(e, n_seg, item_ids, seg_offsets, items);
     if (rc != JG_OK) return rc;
     const uint32_t* d_filt;
-    rc = find_filter(e, filter_id, &d_filt);
+    const uint8_t* d_kinds;
+    rc = find_filter(e, filter_id, &d_filt, &d_kinds);
     if (rc != JG_OK) return rc;
     const int64_t n = seg_offsets[n_seg];
     if (n > 0 && (!d_transforms || !d_out)) return JG_ERR_INVALID;
@@ -465,7 +510,7 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
     PieceCursor cur;
     Piece p;
     while (next_piece(e, n_seg, items.data(), seg_offsets, max_q, cur, p))
-        JG_CUDA(e, launch_detect(e->L, p.tab, (const float4*)d_transforms + p.off, d_filt, mode, d_out + p.off, e->main_ctx.sc,
+        JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, (const float4*)d_transforms + p.off, d_filt, d_kinds, mode, d_out + p.off, e->main_ctx.sc,
                                  e->n_sms, e->compute, &launches));
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
     e->timing_valid = true;
@@ -484,7 +529,8 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
     rc = resolve_segments(e, n_seg, item_ids, seg_offsets, items);
     if (rc != JG_OK) return rc;
     const uint32_t* d_filt;
-    rc = find_filter(e, filter_id, &d_filt);
+    const uint8_t* d_kinds;
+    rc = find_filter(e, filter_id, &d_filt, &d_kinds);
     if (rc != JG_OK) return rc;
     const int64_t n = seg_offsets[n_seg];
     if (n > 0 && (!transforms || !out)) return JG_ERR_INVALID;
@@ -500,7 +546,7 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
         if (rc != JG_OK) return rc;
         JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * p.off, (size_t)p.m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
         int launches = 0;
-        JG_CUDA(e, launch_detect(e->L, p.tab, c.d_xf, d_filt, mode, c.d_out, c.sc, e->n_sms, c.st, &launches));
+        JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, c.d_xf, d_filt, d_kinds, mode, c.d_out, c.sc, e->n_sms, c.st, &launches));
         JG_CUDA(e, cudaMemcpyAsync(out + p.off, c.d_out, (size_t)p.m, cudaMemcpyDeviceToHost, c.st));
         e->stat_launches += launches;
         e->stat_h2d += (uint64_t)p.m * sizeof(float4);
@@ -619,7 +665,10 @@ int jg_engine_stats(const JgEngine* e, uint64_t out[8]) {
     if (e->main_ctx.sc.ctl) {  // survivors of the last *_device detect launch sequence
         DetectCtl c;
         cudaSetDevice(e->device);
-        if (cudaMemcpy(&c, e->main_ctx.sc.ctl, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) out[5] = (uint64_t)c.n_surv;
+        if (cudaMemcpy(&c, e->main_ctx.sc.ctl, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            out[5] = (uint64_t)c.n_surv;
+            out[6] = (uint64_t)c.fallbacks;
+        }
     }
     return JG_OK;
 }

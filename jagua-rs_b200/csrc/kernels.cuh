@@ -42,6 +42,11 @@ __device__ __forceinline__ Rect ld_rect(const float4* p) {
     const float4 v = __ldg(p);
     return Rect{v.x, v.y, v.z, v.w};
 }
+// same for a pointer that may be shared memory (staged node arrays)
+__device__ __forceinline__ Rect ld_rect_any(const float4* p) {
+    const float4 v = *p;
+    return Rect{v.x, v.y, v.z, v.w};
+}
 __device__ __forceinline__ Seg ld_seg(const float4* p) {
     const float4 v = __ldg(p);
     return Seg{v.x, v.y, v.z, v.w};

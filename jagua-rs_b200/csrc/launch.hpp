@@ -28,33 +28,34 @@ struct SegTable {
 
 // Work counters of one detect launch sequence (device memory, zeroed by launch_detect).
 struct DetectCtl {
-    int s1_next;  // next unclaimed position of the sorted query order (k_s1_poles)
-    int s2_next;  // next unclaimed survivor (k_s2_edges)
-    int n_surv;   // survivors of the surrogate stage
-    int pad;
+    int s1_next;    // next unclaimed query (k_s1_surr takes 32 at a time)
+    int s2_next;    // next unclaimed survivor (k_s2_poly takes a group at a time)
+    int n_surv;     // survivors of the surrogate stage
+    int fallbacks;  // work items resolved by the register-only walk because a warp stack was full
 };
-
-// Queries that passed the surrogate stage. Appended in warp-sized bursts in arbitrary order (results are
-// written by query index, so the order is never observable).
-struct Survivors {
-    int* entry;    // query index within the batch (low 26 bits) | segment (high 6 bits)
-    int* vroot;    // virtual-root node of the transformed bbox, -1 = bbox not inside the CDE bbox
-    float4* bbox;  // transformed bbox
-};
-#define JG_MAX_LAUNCH_QUERIES (1 << 26)
+#define JG_MAX_LAUNCH_QUERIES (1 << 26)  // survivor entries keep the query index in 26 bits
+#define JG_MAX_NODES (1 << 20)           // stage-2 pair words keep the node index in >= 20 bits
+#define JG_MAX_ITEM_VERTS 4096           // ... and the edge index in 12
 
 // Device scratch of one detect launch sequence (sized for the largest batch piece seen so far).
 struct DetectScratch {
     DetectCtl* ctl;
-    int* keys;   // bin key per query
-    int* order;  // queries sorted by bin
-    int* hist;   // bin counters / cursors, detect_bin_words(n_seg) ints
-    Survivors sv;
+    int* sv_entry;  // survivors of stage 1: query index within the batch (low 26 bits) | segment (high 6 bits)
 };
-size_t detect_bin_words(int n_seg);
+// Per-layout launch parameters (make_detect_plan).
+struct DetectPlan {
+    int nodes_in_smem;  // node meta / bbox / kind staged into shared memory by every CTA
+    int cap_in;         // capacity of a warp's inner-pair stack
+    int gbits;          // log2 of the survivors a stage-2 warp resolves together
+};
+DetectPlan make_detect_plan(int n_nodes, int depth);
+size_t detect_kinds_bytes(int n_nodes);
 
-cudaError_t launch_detect(const DevLayout& L, const SegTable& tab, const float4* d_xf, const uint32_t* d_filt, int mode,
-                          uint8_t* d_out, const DetectScratch& sc, int n_sms, cudaStream_t st, int* n_launches);
+// per-filter node summary read by the detect kernels; d_filt == nullptr is NoFilter
+cudaError_t launch_node_kinds(const DevLayout& L, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st);
+cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const float4* d_xf,
+                          const uint32_t* d_filt, const uint8_t* d_kinds, int mode, uint8_t* d_out, const DetectScratch& sc,
+                          int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,
                            uint32_t* d_out_bits, int words, int group, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_fp32_nofma(float* d_out, int blocks, int iters, cudaStream_t st);

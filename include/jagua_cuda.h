@@ -141,6 +141,14 @@ int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams);
 /* Lanes per query (0 = choose from the item's vertex count, else 4, 8, 16 or 32) of the detect
  * stage-2 and collect kernels. A tuning knob; results do not depend on it. */
 int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group);
+/* Which detect kernels serve the next layout uploads: JG_PATH_AUTO (grid kernels when the quadtree is at
+ * most 5 deep and the batch has no surrogate piers, else the quadtree-walk kernels) or JG_PATH_WALK (always
+ * the walk kernels). Takes effect immediately for the current layout. Results do not depend on it. */
+#define JG_PATH_AUTO 0
+#define JG_PATH_WALK 1
+int jg_engine_set_detect_path(JgEngine* e, int path);
+/* 1 when the current layout is served by the grid kernels, 0 when by the quadtree-walk kernels. */
+int jg_engine_detect_path(const JgEngine* e);
 
 /* Memory helpers (pinned host / device) so callers can keep the C ABI free of CUDA headers. */
 int jg_host_alloc(size_t bytes, void** out);

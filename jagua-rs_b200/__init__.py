@@ -72,6 +72,8 @@ C_ABI = {
     "jg_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "jg_engine_set_batching": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "jg_engine_set_groups": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "jg_engine_set_detect_path": (C.c_int, [_vp, C.c_int]),
+    "jg_engine_detect_path": (C.c_int, [_vp]),
     "jg_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "jg_host_free": (C.c_int, [_vp]),
     "jg_device_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -473,6 +475,13 @@ class CDEngine:
 
     def set_groups(self, detect_group: int = 0, collect_group: int = 0):
         self._chk(self._lib.jg_engine_set_groups(self._eng, int(detect_group), int(collect_group)))
+
+    def set_detect_path(self, walk: bool):
+        """JG_PATH_WALK keeps the quadtree-walk kernels even where the grid kernels apply (same results)."""
+        self._chk(self._lib.jg_engine_set_detect_path(self._eng, 1 if walk else 0))
+
+    def detect_path(self) -> str:
+        return "grid" if self._lib.jg_engine_detect_path(self._eng) else "walk"
 
     def fp32_nofma_peak(self):
         g, ms = C.c_double(0), C.c_float(0)

@@ -611,6 +611,10 @@ k_s2_poly(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_
     }
 }
 
+}  // namespace jg
+#include "detect_grid.cuh"
+namespace jg {
+
 // ---------------------------------------------------------------------------------------------------
 static int g_occ[8];
 static size_t g_occ_smem[8];
@@ -626,12 +630,22 @@ static int persistent_grid(K kernel, int slot, int n_sms, size_t smem) {
     return n_sms * g_occ[slot];
 }
 
-size_t detect_kinds_bytes(int n_nodes) { return kinds_bytes(n_nodes); }
+// the per-(layout, filter) summary buffer: [kinds][GridDev]
+size_t detect_kinds_bytes(int n_nodes) { return kinds_bytes(n_nodes) + sizeof(GridDev); }
+static const GridDev* grid_of(const uint8_t* d_kinds, int n_nodes) { return (const GridDev*)(d_kinds + kinds_bytes(n_nodes)); }
 
-cudaError_t launch_node_kinds(const DevLayout& L, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st) {
+cudaError_t launch_node_kinds(const DevLayout& L, int depth, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st) {
     cudaMemsetAsync(d_kinds, 0, kinds_bytes(L.n_nodes), st);
     k_node_kinds<<<(L.n_nodes + 255) / 256, 256, 0, st>>>(L, d_filt, d_kinds);
+    k_grid_build<<<1, 1024, 0, st>>>(L, depth, d_kinds, (GridDev*)(d_kinds + kinds_bytes(L.n_nodes)));
     return cudaGetLastError();
+}
+// 1 when the grid kernels can serve this layout (k_grid_build's verdict); synchronises the stream
+cudaError_t detect_grid_usable(const uint8_t* d_kinds, int n_nodes, cudaStream_t st, int* ok) {
+    *ok = 0;
+    cudaError_t err = cudaMemcpyAsync(ok, &grid_of(d_kinds, n_nodes)->ok, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (err != cudaSuccess) return err;
+    return cudaStreamSynchronize(st);
 }
 
 cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const float4* d_xf,
@@ -643,6 +657,34 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
     const size_t smem1 = common + S_WARPS * (32 * sizeof(float4) + ((size_t)plan.cap_in + LEAF_CAP + 4) * sizeof(uint32_t));
     const size_t smem2 = common + S_WARPS * (sizeof(S2Slots) + ((size_t)plan.cap_in + LEAF_CAP) * sizeof(uint32_t));
     const int want1 = (n + S_THREADS - 1) / S_THREADS;                               // 32 queries per warp batch
+    bool grid = plan.use_grid != 0;
+    for (int k = 0; k < tab.n_seg; k++) grid = grid && tab.seg[k].n_piers == 0;
+    if (grid) {
+        const GridDev* gd = grid_of(d_kinds, L.n_nodes);
+        const size_t gcommon = ((sizeof(SegTable) + 15) & ~(size_t)15) + ((sizeof(GridDev) + 15) & ~(size_t)15);
+        const size_t gs1 = gcommon + S_WARPS * (32 * sizeof(float4) + (G1_PAIR_CAP + 4) * sizeof(uint32_t));
+        const size_t gs2 = gcommon + S_WARPS * sizeof(G2Slots);
+        const int want2g = (n + S_WARPS * S2_MAX_GROUP - 1) / (S_WARPS * S2_MAX_GROUP);
+        if (mode & JG_MODE_POLY_ONLY) {
+            const int gs = want1 < n_sms * 8 ? want1 : n_sms * 8;
+            k_s1_all_survive<<<gs, S_THREADS, 0, st>>>(tab, sc.ctl, sc.sv_entry);
+        } else if (d_filt) {
+            const int g = persistent_grid(k_s1_grid<true>, 4, n_sms, gs1);
+            k_s1_grid<true><<<want1 < g ? want1 : g, S_THREADS, gs1, st>>>(L, tab, gd, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
+        } else {
+            const int g = persistent_grid(k_s1_grid<false>, 5, n_sms, gs1);
+            k_s1_grid<false><<<want1 < g ? want1 : g, S_THREADS, gs1, st>>>(L, tab, gd, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
+        }
+        if (d_filt) {
+            const int g = persistent_grid(k_s2_grid<true>, 6, n_sms, gs2);
+            k_s2_grid<true><<<want2g < g ? want2g : g, S_THREADS, gs2, st>>>(L, tab, gd, d_kinds, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
+        } else {
+            const int g = persistent_grid(k_s2_grid<false>, 7, n_sms, gs2);
+            k_s2_grid<false><<<want2g < g ? want2g : g, S_THREADS, gs2, st>>>(L, tab, gd, d_kinds, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
+        }
+        if (n_launches) *n_launches += 2;
+        return cudaGetLastError();
+    }
     const int want2 = (n + S_WARPS * (1 << plan.gbits) - 1) / (S_WARPS * (1 << plan.gbits));  // upper bound
     if (mode & JG_MODE_POLY_ONLY) {
         const int gs = want1 < n_sms * 8 ? want1 : n_sms * 8;
@@ -677,6 +719,7 @@ DetectPlan make_detect_plan(int n_nodes, int depth) {
     p.gbits = 3;
     while (p.gbits > 0 && ((uint64_t)n_nodes >> (32 - 12 - p.gbits)) != 0) p.gbits--;
     p.nodes_in_smem = node_smem_bytes(n_nodes) <= 72 * 1024 ? 1 : 0;
+    p.use_grid = 0;  // set by the engine after k_grid_build has run (detect_grid_usable)
     return p;
 }
 

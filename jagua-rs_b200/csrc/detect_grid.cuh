@@ -1,0 +1,571 @@
+// Grid form of the detect pipeline (sm_100a) for quadtrees of depth <= 5 without surrogate piers
+// (CDEConfig defaults: depth 5, lbf/src/config.rs:33-41). Included by detect.cu.
+//
+// QTNode::collides (qt_node.rs:99-147) is a depth-first walk, but its verdict is an OR over the TERMINAL
+// nodes it reaches: nodes whose strongest hazard (qt_hazard_vec.rs:60-63) is Entire (-> hit, qt_node.rs:108)
+// or Partial without children (-> edge tests, qt_node.rs:128-143). With depth D <= 5 the terminals tile a
+// 2^D x 2^D grid of finest cells whose boundaries xs[], ys[] are the nested midpoints of rect.rs:141-151 /
+// :248-253 (k_grid_build recomputes them and checks every node bbox against them bit for bit). Per
+// (layout, filter) the grid keeps, per row of finest cells, the bit masks of cells covered by an Entire
+// terminal and of leaf cells, plus per cell its terminal's level and leaf entry range. Both stages then go
+// straight to the terminals that can matter instead of walking the inner nodes:
+//
+//  circles (surrogate poles, cd_engine.rs:204-223). Circle-Rect (circle.rs:115-128) is monotone under
+//      nesting in f32: clamping to a larger interval never moves the clamped point away, and fl(-), fl(x*x),
+//      fl(+) and <= are monotone. Hence a node is reached iff its own bbox test passes (all ancestors then
+//      pass too), and a coarse Entire terminal passes iff one of its finest cells does (the cell holding the
+//      clamped point yields the same clamped point). So: hit iff some Entire-flagged finest cell passes
+//      circ_rect (per row only the flagged cells nearest to the centre column need testing, again by
+//      monotonicity) or some leaf cell passes circ_rect and QTHazPartial::collides_with. EXACT, no walk.
+//
+//  edges (polygon stage, cd_engine.rs:160-197). Edge::collides_with_quadrants (qt_traits.rs:19-106) is not
+//      monotone, so terminals are CANDIDATES that are verified: a terminal T matters only if it
+//      would produce a hit (Entire, or a leaf whose edge tests succeed - both independent of the path), and
+//      then T is reached by the reference iff every ancestor below the virtual root flags the quadrant
+//      towards T: at most D seg_quadrants evaluations, run only for would-be hits. Candidates = finest cells
+//      meeting the edge's bbox inflated by delta, clipped to the virtual root's cells. That is a superset of
+//      the reached terminals: a quadrant is flagged either because it holds an endpoint, or because
+//      edge_intersection_half (qt_traits.rs:144-177) reports a crossing with a side/bisector half lying on
+//      that quadrant's boundary. Sides and bisectors are axis-aligned, so one product of t_nom and of denom is
+//      exactly zero and t in [0,1] places the side's coordinate within 5 ulp-relative of the edge's own
+//      range, while the crossing's position along the side is off by < 2^-20 of the coordinate scale M;
+//      delta = M * 2^-13 exceeds that bound by two orders of magnitude.
+#pragma once
+
+namespace jg {
+
+#define GRID_MAX_D 5
+#define GRID_G 32            // row stride of the per-cell arrays (finest cells per side <= 32)
+#define GRID_MIP_NODES 1365  // 1 + 4 + ... + 4^5
+
+struct GridDev {
+    int ok;       // 1 = usable (depth <= 5, node boxes match the grid, leaf records fit)
+    int D, G, n_nodes;
+    float delta;  // candidate inflation for edges
+    float x0, y0, inv_cw, inv_ch;
+    float slack;  // absolute slack added to circle windows
+    int pad[2];
+    float xs[GRID_G + 4], ys[GRID_G + 4];
+    uint32_t ent_rows[GRID_G], leaf_rows[GRID_G];
+    uint32_t cell_leaf[GRID_G * GRID_G];   // leaf cells: first Partial entry << 8 | n_partial
+    uint16_t mip_node[GRID_MIP_NODES + 3];  // node index at (level, j, i), 0xFFFF = no such node
+    uint8_t cell_level[GRID_G * GRID_G];   // level (0 = root) of the terminal covering the cell
+};
+
+__host__ __device__ inline int mip_off(int level) { return ((1 << (2 * level)) - 1) / 3; }
+// quadrant index (NE, NW, SW, SE; rect.rs:141-161) of a child from the low bits of its column / row
+__host__ __device__ inline int quad_of(int dx, int dy) { return dy ? (dx ? 0 : 1) : (dx ? 3 : 2); }
+
+// One CTA of 1024 threads per (layout, filter): fills GridDev from the node arrays and the kinds summary.
+__global__ void __launch_bounds__(1024) k_grid_build(const DevLayout L, int depth, const uint8_t* __restrict__ kinds,
+                                                      GridDev* __restrict__ g) {
+    __shared__ int s_ok;
+    const int tid = threadIdx.x;
+    const int D = depth, G = 1 << (depth <= GRID_MAX_D ? depth : 0);
+    if (tid == 0) {
+        s_ok = (depth >= 0 && depth <= GRID_MAX_D) ? 1 : 0;
+        g->D = D;
+        g->G = G;
+        g->n_nodes = L.n_nodes;
+        const float4 b = L.node_bbox[0];
+        g->xs[0] = b.x, g->xs[G] = b.z, g->ys[0] = b.y, g->ys[G] = b.w;
+        for (int step = G; step >= 2; step >>= 1)
+            for (int a = 0; a < G; a += step) {
+                g->xs[a + step / 2] = (g->xs[a] + g->xs[a + step]) / 2.0f;  // rect.rs:248-253 centroid
+                g->ys[a + step / 2] = (g->ys[a] + g->ys[a + step]) / 2.0f;
+            }
+        const float M = fmaxf(fmaxf(fabsf(b.x), fabsf(b.z)), fmaxf(fabsf(b.y), fabsf(b.w)));
+        g->delta = M * (1.0f / 8192.0f);
+        g->slack = M * (1.0f / 1048576.0f);
+        g->x0 = b.x, g->y0 = b.y;
+        g->inv_cw = (float)G / (b.z - b.x);
+        g->inv_ch = (float)G / (b.w - b.y);
+        if (!(b.z > b.x && b.w > b.y)) s_ok = 0;
+    }
+    for (int i = tid; i < GRID_G; i += blockDim.x) g->ent_rows[i] = 0u, g->leaf_rows[i] = 0u;
+    for (int i = tid; i < GRID_G * GRID_G; i += blockDim.x) g->cell_leaf[i] = 0u, g->cell_level[i] = 0;
+    for (int i = tid; i < GRID_MIP_NODES + 3; i += blockDim.x) g->mip_node[i] = 0xFFFF;
+    __syncthreads();
+    if (!s_ok) {
+        if (tid == 0) g->ok = 0;
+        return;
+    }
+    // every node: (level, column, row) from its chain of parents; its bbox must be the grid's
+    for (int n = tid; n < L.n_nodes; n += blockDim.x) {
+        int level = 0, ci = 0, cj = 0, cur = n;
+        bool bad = n > 0xFFFE;
+        while (cur > 0 && level <= D) {
+            const int q = (cur - 1) & 3;  // children blocks start at 1 + 4k
+            ci |= ((q == 0 || q == 3) ? 1 : 0) << level;
+            cj |= ((q == 0 || q == 1) ? 1 : 0) << level;
+            level++;
+            const int par = L.node_meta[cur].w;
+            if (par < 0 || L.node_meta[par].x != ((cur - 1) & ~3) + 1) { bad = true; break; }
+            cur = par;
+        }
+        if (level > D || cur != 0) bad = true;
+        if (!bad) {
+            const int s = D - level;
+            const float4 b = L.node_bbox[n];
+            if (!(b.x == g->xs[ci << s] && b.z == g->xs[(ci + 1) << s] && b.y == g->ys[cj << s] && b.w == g->ys[(cj + 1) << s])) bad = true;
+            if (!bad) g->mip_node[mip_off(level) + cj * (1 << level) + ci] = (uint16_t)n;
+        }
+        if (bad) atomicExch(&s_ok, 0);
+    }
+    __syncthreads();
+    // every finest cell: the terminal the reference's descent from the root ends in
+    for (int c = tid; c < G * G; c += blockDim.x) {
+        const int i = c % G, j = c / G;
+        int node = 0, level = 0;
+        while (kinds[node + 3] == 1 /*KIND_INNER*/ && level < D) {
+            level++;
+            const int ci = i >> (D - level), cj = j >> (D - level);
+            node = L.node_meta[node].x + quad_of(ci & 1, cj & 1);
+        }
+        const int k = kinds[node + 3];
+        g->cell_level[j * GRID_G + i] = (uint8_t)level;
+        if (k == 2 /*KIND_ENTIRE*/) atomicOr(&g->ent_rows[j], 1u << i);
+        if (k == 3 /*KIND_LEAF*/) {
+            const int4 m = L.node_meta[node];
+            const int n_entire = m.z & 0xFFFF, n_partial = (m.z >> 16) & 0xFFFF;
+            if (level != D || n_partial > 255 || m.y + n_entire >= (1 << 24)) atomicExch(&s_ok, 0);
+            g->cell_leaf[j * GRID_G + i] = ((uint32_t)(m.y + n_entire) << 8) | (uint32_t)(n_partial & 255);
+            atomicOr(&g->leaf_rows[j], 1u << i);
+        }
+        if (k == 1) atomicExch(&s_ok, 0);  // an inner node at the finest level cannot exist
+    }
+    __syncthreads();
+    if (tid == 0) g->ok = s_ok;
+}
+
+// ---- staged copy -------------------------------------------------------------------------------------
+__device__ __forceinline__ const GridDev* stage_grid(unsigned char*& p, const GridDev* g) {
+    uint4* dst = (uint4*)p;
+    const uint4* src = (const uint4*)g;
+    const int n16 = (int)((sizeof(GridDev) + 15) / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    p += (size_t)n16 * 16;
+    return (const GridDev*)dst;
+}
+
+// first cell whose upper boundary is >= v / last cell whose lower boundary is <= v (clamped to the grid)
+__device__ __forceinline__ int cell_lo(const float* b, int G, float v, float b0, float inv) {
+    int i = (int)((v - b0) * inv);
+    i = i < 0 ? 0 : (i > G - 1 ? G - 1 : i);
+    while (i > 0 && b[i] >= v) i--;
+    while (i < G - 1 && b[i + 1] < v) i++;
+    return i;
+}
+__device__ __forceinline__ int cell_hi(const float* b, int G, float v, float b0, float inv) {
+    int i = (int)((v - b0) * inv);
+    i = i < 0 ? 0 : (i > G - 1 ? G - 1 : i);
+    while (i < G - 1 && b[i + 1] <= v) i++;
+    while (i > 0 && b[i] > v) i--;
+    return i;
+}
+__device__ __forceinline__ uint32_t col_mask(int lo, int hi) {  // bits lo..hi, 0 <= lo, hi <= 31
+    return hi < lo ? 0u : ((0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo));
+}
+
+// QTHazPartial::collides_with (qt_partial_hazard.rs:67-72) over the relevant Partial entries of a leaf cell
+template <class Ent, bool FILT>
+__device__ __forceinline__ bool leaf_cell_collides(const DevLayout& L, uint32_t rec, const Ent& ent, const uint32_t* filt) {
+    const int e0 = (int)(rec >> 8), n_partial = (int)(rec & 255u);
+    for (int i = 0; i < n_partial; i++) {
+        const int4 em = __ldg(&L.entry_meta[e0 + i]);
+        if (FILT && filt_bit(filt, em.x)) continue;
+        if (!ent_rect(ent, ld_rect(&L.entry_ff[e0 + i]))) continue;
+        for (int k = 0; k < em.z; k++)
+            if (ent_seg(ent, ld_seg(&L.edges[em.y + k]))) return true;
+    }
+    return false;
+}
+
+// Does the circle pass circ_rect (circle.rs:115-128) for some Entire-flagged finest cell? Rows of the
+// conservative window; per row the flagged cells nearest to the centre's column on either side.
+__device__ __forceinline__ bool circ_touches_entire(const GridDev& g, const Circ& c, int i0, int i1, int j0, int j1) {
+    const int G = g.G;
+    const uint32_t cm = col_mask(i0, i1);
+    // column holding the centre (any column whose closed range holds cx; outermost column if outside)
+    int ic = cell_lo(g.xs, G, c.cx, g.x0, g.inv_cw);
+    const float r2 = c.r * c.r;
+    for (int j = j0; j <= j1; j++) {
+        const uint32_t m = g.ent_rows[j] & cm;
+        if (!m) continue;
+        const float ny = fmaxf(g.ys[j], fminf(c.cy, g.ys[j + 1]));
+        const float dy2 = (ny - c.cy) * (ny - c.cy);
+        const uint32_t right = m >> ic, left = m & ((1u << ic) - 1u);
+        if (right) {
+            const int i = ic + __ffs(right) - 1;
+            const float nx = fmaxf(g.xs[i], fminf(c.cx, g.xs[i + 1]));
+            if ((nx - c.cx) * (nx - c.cx) + dy2 <= r2) return true;
+        }
+        if (left) {
+            const int i = 31 - __clz(left);
+            const float nx = fmaxf(g.xs[i], fminf(c.cx, g.xs[i + 1]));
+            if ((nx - c.cx) * (nx - c.cx) + dy2 <= r2) return true;
+        }
+    }
+    return false;
+}
+
+#define G1_PAIR_CAP 192  // leaf pairs waiting per warp: drained below 32 before every push round of <= 4 per lane
+#define G1_PUSH 4
+
+// ---------------------------------------------------------------------------------------------------
+// stage 1 on the grid: surrogate poles. Lane = query.
+// ---------------------------------------------------------------------------------------------------
+template <bool FILT>
+__global__ void __launch_bounds__(S_THREADS)
+k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
+          const float4* __restrict__ xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
+          DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SegTable* t = (SegTable*)smem;
+    for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
+    unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
+    const GridDev& g = *stage_grid(p, ggrid);
+    __syncthreads();
+    const SegTable& tab = *t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t per_warp = 32 * sizeof(float4) + (G1_PAIR_CAP + 4) * sizeof(uint32_t);
+    unsigned char* wp = p + (size_t)warp * per_warp;
+    float4* s_circ = (float4*)wp;  // the current pole of each lane's query
+    uint32_t* s_pair = (uint32_t*)(wp + 32 * sizeof(float4));
+    unsigned* s_hit = (unsigned*)(s_pair + G1_PAIR_CAP);
+    int* s_cnt = (int*)(s_hit + 1);
+    const int n = tab.n_queries, G = g.G;
+
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->s1_next, 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) break;
+        const int q = base + lane;
+        const bool valid = q < n;
+        Xf xf{1.0f, 0.0f, 0.0f, 0.0f};
+        int k = 0, n_poles = 0;
+        if (valid) {
+            const float4 t4 = __ldg(&xforms[q]);
+            xf = Xf{t4.x, t4.y, t4.z, t4.w};
+            k = seg_of_query(tab, q);
+            n_poles = tab.seg[k].n_poles;
+        }
+        bool hit = false;
+        const int max_poles = __reduce_max_sync(FULL, n_poles);
+        for (int j = 0; j < max_poles; j++) {  // cd_engine.rs:210-215: the first colliding pole decides
+            bool act = valid && !hit && j < n_poles;
+            if (!__any_sync(FULL, act)) break;
+            Circ c{0.0f, 0.0f, 0.0f};
+            int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+            if (act) {  // circle.rs:79-85: centre transformed, radius unchanged
+                const float4 pl = __ldg(&tab.seg[k].poles[j]);
+                xf_point(xf, pl.x, pl.y, c.cx, c.cy);
+                c.r = pl.z;
+                s_circ[lane] = make_float4(c.cx, c.cy, c.r, 0.0f);
+                const float rk = c.r * 1.001f + g.slack;
+                i0 = cell_lo(g.xs, G, c.cx - rk, g.x0, g.inv_cw);
+                i1 = cell_hi(g.xs, G, c.cx + rk, g.x0, g.inv_cw);
+                j0 = cell_lo(g.ys, G, c.cy - rk, g.y0, g.inv_ch);
+                j1 = cell_hi(g.ys, G, c.cy + rk, g.y0, g.inv_ch);
+                // a window entirely beside the grid holds no cell the circle can reach
+                if (c.cx + rk < g.xs[0] || c.cx - rk > g.xs[G] || c.cy + rk < g.ys[0] || c.cy - rk > g.ys[G]) i1 = -1, j1 = -1;
+                hit = circ_touches_entire(g, c, i0, i1, j0, j1);
+                act = !hit && j1 >= j0 && i1 >= i0;
+            }
+            // leaf cells of the window that pass circ_rect -> (lane, cell) pairs, resolved 32 at a time
+            if (!__any_sync(FULL, act)) continue;
+            if (lane == 0) *s_hit = 0u, *s_cnt = 0;
+            __syncwarp();
+            const uint32_t cm = col_mask(i0, i1);
+            const float r2 = c.r * c.r;
+            int row = j0;
+            uint32_t bits = 0u;
+            float dy2 = 0.0f;
+            bool more = act;
+            if (more) {
+                bits = g.leaf_rows[row] & cm;
+                const float ny = fmaxf(g.ys[row], fminf(c.cy, g.ys[row + 1]));
+                dy2 = (ny - c.cy) * (ny - c.cy);
+            }
+            for (;;) {
+                // generation round: up to G1_PUSH cells per lane
+                if (more) {
+                    int pushed = 0;
+                    uint32_t mine[G1_PUSH];
+                    while (pushed < G1_PUSH) {
+                        if (!bits) {
+                            if (row >= j1) { more = false; break; }
+                            row++;
+                            bits = g.leaf_rows[row] & cm;
+                            const float ny = fmaxf(g.ys[row], fminf(c.cy, g.ys[row + 1]));
+                            dy2 = (ny - c.cy) * (ny - c.cy);
+                            continue;
+                        }
+                        const int i = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const float nx = fmaxf(g.xs[i], fminf(c.cx, g.xs[i + 1]));
+                        if ((nx - c.cx) * (nx - c.cx) + dy2 <= r2) mine[pushed++] = ((uint32_t)(row * GRID_G + i) << 5) | (uint32_t)lane;
+                    }
+                    if (pushed) {
+                        const int o = atomicAdd(s_cnt, pushed);
+#pragma unroll
+                        for (int u = 0; u < G1_PUSH; u++)
+                            if (u < pushed) s_pair[o + u] = mine[u];
+                    }
+                }
+                __syncwarp();
+                const bool any_more = __any_sync(FULL, more);
+                int cnt = *(volatile int*)s_cnt;
+                __syncwarp();
+                // drain: while a full warp of pairs waits (or generation is over)
+                while (cnt >= 32 || (!any_more && cnt > 0)) {
+                    const int take = cnt < 32 ? cnt : 32;
+                    cnt -= take;
+                    bool lanehit = false;
+                    int ol = 0;
+                    if (lane < take) {
+                        const uint32_t pr = s_pair[cnt + lane];
+                        ol = pr & 31;
+                        if (!((*(volatile unsigned*)s_hit >> ol) & 1u)) {
+                            const float4 e4 = s_circ[ol];
+                            lanehit = leaf_cell_collides<Circ, FILT>(L, g.cell_leaf[pr >> 5], Circ{e4.x, e4.y, e4.z}, filt);
+                        }
+                    }
+                    if (lanehit) atomicOr(s_hit, 1u << ol);
+                    __syncwarp();
+                }
+                if (lane == 0) *s_cnt = cnt;
+                __syncwarp();
+                const unsigned hm = *(volatile unsigned*)s_hit;
+                if ((hm >> lane) & 1u) hit = true, more = false;
+                if (!any_more) break;
+                __syncwarp();
+            }
+            __syncwarp();
+        }
+        if (valid) out[q] = hit ? (uint8_t)JG_VERDICT_SURROGATE : (uint8_t)0;
+        const unsigned sm = __ballot_sync(FULL, valid && !hit);  // survivors keep the query order
+        if (sm) {
+            int sb = 0;
+            if (lane == 0) sb = atomicAdd(&ctl->n_surv, __popc(sm));
+            sb = __shfl_sync(FULL, sb, 0);
+            if (valid && !hit) sv_entry[sb + __popc(sm & lanemask_lt())] = sv_pack(q, k);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 2 on the grid: polygon edges of the survivors
+// ---------------------------------------------------------------------------------------------------
+struct G2Slots {  // per-warp state of the survivors of the current group
+    float4 xf[S2_MAX_GROUP];
+    float4 bb[S2_MAX_GROUP];
+    int q[S2_MAX_GROUP];
+    int seg[S2_MAX_GROUP];
+    int vnode[S2_MAX_GROUP];  // virtual root: node index
+    int vcell[S2_MAX_GROUP];  // ... and level << 16 | row << 8 | column at its level
+    int ebeg[S2_MAX_GROUP + 1];
+    unsigned hit;
+    int pad[2];
+};
+
+// CDEngine::get_virtual_root (cd_engine.rs:314-327) on the grid: at each level the FIRST child (NE, NW, SW,
+// SE) whose bbox surrounds `bb` (rect.rs:46-65); children exist iff the mip map has them.
+__device__ __forceinline__ int virtual_root_grid(const GridDev& g, const Rect& bb, int& node) {
+    int level = 0, ci = 0, cj = 0;
+    node = 0;
+    while (level < g.D) {
+        const int nl = level + 1, s = g.D - nl, w = 1 << nl;
+        const int base = mip_off(nl);
+        if (g.mip_node[base + (2 * cj) * w + 2 * ci] == 0xFFFF) break;  // no children
+        int found = -1;
+#pragma unroll
+        for (int qd = 0; qd < 4; qd++) {
+            const int dx = (qd == 0 || qd == 3) ? 1 : 0, dy = (qd == 0 || qd == 1) ? 1 : 0;
+            const int xi = 2 * ci + dx, yj = 2 * cj + dy;
+            const Rect cb{g.xs[xi << s], g.ys[yj << s], g.xs[(xi + 1) << s], g.ys[(yj + 1) << s]};
+            if (found < 0 && rect_relation(cb, bb) == REL_SURROUNDING) found = qd;
+        }
+        if (found < 0) break;
+        ci = 2 * ci + ((found == 0 || found == 3) ? 1 : 0);
+        cj = 2 * cj + ((found == 0 || found == 1) ? 1 : 0);
+        level = nl;
+        node = g.mip_node[base + cj * w + ci];
+    }
+    return (level << 16) | (cj << 8) | ci;
+}
+
+// Is the terminal of finest cell (i, j), at level lt, reached by QTNode::collides from the virtual root
+// (level l0)? Every ancestor from the virtual root down must flag the quadrant towards the cell
+// (qt_node.rs:111-126 with qt_traits.rs:19-106).
+__device__ __forceinline__ bool path_reaches(const GridDev& g, const Seg& sg, int l0, int lt, int i, int j) {
+    const int D = g.D;
+    for (int l = l0; l < lt; l++) {
+        const int s = D - l;
+        const int ci = i >> s, cj = j >> s;
+        const Rect nb{g.xs[ci << s], g.ys[cj << s], g.xs[(ci + 1) << s], g.ys[(cj + 1) << s]};
+        const unsigned mask = seg_quadrants(sg, nb);
+        const int qd = quad_of((i >> (s - 1)) & 1, (j >> (s - 1)) & 1);
+        if (!((mask >> qd) & 1u)) return false;
+    }
+    return true;
+}
+
+template <bool FILT>
+__global__ void __launch_bounds__(S_THREADS)
+k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
+          const uint8_t* __restrict__ g_kinds, const float4* __restrict__ xforms, const uint32_t* __restrict__ filt,
+          uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, const int* __restrict__ sv_entry) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SegTable* t = (SegTable*)smem;
+    for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
+    unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
+    const GridDev& g = *stage_grid(p, ggrid);
+    __syncthreads();
+    const SegTable& tab = *t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    G2Slots& W = *(G2Slots*)(p + (size_t)warp * sizeof(G2Slots));
+    const int GS = S2_MAX_GROUP;
+    const int total = ctl->n_surv;
+    const int D = g.D, G = g.G;
+
+    for (;;) {
+        int gbase = 0;
+        if (lane == 0) gbase = atomicAdd(&ctl->s2_next, GS);
+        gbase = __shfl_sync(FULL, gbase, 0);
+        if (gbase >= total) break;
+        const int ng = (total - gbase) < GS ? (total - gbase) : GS;
+        if (lane < ng) {
+            const int ent = sv_entry[gbase + lane];
+            const int q = ent & 0x3FFFFFF;
+            W.q[lane] = q;
+            W.seg[lane] = (int)((unsigned)ent >> 26);
+            W.xf[lane] = __ldg(&xforms[q]);
+        }
+        __syncwarp();
+        // SPolygon::transform_from + generate_bounding_box (simple_polygon.rs:226-253, 122-133)
+        for (int s = 0; s < ng; s++) {
+            const SegDesc& sd = tab.seg[W.seg[s]];
+            const float4 t4 = W.xf[s];
+            const Xf xf{t4.x, t4.y, t4.z, t4.w};
+            float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
+            for (int j = lane; j < sd.n_verts; j += 32) {
+                const float2 v = __ldg(&sd.verts[j]);
+                float x, y;
+                xf_point(xf, v.x, v.y, x, y);
+                x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o));
+                y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o));
+                x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
+                y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
+            }
+            if (lane == 0) W.bb[s] = make_float4(x0, y0, x1, y1);
+        }
+        __syncwarp();
+        int verdict = -1, nE = 0;
+        if (lane < ng) {
+            const float4 b4 = W.bb[lane];
+            const Rect bb{b4.x, b4.y, b4.z, b4.w};
+            if (rect_relation(L.cde_bbox, bb) != REL_SURROUNDING) {
+                verdict = JG_VERDICT_POLY;  // cd_engine.rs:161-163
+            } else {
+                int vnode;
+                const int vc = virtual_root_grid(g, bb, vnode);
+                const int vk = __ldg(&g_kinds[vnode + 3]);
+                W.vnode[lane] = vnode;
+                W.vcell[lane] = vc;
+                if (vk == KIND_ENTIRE) verdict = JG_VERDICT_POLY;  // every edge sees it (qt_node.rs:108)
+                else if (vk != KIND_NONE) nE = tab.seg[W.seg[lane]].n_verts;
+            }
+        }
+        int incl = nE;
+#pragma unroll
+        for (int o = 1; o < S2_MAX_GROUP; o <<= 1) {
+            const int tt = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += tt;
+        }
+        const int E = __shfl_sync(FULL, incl, S2_MAX_GROUP - 1);
+        if (lane < S2_MAX_GROUP) W.ebeg[lane + 1] = incl;
+        if (lane == 0) {
+            W.ebeg[0] = 0;
+            W.hit = 0u;
+        }
+        const unsigned need = __ballot_sync(FULL, nE > 0);
+        __syncwarp();
+
+        for (int f0 = 0; f0 < E; f0 += 32) {
+            const unsigned hm = *(volatile unsigned*)&W.hit;
+            if ((hm & need) == need) break;  // every survivor with edges already has a colliding one
+            const int f = f0 + lane;
+            bool lanehit = false;
+            int slot = 0;
+            if (f < E) {
+                for (int j = 1; j < GS; j++) slot += (W.ebeg[j] <= f) ? 1 : 0;
+                if (!((hm >> slot) & 1u)) {
+                    const float4 t4 = W.xf[slot];
+                    const Seg sg = item_edge(tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, f - W.ebeg[slot]);
+                    const int vc = W.vcell[slot];
+                    const int l0 = vc >> 16, s0 = D - l0;
+                    // candidate cells: the edge's bbox inflated by delta, clipped to the virtual root's cells
+                    int i0 = cell_lo(g.xs, G, fminf(sg.sx, sg.ex) - g.delta, g.x0, g.inv_cw);
+                    int i1 = cell_hi(g.xs, G, fmaxf(sg.sx, sg.ex) + g.delta, g.x0, g.inv_cw);
+                    int j0 = cell_lo(g.ys, G, fminf(sg.sy, sg.ey) - g.delta, g.y0, g.inv_ch);
+                    int j1 = cell_hi(g.ys, G, fmaxf(sg.sy, sg.ey) + g.delta, g.y0, g.inv_ch);
+                    const int vi0 = (vc & 255) << s0, vj0 = ((vc >> 8) & 255) << s0;
+                    i0 = max(i0, vi0), i1 = min(i1, vi0 + (1 << s0) - 1);
+                    j0 = max(j0, vj0), j1 = min(j1, vj0 + (1 << s0) - 1);
+                    const uint32_t cm = col_mask(i0, i1);
+                    for (int j = j0; j <= j1 && !lanehit; j++) {
+                        const uint32_t er = g.ent_rows[j] & cm;
+                        uint32_t bits = er | (g.leaf_rows[j] & cm);
+                        while (bits && !lanehit) {
+                            const int i = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            bool h = (er >> i) & 1u;
+                            if (!h) h = leaf_cell_collides<Seg, FILT>(L, g.cell_leaf[j * GRID_G + i], sg, filt);
+                            if (h) lanehit = path_reaches(g, sg, l0, g.cell_level[j * GRID_G + i], i, j);
+                        }
+                    }
+                }
+            }
+            if (lanehit) atomicOr(&W.hit, 1u << slot);
+            __syncwarp();
+        }
+        __syncwarp();
+        const unsigned hm = *(volatile unsigned*)&W.hit;
+        // cd_engine.rs:174-193: survivors without an edge hit -> `unreachable!` or containment tests
+        for (int s = 0; s < ng; s++) {
+            if (__shfl_sync(FULL, verdict, s) >= 0) continue;
+            int v = 0;
+            if ((hm >> s) & 1u) {
+                v = JG_VERDICT_POLY;
+            } else {
+                const int4 m = __ldg(&L.node_meta[W.vnode[s]]);
+                const int n_entire = m.z & 0xFFFF, n_partial = (m.z >> 16) & 0xFFFF;
+                if (n_entire > 0) {
+                    v = JG_VERDICT_REF_PANIC;  // cd_engine.rs:179, reachable only under a filter
+                } else {
+                    const SegDesc& sd = tab.seg[W.seg[s]];
+                    const float4 t4 = W.xf[s], b4 = W.bb[s];
+                    bool c = false;
+                    for (int j = lane; j < n_partial && !c; j += 32) {
+                        const int hs = __ldg(&L.entry_meta[m.y + j]).x;
+                        if (FILT && filt_bit(filt, hs)) continue;
+                        c = containment_collision(L, sd.verts, sd.n_verts, sd.poi_x, sd.poi_y, Xf{t4.x, t4.y, t4.z, t4.w},
+                                                  Rect{b4.x, b4.y, b4.z, b4.w}, hs);
+                    }
+                    if (__any_sync(FULL, c)) v = JG_VERDICT_POLY;
+                }
+            }
+            if (lane == s) verdict = v;
+        }
+        if (lane < ng) out[W.q[lane]] = (uint8_t)verdict;
+        __syncwarp();
+    }
+}
+
+}  // namespace jg

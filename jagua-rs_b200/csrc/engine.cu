@@ -57,7 +57,8 @@ struct JgEngine {
     bool has_layout = false;
     uint64_t epoch = 0;
     uint64_t layout_version = 0;  // bumped by every upload; per-filter node summaries are keyed on it
-    DetectPlan plan{0, 0, 0};
+    DetectPlan plan{0, 0, 0, 0};
+    bool force_walk = false;  // jg_engine_set_detect_path: keep the quadtree-walk kernels even when the grid applies
     uint8_t* d_kinds = nullptr;   // node summary under NoFilter
     size_t kinds_cap = 0;
 
@@ -318,9 +319,13 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
         JG_CUDA(e, cudaMalloc(&e->d_kinds, cap));
         e->kinds_cap = cap;
     }
-    JG_CUDA(e, launch_node_kinds(e->L, nullptr, e->d_kinds, e->compute));
-    JG_CUDA(e, cudaStreamSynchronize(e->compute));
-    e->stat_launches++;
+    JG_CUDA(e, launch_node_kinds(e->L, (int)h.root_level, nullptr, e->d_kinds, e->compute));
+    {
+        int ok = 0;
+        JG_CUDA(e, detect_grid_usable(e->d_kinds, (int)h.n_nodes, e->compute, &ok));
+        e->plan.use_grid = (ok && !e->force_walk) ? 1 : 0;
+    }
+    e->stat_launches += 2;
     e->epoch = epoch;
     e->stat_uploads++;
     if (!src_on_device) e->stat_h2d += h.total_bytes;
@@ -414,9 +419,9 @@ static int find_filter(JgEngine* e, int filter_id, const uint32_t** d_filt, cons
             JG_CUDA(e, cudaMalloc(&f.kinds, need * 2));
             f.kinds_cap = need * 2;
         }
-        JG_CUDA(e, launch_node_kinds(e->L, f.bits, f.kinds, e->compute));
+        JG_CUDA(e, launch_node_kinds(e->L, (int)e->hdr.root_level, f.bits, f.kinds, e->compute));
         JG_CUDA(e, cudaStreamSynchronize(e->compute));
-        e->stat_launches++;
+        e->stat_launches += 2;
         f.kinds_version = e->layout_version;
     }
     *d_filt = f.bits;
@@ -728,6 +733,19 @@ int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group) {
     e->collect_group = collect_group;
     return JG_OK;
 }
+
+int jg_engine_set_detect_path(JgEngine* e, int path) {
+    if (!e || (path != JG_PATH_AUTO && path != JG_PATH_WALK)) return JG_ERR_INVALID;
+    e->force_walk = path == JG_PATH_WALK;
+    if (e->has_layout && e->d_kinds) {
+        int ok = 0;
+        JG_CUDA(e, cudaSetDevice(e->device));
+        JG_CUDA(e, detect_grid_usable(e->d_kinds, (int)e->hdr.n_nodes, e->compute, &ok));
+        e->plan.use_grid = (ok && !e->force_walk) ? 1 : 0;
+    }
+    return JG_OK;
+}
+int jg_engine_detect_path(const JgEngine* e) { return e && e->plan.use_grid ? 1 : 0; }
 
 int jg_host_alloc(size_t bytes, void** out) {
     if (!out) return JG_ERR_INVALID;

@@ -47,12 +47,14 @@ struct DetectPlan {
     int nodes_in_smem;  // node meta / bbox / kind staged into shared memory by every CTA
     int cap_in;         // capacity of a warp's inner-pair stack
     int gbits;          // log2 of the survivors a stage-2 warp resolves together
+    int use_grid;       // depth <= 5 and the node boxes match the nested-midpoint grid: k_s1_grid / k_s2_grid
 };
 DetectPlan make_detect_plan(int n_nodes, int depth);
 size_t detect_kinds_bytes(int n_nodes);
 
 // per-filter node summary read by the detect kernels; d_filt == nullptr is NoFilter
-cudaError_t launch_node_kinds(const DevLayout& L, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st);
+cudaError_t launch_node_kinds(const DevLayout& L, int depth, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st);
+cudaError_t detect_grid_usable(const uint8_t* d_kinds, int n_nodes, cudaStream_t st, int* ok);
 cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const float4* d_xf,
                           const uint32_t* d_filt, const uint8_t* d_kinds, int mode, uint8_t* d_out, const DetectScratch& sc,
                           int n_sms, cudaStream_t st, int* n_launches);

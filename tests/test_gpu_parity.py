@@ -122,3 +122,48 @@ def test_empty_batch(jg, engines):
     wl, cde, w = engines("swim_half")
     assert len(cde.detect_batch(0, np.zeros((0, 4), np.float32))) == 0
     assert cde.collect_batch(0, np.zeros((0, 4), np.float32)).shape[0] == 0
+
+
+GRID_WORKLOADS = [n for n in ALL_WORKLOADS if n != "shirts_full_d10"]  # depth <= 5: served by the grid kernels
+
+
+@pytest.mark.parametrize("name", GRID_WORKLOADS)
+def test_grid_and_walk_paths_agree_with_oracle(jg, engines, name):
+    """The grid kernels (depth <= 5) and the quadtree-walk kernels are two implementations of the same
+    reference semantics: both must match the oracle, with and without the surrogate stage."""
+    wl, cde, w = engines(name)
+    assert cde.detect_path() == "grid"
+    try:
+        for item_id in range(len(wl.items)):
+            t = jg.make_queries(wl, item_id, 3000, seed=11)
+            exp = w.detect_batch(item_id, t)
+            exp_p = w.detect_batch(item_id, t, poly_only=True)
+            for walk in (False, True):
+                cde.set_detect_path(walk)
+                assert cde.detect_path() == ("walk" if walk else "grid")
+                got = cde.detect_batch(item_id, t)
+                assert np.array_equal(got, exp), f"{name} item {item_id} walk={walk}: {(got != exp).sum()} mismatches"
+                assert np.array_equal(cde.detect_batch(item_id, t, poly_only=True), exp_p)
+    finally:
+        cde.set_detect_path(False)
+
+
+def test_deep_quadtree_uses_walk_path(jg, engines):
+    wl, cde, w = engines("shirts_full_d10")
+    assert cde.detect_path() == "walk"
+
+
+def test_grid_path_near_item_placements(jg, engines):
+    """Queries concentrated where edges graze hazards: translations of placed items jittered by a few
+    units, so that most survivors reach the leaf edge tests and the candidate verification."""
+    wl, cde, w = engines("swim_half")
+    rng = np.random.default_rng(5)
+    placed = [h for h in wl.hazards if h.kind == 0]
+    for item_id in range(len(wl.items)):
+        c = np.stack([h.verts.mean(0) for h in placed])[rng.integers(0, len(placed), 4000)]
+        jit = rng.normal(0, 40.0, c.shape)
+        rot = np.asarray(wl.items[item_id].rotations, np.float32)[rng.integers(0, 2, len(c))]
+        t = jg.compose(np.concatenate([rot[:, None], (c + jit).astype(np.float32)], 1).astype(np.float32))
+        exp = w.detect_batch(item_id, t, poly_only=True)
+        got = cde.detect_batch(item_id, t, poly_only=True)
+        assert np.array_equal(got, exp), f"item {item_id}: {(got != exp).sum()} mismatches"

@@ -355,6 +355,67 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
     }
 }
 
+// SPolygon::collides_with(Point) (simple_polygon.rs:255-292) by a whole warp: lanes take polygon edges, the
+// crossing count is the sum of the per-edge contributions (its parity does not depend on the order).
+template <bool XF>
+__device__ __forceinline__ bool poly_point_warp(const float2* verts, int n, const Rect& bbox, float px, float py, const Xf& t,
+                                                int lane) {
+    if (!rect_point(bbox, px, py)) return false;
+    const Seg ray{px, py, bbox.x_max + (bbox.x_max - bbox.x_min), py};
+    int n_int = 0;
+    for (int b = 0; b < n; b += 32) {
+        const int i = b + lane;
+        bool cross = false;
+        if (i < n) {
+            const float2 a = __ldg(&verts[i]), bb = __ldg(&verts[i == n - 1 ? 0 : i + 1]);
+            float sx = a.x, sy = a.y, ex = bb.x, ey = bb.y;
+            if (XF) {
+                xf_point(t, a.x, a.y, sx, sy);
+                xf_point(t, bb.x, bb.y, ex, ey);
+            }
+            if ((approx_eq(sy, py) && fpa_gt(sx, px)) || (approx_eq(ey, py) && fpa_gt(ex, px))) cross = fpa_lt(sy, py) || fpa_lt(ey, py);
+            else cross = seg_seg(ray, Seg{sx, sy, ex, ey});
+        }
+        n_int += __popc(__ballot_sync(FULL, cross));
+    }
+    return (n_int & 1) == 1;
+}
+
+// CDEngine::detect_containment_collision (cd_engine.rs:231-255) for up to 32 hazards at once: lane l holds
+// hazard slot hs (or -1). The bbox relations are evaluated per lane; the (rare) point-in-polygon tests run one
+// hazard at a time with the whole warp. Returns the OR over the lanes' hazards, uniform across the warp.
+__device__ __forceinline__ bool containment_collision_warp(const DevLayout& L, const float2* iverts, int n_iverts, float ipoi_x,
+                                                           float ipoi_y, const Xf& xf, const Rect& sb, int hs, int lane) {
+    int rel = REL_DISJOINT, scope_interior = 1;
+    if (hs >= 0) {
+        scope_interior = __ldg(&L.haz_meta[hs]).x == 1 ? 1 : 0;
+        rel = rect_almost_relation(ld_rect(&L.haz_bbox[hs]), sb);
+    }
+    const bool pip = hs >= 0 && (rel == REL_SURROUNDING || rel == REL_ENCLOSED);
+    // no point-in-polygon needed: contained = false -> collision iff the hazard's scope is Exterior (hazard.rs:55-62)
+    bool c = hs >= 0 && !pip && !scope_interior;
+    unsigned todo = __ballot_sync(FULL, pip);
+    if (__any_sync(FULL, c)) return true;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int h = __shfl_sync(FULL, hs, src), r = __shfl_sync(FULL, rel, src), si = __shfl_sync(FULL, scope_interior, src);
+        const int4 hm = __ldg(&L.haz_meta[h]);
+        const Rect hb = ld_rect(&L.haz_bbox[h]);
+        bool contained;
+        if (r == REL_SURROUNDING) {
+            float px, py;
+            xf_point(xf, ipoi_x, ipoi_y, px, py);
+            contained = poly_point_warp<false>(L.haz_verts + hm.y, hm.z, hb, px, py, xf, lane);
+        } else {
+            const float4 hp = __ldg(&L.haz_poi[h]);
+            contained = poly_point_warp<true>(iverts, n_iverts, sb, hp.x, hp.y, xf, lane);
+        }
+        if (si ? contained : !contained) return true;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // stage 2 on the grid: polygon edges of the survivors
 // ---------------------------------------------------------------------------------------------------
@@ -498,41 +559,67 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
         __syncwarp();
 
         for (int f0 = 0; f0 < E; f0 += 32) {
-            const unsigned hm = *(volatile unsigned*)&W.hit;
-            if ((hm & need) == need) break;  // every survivor with edges already has a colliding one
+            const unsigned hm0 = *(volatile unsigned*)&W.hit;
+            if ((hm0 & need) == need) break;  // every survivor with edges already has a colliding one
             const int f = f0 + lane;
-            bool lanehit = false;
             int slot = 0;
+            bool scanning = false;
+            Seg sg{0.0f, 0.0f, 0.0f, 0.0f};
+            int l0 = 0, j = 0, j1 = -1;
+            uint32_t cm = 0u, bits = 0u, er = 0u;
             if (f < E) {
-                for (int j = 1; j < GS; j++) slot += (W.ebeg[j] <= f) ? 1 : 0;
-                if (!((hm >> slot) & 1u)) {
+                for (int jj = 1; jj < GS; jj++) slot += (W.ebeg[jj] <= f) ? 1 : 0;
+                if (!((hm0 >> slot) & 1u)) {
                     const float4 t4 = W.xf[slot];
-                    const Seg sg = item_edge(tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, f - W.ebeg[slot]);
+                    sg = item_edge(tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, f - W.ebeg[slot]);
                     const int vc = W.vcell[slot];
-                    const int l0 = vc >> 16, s0 = D - l0;
+                    l0 = vc >> 16;
+                    const int s0 = D - l0;
                     // candidate cells: the edge's bbox inflated by delta, clipped to the virtual root's cells
                     int i0 = cell_lo(g.xs, G, fminf(sg.sx, sg.ex) - g.delta, g.x0, g.inv_cw);
                     int i1 = cell_hi(g.xs, G, fmaxf(sg.sx, sg.ex) + g.delta, g.x0, g.inv_cw);
-                    int j0 = cell_lo(g.ys, G, fminf(sg.sy, sg.ey) - g.delta, g.y0, g.inv_ch);
-                    int j1 = cell_hi(g.ys, G, fmaxf(sg.sy, sg.ey) + g.delta, g.y0, g.inv_ch);
+                    j = cell_lo(g.ys, G, fminf(sg.sy, sg.ey) - g.delta, g.y0, g.inv_ch);
+                    j1 = cell_hi(g.ys, G, fmaxf(sg.sy, sg.ey) + g.delta, g.y0, g.inv_ch);
                     const int vi0 = (vc & 255) << s0, vj0 = ((vc >> 8) & 255) << s0;
                     i0 = max(i0, vi0), i1 = min(i1, vi0 + (1 << s0) - 1);
-                    j0 = max(j0, vj0), j1 = min(j1, vj0 + (1 << s0) - 1);
-                    const uint32_t cm = col_mask(i0, i1);
-                    for (int j = j0; j <= j1 && !lanehit; j++) {
-                        const uint32_t er = g.ent_rows[j] & cm;
-                        uint32_t bits = er | (g.leaf_rows[j] & cm);
-                        while (bits && !lanehit) {
-                            const int i = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            bool h = (er >> i) & 1u;
-                            if (!h) h = leaf_cell_collides<Seg, FILT>(L, g.cell_leaf[j * GRID_G + i], sg, filt);
-                            if (h) lanehit = path_reaches(g, sg, l0, g.cell_level[j * GRID_G + i], i, j);
-                        }
+                    j = max(j, vj0), j1 = min(j1, vj0 + (1 << s0) - 1);
+                    cm = col_mask(i0, i1);
+                    scanning = j <= j1 && cm != 0u;
+                    if (scanning) {
+                        er = g.ent_rows[j] & cm;
+                        bits = er | (g.leaf_rows[j] & cm);
                     }
                 }
             }
-            if (lanehit) atomicOr(&W.hit, 1u << slot);
+            // rounds: every lane scans on to its next would-be hit (an Entire cell, or a leaf cell whose edge
+            // tests succeed), then the lanes that found one verify together that the reference reaches it
+            for (;;) {
+                int hi = -1;
+                while (scanning) {
+                    if (!bits) {
+                        if (j >= j1) { scanning = false; break; }
+                        j++;
+                        er = g.ent_rows[j] & cm;
+                        bits = er | (g.leaf_rows[j] & cm);
+                        continue;
+                    }
+                    const int i = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (((er >> i) & 1u) || leaf_cell_collides<Seg, FILT>(L, g.cell_leaf[j * GRID_G + i], sg, filt)) { hi = i; break; }
+                }
+                if (!__any_sync(FULL, hi >= 0)) break;
+                bool lanehit = false;
+                if (hi >= 0) {
+                    // a finest cell that holds an endpoint is flagged at every level (qt_traits.rs:36-44: not range-
+                    // rejected, `contains` true, and half_intersect only ever adds quadrants)
+                    const Rect cb{g.xs[hi], g.ys[j], g.xs[hi + 1], g.ys[j + 1]};
+                    lanehit = rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) ||
+                              path_reaches(g, sg, l0, g.cell_level[j * GRID_G + hi], hi, j);
+                }
+                if (lanehit) atomicOr(&W.hit, 1u << slot);
+                __syncwarp();
+                if ((*(volatile unsigned*)&W.hit >> slot) & 1u) scanning = false;
+            }
             __syncwarp();
         }
         __syncwarp();
@@ -552,11 +639,15 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
                     const SegDesc& sd = tab.seg[W.seg[s]];
                     const float4 t4 = W.xf[s], b4 = W.bb[s];
                     bool c = false;
-                    for (int j = lane; j < n_partial && !c; j += 32) {
-                        const int hs = __ldg(&L.entry_meta[m.y + j]).x;
-                        if (FILT && filt_bit(filt, hs)) continue;
-                        c = containment_collision(L, sd.verts, sd.n_verts, sd.poi_x, sd.poi_y, Xf{t4.x, t4.y, t4.z, t4.w},
-                                                  Rect{b4.x, b4.y, b4.z, b4.w}, hs);
+                    for (int j0 = 0; j0 < n_partial && !c; j0 += 32) {
+                        const int j = j0 + lane;
+                        int hs = -1;
+                        if (j < n_partial) {
+                            hs = __ldg(&L.entry_meta[m.y + j]).x;
+                            if (FILT && filt_bit(filt, hs)) hs = -1;
+                        }
+                        c = containment_collision_warp(L, sd.verts, sd.n_verts, sd.poi_x, sd.poi_y, Xf{t4.x, t4.y, t4.z, t4.w},
+                                                       Rect{b4.x, b4.y, b4.z, b4.w}, hs, lane);
                     }
                     if (__any_sync(FULL, c)) v = JG_VERDICT_POLY;
                 }

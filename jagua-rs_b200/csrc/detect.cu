@@ -662,7 +662,7 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
     if (grid) {
         const GridDev* gd = grid_of(d_kinds, L.n_nodes);
         const size_t gcommon = ((sizeof(SegTable) + 15) & ~(size_t)15) + ((sizeof(GridDev) + 15) & ~(size_t)15);
-        const size_t gs1 = gcommon + S_WARPS * (32 * sizeof(float4) + (G1_PAIR_CAP + 4) * sizeof(uint32_t));
+        const size_t gs1 = gcommon + S_WARPS * G1_WARP_BYTES;
         const size_t gs2 = gcommon + S_WARPS * sizeof(G2Slots);
         const int want2g = (n + S_WARPS * S2_MAX_GROUP - 1) / (S_WARPS * S2_MAX_GROUP);
         if (mode & JG_MODE_POLY_ONLY) {

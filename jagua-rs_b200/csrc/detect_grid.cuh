@@ -81,6 +81,11 @@ __global__ void __launch_bounds__(1024) k_grid_build(const DevLayout L, int dept
         g->inv_cw = (float)G / (b.z - b.x);
         g->inv_ch = (float)G / (b.w - b.y);
         if (!(b.z > b.x && b.w > b.y)) s_ok = 0;
+        for (int k = 0; k <= G && s_ok; k++) {  // the premise of cell_lo / cell_hi
+            const int gx = cell_guess(g->xs[k], g->x0, g->inv_cw), gy = cell_guess(g->ys[k], g->y0, g->inv_ch);
+            if (gx < k - 1 || gx > k || gy < k - 1 || gy > k) s_ok = 0;
+            if (k > 0 && !(g->xs[k] > g->xs[k - 1] && g->ys[k] > g->ys[k - 1])) s_ok = 0;
+        }
     }
     for (int i = tid; i < GRID_G; i += blockDim.x) g->ent_rows[i] = 0u, g->leaf_rows[i] = 0u;
     for (int i = tid; i < GRID_G * GRID_G; i += blockDim.x) g->cell_leaf[i] = 0u, g->cell_level[i] = 0;
@@ -148,20 +153,18 @@ __device__ __forceinline__ const GridDev* stage_grid(unsigned char*& p, const Gr
     return (const GridDev*)dst;
 }
 
-// first cell whose upper boundary is >= v / last cell whose lower boundary is <= v (clamped to the grid)
+// first cell whose upper boundary is >= v / last cell whose lower boundary is <= v (clamped to the grid).
+// The arithmetic guess floor((v - b0) * inv) is within one cell of the answer - k_grid_build checks, for every
+// boundary b[k], that the guess there is k - 1 or k; the guess is monotone in v, so inside cell k it is
+// k - 1, k or k + 1 - and one exact comparison against each neighbouring boundary settles it.
+__device__ __forceinline__ int cell_guess(float v, float b0, float inv) { return __float2int_rd((v - b0) * inv); }
 __device__ __forceinline__ int cell_lo(const float* b, int G, float v, float b0, float inv) {
-    int i = (int)((v - b0) * inv);
-    i = i < 0 ? 0 : (i > G - 1 ? G - 1 : i);
-    while (i > 0 && b[i] >= v) i--;
-    while (i < G - 1 && b[i + 1] < v) i++;
-    return i;
+    const int g = min(max(cell_guess(v, b0, inv), 0), G - 1);
+    return g - ((g > 0 && b[g] >= v) ? 1 : 0) + ((g < G - 1 && b[g + 1] < v) ? 1 : 0);
 }
 __device__ __forceinline__ int cell_hi(const float* b, int G, float v, float b0, float inv) {
-    int i = (int)((v - b0) * inv);
-    i = i < 0 ? 0 : (i > G - 1 ? G - 1 : i);
-    while (i < G - 1 && b[i + 1] <= v) i++;
-    while (i > 0 && b[i] > v) i--;
-    return i;
+    const int g = min(max(cell_guess(v, b0, inv), 0), G - 1);
+    return g + ((g < G - 1 && b[g + 1] <= v) ? 1 : 0) - ((g > 0 && b[g] > v) ? 1 : 0);
 }
 __device__ __forceinline__ uint32_t col_mask(int lo, int hi) {  // bits lo..hi, 0 <= lo, hi <= 31
     return hi < lo ? 0u : ((0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo));
@@ -211,10 +214,31 @@ __device__ __forceinline__ bool circ_touches_entire(const GridDev& g, const Circ
 
 #define G1_PAIR_CAP 192  // leaf pairs waiting per warp: drained below 32 before every push round of <= 4 per lane
 #define G1_PUSH 4
+#define G1_WARP_BYTES (32 * sizeof(float4) + (G1_PAIR_CAP + 64 + 4) * sizeof(uint32_t))
 
 // ---------------------------------------------------------------------------------------------------
 // stage 1 on the grid: surrogate poles. Lane = query.
+//   phase A (every query): do the poles touch an Entire terminal? Uniform, cheap, decides ~60 % of a uniform
+//           batch. Undecided queries go to a warp-local queue.
+//   phase B (32 queued queries at a time, so the lanes are dense again): the leaf cells inside each pole's
+//           window that pass circ_rect become (query, cell) pairs, resolved 32 at a time.
 // ---------------------------------------------------------------------------------------------------
+struct PoleWin {
+    int i0, i1, j0, j1;
+};
+__device__ __forceinline__ PoleWin pole_window(const GridDev& g, const Circ& c) {
+    const int G = g.G;
+    const float rk = c.r * 1.001f + g.slack;
+    PoleWin w;
+    w.i0 = cell_lo(g.xs, G, c.cx - rk, g.x0, g.inv_cw);
+    w.i1 = cell_hi(g.xs, G, c.cx + rk, g.x0, g.inv_cw);
+    w.j0 = cell_lo(g.ys, G, c.cy - rk, g.y0, g.inv_ch);
+    w.j1 = cell_hi(g.ys, G, c.cy + rk, g.y0, g.inv_ch);
+    // a window entirely beside the grid holds no cell the circle can reach
+    if (c.cx + rk < g.xs[0] || c.cx - rk > g.xs[G] || c.cy + rk < g.ys[0] || c.cy - rk > g.ys[G]) w.i1 = -1, w.j1 = -1;
+    return w;
+}
+
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
 k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
@@ -228,58 +252,88 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
     __syncthreads();
     const SegTable& tab = *t;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t per_warp = 32 * sizeof(float4) + (G1_PAIR_CAP + 4) * sizeof(uint32_t);
-    unsigned char* wp = p + (size_t)warp * per_warp;
-    float4* s_circ = (float4*)wp;  // the current pole of each lane's query
+    unsigned char* wp = p + (size_t)warp * G1_WARP_BYTES;
+    float4* s_circ = (float4*)wp;  // phase B: the current pole of each lane's query
     uint32_t* s_pair = (uint32_t*)(wp + 32 * sizeof(float4));
-    unsigned* s_hit = (unsigned*)(s_pair + G1_PAIR_CAP);
+    int* s_pend = (int*)(s_pair + G1_PAIR_CAP);  // queries waiting for phase B
+    unsigned* s_hit = (unsigned*)(s_pend + 64);
     int* s_cnt = (int*)(s_hit + 1);
-    const int n = tab.n_queries, G = g.G;
+    const int n = tab.n_queries;
+    int n_pend = 0, seg_hint = 0;
+    bool feeding = true;
 
     for (;;) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->s1_next, 32);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= n) break;
-        const int q = base + lane;
-        const bool valid = q < n;
+        if (feeding && n_pend < 32) {
+            // ---- phase A on the next 32 queries
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->s1_next, 32);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n) {
+                feeding = false;
+                continue;
+            }
+            const int q = base + lane;
+            const bool valid = q < n;
+            bool hit = false;
+            // batches are claimed in increasing order: the segment of `base` is at or after the last one seen
+            while (seg_hint + 1 < tab.n_seg && base >= tab.seg[seg_hint + 1].begin) seg_hint++;
+            int k = seg_hint;
+            if (valid) {
+                while (k + 1 < tab.n_seg && q >= tab.seg[k + 1].begin) k++;
+                const float4 t4 = __ldg(&xforms[q]);
+                const Xf xf{t4.x, t4.y, t4.z, t4.w};
+                const SegDesc& sd = tab.seg[k];
+                for (int j = 0; j < sd.n_poles && !hit; j++) {  // circle.rs:79-85: centre transformed, radius unchanged
+                    const float4 pl = __ldg(&sd.poles[j]);
+                    Circ c;
+                    xf_point(xf, pl.x, pl.y, c.cx, c.cy);
+                    c.r = pl.z;
+                    const PoleWin w = pole_window(g, c);
+                    hit = circ_touches_entire(g, c, w.i0, w.i1, w.j0, w.j1);
+                }
+                if (hit) out[q] = (uint8_t)JG_VERDICT_SURROGATE;
+            }
+            const unsigned um = __ballot_sync(FULL, valid && !hit);
+            if (valid && !hit) s_pend[n_pend + __popc(um & lanemask_lt())] = sv_pack(q, k);
+            n_pend += __popc(um);
+            __syncwarp();
+            continue;
+        }
+        if (n_pend == 0) break;
+        // ---- phase B on up to 32 queued queries
+        const int take = n_pend < 32 ? n_pend : 32;
+        n_pend -= take;
+        const bool valid = lane < take;
+        const int qk = valid ? s_pend[n_pend + lane] : 0;
+        const int q = qk & 0x3FFFFFF, k = (int)((unsigned)qk >> 26);
         Xf xf{1.0f, 0.0f, 0.0f, 0.0f};
-        int k = 0, n_poles = 0;
+        int n_poles = 0;
         if (valid) {
             const float4 t4 = __ldg(&xforms[q]);
             xf = Xf{t4.x, t4.y, t4.z, t4.w};
-            k = seg_of_query(tab, q);
             n_poles = tab.seg[k].n_poles;
         }
         bool hit = false;
         const int max_poles = __reduce_max_sync(FULL, n_poles);
-        for (int j = 0; j < max_poles; j++) {  // cd_engine.rs:210-215: the first colliding pole decides
+        for (int j = 0; j < max_poles; j++) {  // cd_engine.rs:210-215: any colliding pole decides
             bool act = valid && !hit && j < n_poles;
             if (!__any_sync(FULL, act)) break;
             Circ c{0.0f, 0.0f, 0.0f};
-            int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
-            if (act) {  // circle.rs:79-85: centre transformed, radius unchanged
+            PoleWin w{0, -1, 0, -1};
+            if (act) {
                 const float4 pl = __ldg(&tab.seg[k].poles[j]);
                 xf_point(xf, pl.x, pl.y, c.cx, c.cy);
                 c.r = pl.z;
                 s_circ[lane] = make_float4(c.cx, c.cy, c.r, 0.0f);
-                const float rk = c.r * 1.001f + g.slack;
-                i0 = cell_lo(g.xs, G, c.cx - rk, g.x0, g.inv_cw);
-                i1 = cell_hi(g.xs, G, c.cx + rk, g.x0, g.inv_cw);
-                j0 = cell_lo(g.ys, G, c.cy - rk, g.y0, g.inv_ch);
-                j1 = cell_hi(g.ys, G, c.cy + rk, g.y0, g.inv_ch);
-                // a window entirely beside the grid holds no cell the circle can reach
-                if (c.cx + rk < g.xs[0] || c.cx - rk > g.xs[G] || c.cy + rk < g.ys[0] || c.cy - rk > g.ys[G]) i1 = -1, j1 = -1;
-                hit = circ_touches_entire(g, c, i0, i1, j0, j1);
-                act = !hit && j1 >= j0 && i1 >= i0;
+                w = pole_window(g, c);
+                act = w.j1 >= w.j0 && w.i1 >= w.i0;
             }
-            // leaf cells of the window that pass circ_rect -> (lane, cell) pairs, resolved 32 at a time
             if (!__any_sync(FULL, act)) continue;
             if (lane == 0) *s_hit = 0u, *s_cnt = 0;
             __syncwarp();
-            const uint32_t cm = col_mask(i0, i1);
+            const uint32_t cm = col_mask(w.i0, w.i1);
             const float r2 = c.r * c.r;
-            int row = j0;
+            int row = w.j0;
             uint32_t bits = 0u;
             float dy2 = 0.0f;
             bool more = act;
@@ -289,13 +343,12 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
                 dy2 = (ny - c.cy) * (ny - c.cy);
             }
             for (;;) {
-                // generation round: up to G1_PUSH cells per lane
-                if (more) {
+                if (more) {  // generation round: up to G1_PUSH cells per lane
                     int pushed = 0;
                     uint32_t mine[G1_PUSH];
                     while (pushed < G1_PUSH) {
                         if (!bits) {
-                            if (row >= j1) { more = false; break; }
+                            if (row >= w.j1) { more = false; break; }
                             row++;
                             bits = g.leaf_rows[row] & cm;
                             const float ny = fmaxf(g.ys[row], fminf(c.cy, g.ys[row + 1]));
@@ -318,13 +371,12 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
                 const bool any_more = __any_sync(FULL, more);
                 int cnt = *(volatile int*)s_cnt;
                 __syncwarp();
-                // drain: while a full warp of pairs waits (or generation is over)
-                while (cnt >= 32 || (!any_more && cnt > 0)) {
-                    const int take = cnt < 32 ? cnt : 32;
-                    cnt -= take;
+                while (cnt >= 32 || (!any_more && cnt > 0)) {  // drain
+                    const int tk = cnt < 32 ? cnt : 32;
+                    cnt -= tk;
                     bool lanehit = false;
                     int ol = 0;
-                    if (lane < take) {
+                    if (lane < tk) {
                         const uint32_t pr = s_pair[cnt + lane];
                         ol = pr & 31;
                         if (!((*(volatile unsigned*)s_hit >> ol) & 1u)) {
@@ -337,21 +389,21 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
                 }
                 if (lane == 0) *s_cnt = cnt;
                 __syncwarp();
-                const unsigned hm = *(volatile unsigned*)s_hit;
-                if ((hm >> lane) & 1u) hit = true, more = false;
+                if ((*(volatile unsigned*)s_hit >> lane) & 1u) hit = true, more = false;
                 if (!any_more) break;
                 __syncwarp();
             }
             __syncwarp();
         }
         if (valid) out[q] = hit ? (uint8_t)JG_VERDICT_SURROGATE : (uint8_t)0;
-        const unsigned sm = __ballot_sync(FULL, valid && !hit);  // survivors keep the query order
+        const unsigned sm = __ballot_sync(FULL, valid && !hit);
         if (sm) {
             int sb = 0;
             if (lane == 0) sb = atomicAdd(&ctl->n_surv, __popc(sm));
             sb = __shfl_sync(FULL, sb, 0);
             if (valid && !hit) sv_entry[sb + __popc(sm & lanemask_lt())] = sv_pack(q, k);
         }
+        __syncwarp();
     }
 }
 

@@ -2,6 +2,7 @@
 // stream-overlapped batching of host buffers, kernel launches, counters.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -40,6 +41,7 @@ struct ChunkCtx {
     size_t cap_q = 0, cap_out = 0;
     DetectScratch sc{nullptr, nullptr};
     size_t cap_sv = 0;
+    cudaEvent_t done = nullptr;  // join point of device-resident batches spread over the chunk streams
 };
 
 }  // namespace
@@ -131,6 +133,7 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
 static void free_ctx(ChunkCtx& c) {
     cudaFree(c.d_xf), cudaFree(c.d_out);
     cudaFree(c.sc.ctl), cudaFree(c.sc.sv_entry);
+    if (c.done) cudaEventDestroy(c.done);
     c = ChunkCtx{};
 }
 
@@ -492,6 +495,7 @@ static int resolve_segments(JgEngine* e, int n_seg, const int* item_ids, const i
     return JG_OK;
 }
 
+#define JG_DEVICE_PIECE_MIN (1 << 16)
 static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
                                const float* d_transforms, int filter_id, int mode, uint8_t* d_out) {
     int rc = check_ready(e);
@@ -507,16 +511,41 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
     if (n > 0 && (!d_transforms || !d_out)) return JG_ERR_INVALID;
     if (n == 0) return JG_OK;
     JG_CUDA(e, cudaSetDevice(e->device));
-    const int64_t max_q = JG_MAX_LAUNCH_QUERIES;
-    rc = ensure_ctx(e, e->main_ctx, (size_t)(n < max_q ? n : max_q), 0, false);
-    if (rc != JG_OK) return rc;
     int launches = 0;
     JG_CUDA(e, cudaEventRecord(e->ev0, e->compute));
     PieceCursor cur;
     Piece p;
-    while (next_piece(e, n_seg, items.data(), seg_offsets, max_q, cur, p))
-        JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, (const float4*)d_transforms + p.off, d_filt, d_kinds, mode, d_out + p.off, e->main_ctx.sc,
-                                 e->n_sms, e->compute, &launches));
+    static const int n_pieces = [] { const char* v = getenv("JG_DEVICE_PIECES"); int k = v ? atoi(v) : 1; return k < 1 ? 1 : k; }();
+    if (n_pieces > 1 && n >= 2 * JG_DEVICE_PIECE_MIN && e->chunks.size() >= 2) {
+        // Large device-resident batch: a few pieces on the chunk streams, so that the tail of one piece's
+        // persistent kernels (SMs draining their last work items) is filled by the next piece's kernels.
+        int64_t piece = (n + n_pieces - 1) / n_pieces;
+        if (piece < JG_DEVICE_PIECE_MIN) piece = JG_DEVICE_PIECE_MIN;
+        if (piece > JG_MAX_LAUNCH_QUERIES) piece = JG_MAX_LAUNCH_QUERIES;
+        for (ChunkCtx& c : e->chunks) {
+            if (!c.done) JG_CUDA(e, cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+            JG_CUDA(e, cudaStreamWaitEvent(c.st, e->ev0, 0));
+        }
+        size_t k = 0;
+        while (next_piece(e, n_seg, items.data(), seg_offsets, piece, cur, p)) {
+            ChunkCtx& c = e->chunks[k++ % e->chunks.size()];
+            rc = ensure_ctx(e, c, (size_t)piece, 0, false);
+            if (rc != JG_OK) return rc;
+            JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, (const float4*)d_transforms + p.off, d_filt, d_kinds, mode, d_out + p.off, c.sc,
+                                     e->n_sms, c.st, &launches));
+        }
+        for (ChunkCtx& c : e->chunks) {
+            JG_CUDA(e, cudaEventRecord(c.done, c.st));
+            JG_CUDA(e, cudaStreamWaitEvent(e->compute, c.done, 0));
+        }
+    } else {
+        const int64_t max_q = JG_MAX_LAUNCH_QUERIES;
+        rc = ensure_ctx(e, e->main_ctx, (size_t)(n < max_q ? n : max_q), 0, false);
+        if (rc != JG_OK) return rc;
+        while (next_piece(e, n_seg, items.data(), seg_offsets, max_q, cur, p))
+            JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, (const float4*)d_transforms + p.off, d_filt, d_kinds, mode, d_out + p.off,
+                                     e->main_ctx.sc, e->n_sms, e->compute, &launches));
+    }
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
     e->timing_valid = true;
     e->stat_launches += launches;

@@ -18,7 +18,7 @@ HEADERS = ["kernels.cuh", "detect_grid.cuh", "launch.hpp", "predicates.cuh", "la
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    *os.environ.get("JG_EXTRA_NVCC", "").split(), "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unknown-pragmas",
 ]
 

@@ -56,6 +56,9 @@ __host__ __device__ inline int mip_off(int level) { return ((1 << (2 * level)) -
 // quadrant index (NE, NW, SW, SE; rect.rs:141-161) of a child from the low bits of its column / row
 __host__ __device__ inline int quad_of(int dx, int dy) { return dy ? (dx ? 0 : 1) : (dx ? 3 : 2); }
 
+// arithmetic guess of the cell holding coordinate v (see cell_lo / cell_hi)
+__device__ __forceinline__ int cell_guess(float v, float b0, float inv) { return __float2int_rd((v - b0) * inv); }
+
 // One CTA of 1024 threads per (layout, filter): fills GridDev from the node arrays and the kinds summary.
 __global__ void __launch_bounds__(1024) k_grid_build(const DevLayout L, int depth, const uint8_t* __restrict__ kinds,
                                                       GridDev* __restrict__ g) {
@@ -157,7 +160,6 @@ __device__ __forceinline__ const GridDev* stage_grid(unsigned char*& p, const Gr
 // The arithmetic guess floor((v - b0) * inv) is within one cell of the answer - k_grid_build checks, for every
 // boundary b[k], that the guess there is k - 1 or k; the guess is monotone in v, so inside cell k it is
 // k - 1, k or k + 1 - and one exact comparison against each neighbouring boundary settles it.
-__device__ __forceinline__ int cell_guess(float v, float b0, float inv) { return __float2int_rd((v - b0) * inv); }
 __device__ __forceinline__ int cell_lo(const float* b, int G, float v, float b0, float inv) {
     const int g = min(max(cell_guess(v, b0, inv), 0), G - 1);
     return g - ((g > 0 && b[g] >= v) ? 1 : 0) + ((g < G - 1 && b[g + 1] < v) ? 1 : 0);
@@ -315,7 +317,12 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
         }
         bool hit = false;
         const int max_poles = __reduce_max_sync(FULL, n_poles);
-        for (int j = 0; j < max_poles; j++) {  // cd_engine.rs:210-215: any colliding pole decides
+#ifdef G1_SKIP_B
+        const int max_poles_dbg = 0;
+#else
+        const int max_poles_dbg = max_poles;
+#endif
+        for (int j = 0; j < max_poles_dbg; j++) {  // cd_engine.rs:210-215: any colliding pole decides
             bool act = valid && !hit && j < n_poles;
             if (!__any_sync(FULL, act)) break;
             Circ c{0.0f, 0.0f, 0.0f};

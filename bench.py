@@ -274,7 +274,7 @@ def main():
             roofline = {"bound": "fp32_nofma", "achieved": ach, "peak": peak_gflops / 1e3, "unit": "TFLOP/s",
                         "frac": ach / (peak_gflops / 1e3), "traffic": None,
                         "peak_source": "measured live: jg_fp32_nofma_peak (independent FADD/FMUL chains)",
-                        "flops_per_query": flops_per_q, "kernels": "k_s1_surr + k_s2_poly, one launch pair for the 10 item segments",
+                        "flops_per_query": flops_per_q, "kernels": f"{cde.detect_path()} path: " + ("k_s1_grid + k_s2_grid" if cde.detect_path() == "grid" else "k_s1_surr + k_s2_poly") + ", one launch pair for the 10 item segments",
                         "hbm": {"achieved": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9, "peak": 6555.2,
                                 "unit": "GB/s", "frac": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9 / 6555.2,
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}

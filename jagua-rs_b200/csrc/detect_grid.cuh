@@ -192,26 +192,23 @@ __device__ __forceinline__ bool circ_touches_entire(const GridDev& g, const Circ
     const int G = g.G;
     const uint32_t cm = col_mask(i0, i1);
     // column holding the centre (any column whose closed range holds cx; outermost column if outside)
-    int ic = cell_lo(g.xs, G, c.cx, g.x0, g.inv_cw);
+    const int ic = cell_lo(g.xs, G, c.cx, g.x0, g.inv_cw);
+    const uint32_t below = (1u << ic) - 1u;
     const float r2 = c.r * c.r;
-    for (int j = j0; j <= j1; j++) {
+    bool hit = false;
+    for (int j = j0; j <= j1; j++) {  // branch-free body: the lanes of a warp run nearly the same row counts
         const uint32_t m = g.ent_rows[j] & cm;
-        if (!m) continue;
         const float ny = fmaxf(g.ys[j], fminf(c.cy, g.ys[j + 1]));
         const float dy2 = (ny - c.cy) * (ny - c.cy);
-        const uint32_t right = m >> ic, left = m & ((1u << ic) - 1u);
-        if (right) {
-            const int i = ic + __ffs(right) - 1;
-            const float nx = fmaxf(g.xs[i], fminf(c.cx, g.xs[i + 1]));
-            if ((nx - c.cx) * (nx - c.cx) + dy2 <= r2) return true;
-        }
-        if (left) {
-            const int i = 31 - __clz(left);
-            const float nx = fmaxf(g.xs[i], fminf(c.cx, g.xs[i + 1]));
-            if ((nx - c.cx) * (nx - c.cx) + dy2 <= r2) return true;
-        }
+        const uint32_t right = m >> ic, left = m & below;
+        const int ir = right ? ic + __ffs(right) - 1 : ic;
+        const int il = left ? 31 - __clz(left) : ic;
+        const float nxr = fmaxf(g.xs[ir], fminf(c.cx, g.xs[ir + 1]));
+        const float nxl = fmaxf(g.xs[il], fminf(c.cx, g.xs[il + 1]));
+        const bool hr = (nxr - c.cx) * (nxr - c.cx) + dy2 <= r2, hl = (nxl - c.cx) * (nxl - c.cx) + dy2 <= r2;
+        hit = hit || (right != 0u && hr) || (left != 0u && hl);
     }
-    return false;
+    return hit;
 }
 
 #define G1_PAIR_CAP 192  // leaf pairs waiting per warp: drained below 32 before every push round of <= 4 per lane
@@ -488,6 +485,8 @@ struct G2Slots {  // per-warp state of the survivors of the current group
     int ebeg[S2_MAX_GROUP + 1];
     unsigned hit;
     int pad[2];
+    int q_verdict[S2_MAX_GROUP];  // classification of each survivor (-1 = undecided) and its edge count
+    int q_ne[S2_MAX_GROUP];
 };
 
 // CDEngine::get_virtual_root (cd_engine.rs:314-327) on the grid: at each level the FIRST child (NE, NW, SW,
@@ -546,8 +545,11 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
     const SegTable& tab = *t;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     G2Slots& W = *(G2Slots*)(p + (size_t)warp * sizeof(G2Slots));
-    const int GS = S2_MAX_GROUP;
     const int total = ctl->n_surv;
+    // survivors per group: 8 when every warp has plenty to do (best lane use); fewer when the launch is small,
+    // where the length of a warp's dependent chain, not the issue rate, sets the kernel's duration
+    const int per_warp = total / (int)(gridDim.x * S_WARPS);
+    const int GS = per_warp >= 16 ? 8 : per_warp >= 6 ? 4 : per_warp >= 2 ? 2 : 1;
     const int D = g.D, G = g.G;
 
     for (;;) {
@@ -564,44 +566,107 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
             W.xf[lane] = __ldg(&xforms[q]);
         }
         __syncwarp();
-        // SPolygon::transform_from + generate_bounding_box (simple_polygon.rs:226-253, 122-133)
-        for (int s = 0; s < ng; s++) {
-            const SegDesc& sd = tab.seg[W.seg[s]];
-            const float4 t4 = W.xf[s];
-            const Xf xf{t4.x, t4.y, t4.z, t4.w};
+        // SPolygon::transform_from + generate_bounding_box (simple_polygon.rs:226-253, 122-133): min/max folds are
+        // exact in any order. Four lanes per survivor (quad = survivor) for ordinary items, the whole warp per
+        // survivor for long vertex lists.
+        const int qs = lane >> 2, sub = lane & 3;
+        int nv_mine = 0;
+        if (qs < ng) nv_mine = tab.seg[W.seg[qs]].n_verts;
+        if (__reduce_max_sync(FULL, nv_mine) <= 128) {
             float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
-            for (int j = lane; j < sd.n_verts; j += 32) {
-                const float2 v = __ldg(&sd.verts[j]);
-                float x, y;
-                xf_point(xf, v.x, v.y, x, y);
-                x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
+            if (qs < ng) {
+                const SegDesc& sd = tab.seg[W.seg[qs]];
+                const float4 t4 = W.xf[qs];
+                const Xf xf{t4.x, t4.y, t4.z, t4.w};
+                for (int j = sub; j < nv_mine; j += 4) {
+                    const float2 v = __ldg(&sd.verts[j]);
+                    float x, y;
+                    xf_point(xf, v.x, v.y, x, y);
+                    x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
+                }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = 2; o > 0; o >>= 1) {
                 x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o));
                 y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o));
                 x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
                 y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
             }
-            if (lane == 0) W.bb[s] = make_float4(x0, y0, x1, y1);
+            if (qs < ng && sub == 0) W.bb[qs] = make_float4(x0, y0, x1, y1);
+        } else {
+            for (int s = 0; s < ng; s++) {
+                const SegDesc& sd = tab.seg[W.seg[s]];
+                const float4 t4 = W.xf[s];
+                const Xf xf{t4.x, t4.y, t4.z, t4.w};
+                float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
+                for (int j = lane; j < sd.n_verts; j += 32) {
+                    const float2 v = __ldg(&sd.verts[j]);
+                    float x, y;
+                    xf_point(xf, v.x, v.y, x, y);
+                    x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o));
+                    y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o));
+                    x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
+                    y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
+                }
+                if (lane == 0) W.bb[s] = make_float4(x0, y0, x1, y1);
+            }
+        }
+        __syncwarp();
+        // cd_engine.rs:161-163 + get_virtual_root (cd_engine.rs:314-327): quad = survivor, lane = child quadrant
+        // (NE, NW, SW, SE), so "the first child that surrounds the bbox" is the lowest set bit of the quad's ballot
+        {
+            Rect bb{0.0f, 0.0f, 0.0f, 0.0f};
+            bool walking = false;
+            if (qs < ng) {
+                const float4 b4 = W.bb[qs];
+                bb = Rect{b4.x, b4.y, b4.z, b4.w};
+                walking = rect_relation(L.cde_bbox, bb) == REL_SURROUNDING;
+            }
+            const bool inside = walking;
+            int level = 0, ci = 0, cj = 0, vnode = 0;
+            for (;;) {
+                bool sur = false;
+                const int nl = level + 1, sh = D - nl, w = 1 << nl, base = mip_off(nl);
+                if (walking && level < D && g.mip_node[base + (2 * cj) * w + 2 * ci] != 0xFFFF) {
+                    const int xi = 2 * ci + ((sub == 0 || sub == 3) ? 1 : 0), yj = 2 * cj + ((sub == 0 || sub == 1) ? 1 : 0);
+                    const Rect cb{g.xs[xi << sh], g.ys[yj << sh], g.xs[(xi + 1) << sh], g.ys[(yj + 1) << sh]};
+                    sur = rect_relation(cb, bb) == REL_SURROUNDING;
+                }
+                const unsigned all = __ballot_sync(FULL, sur);
+                if (!all) break;
+                const unsigned mine = (all >> (qs * 4)) & 0xFu;
+                if (mine) {
+                    const int found = __ffs(mine) - 1;
+                    ci = 2 * ci + ((found == 0 || found == 3) ? 1 : 0);
+                    cj = 2 * cj + ((found == 0 || found == 1) ? 1 : 0);
+                    level = nl;
+                    vnode = g.mip_node[base + cj * w + ci];
+                } else {
+                    walking = false;
+                }
+            }
+            if (qs < ng && sub == 0) {
+                int v = -1, ne = 0;
+                if (!inside) {
+                    v = JG_VERDICT_POLY;
+                } else {
+                    const int vk = __ldg(&g_kinds[vnode + 3]);
+                    W.vnode[qs] = vnode;
+                    W.vcell[qs] = (level << 16) | (cj << 8) | ci;
+                    if (vk == KIND_ENTIRE) v = JG_VERDICT_POLY;  // every edge sees it (qt_node.rs:108)
+                    else if (vk != KIND_NONE) ne = tab.seg[W.seg[qs]].n_verts;
+                }
+                W.q_verdict[qs] = v;
+                W.q_ne[qs] = ne;
+            }
         }
         __syncwarp();
         int verdict = -1, nE = 0;
-        if (lane < ng) {
-            const float4 b4 = W.bb[lane];
-            const Rect bb{b4.x, b4.y, b4.z, b4.w};
-            if (rect_relation(L.cde_bbox, bb) != REL_SURROUNDING) {
-                verdict = JG_VERDICT_POLY;  // cd_engine.rs:161-163
-            } else {
-                int vnode;
-                const int vc = virtual_root_grid(g, bb, vnode);
-                const int vk = __ldg(&g_kinds[vnode + 3]);
-                W.vnode[lane] = vnode;
-                W.vcell[lane] = vc;
-                if (vk == KIND_ENTIRE) verdict = JG_VERDICT_POLY;  // every edge sees it (qt_node.rs:108)
-                else if (vk != KIND_NONE) nE = tab.seg[W.seg[lane]].n_verts;
-            }
-        }
+        if (lane < ng) verdict = W.q_verdict[lane], nE = W.q_ne[lane];
         int incl = nE;
 #pragma unroll
         for (int o = 1; o < S2_MAX_GROUP; o <<= 1) {

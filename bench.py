@@ -216,6 +216,22 @@ def main():
         cde.detect_multi(item_ids, offs, host_t.array, out=host_out.array, wait=False)
         cde.sync()
 
+    # the same batch in the compact wire form (rotation index u8 + translation 2 x f32 = 9 B/query)
+    host_ridx = jg.PinnedBuffer((n_q,), np.uint8)
+    host_txy = jg.PinnedBuffer((n_q, 2), np.float32)
+    host_out_ix = jg.PinnedBuffer((n_q,), np.uint8)
+    indexed_ok = all(it.rotations is not None and len(it.rotations) > 0 for it in wl.items)
+    if indexed_ok:
+        for i, n in enumerate(sizes):
+            cde.set_item_rotations(i, wl.items[i].rotations)
+            r, t = jg.make_queries_indexed(wl, i, n, seed=rank)
+            host_ridx.array[offs[i]:offs[i + 1]] = r
+            host_txy.array[offs[i]:offs[i + 1]] = t
+
+    def step_e2e_indexed():
+        cde.detect_multi_indexed(item_ids, offs, host_ridx.array, host_txy.array, out=host_out_ix.array, wait=False)
+        cde.sync()
+
     def barrier():
         cde.sync()
         if dist is not None:
@@ -251,16 +267,27 @@ def main():
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_ix_s = 0.0
+    if indexed_ok:
+        for _ in range(max(args.warmup, 3)):
+            step_e2e_indexed()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e_indexed()
+        barrier()
+        e2e_ix_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
     if dist is not None:
         import torch
-        tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dev_ms, e2e_s, e2e_ix_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(tt[0]), float(tt[1])
+        dev_ms, e2e_s, e2e_ix_s = float(tt[0]), float(tt[1]), float(tt[2])
 
     # verdicts of the last e2e step vs the device-resident path (same inputs -> identical)
     same = np.array_equal(host_out.array, dev_out.download((n_q,), np.uint8))
+    same_ix = bool(indexed_ok and np.array_equal(host_out.array, host_out_ix.array))
 
     if rank == 0:
         total_q = args.queries * world
@@ -287,7 +314,13 @@ def main():
                            "verdict_split": flops_info.get("verdicts")},
                 "clocks": clocks, "gpu_launches": int(gpu_launches),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 16 * args.queries, "d2h_bytes_per_step": args.queries,
-                        "ms_per_step": e2e_s / args.steps * 1e3, "same_verdicts_as_device_path": bool(same)},
+                        "ms_per_step": e2e_s / args.steps * 1e3, "same_verdicts_as_device_path": bool(same),
+                        "input": "composed (cos, sin, tx, ty) f32 records, 16 B/query, pinned host memory",
+                        "compact_input": None if not indexed_ok else {
+                            "value": total_q * args.steps / e2e_ix_s, "unit": UNIT, "ms_per_step": e2e_ix_s / args.steps * 1e3,
+                            "h2d_bytes_per_step": 9 * args.queries, "d2h_bytes_per_step": args.queries,
+                            "input": "jg_detect_multi_indexed: rotation index u8 + translation 2 x f32 = 9 B/query (items with discrete "
+                                     "allowed orientations), same queries", "same_verdicts": same_ix}},
                 "roofline": roofline, "layout_setup_ms": layout_setup_ms}
         if world == 1 and not args.no_cpu_baseline:
             orc, oracle_world = load_oracle()

@@ -107,6 +107,17 @@ int jg_detect_multi(JgEngine* e, int n_seg, const int* item_ids, const int64_t* 
                     int filter_id, int mode, uint8_t* out);
 int jg_detect_multi_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
                           const float* transforms, int filter_id, int mode, uint8_t* out);
+/* Compact query form for items with a discrete set of allowed orientations (geo_enums.rs RotationRange::Discrete,
+ * sampled by lbf/src/samplers/rotation_distr.rs:42-48): the caller registers, per item, (cos, sin) of every allowed
+ * rotation - composed on the host with the platform libm exactly like transformation.rs:131-139 - and a query is
+ * (index of the rotation: 1 byte, translation: 2 floats) = 9 B instead of 16 B over PCIe. The kernels rebuild the
+ * same (cos, sin, tx, ty) record, so verdicts are identical to jg_detect_multi on the composed transforms.
+ * rot_cos_sin: n_rot pairs, 1 <= n_rot <= 256. Indices >= n_rot are clamped to n_rot - 1. */
+int jg_item_set_rotations(JgEngine* e, int item_id, const float* rot_cos_sin, int n_rot);
+int jg_detect_multi_indexed(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const uint8_t* rot_idx,
+                            const float* txy, int filter_id, int mode, uint8_t* out);
+int jg_detect_multi_indexed_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
+                                  const uint8_t* rot_idx, const float* txy, int filter_id, int mode, uint8_t* out);
 int jg_detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
                            const float* d_transforms, int filter_id, int mode, uint8_t* d_out);
 /* Same with DEVICE pointers; asynchronous on the engine's compute stream (jg_sync to wait). */

@@ -62,6 +62,9 @@ C_ABI = {
     "jg_detect_multi": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "jg_detect_multi_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "jg_detect_multi_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_item_set_rotations": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
+    "jg_detect_multi_indexed": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_detect_multi_indexed_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "jg_detect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "jg_collect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
     "jg_collect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
@@ -431,6 +434,28 @@ class CDEngine:
                      MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data))
         return out
 
+    def set_item_rotations(self, item_id: int, rotations):
+        """Registers an item's allowed orientations (radians) for the compact query form. (cos, sin) are
+        composed on the host by the same libm call as every other transformation (compose())."""
+        self._need_engine()
+        rots = np.asarray(rotations, np.float32).reshape(-1)
+        cs = np.ascontiguousarray(compose(np.stack([rots, np.zeros_like(rots), np.zeros_like(rots)], 1))[:, :2])
+        self._chk(self._lib.jg_item_set_rotations(self._eng, int(item_id), cs.ctypes.data, len(rots)))
+
+    def detect_multi_indexed(self, item_ids, seg_offsets, rot_idx: np.ndarray, txy: np.ndarray, filter_id: int = -1,
+                             poly_only: bool = False, out: Optional[np.ndarray] = None, wait: bool = True) -> np.ndarray:
+        """detect_multi with the queries as (index into the item's allowed rotations: u8, translation: 2 x f32)."""
+        self.sync_layout()
+        ids, offs = self._segments(item_ids, seg_offsets)
+        assert rot_idx.dtype == np.uint8 and rot_idx.flags.c_contiguous and txy.dtype == np.float32 and txy.flags.c_contiguous
+        assert rot_idx.size == int(offs[-1]) and txy.size == 2 * int(offs[-1])
+        if out is None:
+            out = np.empty(int(offs[-1]), np.uint8)
+        fn = self._lib.jg_detect_multi_indexed if wait else self._lib.jg_detect_multi_indexed_async
+        self._chk(fn(self._eng, len(ids), ids.ctypes.data, offs.ctypes.data, rot_idx.ctypes.data, txy.ctypes.data, int(filter_id),
+                     MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data))
+        return out
+
     def detect_multi_device(self, item_ids, seg_offsets, d_transforms: int, d_out: int, filter_id: int = -1, poly_only: bool = False):
         self.sync_layout()
         ids, offs = self._segments(item_ids, seg_offsets)
@@ -492,4 +517,4 @@ class CDEngine:
         self._chk(self._lib.jg_flush_l2(self._eng))
 
 
-from .workload import Workload, load_workload, build_engine, make_queries, split_batch  # noqa: E402
+from .workload import Workload, load_workload, build_engine, make_queries, make_queries_indexed, split_batch  # noqa: E402

@@ -223,7 +223,7 @@ __device__ __forceinline__ Seg item_edge(const SegDesc& sd, const Xf& xf, int e)
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
 k_s1_surr(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_t* __restrict__ g_kinds, int nodes_in_smem,
-          int cap_in, const float4* __restrict__ xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
+          int cap_in, const XfSrc xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
           DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SegTable* tabp;
@@ -249,9 +249,9 @@ k_s1_surr(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_
         Xf xf{1.0f, 0.0f, 0.0f, 0.0f};
         int k = 0, n_poles = 0, n_ent = 0;
         if (valid) {
-            const float4 t4 = __ldg(&xforms[q]);
-            xf = Xf{t4.x, t4.y, t4.z, t4.w};
             k = seg_of_query(tab, q);
+            const float4 t4 = load_xf(xforms, tab.seg[k], q);
+            xf = Xf{t4.x, t4.y, t4.z, t4.w};
             n_poles = tab.seg[k].n_poles;
             n_ent = n_poles + tab.seg[k].n_piers;
         }
@@ -409,7 +409,7 @@ __device__ __forceinline__ int virtual_root_nv(const NodeView& nv, const Rect& b
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
 k_s2_poly(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_t* __restrict__ g_kinds, int nodes_in_smem,
-          int cap_in, int gbits, const float4* __restrict__ xforms, const uint32_t* __restrict__ filt,
+          int cap_in, int gbits, const XfSrc xforms, const uint32_t* __restrict__ filt,
           uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, const int* __restrict__ sv_entry) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SegTable* tabp;
@@ -438,7 +438,7 @@ k_s2_poly(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_
             const int q = ent & 0x3FFFFFF;
             W.q[lane] = q;
             W.seg[lane] = (int)((unsigned)ent >> 26);
-            W.xf[lane] = __ldg(&xforms[q]);
+            W.xf[lane] = load_xf(xforms, tab.seg[(unsigned)ent >> 26], q);
         }
         __syncwarp();
         // SPolygon::transform_from + generate_bounding_box (simple_polygon.rs:226-253, 122-133): min/max folds
@@ -648,7 +648,7 @@ cudaError_t detect_grid_usable(const uint8_t* d_kinds, int n_nodes, cudaStream_t
     return cudaStreamSynchronize(st);
 }
 
-cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const float4* d_xf,
+cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const XfSrc& d_xf,
                           const uint32_t* d_filt, const uint8_t* d_kinds, int mode, uint8_t* d_out, const DetectScratch& sc,
                           int n_sms, cudaStream_t st, int* n_launches) {
     const int n = tab.n_queries;

@@ -241,7 +241,7 @@ __device__ __forceinline__ PoleWin pole_window(const GridDev& g, const Circ& c) 
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
 k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
-          const float4* __restrict__ xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
+          const XfSrc xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
           DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
     extern __shared__ __align__(16) unsigned char smem[];
     SegTable* t = (SegTable*)smem;
@@ -279,9 +279,9 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
             int k = seg_hint;
             if (valid) {
                 while (k + 1 < tab.n_seg && q >= tab.seg[k + 1].begin) k++;
-                const float4 t4 = __ldg(&xforms[q]);
-                const Xf xf{t4.x, t4.y, t4.z, t4.w};
                 const SegDesc& sd = tab.seg[k];
+                const float4 t4 = load_xf(xforms, sd, q);
+                const Xf xf{t4.x, t4.y, t4.z, t4.w};
                 for (int j = 0; j < sd.n_poles && !hit; j++) {  // circle.rs:79-85: centre transformed, radius unchanged
                     const float4 pl = __ldg(&sd.poles[j]);
                     Circ c;
@@ -308,7 +308,7 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
         Xf xf{1.0f, 0.0f, 0.0f, 0.0f};
         int n_poles = 0;
         if (valid) {
-            const float4 t4 = __ldg(&xforms[q]);
+            const float4 t4 = load_xf(xforms, tab.seg[k], q);
             xf = Xf{t4.x, t4.y, t4.z, t4.w};
             n_poles = tab.seg[k].n_poles;
         }
@@ -534,7 +534,7 @@ __device__ __forceinline__ bool path_reaches(const GridDev& g, const Seg& sg, in
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
 k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
-          const uint8_t* __restrict__ g_kinds, const float4* __restrict__ xforms, const uint32_t* __restrict__ filt,
+          const uint8_t* __restrict__ g_kinds, const XfSrc xforms, const uint32_t* __restrict__ filt,
           uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, const int* __restrict__ sv_entry) {
     extern __shared__ __align__(16) unsigned char smem[];
     SegTable* t = (SegTable*)smem;
@@ -563,7 +563,7 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
             const int q = ent & 0x3FFFFFF;
             W.q[lane] = q;
             W.seg[lane] = (int)((unsigned)ent >> 26);
-            W.xf[lane] = __ldg(&xforms[q]);
+            W.xf[lane] = load_xf(xforms, tab.seg[(unsigned)ent >> 26], q);
         }
         __syncwarp();
         // SPolygon::transform_from + generate_bounding_box (simple_polygon.rs:226-253, 122-133): min/max folds are

@@ -25,6 +25,8 @@ struct ItemDev {
     int n_poles = 0;
     float4* piers = nullptr;
     int n_piers = 0;
+    float2* rots = nullptr;  // (cos, sin) per allowed rotation (jg_item_set_rotations)
+    int n_rots = 0;
 };
 struct FilterDev {
     uint32_t* bits = nullptr;
@@ -197,6 +199,7 @@ void jg_engine_destroy(JgEngine* e) {
         cudaFree(kv.second.verts);
         cudaFree(kv.second.poles);
         cudaFree(kv.second.piers);
+        cudaFree(kv.second.rots);
     }
     for (auto& kv : e->filters) cudaFree(kv.second.bits), cudaFree(kv.second.kinds);
     if (e->d_kinds) cudaFree(e->d_kinds);
@@ -354,6 +357,7 @@ int jg_item_upload(JgEngine* e, int item_id, const float* verts_xy, int n_verts,
     cudaFree(it.verts);
     cudaFree(it.poles);
     cudaFree(it.piers);
+    cudaFree(it.rots);
     it = ItemDev{};
     it.n_verts = n_verts;
     it.poi_x = poi_xy[0];
@@ -373,6 +377,23 @@ int jg_item_upload(JgEngine* e, int item_id, const float* verts_xy, int n_verts,
         JG_CUDA(e, cudaMalloc(&it.piers, (size_t)n_piers * sizeof(float4)));
         JG_CUDA(e, cudaMemcpy(it.piers, piers, (size_t)n_piers * sizeof(float4), cudaMemcpyHostToDevice));
     }
+    return JG_OK;
+}
+
+int jg_item_set_rotations(JgEngine* e, int item_id, const float* rot_cos_sin, int n_rot) {
+    if (!e || !rot_cos_sin || n_rot < 1 || n_rot > 256) return JG_ERR_INVALID;
+    auto f = e->items.find(item_id);
+    if (f == e->items.end()) return fail(e, JG_ERR_INVALID, "unknown item id");
+    JG_CUDA(e, cudaSetDevice(e->device));
+    int rc = jg_sync(e);
+    if (rc != JG_OK) return rc;
+    ItemDev& it = f->second;
+    cudaFree(it.rots);
+    it.rots = nullptr;
+    it.n_rots = 0;
+    JG_CUDA(e, cudaMalloc(&it.rots, (size_t)n_rot * sizeof(float2)));
+    JG_CUDA(e, cudaMemcpy(it.rots, rot_cos_sin, (size_t)n_rot * sizeof(float2), cudaMemcpyHostToDevice));
+    it.n_rots = n_rot;
     return JG_OK;
 }
 
@@ -472,6 +493,9 @@ static bool next_piece(const JgEngine* e, int n_seg, const ItemDev* const* items
         sd.piers = it.piers;
         sd.poi_x = it.poi_x;
         sd.poi_y = it.poi_y;
+        sd.rots = it.rots;
+        sd.n_rots = it.n_rots;
+        sd.pad = 0;
         covered += len;
         edge_pairs += len * it.n_verts;
         if (b + len < seg_offsets[sgi + 1]) break;  // segment cut: the rest goes to the next piece
@@ -531,7 +555,7 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
             ChunkCtx& c = e->chunks[k++ % e->chunks.size()];
             rc = ensure_ctx(e, c, (size_t)piece, 0, false);
             if (rc != JG_OK) return rc;
-            JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, (const float4*)d_transforms + p.off, d_filt, d_kinds, mode, d_out + p.off, c.sc,
+            JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off, c.sc,
                                      e->n_sms, c.st, &launches));
         }
         for (ChunkCtx& c : e->chunks) {
@@ -543,7 +567,7 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
         rc = ensure_ctx(e, e->main_ctx, (size_t)(n < max_q ? n : max_q), 0, false);
         if (rc != JG_OK) return rc;
         while (next_piece(e, n_seg, items.data(), seg_offsets, max_q, cur, p))
-            JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, (const float4*)d_transforms + p.off, d_filt, d_kinds, mode, d_out + p.off,
+            JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off,
                                      e->main_ctx.sc, e->n_sms, e->compute, &launches));
     }
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
@@ -555,8 +579,9 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
 
 // Host-pointer batches: pieces of at most chunk_queries queries, piece k on stream k mod n_streams, so
 // the H2D copy of piece k+1 overlaps the kernels of piece k and the D2H copy of piece k-1.
+// `transforms` (16 B/query) or, when it is null, the compact form `rot_idx` + `txy` (9 B/query)
 static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
-                             int filter_id, int mode, uint8_t* out, bool wait) {
+                             const uint8_t* rot_idx, const float* txy, int filter_id, int mode, uint8_t* out, bool wait) {
     int rc = check_ready(e);
     if (rc != JG_OK) return rc;
     std::vector<const ItemDev*> items;
@@ -567,23 +592,47 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
     rc = find_filter(e, filter_id, &d_filt, &d_kinds);
     if (rc != JG_OK) return rc;
     const int64_t n = seg_offsets[n_seg];
-    if (n > 0 && (!transforms || !out)) return JG_ERR_INVALID;
+    const bool indexed = transforms == nullptr;
+    if (n > 0 && (!out || (indexed && (!rot_idx || !txy)))) return JG_ERR_INVALID;
+    if (indexed)
+        for (int k = 0; k < n_seg; k++)
+            if (seg_offsets[k + 1] > seg_offsets[k] && items[k]->n_rots == 0)
+                return fail(e, JG_ERR_INVALID, "indexed queries need jg_item_set_rotations for every item of the batch");
     if (n == 0) return JG_OK;
     JG_CUDA(e, cudaSetDevice(e->device));
     const int64_t chunk = e->chunk_queries;
     PieceCursor cur;
     Piece p;
-    while (next_piece(e, n_seg, items.data(), seg_offsets, chunk, cur, p)) {
+    // The pipeline is bound by the H2D copies; what stays exposed is the kernels + D2H of the LAST piece, so
+    // the pieces taper towards the end of the batch (halving down to JG_TAPER_MIN queries).
+    static const int64_t taper_min = [] { const char* v = getenv("JG_TAPER_MIN"); return v ? (int64_t)atoll(v) : (int64_t)0; }();
+    auto piece_size = [&](int64_t done) {
+        const int64_t rem = n - done;
+        if (taper_min <= 0 || rem > chunk + chunk / 2) return chunk;
+        if (rem > 2 * taper_min) return (rem / 2 + 31) & ~(int64_t)31;
+        return rem;
+    };
+    while (next_piece(e, n_seg, items.data(), seg_offsets, piece_size(cur.q), cur, p)) {
         ChunkCtx& c = e->chunks[e->next_chunk++ % e->chunks.size()];
         JG_CUDA(e, cudaStreamSynchronize(c.st));  // buffers of this slot are free again
         rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n), true);
         if (rc != JG_OK) return rc;
-        JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * p.off, (size_t)p.m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
+        XfSrc src{c.d_xf, nullptr, nullptr};
+        if (!indexed) {
+            JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * p.off, (size_t)p.m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
+            e->stat_h2d += (uint64_t)p.m * sizeof(float4);
+        } else {  // the staging buffer holds the translations followed by the rotation indices
+            float2* d_txy = (float2*)c.d_xf;
+            uint8_t* d_ridx = (uint8_t*)(d_txy + p.m);
+            JG_CUDA(e, cudaMemcpyAsync(d_txy, txy + 2 * p.off, (size_t)p.m * sizeof(float2), cudaMemcpyHostToDevice, c.st));
+            JG_CUDA(e, cudaMemcpyAsync(d_ridx, rot_idx + p.off, (size_t)p.m, cudaMemcpyHostToDevice, c.st));
+            src = XfSrc{nullptr, d_ridx, d_txy};
+            e->stat_h2d += (uint64_t)p.m * 9;
+        }
         int launches = 0;
-        JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, c.d_xf, d_filt, d_kinds, mode, c.d_out, c.sc, e->n_sms, c.st, &launches));
+        JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, src, d_filt, d_kinds, mode, c.d_out, c.sc, e->n_sms, c.st, &launches));
         JG_CUDA(e, cudaMemcpyAsync(out + p.off, c.d_out, (size_t)p.m, cudaMemcpyDeviceToHost, c.st));
         e->stat_launches += launches;
-        e->stat_h2d += (uint64_t)p.m * sizeof(float4);
         e->stat_d2h += (uint64_t)p.m;
     }
     if (wait)
@@ -594,11 +643,21 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
 
 int jg_detect_multi(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
                     int filter_id, int mode, uint8_t* out) {
-    return detect_multi_host(e, n_seg, item_ids, seg_offsets, transforms, filter_id, mode, out, true);
+    return detect_multi_host(e, n_seg, item_ids, seg_offsets, transforms, nullptr, nullptr, filter_id, mode, out, true);
 }
 int jg_detect_multi_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
                           int filter_id, int mode, uint8_t* out) {
-    return detect_multi_host(e, n_seg, item_ids, seg_offsets, transforms, filter_id, mode, out, false);
+    return detect_multi_host(e, n_seg, item_ids, seg_offsets, transforms, nullptr, nullptr, filter_id, mode, out, false);
+}
+int jg_detect_multi_indexed(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const uint8_t* rot_idx,
+                            const float* txy, int filter_id, int mode, uint8_t* out) {
+    if (!rot_idx || !txy) return JG_ERR_INVALID;
+    return detect_multi_host(e, n_seg, item_ids, seg_offsets, nullptr, rot_idx, txy, filter_id, mode, out, true);
+}
+int jg_detect_multi_indexed_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const uint8_t* rot_idx,
+                                  const float* txy, int filter_id, int mode, uint8_t* out) {
+    if (!rot_idx || !txy) return JG_ERR_INVALID;
+    return detect_multi_host(e, n_seg, item_ids, seg_offsets, nullptr, rot_idx, txy, filter_id, mode, out, false);
 }
 int jg_detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* d_transforms,
                            int filter_id, int mode, uint8_t* d_out) {
@@ -607,13 +666,13 @@ int jg_detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const in
 int jg_detect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode, uint8_t* out) {
     if (n < 0) return JG_ERR_INVALID;
     const int64_t offs[2] = {0, n};
-    return detect_multi_host(e, 1, &item_id, offs, transforms, filter_id, mode, out, true);
+    return detect_multi_host(e, 1, &item_id, offs, transforms, nullptr, nullptr, filter_id, mode, out, true);
 }
 int jg_detect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int filter_id, int mode,
                           uint8_t* out) {
     if (n < 0) return JG_ERR_INVALID;
     const int64_t offs[2] = {0, n};
-    return detect_multi_host(e, 1, &item_id, offs, transforms, filter_id, mode, out, false);
+    return detect_multi_host(e, 1, &item_id, offs, transforms, nullptr, nullptr, filter_id, mode, out, false);
 }
 int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int filter_id, int mode,
                            uint8_t* d_out) {

@@ -19,12 +19,31 @@ struct SegDesc {
     const float4* poles;  // (x, y, r, 0); only the first n_ff poles are counted in n_poles
     const float4* piers;
     float poi_x, poi_y;
+    const float2* rots;  // (cos, sin) of the item's allowed rotations (jg_item_set_rotations), or null
+    int n_rots;
+    int pad;
 };
 struct SegTable {
     int n_seg;
     int n_queries;
     SegDesc seg[JG_MAX_SEG];
 };
+
+// Where the queries of a launch come from: composed (cos, sin, tx, ty) records, or the compact form
+// (index into the item's allowed rotations + translation; transformation.rs:131-139 composed on the host once
+// per allowed rotation).
+struct XfSrc {
+    const float4* xf;
+    const uint8_t* ridx;
+    const float2* txy;
+};
+__device__ __forceinline__ float4 load_xf(const XfSrc& s, const SegDesc& sd, int q) {
+    if (s.xf) return __ldg(&s.xf[q]);
+    const int r = (int)__ldg(&s.ridx[q]);
+    const float2 cs = __ldg(&sd.rots[r < sd.n_rots ? r : sd.n_rots - 1]);  // out-of-range indices are clamped
+    const float2 t = __ldg(&s.txy[q]);
+    return make_float4(cs.x, cs.y, t.x, t.y);
+}
 
 // Work counters of one detect launch sequence (device memory, zeroed by launch_detect).
 struct DetectCtl {
@@ -55,7 +74,7 @@ size_t detect_kinds_bytes(int n_nodes);
 // per-filter node summary read by the detect kernels; d_filt == nullptr is NoFilter
 cudaError_t launch_node_kinds(const DevLayout& L, int depth, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st);
 cudaError_t detect_grid_usable(const uint8_t* d_kinds, int n_nodes, cudaStream_t st, int* ok);
-cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const float4* d_xf,
+cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const XfSrc& d_xf,
                           const uint32_t* d_filt, const uint8_t* d_kinds, int mode, uint8_t* d_out, const DetectScratch& sc,
                           int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,

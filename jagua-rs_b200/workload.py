@@ -114,6 +114,20 @@ def build_engine(w: Workload, device: Optional[int] = 0):
     return cde
 
 
+def make_queries_indexed(w: Workload, item_id: int, n: int, seed: int = 0):
+    """The same n seeded queries as make_queries in their compact form: (rot_idx u8, txy (n, 2) f32). Only for
+    items with a discrete set of allowed orientations."""
+    rng = np.random.Generator(np.random.Philox(key=[seed, item_id]))
+    it = w.items[item_id]
+    b = w.cde_bbox.astype(np.float32)
+    u = rng.random((n, 2), dtype=np.float32)
+    tx = (b[0] + (b[2] - b[0]) * u[:, 0]).astype(np.float32)
+    ty = (b[1] + (b[3] - b[1]) * u[:, 1]).astype(np.float32)
+    assert it.rotations is not None and len(it.rotations) > 0, "item has no discrete rotation set"
+    idx = rng.integers(0, len(it.rotations), n)
+    return idx.astype(np.uint8), np.ascontiguousarray(np.stack([tx, ty], 1))
+
+
 def make_queries(w: Workload, item_id: int, n: int, seed: int = 0) -> np.ndarray:
     """n seeded (cos, sin, tx, ty) queries for one item: translation uniform over the CDE bbox
     (UniformRectSampler::new(cde.bbox(), item), lbf/src/samplers/uniform_rect_sampler.rs:18-36;

@@ -167,3 +167,34 @@ def test_grid_path_near_item_placements(jg, engines):
         exp = w.detect_batch(item_id, t, poly_only=True)
         got = cde.detect_batch(item_id, t, poly_only=True)
         assert np.array_equal(got, exp), f"item {item_id}: {(got != exp).sum()} mismatches"
+
+
+@pytest.mark.parametrize("name", ["swim_half", "shirts_full", "shirts_full_d10"])
+def test_indexed_queries_match_composed_queries(jg, engines, name):
+    """The compact (rotation index, translation) form resolves to the same verdicts as the composed
+    (cos, sin, tx, ty) form of the same queries, on the grid and on the walk kernels."""
+    wl, cde, w = engines(name)
+    ids = list(range(len(wl.items)))
+    for i in ids:
+        cde.set_item_rotations(i, wl.items[i].rotations)
+    sizes = [1500 + 37 * i for i in ids]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    comp = np.concatenate([jg.make_queries(wl, i, n, seed=9) for i, n in zip(ids, sizes)])
+    pairs = [jg.make_queries_indexed(wl, i, n, seed=9) for i, n in zip(ids, sizes)]
+    ridx = np.ascontiguousarray(np.concatenate([p[0] for p in pairs]))
+    txy = np.ascontiguousarray(np.concatenate([p[1] for p in pairs]))
+    exp = np.concatenate([w.detect_batch(i, jg.make_queries(wl, i, n, seed=9)) for i, n in zip(ids, sizes)])
+    assert np.array_equal(cde.detect_multi(ids, offs, comp), exp)
+    assert np.array_equal(cde.detect_multi_indexed(ids, offs, ridx, txy), exp)
+    assert np.array_equal(cde.detect_multi_indexed(ids, offs, ridx, txy, poly_only=True),
+                          cde.detect_multi(ids, offs, comp, poly_only=True))
+
+
+def test_indexed_queries_need_registered_rotations(jg):
+    wl = jg.load_workload("albano_half")
+    cde = jg.build_engine(wl, device=0)
+    try:
+        with pytest.raises(jg.JaguaCudaError):
+            cde.detect_multi_indexed([0], [0, 4], np.zeros(4, np.uint8), np.zeros((4, 2), np.float32))
+    finally:
+        cde.close()

@@ -296,10 +296,19 @@ def main():
         ms_per_step = dev_ms / args.steps
         flops_per_q = flops_info["detect_flops_per_query"] if args.queries == flops_info["queries"] else None
         roofline = None
+        traffic = None
+        try:  # DRAM bytes of the two kernels from the committed ncu capture of this same step
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f)
+            if cde.detect_path() == "grid" and args.queries == TOTAL_QUERIES:
+                traffic = {"bytes_per_step": tr["k_s1_grid"] + tr["k_s2_grid"], "algorithmic_bytes_per_step": ALG_BYTES_PER_QUERY * args.queries,
+                           "source": tr["source"]}
+        except (OSError, KeyError, ValueError):
+            pass
         if flops_per_q:
             ach = flops_per_q * args.queries / (ms_per_step * 1e-3) / 1e12  # per GPU
             roofline = {"bound": "fp32_nofma", "achieved": ach, "peak": peak_gflops / 1e3, "unit": "TFLOP/s",
-                        "frac": ach / (peak_gflops / 1e3), "traffic": None,
+                        "frac": ach / (peak_gflops / 1e3), "traffic": traffic,
                         "peak_source": "measured live: jg_fp32_nofma_peak (independent FADD/FMUL chains)",
                         "flops_per_query": flops_per_q, "kernels": f"{cde.detect_path()} path: " + ("k_s1_grid + k_s2_grid" if cde.detect_path() == "grid" else "k_s1_surr + k_s2_poly") + ", one launch pair for the 10 item segments",
                         "hbm": {"achieved": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9, "peak": 6555.2,

@@ -173,20 +173,16 @@ def main():
     t_b0 = time.perf_counter()
     if world > 1:
         import torch
+        from jagua_rs_b200 import multigpu
+        blob = None
         if rank == 0:
             cde = jg.build_engine(wl, device=local_rank)
             blob = cde.flatten()
-            size = torch.tensor([blob.nbytes], dtype=torch.int64, device="cuda")
         else:
             cde = jg.CDEngine(wl.cde_bbox, wl.quadtree_depth, wl.cd_threshold, wl.n_ff_poles, wl.n_ff_piers, device=local_rank)
             for i, it in enumerate(wl.items):
                 cde.upload_item(i, jg.ItemShape(it.verts, it.poi, it.poles, it.piers))
-            size = torch.zeros(1, dtype=torch.int64, device="cuda")
-        dist.broadcast(size, 0)
-        d_blob = torch.empty(int(size.item()), dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            d_blob.copy_(torch.from_numpy(blob))
-        dist.broadcast(d_blob, 0)
+        d_blob = multigpu.broadcast_blob(blob, dist, src=0, device=f"cuda:{local_rank}")
         torch.cuda.synchronize()
         cde.upload_layout_device(d_blob.data_ptr(), d_blob.numel(), epoch=1)
     else:

@@ -157,8 +157,13 @@ int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group);
  * the walk kernels). Takes effect immediately for the current layout. Results do not depend on it. */
 #define JG_PATH_AUTO 0
 #define JG_PATH_WALK 1
+/* JG_PATH_FUSED (experimental): where the grid kernels apply, ONE persistent kernel per batch runs both stages
+ * (every warp resolves its own survivors) and, for host batches of >= 128 Ki queries, follows the H2D copy front
+ * through an arrival counter instead of waiting for whole chunks. Same results; measured slower than the
+ * two-kernel sequence on B200 (the merged instruction footprint), so it is not the default. */
+#define JG_PATH_FUSED 2
 int jg_engine_set_detect_path(JgEngine* e, int path);
-/* 1 when the current layout is served by the grid kernels, 0 when by the quadtree-walk kernels. */
+/* 0: quadtree-walk kernels, 1: grid kernels, 2: fused grid kernel (JG_PATH_FUSED). */
 int jg_engine_detect_path(const JgEngine* e);
 
 /* Memory helpers (pinned host / device) so callers can keep the C ABI free of CUDA headers. */

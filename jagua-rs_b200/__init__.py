@@ -501,12 +501,13 @@ class CDEngine:
     def set_groups(self, detect_group: int = 0, collect_group: int = 0):
         self._chk(self._lib.jg_engine_set_groups(self._eng, int(detect_group), int(collect_group)))
 
-    def set_detect_path(self, walk: bool):
-        """JG_PATH_WALK keeps the quadtree-walk kernels even where the grid kernels apply (same results)."""
-        self._chk(self._lib.jg_engine_set_detect_path(self._eng, 1 if walk else 0))
+    def set_detect_path(self, walk: bool = False, fused: bool = False):
+        """JG_PATH_WALK keeps the quadtree-walk kernels even where the grid kernels apply; JG_PATH_FUSED selects
+        the experimental single-kernel, copy-following form of the grid path. Same results in every case."""
+        self._chk(self._lib.jg_engine_set_detect_path(self._eng, 1 if walk else (2 if fused else 0)))
 
     def detect_path(self) -> str:
-        return "grid" if self._lib.jg_engine_detect_path(self._eng) else "walk"
+        return ("walk", "grid", "fused")[self._lib.jg_engine_detect_path(self._eng)]
 
     def fp32_nofma_peak(self):
         g, ms = C.c_double(0), C.c_float(0)

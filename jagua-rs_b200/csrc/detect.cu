@@ -616,8 +616,8 @@ k_s2_poly(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_
 namespace jg {
 
 // ---------------------------------------------------------------------------------------------------
-static int g_occ[8];
-static size_t g_occ_smem[8];
+static int g_occ[12];
+static size_t g_occ_smem[12];
 template <class K>
 static int persistent_grid(K kernel, int slot, int n_sms, size_t smem) {
     if (g_occ[slot] == 0 || g_occ_smem[slot] != smem) {
@@ -708,6 +708,30 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
                                                                         plan.gbits, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
     }
     if (n_launches) *n_launches += 2;
+    return cudaGetLastError();
+}
+
+bool detect_fused_applicable(const DetectPlan& plan, const SegTable& tab, int mode) {
+    if (!plan.use_grid || (mode & JG_MODE_POLY_ONLY)) return false;
+    for (int k = 0; k < tab.n_seg; k++)
+        if (tab.seg[k].n_piers != 0) return false;
+    return true;
+}
+
+cudaError_t launch_detect_fused(const DevLayout& L, const SegTable& tab, const XfSrc& d_xf, const uint32_t* d_filt,
+                                const uint8_t* d_kinds, uint8_t* d_out, const DetectScratch& sc, int n_sms, int avail_all,
+                                cudaStream_t st, int* n_launches) {
+    const GridDev* gd = grid_of(d_kinds, L.n_nodes);
+    const size_t smem = ((sizeof(SegTable) + 15) & ~(size_t)15) + ((sizeof(GridDev) + 15) & ~(size_t)15) + S_WARPS * GF_WARP_BYTES;
+    const int want = (tab.n_queries + S_THREADS - 1) / S_THREADS;
+    if (d_filt) {
+        const int g = persistent_grid(k_detect_fused<true>, 8, n_sms, smem);
+        k_detect_fused<true><<<want < g ? want : g, S_THREADS, smem, st>>>(L, tab, gd, d_kinds, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry, avail_all);
+    } else {
+        const int g = persistent_grid(k_detect_fused<false>, 9, n_sms, smem);
+        k_detect_fused<false><<<want < g ? want : g, S_THREADS, smem, st>>>(L, tab, gd, d_kinds, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry, avail_all);
+    }
+    if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
 

@@ -213,7 +213,9 @@ __device__ __forceinline__ bool circ_touches_entire(const GridDev& g, const Circ
 
 #define G1_PAIR_CAP 192  // leaf pairs waiting per warp: drained below 32 before every push round of <= 4 per lane
 #define G1_PUSH 4
-#define G1_WARP_BYTES (32 * sizeof(float4) + (G1_PAIR_CAP + 64 + 4) * sizeof(uint32_t))
+#define G1_SURV_CAP 40  // local survivors: fewer than 8 left over + up to 32 new ones
+#define G1_WARP_BYTES (32 * sizeof(float4) + (G1_PAIR_CAP + 64 + 4 + G1_SURV_CAP) * sizeof(uint32_t))
+#define GF_WARP_BYTES (G1_WARP_BYTES + ((sizeof(G2Slots) + 15) & ~(size_t)15))
 
 // ---------------------------------------------------------------------------------------------------
 // stage 1 on the grid: surrogate poles. Lane = query.
@@ -238,6 +240,185 @@ __device__ __forceinline__ PoleWin pole_window(const GridDev& g, const Circ& c) 
     return w;
 }
 
+// what every warp-level routine of the grid kernels needs
+struct GCtx {
+    const DevLayout& L;
+    const SegTable& tab;
+    const GridDev& g;
+    const XfSrc& xforms;
+    const uint32_t* filt;
+    const uint8_t* g_kinds;
+    uint8_t* out;
+    DetectCtl* ctl;
+    int* sv_entry;
+};
+struct G1Warp {  // stage-1 state of a warp (shared memory + two counters)
+    float4* s_circ;    // phase B: the current pole of each lane's query
+    uint32_t* s_pair;  // (query lane, leaf cell) pairs waiting for their edge tests
+    int* s_pend;       // queries waiting for phase B
+    unsigned* s_hit;
+    int* s_cnt;
+    int* s_surv;       // fused kernel: this warp's survivors waiting for stage 2
+    int n_pend, seg_hint, n_sv;
+    __device__ __forceinline__ void bind(unsigned char* wp) {
+        s_circ = (float4*)wp;
+        s_pair = (uint32_t*)(wp + 32 * sizeof(float4));
+        s_pend = (int*)(s_pair + G1_PAIR_CAP);
+        s_hit = (unsigned*)(s_pend + 64);
+        s_cnt = (int*)(s_hit + 1);
+        s_surv = s_cnt + 3;
+        n_pend = 0, seg_hint = 0, n_sv = 0;
+    }
+};
+
+// phase A on the 32 queries starting at `base` (base < n_queries)
+template <bool FILT>
+__device__ __forceinline__ void g1_phase_a(const GCtx& c, G1Warp& w, int base, int lane) {
+    const int q = base + lane;
+    const bool valid = q < c.tab.n_queries;
+    bool hit = false;
+    // batches are claimed in increasing order: the segment of `base` is at or after the last one seen
+    while (w.seg_hint + 1 < c.tab.n_seg && base >= c.tab.seg[w.seg_hint + 1].begin) w.seg_hint++;
+    int k = w.seg_hint;
+    if (valid) {
+        while (k + 1 < c.tab.n_seg && q >= c.tab.seg[k + 1].begin) k++;
+        const SegDesc& sd = c.tab.seg[k];
+        const float4 t4 = load_xf(c.xforms, sd, q);
+        const Xf xf{t4.x, t4.y, t4.z, t4.w};
+        for (int j = 0; j < sd.n_poles && !hit; j++) {  // circle.rs:79-85: centre transformed, radius unchanged
+            const float4 pl = __ldg(&sd.poles[j]);
+            Circ cc;
+            xf_point(xf, pl.x, pl.y, cc.cx, cc.cy);
+            cc.r = pl.z;
+            const PoleWin pw = pole_window(c.g, cc);
+            hit = circ_touches_entire(c.g, cc, pw.i0, pw.i1, pw.j0, pw.j1);
+        }
+        if (hit) c.out[q] = (uint8_t)JG_VERDICT_SURROGATE;
+    }
+    const unsigned um = __ballot_sync(FULL, valid && !hit);
+    if (valid && !hit) w.s_pend[w.n_pend + __popc(um & lanemask_lt())] = sv_pack(q, k);
+    w.n_pend += __popc(um);
+    __syncwarp();
+}
+
+// phase B on up to 32 queued queries; survivors go to the survivor list (FUSED: published in order)
+template <bool FILT, bool FUSED>
+__device__ __forceinline__ void g1_phase_b(const GCtx& c, G1Warp& w, int lane) {
+    const int take = w.n_pend < 32 ? w.n_pend : 32;
+    w.n_pend -= take;
+    const bool valid = lane < take;
+    const int qk = valid ? w.s_pend[w.n_pend + lane] : 0;
+    const int q = qk & 0x3FFFFFF, k = (int)((unsigned)qk >> 26);
+    Xf xf{1.0f, 0.0f, 0.0f, 0.0f};
+    int n_poles = 0;
+    if (valid) {
+        const float4 t4 = load_xf(c.xforms, c.tab.seg[k], q);
+        xf = Xf{t4.x, t4.y, t4.z, t4.w};
+        n_poles = c.tab.seg[k].n_poles;
+    }
+    bool hit = false;
+    const int max_poles = __reduce_max_sync(FULL, n_poles);
+#ifdef G1_SKIP_B
+    const int max_poles_dbg = 0;
+#else
+    const int max_poles_dbg = max_poles;
+#endif
+    for (int j = 0; j < max_poles_dbg; j++) {  // cd_engine.rs:210-215: any colliding pole decides
+        bool act = valid && !hit && j < n_poles;
+        if (!__any_sync(FULL, act)) break;
+        Circ cc{0.0f, 0.0f, 0.0f};
+        PoleWin pw{0, -1, 0, -1};
+        if (act) {
+            const float4 pl = __ldg(&c.tab.seg[k].poles[j]);
+            xf_point(xf, pl.x, pl.y, cc.cx, cc.cy);
+            cc.r = pl.z;
+            w.s_circ[lane] = make_float4(cc.cx, cc.cy, cc.r, 0.0f);
+            pw = pole_window(c.g, cc);
+            act = pw.j1 >= pw.j0 && pw.i1 >= pw.i0;
+        }
+        if (!__any_sync(FULL, act)) continue;
+        if (lane == 0) *w.s_hit = 0u, *w.s_cnt = 0;
+        __syncwarp();
+        const uint32_t cm = col_mask(pw.i0, pw.i1);
+        const float r2 = cc.r * cc.r;
+        int row = pw.j0;
+        uint32_t bits = 0u;
+        float dy2 = 0.0f;
+        bool more = act;
+        if (more) {
+            bits = c.g.leaf_rows[row] & cm;
+            const float ny = fmaxf(c.g.ys[row], fminf(cc.cy, c.g.ys[row + 1]));
+            dy2 = (ny - cc.cy) * (ny - cc.cy);
+        }
+        for (;;) {
+            if (more) {  // generation round: up to G1_PUSH cells per lane
+                int pushed = 0;
+                uint32_t mine[G1_PUSH];
+                while (pushed < G1_PUSH) {
+                    if (!bits) {
+                        if (row >= pw.j1) { more = false; break; }
+                        row++;
+                        bits = c.g.leaf_rows[row] & cm;
+                        const float ny = fmaxf(c.g.ys[row], fminf(cc.cy, c.g.ys[row + 1]));
+                        dy2 = (ny - cc.cy) * (ny - cc.cy);
+                        continue;
+                    }
+                    const int i = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const float nx = fmaxf(c.g.xs[i], fminf(cc.cx, c.g.xs[i + 1]));
+                    if ((nx - cc.cx) * (nx - cc.cx) + dy2 <= r2) mine[pushed++] = ((uint32_t)(row * GRID_G + i) << 5) | (uint32_t)lane;
+                }
+                if (pushed) {
+                    const int o = atomicAdd(w.s_cnt, pushed);
+#pragma unroll
+                    for (int u = 0; u < G1_PUSH; u++)
+                        if (u < pushed) w.s_pair[o + u] = mine[u];
+                }
+            }
+            __syncwarp();
+            const bool any_more = __any_sync(FULL, more);
+            int cnt = *(volatile int*)w.s_cnt;
+            __syncwarp();
+            while (cnt >= 32 || (!any_more && cnt > 0)) {  // drain
+                const int tk = cnt < 32 ? cnt : 32;
+                cnt -= tk;
+                bool lanehit = false;
+                int ol = 0;
+                if (lane < tk) {
+                    const uint32_t pr = w.s_pair[cnt + lane];
+                    ol = pr & 31;
+                    if (!((*(volatile unsigned*)w.s_hit >> ol) & 1u)) {
+                        const float4 e4 = w.s_circ[ol];
+                        lanehit = leaf_cell_collides<Circ, FILT>(c.L, c.g.cell_leaf[pr >> 5], Circ{e4.x, e4.y, e4.z}, c.filt);
+                    }
+                }
+                if (lanehit) atomicOr(w.s_hit, 1u << ol);
+                __syncwarp();
+            }
+            if (lane == 0) *w.s_cnt = cnt;
+            __syncwarp();
+            if ((*(volatile unsigned*)w.s_hit >> lane) & 1u) hit = true, more = false;
+            if (!any_more) break;
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+    if (valid) c.out[q] = hit ? (uint8_t)JG_VERDICT_SURROGATE : (uint8_t)0;
+    const unsigned sm = __ballot_sync(FULL, valid && !hit);
+    if (sm) {
+        if (FUSED) {  // the warp resolves its own survivors (k_detect_fused)
+            if (valid && !hit) w.s_surv[w.n_sv + __popc(sm & lanemask_lt())] = sv_pack(q, k);
+            w.n_sv += __popc(sm);
+        } else {
+            int sb = 0;
+            if (lane == 0) sb = atomicAdd(&c.ctl->n_surv, __popc(sm));
+            sb = __shfl_sync(FULL, sb, 0);
+            if (valid && !hit) c.sv_entry[sb + __popc(sm & lanemask_lt())] = sv_pack(q, k);
+        }
+    }
+    __syncwarp();
+}
+
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
 k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
@@ -249,165 +430,23 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
     unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
     const GridDev& g = *stage_grid(p, ggrid);
     __syncthreads();
-    const SegTable& tab = *t;
+    const GCtx c{L, *t, g, xforms, filt, nullptr, out, ctl, sv_entry};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* wp = p + (size_t)warp * G1_WARP_BYTES;
-    float4* s_circ = (float4*)wp;  // phase B: the current pole of each lane's query
-    uint32_t* s_pair = (uint32_t*)(wp + 32 * sizeof(float4));
-    int* s_pend = (int*)(s_pair + G1_PAIR_CAP);  // queries waiting for phase B
-    unsigned* s_hit = (unsigned*)(s_pend + 64);
-    int* s_cnt = (int*)(s_hit + 1);
-    const int n = tab.n_queries;
-    int n_pend = 0, seg_hint = 0;
+    G1Warp w;
+    w.bind(p + (size_t)warp * G1_WARP_BYTES);
+    const int n = c.tab.n_queries;
     bool feeding = true;
-
     for (;;) {
-        if (feeding && n_pend < 32) {
-            // ---- phase A on the next 32 queries
+        if (feeding && w.n_pend < 32) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&ctl->s1_next, 32);
             base = __shfl_sync(FULL, base, 0);
-            if (base >= n) {
-                feeding = false;
-                continue;
-            }
-            const int q = base + lane;
-            const bool valid = q < n;
-            bool hit = false;
-            // batches are claimed in increasing order: the segment of `base` is at or after the last one seen
-            while (seg_hint + 1 < tab.n_seg && base >= tab.seg[seg_hint + 1].begin) seg_hint++;
-            int k = seg_hint;
-            if (valid) {
-                while (k + 1 < tab.n_seg && q >= tab.seg[k + 1].begin) k++;
-                const SegDesc& sd = tab.seg[k];
-                const float4 t4 = load_xf(xforms, sd, q);
-                const Xf xf{t4.x, t4.y, t4.z, t4.w};
-                for (int j = 0; j < sd.n_poles && !hit; j++) {  // circle.rs:79-85: centre transformed, radius unchanged
-                    const float4 pl = __ldg(&sd.poles[j]);
-                    Circ c;
-                    xf_point(xf, pl.x, pl.y, c.cx, c.cy);
-                    c.r = pl.z;
-                    const PoleWin w = pole_window(g, c);
-                    hit = circ_touches_entire(g, c, w.i0, w.i1, w.j0, w.j1);
-                }
-                if (hit) out[q] = (uint8_t)JG_VERDICT_SURROGATE;
-            }
-            const unsigned um = __ballot_sync(FULL, valid && !hit);
-            if (valid && !hit) s_pend[n_pend + __popc(um & lanemask_lt())] = sv_pack(q, k);
-            n_pend += __popc(um);
-            __syncwarp();
+            if (base >= n) feeding = false;
+            else g1_phase_a<FILT>(c, w, base, lane);
             continue;
         }
-        if (n_pend == 0) break;
-        // ---- phase B on up to 32 queued queries
-        const int take = n_pend < 32 ? n_pend : 32;
-        n_pend -= take;
-        const bool valid = lane < take;
-        const int qk = valid ? s_pend[n_pend + lane] : 0;
-        const int q = qk & 0x3FFFFFF, k = (int)((unsigned)qk >> 26);
-        Xf xf{1.0f, 0.0f, 0.0f, 0.0f};
-        int n_poles = 0;
-        if (valid) {
-            const float4 t4 = load_xf(xforms, tab.seg[k], q);
-            xf = Xf{t4.x, t4.y, t4.z, t4.w};
-            n_poles = tab.seg[k].n_poles;
-        }
-        bool hit = false;
-        const int max_poles = __reduce_max_sync(FULL, n_poles);
-#ifdef G1_SKIP_B
-        const int max_poles_dbg = 0;
-#else
-        const int max_poles_dbg = max_poles;
-#endif
-        for (int j = 0; j < max_poles_dbg; j++) {  // cd_engine.rs:210-215: any colliding pole decides
-            bool act = valid && !hit && j < n_poles;
-            if (!__any_sync(FULL, act)) break;
-            Circ c{0.0f, 0.0f, 0.0f};
-            PoleWin w{0, -1, 0, -1};
-            if (act) {
-                const float4 pl = __ldg(&tab.seg[k].poles[j]);
-                xf_point(xf, pl.x, pl.y, c.cx, c.cy);
-                c.r = pl.z;
-                s_circ[lane] = make_float4(c.cx, c.cy, c.r, 0.0f);
-                w = pole_window(g, c);
-                act = w.j1 >= w.j0 && w.i1 >= w.i0;
-            }
-            if (!__any_sync(FULL, act)) continue;
-            if (lane == 0) *s_hit = 0u, *s_cnt = 0;
-            __syncwarp();
-            const uint32_t cm = col_mask(w.i0, w.i1);
-            const float r2 = c.r * c.r;
-            int row = w.j0;
-            uint32_t bits = 0u;
-            float dy2 = 0.0f;
-            bool more = act;
-            if (more) {
-                bits = g.leaf_rows[row] & cm;
-                const float ny = fmaxf(g.ys[row], fminf(c.cy, g.ys[row + 1]));
-                dy2 = (ny - c.cy) * (ny - c.cy);
-            }
-            for (;;) {
-                if (more) {  // generation round: up to G1_PUSH cells per lane
-                    int pushed = 0;
-                    uint32_t mine[G1_PUSH];
-                    while (pushed < G1_PUSH) {
-                        if (!bits) {
-                            if (row >= w.j1) { more = false; break; }
-                            row++;
-                            bits = g.leaf_rows[row] & cm;
-                            const float ny = fmaxf(g.ys[row], fminf(c.cy, g.ys[row + 1]));
-                            dy2 = (ny - c.cy) * (ny - c.cy);
-                            continue;
-                        }
-                        const int i = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const float nx = fmaxf(g.xs[i], fminf(c.cx, g.xs[i + 1]));
-                        if ((nx - c.cx) * (nx - c.cx) + dy2 <= r2) mine[pushed++] = ((uint32_t)(row * GRID_G + i) << 5) | (uint32_t)lane;
-                    }
-                    if (pushed) {
-                        const int o = atomicAdd(s_cnt, pushed);
-#pragma unroll
-                        for (int u = 0; u < G1_PUSH; u++)
-                            if (u < pushed) s_pair[o + u] = mine[u];
-                    }
-                }
-                __syncwarp();
-                const bool any_more = __any_sync(FULL, more);
-                int cnt = *(volatile int*)s_cnt;
-                __syncwarp();
-                while (cnt >= 32 || (!any_more && cnt > 0)) {  // drain
-                    const int tk = cnt < 32 ? cnt : 32;
-                    cnt -= tk;
-                    bool lanehit = false;
-                    int ol = 0;
-                    if (lane < tk) {
-                        const uint32_t pr = s_pair[cnt + lane];
-                        ol = pr & 31;
-                        if (!((*(volatile unsigned*)s_hit >> ol) & 1u)) {
-                            const float4 e4 = s_circ[ol];
-                            lanehit = leaf_cell_collides<Circ, FILT>(L, g.cell_leaf[pr >> 5], Circ{e4.x, e4.y, e4.z}, filt);
-                        }
-                    }
-                    if (lanehit) atomicOr(s_hit, 1u << ol);
-                    __syncwarp();
-                }
-                if (lane == 0) *s_cnt = cnt;
-                __syncwarp();
-                if ((*(volatile unsigned*)s_hit >> lane) & 1u) hit = true, more = false;
-                if (!any_more) break;
-                __syncwarp();
-            }
-            __syncwarp();
-        }
-        if (valid) out[q] = hit ? (uint8_t)JG_VERDICT_SURROGATE : (uint8_t)0;
-        const unsigned sm = __ballot_sync(FULL, valid && !hit);
-        if (sm) {
-            int sb = 0;
-            if (lane == 0) sb = atomicAdd(&ctl->n_surv, __popc(sm));
-            sb = __shfl_sync(FULL, sb, 0);
-            if (valid && !hit) sv_entry[sb + __popc(sm & lanemask_lt())] = sv_pack(q, k);
-        }
-        __syncwarp();
+        if (w.n_pend == 0) break;
+        g1_phase_b<FILT, false>(c, w, lane);
     }
 }
 
@@ -531,18 +570,247 @@ __device__ __forceinline__ bool path_reaches(const GridDev& g, const Seg& sg, in
     return true;
 }
 
+// one group of `ng` survivors (ents[0 .. ng): survivor-list entries in global memory, or in the warp's own shared
+// memory when LOCAL) resolved by a warp; GS = slots in use (>= ng)
+template <bool FILT, bool LOCAL>
+__device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* ents, int ng, int GS, int lane) {
+    const int D = c.g.D, G = c.g.G;
+    if (lane < ng) {
+        const int ent = LOCAL ? ents[lane] : __ldcg(&ents[lane]);
+        const int q = ent & 0x3FFFFFF;
+        W.q[lane] = q;
+        W.seg[lane] = (int)((unsigned)ent >> 26);
+        W.xf[lane] = load_xf(c.xforms, c.tab.seg[(unsigned)ent >> 26], q);
+    }
+    __syncwarp();
+    // SPolygon::transform_from + generate_bounding_box (simple_polygon.rs:226-253, 122-133): min/max folds are
+    // exact in any order. Four lanes per survivor (quad = survivor) for ordinary items, the whole warp per
+    // survivor for long vertex lists.
+    const int qs = lane >> 2, sub = lane & 3;
+    int nv_mine = 0;
+    if (qs < ng) nv_mine = c.tab.seg[W.seg[qs]].n_verts;
+    if (__reduce_max_sync(FULL, nv_mine) <= 128) {
+        float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
+        if (qs < ng) {
+            const SegDesc& sd = c.tab.seg[W.seg[qs]];
+            const float4 t4 = W.xf[qs];
+            const Xf xf{t4.x, t4.y, t4.z, t4.w};
+            for (int j = sub; j < nv_mine; j += 4) {
+                const float2 v = __ldg(&sd.verts[j]);
+                float x, y;
+                xf_point(xf, v.x, v.y, x, y);
+                x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
+            }
+        }
+#pragma unroll
+        for (int o = 2; o > 0; o >>= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o));
+            y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o));
+            x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
+            y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
+        }
+        if (qs < ng && sub == 0) W.bb[qs] = make_float4(x0, y0, x1, y1);
+    } else {
+        for (int s = 0; s < ng; s++) {
+            const SegDesc& sd = c.tab.seg[W.seg[s]];
+            const float4 t4 = W.xf[s];
+            const Xf xf{t4.x, t4.y, t4.z, t4.w};
+            float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
+            for (int j = lane; j < sd.n_verts; j += 32) {
+                const float2 v = __ldg(&sd.verts[j]);
+                float x, y;
+                xf_point(xf, v.x, v.y, x, y);
+                x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o));
+                y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o));
+                x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
+                y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
+            }
+            if (lane == 0) W.bb[s] = make_float4(x0, y0, x1, y1);
+        }
+    }
+    __syncwarp();
+    // cd_engine.rs:161-163 + get_virtual_root (cd_engine.rs:314-327): quad = survivor, lane = child quadrant
+    // (NE, NW, SW, SE), so "the first child that surrounds the bbox" is the lowest set bit of the quad's ballot
+    {
+        Rect bb{0.0f, 0.0f, 0.0f, 0.0f};
+        bool walking = false;
+        if (qs < ng) {
+            const float4 b4 = W.bb[qs];
+            bb = Rect{b4.x, b4.y, b4.z, b4.w};
+            walking = rect_relation(c.L.cde_bbox, bb) == REL_SURROUNDING;
+        }
+        const bool inside = walking;
+        int level = 0, ci = 0, cj = 0, vnode = 0;
+        for (;;) {
+            bool sur = false;
+            const int nl = level + 1, sh = D - nl, w = 1 << nl, base = mip_off(nl);
+            if (walking && level < D && c.g.mip_node[base + (2 * cj) * w + 2 * ci] != 0xFFFF) {
+                const int xi = 2 * ci + ((sub == 0 || sub == 3) ? 1 : 0), yj = 2 * cj + ((sub == 0 || sub == 1) ? 1 : 0);
+                const Rect cb{c.g.xs[xi << sh], c.g.ys[yj << sh], c.g.xs[(xi + 1) << sh], c.g.ys[(yj + 1) << sh]};
+                sur = rect_relation(cb, bb) == REL_SURROUNDING;
+            }
+            const unsigned all = __ballot_sync(FULL, sur);
+            if (!all) break;
+            const unsigned mine = (all >> (qs * 4)) & 0xFu;
+            if (mine) {
+                const int found = __ffs(mine) - 1;
+                ci = 2 * ci + ((found == 0 || found == 3) ? 1 : 0);
+                cj = 2 * cj + ((found == 0 || found == 1) ? 1 : 0);
+                level = nl;
+                vnode = c.g.mip_node[base + cj * w + ci];
+            } else {
+                walking = false;
+            }
+        }
+        if (qs < ng && sub == 0) {
+            int v = -1, ne = 0;
+            if (!inside) {
+                v = JG_VERDICT_POLY;
+            } else {
+                const int vk = __ldg(&c.g_kinds[vnode + 3]);
+                W.vnode[qs] = vnode;
+                W.vcell[qs] = (level << 16) | (cj << 8) | ci;
+                if (vk == KIND_ENTIRE) v = JG_VERDICT_POLY;  // every edge sees it (qt_node.rs:108)
+                else if (vk != KIND_NONE) ne = c.tab.seg[W.seg[qs]].n_verts;
+            }
+            W.q_verdict[qs] = v;
+            W.q_ne[qs] = ne;
+        }
+    }
+    __syncwarp();
+    int verdict = -1, nE = 0;
+    if (lane < ng) verdict = W.q_verdict[lane], nE = W.q_ne[lane];
+    int incl = nE;
+#pragma unroll
+    for (int o = 1; o < S2_MAX_GROUP; o <<= 1) {
+        const int tt = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += tt;
+    }
+    const int E = __shfl_sync(FULL, incl, S2_MAX_GROUP - 1);
+    if (lane < S2_MAX_GROUP) W.ebeg[lane + 1] = incl;
+    if (lane == 0) {
+        W.ebeg[0] = 0;
+        W.hit = 0u;
+    }
+    const unsigned need = __ballot_sync(FULL, nE > 0);
+    __syncwarp();
+
+    for (int f0 = 0; f0 < E; f0 += 32) {
+        const unsigned hm0 = *(volatile unsigned*)&W.hit;
+        if ((hm0 & need) == need) break;  // every survivor with edges already has a colliding one
+        const int f = f0 + lane;
+        int slot = 0;
+        bool scanning = false;
+        Seg sg{0.0f, 0.0f, 0.0f, 0.0f};
+        int l0 = 0, j = 0, j1 = -1;
+        uint32_t cm = 0u, bits = 0u, er = 0u;
+        if (f < E) {
+            for (int jj = 1; jj < GS; jj++) slot += (W.ebeg[jj] <= f) ? 1 : 0;
+            if (!((hm0 >> slot) & 1u)) {
+                const float4 t4 = W.xf[slot];
+                sg = item_edge(c.tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, f - W.ebeg[slot]);
+                const int vc = W.vcell[slot];
+                l0 = vc >> 16;
+                const int s0 = D - l0;
+                // candidate cells: the edge's bbox inflated by delta, clipped to the virtual root's cells
+                int i0 = cell_lo(c.g.xs, G, fminf(sg.sx, sg.ex) - c.g.delta, c.g.x0, c.g.inv_cw);
+                int i1 = cell_hi(c.g.xs, G, fmaxf(sg.sx, sg.ex) + c.g.delta, c.g.x0, c.g.inv_cw);
+                j = cell_lo(c.g.ys, G, fminf(sg.sy, sg.ey) - c.g.delta, c.g.y0, c.g.inv_ch);
+                j1 = cell_hi(c.g.ys, G, fmaxf(sg.sy, sg.ey) + c.g.delta, c.g.y0, c.g.inv_ch);
+                const int vi0 = (vc & 255) << s0, vj0 = ((vc >> 8) & 255) << s0;
+                i0 = max(i0, vi0), i1 = min(i1, vi0 + (1 << s0) - 1);
+                j = max(j, vj0), j1 = min(j1, vj0 + (1 << s0) - 1);
+                cm = col_mask(i0, i1);
+                scanning = j <= j1 && cm != 0u;
+                if (scanning) {
+                    er = c.g.ent_rows[j] & cm;
+                    bits = er | (c.g.leaf_rows[j] & cm);
+                }
+            }
+        }
+        // rounds: every lane scans on to its next would-be hit (an Entire cell, or a leaf cell whose edge
+        // tests succeed), then the lanes that found one verify together that the reference reaches it
+        for (;;) {
+            int hi = -1;
+            while (scanning) {
+                if (!bits) {
+                    if (j >= j1) { scanning = false; break; }
+                    j++;
+                    er = c.g.ent_rows[j] & cm;
+                    bits = er | (c.g.leaf_rows[j] & cm);
+                    continue;
+                }
+                const int i = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (((er >> i) & 1u) || leaf_cell_collides<Seg, FILT>(c.L, c.g.cell_leaf[j * GRID_G + i], sg, c.filt)) { hi = i; break; }
+            }
+            if (!__any_sync(FULL, hi >= 0)) break;
+            bool lanehit = false;
+            if (hi >= 0) {
+                // a finest cell that holds an endpoint is flagged at every level (qt_traits.rs:36-44: not range-
+                // rejected, `contains` true, and half_intersect only ever adds quadrants)
+                const Rect cb{c.g.xs[hi], c.g.ys[j], c.g.xs[hi + 1], c.g.ys[j + 1]};
+                lanehit = rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) ||
+                          path_reaches(c.g, sg, l0, c.g.cell_level[j * GRID_G + hi], hi, j);
+            }
+            if (lanehit) atomicOr(&W.hit, 1u << slot);
+            __syncwarp();
+            if ((*(volatile unsigned*)&W.hit >> slot) & 1u) scanning = false;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    const unsigned hm = *(volatile unsigned*)&W.hit;
+    // cd_engine.rs:174-193: survivors without an edge hit -> `unreachable!` or containment tests
+    for (int s = 0; s < ng; s++) {
+        if (__shfl_sync(FULL, verdict, s) >= 0) continue;
+        int v = 0;
+        if ((hm >> s) & 1u) {
+            v = JG_VERDICT_POLY;
+        } else {
+            const int4 m = __ldg(&c.L.node_meta[W.vnode[s]]);
+            const int n_entire = m.z & 0xFFFF, n_partial = (m.z >> 16) & 0xFFFF;
+            if (n_entire > 0) {
+                v = JG_VERDICT_REF_PANIC;  // cd_engine.rs:179, reachable only under a filter
+            } else {
+                const SegDesc& sd = c.tab.seg[W.seg[s]];
+                const float4 t4 = W.xf[s], b4 = W.bb[s];
+                bool col = false;
+                for (int j0 = 0; j0 < n_partial && !col; j0 += 32) {
+                    const int j = j0 + lane;
+                    int hs = -1;
+                    if (j < n_partial) {
+                        hs = __ldg(&c.L.entry_meta[m.y + j]).x;
+                        if (FILT && filt_bit(c.filt, hs)) hs = -1;
+                    }
+                    col = containment_collision_warp(c.L, sd.verts, sd.n_verts, sd.poi_x, sd.poi_y, Xf{t4.x, t4.y, t4.z, t4.w},
+                                                   Rect{b4.x, b4.y, b4.z, b4.w}, hs, lane);
+                }
+                if (__any_sync(FULL, col)) v = JG_VERDICT_POLY;
+            }
+        }
+        if (lane == s) verdict = v;
+    }
+    if (lane < ng) c.out[W.q[lane]] = (uint8_t)verdict;
+    __syncwarp();
+}
+
 template <bool FILT>
 __global__ void __launch_bounds__(S_THREADS)
 k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
           const uint8_t* __restrict__ g_kinds, const XfSrc xforms, const uint32_t* __restrict__ filt,
-          uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, const int* __restrict__ sv_entry) {
+          uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
     extern __shared__ __align__(16) unsigned char smem[];
     SegTable* t = (SegTable*)smem;
     for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
     unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
     const GridDev& g = *stage_grid(p, ggrid);
     __syncthreads();
-    const SegTable& tab = *t;
+    const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     G2Slots& W = *(G2Slots*)(p + (size_t)warp * sizeof(G2Slots));
     const int total = ctl->n_surv;
@@ -550,236 +818,138 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
     // where the length of a warp's dependent chain, not the issue rate, sets the kernel's duration
     const int per_warp = total / (int)(gridDim.x * S_WARPS);
     const int GS = per_warp >= 16 ? 8 : per_warp >= 6 ? 4 : per_warp >= 2 ? 2 : 1;
-    const int D = g.D, G = g.G;
-
     for (;;) {
         int gbase = 0;
         if (lane == 0) gbase = atomicAdd(&ctl->s2_next, GS);
         gbase = __shfl_sync(FULL, gbase, 0);
         if (gbase >= total) break;
-        const int ng = (total - gbase) < GS ? (total - gbase) : GS;
-        if (lane < ng) {
-            const int ent = sv_entry[gbase + lane];
-            const int q = ent & 0x3FFFFFF;
-            W.q[lane] = q;
-            W.seg[lane] = (int)((unsigned)ent >> 26);
-            W.xf[lane] = load_xf(xforms, tab.seg[(unsigned)ent >> 26], q);
-        }
-        __syncwarp();
-        // SPolygon::transform_from + generate_bounding_box (simple_polygon.rs:226-253, 122-133): min/max folds are
-        // exact in any order. Four lanes per survivor (quad = survivor) for ordinary items, the whole warp per
-        // survivor for long vertex lists.
-        const int qs = lane >> 2, sub = lane & 3;
-        int nv_mine = 0;
-        if (qs < ng) nv_mine = tab.seg[W.seg[qs]].n_verts;
-        if (__reduce_max_sync(FULL, nv_mine) <= 128) {
-            float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
-            if (qs < ng) {
-                const SegDesc& sd = tab.seg[W.seg[qs]];
-                const float4 t4 = W.xf[qs];
-                const Xf xf{t4.x, t4.y, t4.z, t4.w};
-                for (int j = sub; j < nv_mine; j += 4) {
-                    const float2 v = __ldg(&sd.verts[j]);
-                    float x, y;
-                    xf_point(xf, v.x, v.y, x, y);
-                    x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
-                }
-            }
-#pragma unroll
-            for (int o = 2; o > 0; o >>= 1) {
-                x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o));
-                y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o));
-                x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
-                y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
-            }
-            if (qs < ng && sub == 0) W.bb[qs] = make_float4(x0, y0, x1, y1);
-        } else {
-            for (int s = 0; s < ng; s++) {
-                const SegDesc& sd = tab.seg[W.seg[s]];
-                const float4 t4 = W.xf[s];
-                const Xf xf{t4.x, t4.y, t4.z, t4.w};
-                float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
-                for (int j = lane; j < sd.n_verts; j += 32) {
-                    const float2 v = __ldg(&sd.verts[j]);
-                    float x, y;
-                    xf_point(xf, v.x, v.y, x, y);
-                    x0 = fminf(x0, x), y0 = fminf(y0, y), x1 = fmaxf(x1, x), y1 = fmaxf(y1, y);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o));
-                    y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o));
-                    x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
-                    y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
-                }
-                if (lane == 0) W.bb[s] = make_float4(x0, y0, x1, y1);
-            }
-        }
-        __syncwarp();
-        // cd_engine.rs:161-163 + get_virtual_root (cd_engine.rs:314-327): quad = survivor, lane = child quadrant
-        // (NE, NW, SW, SE), so "the first child that surrounds the bbox" is the lowest set bit of the quad's ballot
-        {
-            Rect bb{0.0f, 0.0f, 0.0f, 0.0f};
-            bool walking = false;
-            if (qs < ng) {
-                const float4 b4 = W.bb[qs];
-                bb = Rect{b4.x, b4.y, b4.z, b4.w};
-                walking = rect_relation(L.cde_bbox, bb) == REL_SURROUNDING;
-            }
-            const bool inside = walking;
-            int level = 0, ci = 0, cj = 0, vnode = 0;
-            for (;;) {
-                bool sur = false;
-                const int nl = level + 1, sh = D - nl, w = 1 << nl, base = mip_off(nl);
-                if (walking && level < D && g.mip_node[base + (2 * cj) * w + 2 * ci] != 0xFFFF) {
-                    const int xi = 2 * ci + ((sub == 0 || sub == 3) ? 1 : 0), yj = 2 * cj + ((sub == 0 || sub == 1) ? 1 : 0);
-                    const Rect cb{g.xs[xi << sh], g.ys[yj << sh], g.xs[(xi + 1) << sh], g.ys[(yj + 1) << sh]};
-                    sur = rect_relation(cb, bb) == REL_SURROUNDING;
-                }
-                const unsigned all = __ballot_sync(FULL, sur);
-                if (!all) break;
-                const unsigned mine = (all >> (qs * 4)) & 0xFu;
-                if (mine) {
-                    const int found = __ffs(mine) - 1;
-                    ci = 2 * ci + ((found == 0 || found == 3) ? 1 : 0);
-                    cj = 2 * cj + ((found == 0 || found == 1) ? 1 : 0);
-                    level = nl;
-                    vnode = g.mip_node[base + cj * w + ci];
-                } else {
-                    walking = false;
-                }
-            }
-            if (qs < ng && sub == 0) {
-                int v = -1, ne = 0;
-                if (!inside) {
-                    v = JG_VERDICT_POLY;
-                } else {
-                    const int vk = __ldg(&g_kinds[vnode + 3]);
-                    W.vnode[qs] = vnode;
-                    W.vcell[qs] = (level << 16) | (cj << 8) | ci;
-                    if (vk == KIND_ENTIRE) v = JG_VERDICT_POLY;  // every edge sees it (qt_node.rs:108)
-                    else if (vk != KIND_NONE) ne = tab.seg[W.seg[qs]].n_verts;
-                }
-                W.q_verdict[qs] = v;
-                W.q_ne[qs] = ne;
-            }
-        }
-        __syncwarp();
-        int verdict = -1, nE = 0;
-        if (lane < ng) verdict = W.q_verdict[lane], nE = W.q_ne[lane];
-        int incl = nE;
-#pragma unroll
-        for (int o = 1; o < S2_MAX_GROUP; o <<= 1) {
-            const int tt = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += tt;
-        }
-        const int E = __shfl_sync(FULL, incl, S2_MAX_GROUP - 1);
-        if (lane < S2_MAX_GROUP) W.ebeg[lane + 1] = incl;
-        if (lane == 0) {
-            W.ebeg[0] = 0;
-            W.hit = 0u;
-        }
-        const unsigned need = __ballot_sync(FULL, nE > 0);
-        __syncwarp();
+        g2_group<FILT, false>(c, W, sv_entry + gbase, (total - gbase) < GS ? (total - gbase) : GS, GS, lane);
+    }
+}
 
-        for (int f0 = 0; f0 < E; f0 += 32) {
-            const unsigned hm0 = *(volatile unsigned*)&W.hit;
-            if ((hm0 & need) == need) break;  // every survivor with edges already has a colliding one
-            const int f = f0 + lane;
-            int slot = 0;
-            bool scanning = false;
-            Seg sg{0.0f, 0.0f, 0.0f, 0.0f};
-            int l0 = 0, j = 0, j1 = -1;
-            uint32_t cm = 0u, bits = 0u, er = 0u;
-            if (f < E) {
-                for (int jj = 1; jj < GS; jj++) slot += (W.ebeg[jj] <= f) ? 1 : 0;
-                if (!((hm0 >> slot) & 1u)) {
-                    const float4 t4 = W.xf[slot];
-                    sg = item_edge(tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, f - W.ebeg[slot]);
-                    const int vc = W.vcell[slot];
-                    l0 = vc >> 16;
-                    const int s0 = D - l0;
-                    // candidate cells: the edge's bbox inflated by delta, clipped to the virtual root's cells
-                    int i0 = cell_lo(g.xs, G, fminf(sg.sx, sg.ex) - g.delta, g.x0, g.inv_cw);
-                    int i1 = cell_hi(g.xs, G, fmaxf(sg.sx, sg.ex) + g.delta, g.x0, g.inv_cw);
-                    j = cell_lo(g.ys, G, fminf(sg.sy, sg.ey) - g.delta, g.y0, g.inv_ch);
-                    j1 = cell_hi(g.ys, G, fmaxf(sg.sy, sg.ey) + g.delta, g.y0, g.inv_ch);
-                    const int vi0 = (vc & 255) << s0, vj0 = ((vc >> 8) & 255) << s0;
-                    i0 = max(i0, vi0), i1 = min(i1, vi0 + (1 << s0) - 1);
-                    j = max(j, vj0), j1 = min(j1, vj0 + (1 << s0) - 1);
-                    cm = col_mask(i0, i1);
-                    scanning = j <= j1 && cm != 0u;
-                    if (scanning) {
-                        er = g.ent_rows[j] & cm;
-                        bits = er | (g.leaf_rows[j] & cm);
-                    }
-                }
-            }
-            // rounds: every lane scans on to its next would-be hit (an Entire cell, or a leaf cell whose edge
-            // tests succeed), then the lanes that found one verify together that the reference reaches it
-            for (;;) {
-                int hi = -1;
-                while (scanning) {
-                    if (!bits) {
-                        if (j >= j1) { scanning = false; break; }
-                        j++;
-                        er = g.ent_rows[j] & cm;
-                        bits = er | (g.leaf_rows[j] & cm);
-                        continue;
-                    }
-                    const int i = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    if (((er >> i) & 1u) || leaf_cell_collides<Seg, FILT>(L, g.cell_leaf[j * GRID_G + i], sg, filt)) { hi = i; break; }
-                }
-                if (!__any_sync(FULL, hi >= 0)) break;
-                bool lanehit = false;
-                if (hi >= 0) {
-                    // a finest cell that holds an endpoint is flagged at every level (qt_traits.rs:36-44: not range-
-                    // rejected, `contains` true, and half_intersect only ever adds quadrants)
-                    const Rect cb{g.xs[hi], g.ys[j], g.xs[hi + 1], g.ys[j + 1]};
-                    lanehit = rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) ||
-                              path_reaches(g, sg, l0, g.cell_level[j * GRID_G + hi], hi, j);
-                }
-                if (lanehit) atomicOr(&W.hit, 1u << slot);
-                __syncwarp();
-                if ((*(volatile unsigned*)&W.hit >> slot) & 1u) scanning = false;
-            }
-            __syncwarp();
-        }
-        __syncwarp();
-        const unsigned hm = *(volatile unsigned*)&W.hit;
-        // cd_engine.rs:174-193: survivors without an edge hit -> `unreachable!` or containment tests
-        for (int s = 0; s < ng; s++) {
-            if (__shfl_sync(FULL, verdict, s) >= 0) continue;
-            int v = 0;
-            if ((hm >> s) & 1u) {
-                v = JG_VERDICT_POLY;
+// ---------------------------------------------------------------------------------------------------
+// fused, streaming form: ONE persistent kernel in which every warp alternates between the two stages.
+//   * stage-2 groups are taken first whenever 8 published survivors wait, so the polygon stage overlaps the
+//     surrogate stage instead of following it (no second launch, one ramp-up, one tail);
+//   * queries may still be in flight over PCIe: a warp processes its batch of 32 once ctl->avail covers it. The
+//     host batcher copies the batch in chunks and bumps `avail` after each chunk (a 4-byte copy ordered behind
+//     the chunk on the same stream), so compute follows the copy front. avail_all != 0: everything is resident.
+//   * every spin is bounded (JG_SPIN_LIMIT clock ticks without progress set ctl->error and the warp leaves), so a
+//     lost copy cannot hang the device.
+// ---------------------------------------------------------------------------------------------------
+#define JG_SPIN_LIMIT (4000000000ll)  // ~2 s at 1.9 GHz
+template <bool FILT>
+__global__ void __launch_bounds__(S_THREADS)
+k_detect_fused(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
+               const uint8_t* __restrict__ g_kinds, const XfSrc xforms, const uint32_t* __restrict__ filt,
+               uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry, int avail_all) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SegTable* t = (SegTable*)smem;
+    for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
+    unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
+    const GridDev& g = *stage_grid(p, ggrid);
+    __syncthreads();
+    const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wp = p + (size_t)warp * GF_WARP_BYTES;
+    G1Warp w;
+    w.bind(wp);
+    G2Slots& W = *(G2Slots*)(wp + G1_WARP_BYTES);
+    const int n = c.tab.n_queries, n_warps = gridDim.x * S_WARPS;
+    const int GS = S2_MAX_GROUP;
+    // One call site per routine (each is several thousand instructions): the loop is a small state machine.
+    //   MAIN      stage-1 batches as their queries arrive; the warp's own survivors 8 at a time
+    //   BARRIER   leftovers (< 8 per warp) handed to the global list; wait until every warp has done so
+    //   LEFTOVER  the global leftovers in full groups again
+    enum { MAIN = 0, BARRIER = 1, LEFTOVER = 2 };
+    int phase = MAIN, total = 0, base = 0;
+    bool s1_open = true, have_batch = false;
+    long long idle_since = -1;
+    for (;;) {
+        int grp_off = -1, grp_n = 0;
+        bool run_b = false, run_a = false, idle = false;
+        if (phase == MAIN) {
+            if (w.n_sv >= GS) {
+                w.n_sv -= GS;
+                grp_off = w.n_sv, grp_n = GS;
+            } else if (w.n_pend >= 32) {
+                run_b = true;
             } else {
-                const int4 m = __ldg(&L.node_meta[W.vnode[s]]);
-                const int n_entire = m.z & 0xFFFF, n_partial = (m.z >> 16) & 0xFFFF;
-                if (n_entire > 0) {
-                    v = JG_VERDICT_REF_PANIC;  // cd_engine.rs:179, reachable only under a filter
-                } else {
-                    const SegDesc& sd = tab.seg[W.seg[s]];
-                    const float4 t4 = W.xf[s], b4 = W.bb[s];
-                    bool c = false;
-                    for (int j0 = 0; j0 < n_partial && !c; j0 += 32) {
-                        const int j = j0 + lane;
-                        int hs = -1;
-                        if (j < n_partial) {
-                            hs = __ldg(&L.entry_meta[m.y + j]).x;
-                            if (FILT && filt_bit(filt, hs)) hs = -1;
-                        }
-                        c = containment_collision_warp(L, sd.verts, sd.n_verts, sd.poi_x, sd.poi_y, Xf{t4.x, t4.y, t4.z, t4.w},
-                                                       Rect{b4.x, b4.y, b4.z, b4.w}, hs, lane);
+                if (!have_batch && s1_open) {
+                    if (lane == 0) base = atomicAdd(&ctl->s1_next, 32);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base >= n) s1_open = false;
+                    else have_batch = true;
+                }
+                if (have_batch) {
+                    const int need = (base + 32) < n ? (base + 32) : n;
+                    int av = n;
+                    if (!avail_all) {
+                        if (lane == 0) av = *(volatile int*)&ctl->avail;
+                        av = __shfl_sync(FULL, av, 0);
                     }
-                    if (__any_sync(FULL, c)) v = JG_VERDICT_POLY;
+                    if (av >= need) run_a = true;
+                    else if (w.n_pend > 0) run_b = true;  // the batch has not arrived yet: use the time
+                    else idle = true;
+                } else if (w.n_pend > 0) {
+                    run_b = true;  // drain
+                } else {
+                    if (w.n_sv > 0) {  // hand in the leftovers
+                        int sb = 0;
+                        if (lane == 0) sb = atomicAdd(&ctl->n_res, w.n_sv);
+                        sb = __shfl_sync(FULL, sb, 0);
+                        if (lane < w.n_sv) sv_entry[sb + lane] = w.s_surv[lane];
+                        __threadfence();
+                        w.n_sv = 0;
+                    }
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(&ctl->done_warps, 1);
+                    phase = BARRIER;
+                    idle_since = -1;
+                    continue;
                 }
             }
-            if (lane == s) verdict = v;
+        } else if (phase == BARRIER) {
+            int dn = 0;
+            if (lane == 0) dn = *(volatile int*)&ctl->done_warps;
+            dn = __shfl_sync(FULL, dn, 0);
+            if (dn == n_warps) {
+                __threadfence();
+                total = *(volatile int*)&ctl->n_res;
+                phase = LEFTOVER;
+                idle_since = -1;
+                continue;
+            }
+            idle = true;
+        } else {
+            int gbase = 0;
+            if (lane == 0) gbase = atomicAdd(&ctl->s2_next, GS);
+            gbase = __shfl_sync(FULL, gbase, 0);
+            if (gbase >= total) break;
+            grp_n = (total - gbase) < GS ? (total - gbase) : GS;
+            if (lane < grp_n) w.s_surv[lane] = __ldcg(&sv_entry[gbase + lane]);
+            __syncwarp();
+            grp_off = 0;
         }
-        if (lane < ng) out[W.q[lane]] = (uint8_t)verdict;
-        __syncwarp();
+        if (grp_off >= 0) {
+            g2_group<FILT, true>(c, W, w.s_surv + grp_off, grp_n, GS, lane);
+            idle_since = -1;
+        } else if (run_b) {
+            g1_phase_b<FILT, true>(c, w, lane);
+            idle_since = -1;
+        } else if (run_a) {
+            g1_phase_a<FILT>(c, w, base, lane);
+            have_batch = false;
+            idle_since = -1;
+        } else if (idle) {  // wait a little; give up after JG_SPIN_LIMIT ticks without progress
+            const long long now = clock64();
+            if (idle_since < 0) idle_since = now;
+            if (now - idle_since > JG_SPIN_LIMIT) {
+                if (lane == 0) atomicExch(&ctl->error, 1);
+                return;
+            }
+            __nanosleep(100);
+        }
     }
 }
 

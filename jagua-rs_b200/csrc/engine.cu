@@ -15,6 +15,10 @@
 
 using namespace jg;
 
+#define JG_STREAM_MAX_CHUNKS 32          // copy pieces of a streamed batch (and arrival-counter slots)
+#define JG_STREAM_CHUNK (1 << 16)        // ... of at least this many queries
+#define JG_STREAM_MIN_QUERIES (1 << 17)  // smaller host batches keep the chunked pipeline
+
 namespace {
 
 struct ItemDev {
@@ -63,6 +67,7 @@ struct JgEngine {
     uint64_t layout_version = 0;  // bumped by every upload; per-filter node summaries are keyed on it
     DetectPlan plan{0, 0, 0, 0};
     bool force_walk = false;  // jg_engine_set_detect_path: keep the quadtree-walk kernels even when the grid applies
+    bool use_fused = false;   // JG_PATH_FUSED: one fused, copy-following kernel per batch (experimental, slower)
     uint8_t* d_kinds = nullptr;   // node summary under NoFilter
     size_t kinds_cap = 0;
 
@@ -72,6 +77,14 @@ struct JgEngine {
     cudaStream_t compute = nullptr;
     ChunkCtx main_ctx;  // scratch of the *_device calls (compute stream)
     std::vector<ChunkCtx> chunks;
+    // streamed host batches (k_detect_fused follows the copy front): whole-batch buffers on `compute`, the
+    // copies on `st_copy`, the arrival counter values in pinned host memory
+    ChunkCtx stream_ctx;
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_reset = nullptr;
+    int* h_avail = nullptr;
+    bool stream_pending = false;  // a streamed batch may still be in flight: check its error flag at the next sync
+    int* h_err = nullptr;
     int64_t chunk_queries = 1 << 18;
     uint64_t next_chunk = 0;
     int detect_group = 0, collect_group = 0;  // 0 = auto
@@ -181,6 +194,15 @@ int jg_engine_create(int device, const JgConfig* cfg, JgEngine** out) {
         return JG_ERR_CUDA;
     }
     e->main_ctx.st = e->compute;
+    e->stream_ctx.st = e->compute;
+    if (cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_reset, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc((void**)&e->h_avail, (JG_STREAM_MAX_CHUNKS + 1) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+        delete e;
+        return JG_ERR_CUDA;
+    }
+    e->h_err = e->h_avail + JG_STREAM_MAX_CHUNKS;
+    *e->h_err = 0;
     e->chunks.resize(3);
     for (ChunkCtx& c : e->chunks)
         if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) {
@@ -202,6 +224,14 @@ void jg_engine_destroy(JgEngine* e) {
         cudaFree(kv.second.rots);
     }
     for (auto& kv : e->filters) cudaFree(kv.second.bits), cudaFree(kv.second.kinds);
+    {
+        cudaStream_t keep = e->stream_ctx.st;
+        free_ctx(e->stream_ctx);
+        (void)keep;  // = e->compute, destroyed below
+    }
+    if (e->st_copy) cudaStreamDestroy(e->st_copy);
+    if (e->ev_reset) cudaEventDestroy(e->ev_reset);
+    if (e->h_avail) cudaFreeHost(e->h_avail);
     if (e->d_kinds) cudaFree(e->d_kinds);
     for (ChunkCtx& c : e->chunks) {
         cudaStream_t st = c.st;
@@ -225,7 +255,15 @@ int jg_sync(JgEngine* e) {
     if (!e) return JG_ERR_INVALID;
     JG_CUDA(e, cudaSetDevice(e->device));
     for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
+    if (e->st_copy) JG_CUDA(e, cudaStreamSynchronize(e->st_copy));
     JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    if (e->stream_pending) {
+        e->stream_pending = false;
+        if (*e->h_err) {
+            *e->h_err = 0;
+            return fail(e, JG_ERR_CUDA, "streamed detect batch: a warp gave up waiting for its queries (copy lost or stalled)");
+        }
+    }
     return JG_OK;
 }
 
@@ -520,6 +558,17 @@ static int resolve_segments(JgEngine* e, int n_seg, const int* item_ids, const i
 }
 
 #define JG_DEVICE_PIECE_MIN (1 << 16)
+
+// one piece on one stream: the fused kernel when the grid serves it, else the two-kernel sequence
+static cudaError_t launch_piece(JgEngine* e, const Piece& p, const XfSrc& src, const uint32_t* d_filt, const uint8_t* d_kinds, int mode,
+                                uint8_t* d_out, const DetectScratch& sc, cudaStream_t st, int* launches) {
+    if (e->use_fused && detect_fused_applicable(e->plan, p.tab, mode)) {
+        cudaError_t err = cudaMemsetAsync(sc.ctl, 0, sizeof(DetectCtl), st);
+        if (err != cudaSuccess) return err;
+        return launch_detect_fused(e->L, p.tab, src, d_filt, d_kinds, d_out, sc, e->n_sms, 1, st, launches);
+    }
+    return launch_detect(e->L, e->plan, p.tab, src, d_filt, d_kinds, mode, d_out, sc, e->n_sms, st, launches);
+}
 static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
                                const float* d_transforms, int filter_id, int mode, uint8_t* d_out) {
     int rc = check_ready(e);
@@ -555,8 +604,8 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
             ChunkCtx& c = e->chunks[k++ % e->chunks.size()];
             rc = ensure_ctx(e, c, (size_t)piece, 0, false);
             if (rc != JG_OK) return rc;
-            JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off, c.sc,
-                                     e->n_sms, c.st, &launches));
+            JG_CUDA(e, launch_piece(e, p, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off, c.sc,
+                                    c.st, &launches));
         }
         for (ChunkCtx& c : e->chunks) {
             JG_CUDA(e, cudaEventRecord(c.done, c.st));
@@ -567,8 +616,8 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
         rc = ensure_ctx(e, e->main_ctx, (size_t)(n < max_q ? n : max_q), 0, false);
         if (rc != JG_OK) return rc;
         while (next_piece(e, n_seg, items.data(), seg_offsets, max_q, cur, p))
-            JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off,
-                                     e->main_ctx.sc, e->n_sms, e->compute, &launches));
+            JG_CUDA(e, launch_piece(e, p, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off,
+                                    e->main_ctx.sc, e->compute, &launches));
     }
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
     e->timing_valid = true;
@@ -600,6 +649,51 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
                 return fail(e, JG_ERR_INVALID, "indexed queries need jg_item_set_rotations for every item of the batch");
     if (n == 0) return JG_OK;
     JG_CUDA(e, cudaSetDevice(e->device));
+    if (e->use_fused && n >= JG_STREAM_MIN_QUERIES && n <= JG_MAX_LAUNCH_QUERIES && n_seg <= JG_MAX_SEG) {
+        // Whole batch as ONE fused kernel that follows the copy front (see k_detect_fused).
+        PieceCursor cur0;
+        Piece whole;
+        if (next_piece(e, n_seg, items.data(), seg_offsets, n, cur0, whole) && whole.m == n &&
+            detect_fused_applicable(e->plan, whole.tab, mode)) {
+            ChunkCtx& c = e->stream_ctx;
+            JG_CUDA(e, cudaStreamSynchronize(e->compute));  // the previous streamed batch is done with the buffers
+            JG_CUDA(e, cudaStreamSynchronize(e->st_copy));
+            rc = ensure_ctx(e, c, (size_t)n, (size_t)n, true);
+            if (rc != JG_OK) return rc;
+            int64_t sc_q = (n + JG_STREAM_MAX_CHUNKS - 1) / JG_STREAM_MAX_CHUNKS;
+            if (sc_q < JG_STREAM_CHUNK) sc_q = JG_STREAM_CHUNK;
+            sc_q = (sc_q + 31) & ~(int64_t)31;
+            float2* d_txy = (float2*)c.d_xf;
+            uint8_t* d_ridx = (uint8_t*)(d_txy + n);
+            const XfSrc src = indexed ? XfSrc{nullptr, d_ridx, d_txy} : XfSrc{c.d_xf, nullptr, nullptr};
+            JG_CUDA(e, cudaMemsetAsync(c.sc.ctl, 0, sizeof(DetectCtl), e->compute));
+            JG_CUDA(e, cudaEventRecord(e->ev_reset, e->compute));
+            int launches = 0;
+            JG_CUDA(e, launch_detect_fused(e->L, whole.tab, src, d_filt, d_kinds, c.d_out, c.sc, e->n_sms, 0, e->compute, &launches));
+            JG_CUDA(e, cudaMemcpyAsync(out, c.d_out, (size_t)n, cudaMemcpyDeviceToHost, e->compute));
+            JG_CUDA(e, cudaMemcpyAsync(e->h_err, &c.sc.ctl->error, sizeof(int), cudaMemcpyDeviceToHost, e->compute));
+            JG_CUDA(e, cudaStreamWaitEvent(e->st_copy, e->ev_reset, 0));  // avail is bumped only after the reset
+            int k = 0;
+            for (int64_t off = 0; off < n; off += sc_q, k++) {
+                const int64_t m = (n - off) < sc_q ? (n - off) : sc_q;
+                if (!indexed) {
+                    JG_CUDA(e, cudaMemcpyAsync(c.d_xf + off, transforms + 4 * off, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, e->st_copy));
+                } else {
+                    JG_CUDA(e, cudaMemcpyAsync(d_txy + off, txy + 2 * off, (size_t)m * sizeof(float2), cudaMemcpyHostToDevice, e->st_copy));
+                    JG_CUDA(e, cudaMemcpyAsync(d_ridx + off, rot_idx + off, (size_t)m, cudaMemcpyHostToDevice, e->st_copy));
+                }
+                e->h_avail[k] = (int)(off + m);
+                JG_CUDA(e, cudaMemcpyAsync(&c.sc.ctl->avail, &e->h_avail[k], sizeof(int), cudaMemcpyHostToDevice, e->st_copy));
+            }
+            e->stream_pending = true;
+            e->stat_launches += launches;
+            e->stat_h2d += (uint64_t)n * (indexed ? 9 : sizeof(float4));
+            e->stat_d2h += (uint64_t)n;
+            e->stat_queries += (uint64_t)n;
+            if (wait) return jg_sync(e);
+            return JG_OK;
+        }
+    }
     const int64_t chunk = e->chunk_queries;
     PieceCursor cur;
     Piece p;
@@ -630,7 +724,7 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
             e->stat_h2d += (uint64_t)p.m * 9;
         }
         int launches = 0;
-        JG_CUDA(e, launch_detect(e->L, e->plan, p.tab, src, d_filt, d_kinds, mode, c.d_out, c.sc, e->n_sms, c.st, &launches));
+        JG_CUDA(e, launch_piece(e, p, src, d_filt, d_kinds, mode, c.d_out, c.sc, c.st, &launches));
         JG_CUDA(e, cudaMemcpyAsync(out + p.off, c.d_out, (size_t)p.m, cudaMemcpyDeviceToHost, c.st));
         e->stat_launches += launches;
         e->stat_d2h += (uint64_t)p.m;
@@ -823,8 +917,11 @@ int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group) {
 }
 
 int jg_engine_set_detect_path(JgEngine* e, int path) {
-    if (!e || (path != JG_PATH_AUTO && path != JG_PATH_WALK)) return JG_ERR_INVALID;
+    if (!e || (path != JG_PATH_AUTO && path != JG_PATH_WALK && path != JG_PATH_FUSED)) return JG_ERR_INVALID;
+    int rcs = jg_sync(e);
+    if (rcs != JG_OK) return rcs;
     e->force_walk = path == JG_PATH_WALK;
+    e->use_fused = path == JG_PATH_FUSED;
     if (e->has_layout && e->d_kinds) {
         int ok = 0;
         JG_CUDA(e, cudaSetDevice(e->device));
@@ -833,7 +930,7 @@ int jg_engine_set_detect_path(JgEngine* e, int path) {
     }
     return JG_OK;
 }
-int jg_engine_detect_path(const JgEngine* e) { return e && e->plan.use_grid ? 1 : 0; }
+int jg_engine_detect_path(const JgEngine* e) { return e && e->plan.use_grid ? (e->use_fused ? 2 : 1) : 0; }
 
 int jg_host_alloc(size_t bytes, void** out) {
     if (!out) return JG_ERR_INVALID;

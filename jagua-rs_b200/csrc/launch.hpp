@@ -38,10 +38,11 @@ struct XfSrc {
     const float2* txy;
 };
 __device__ __forceinline__ float4 load_xf(const XfSrc& s, const SegDesc& sd, int q) {
-    if (s.xf) return __ldg(&s.xf[q]);
-    const int r = (int)__ldg(&s.ridx[q]);
+    // L2 loads: in a streamed batch the queries land in device memory while the kernel is running
+    if (s.xf) return __ldcg(&s.xf[q]);
+    const int r = (int)__ldcg(&s.ridx[q]);
     const float2 cs = __ldg(&sd.rots[r < sd.n_rots ? r : sd.n_rots - 1]);  // out-of-range indices are clamped
-    const float2 t = __ldg(&s.txy[q]);
+    const float2 t = __ldcg(&s.txy[q]);
     return make_float4(cs.x, cs.y, t.x, t.y);
 }
 
@@ -51,6 +52,11 @@ struct DetectCtl {
     int s2_next;    // next unclaimed survivor (k_s2_poly takes a group at a time)
     int n_surv;     // survivors of the surrogate stage
     int fallbacks;  // work items resolved by the register-only walk because a warp stack was full
+    // fused kernel (k_detect_fused)
+    int n_res;       // survivor slots reserved (n_surv = slots published, in order)
+    int done_warps;  // warps that have finished all their stage-1 work
+    int avail;       // queries whose transforms have arrived in device memory (streamed batches)
+    int error;       // 1: a warp gave up waiting (lost copy); the results are incomplete
 };
 #define JG_MAX_LAUNCH_QUERIES (1 << 26)  // survivor entries keep the query index in 26 bits
 #define JG_MAX_NODES (1 << 20)           // stage-2 pair words keep the node index in >= 20 bits
@@ -77,6 +83,12 @@ cudaError_t detect_grid_usable(const uint8_t* d_kinds, int n_nodes, cudaStream_t
 cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const XfSrc& d_xf,
                           const uint32_t* d_filt, const uint8_t* d_kinds, int mode, uint8_t* d_out, const DetectScratch& sc,
                           int n_sms, cudaStream_t st, int* n_launches);
+// one fused kernel (k_detect_fused) for a piece served by the grid; avail_all = 0: the queries are still being
+// copied and sc.ctl->avail is bumped by the caller's copy stream
+bool detect_fused_applicable(const DetectPlan& plan, const SegTable& tab, int mode);
+cudaError_t launch_detect_fused(const DevLayout& L, const SegTable& tab, const XfSrc& d_xf, const uint32_t* d_filt,
+                                const uint8_t* d_kinds, uint8_t* d_out, const DetectScratch& sc, int n_sms, int avail_all,
+                                cudaStream_t st, int* n_launches);
 cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,
                            uint32_t* d_out_bits, int words, int group, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_fp32_nofma(float* d_out, int blocks, int iters, cudaStream_t st);

@@ -198,3 +198,30 @@ def test_indexed_queries_need_registered_rotations(jg):
             cde.detect_multi_indexed([0], [0, 4], np.zeros(4, np.uint8), np.zeros((4, 2), np.float32))
     finally:
         cde.close()
+
+
+def test_fused_streaming_path_matches_oracle(jg, engines):
+    """JG_PATH_FUSED: one kernel per batch that follows the H2D copy front (host batches >= 128 Ki queries are
+    streamed; smaller ones and device-resident ones run the same kernel with everything resident)."""
+    wl, cde, w = engines("swim_half")
+    ids = list(range(len(wl.items)))
+    sizes = jg.split_batch(150_000, len(ids))
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    ts = [jg.make_queries(wl, i, n, seed=31) for i, n in zip(ids, sizes)]
+    exp = np.concatenate([w.detect_batch(i, q) for i, q in zip(ids, ts)])
+    t = jg.PinnedBuffer((int(offs[-1]), 4), np.float32)
+    t.array[:] = np.concatenate(ts)
+    out = jg.PinnedBuffer((int(offs[-1]),), np.uint8)
+    cde.set_detect_path(fused=True)
+    try:
+        assert cde.detect_path() == "fused"
+        for _ in range(3):  # streamed (>= 128 Ki queries), repeated to reuse the buffers
+            out.array[:] = 0xFF
+            cde.detect_multi(ids, offs, t.array, out=out.array)
+            assert np.array_equal(out.array, exp)
+        small = jg.make_queries(wl, 3, 5000, seed=32)
+        assert np.array_equal(cde.detect_batch(3, small), w.detect_batch(3, small))
+    finally:
+        cde.set_detect_path()
+    assert cde.detect_path() == "grid"
+    t.free(), out.free()

@@ -225,3 +225,46 @@ def test_fused_streaming_path_matches_oracle(jg, engines):
         cde.set_detect_path()
     assert cde.detect_path() == "grid"
     t.free(), out.free()
+
+
+@pytest.mark.parametrize("name", ["swim_half", "shirts_full", "baldacci1_bin", "swim_half_d3"])
+def test_queries_aligned_with_cell_boundaries(jg, engines, name):
+    """Adversarial placements for the grid kernels: translations that put an item vertex (or a pole centre, or a
+    pole's extreme point) exactly on a quadtree cell boundary, where every inclusive / strict comparison of the
+    reference (rect.rs:282-288, qt_traits.rs:36-44, circle.rs:115-128) decides the verdict."""
+    wl, cde, w = engines(name)
+    rng = np.random.default_rng(17)
+    b = wl.cde_bbox.astype(np.float32)
+    G = 1 << wl.quadtree_depth
+    xs, ys = np.zeros(G + 1, np.float32), np.zeros(G + 1, np.float32)
+    xs[0], xs[G], ys[0], ys[G] = b[0], b[2], b[1], b[3]
+    step = G
+    while step >= 2:  # nested midpoints, rect.rs:248-253
+        for a in range(0, G, step):
+            xs[a + step // 2] = (xs[a] + xs[a + step]) / np.float32(2)
+            ys[a + step // 2] = (ys[a] + ys[a + step]) / np.float32(2)
+        step //= 2
+    for item_id, it in enumerate(wl.items):
+        n = 3000
+        rots = np.zeros(n, np.float32) if it.rotations is None or len(it.rotations) == 0 else \
+            np.asarray(it.rotations, np.float32)[rng.integers(0, len(it.rotations), n)]
+        cs = jg.compose(np.stack([rots, np.zeros(n, np.float32), np.zeros(n, np.float32)], 1))
+        # anchor points of the item in its own frame: vertices, pole centres, pole extreme points
+        anchors = [it.verts]
+        for p in it.poles[:wl.n_ff_poles]:
+            anchors.append(np.array([[p[0], p[1]], [p[0] + p[2], p[1]], [p[0] - p[2], p[1]], [p[0], p[1] + p[2]], [p[0], p[1] - p[2]]], np.float32))
+        anchors = np.concatenate(anchors).astype(np.float32)
+        a = anchors[rng.integers(0, len(anchors), n)]
+        ax = cs[:, 0] * a[:, 0] - cs[:, 1] * a[:, 1]  # rotated anchor (float32, like the device would)
+        ay = cs[:, 1] * a[:, 0] + cs[:, 0] * a[:, 1]
+        tx = xs[rng.integers(0, G + 1, n)] - ax.astype(np.float32)
+        ty = ys[rng.integers(0, G + 1, n)] - ay.astype(np.float32)
+        free_axis = rng.integers(0, 3, n)  # align x only, y only, or both
+        tx = np.where(free_axis == 1, (b[0] + (b[2] - b[0]) * rng.random(n)).astype(np.float32), tx).astype(np.float32)
+        ty = np.where(free_axis == 0, (b[1] + (b[3] - b[1]) * rng.random(n)).astype(np.float32), ty).astype(np.float32)
+        t = np.ascontiguousarray(np.stack([cs[:, 0], cs[:, 1], tx, ty], 1).astype(np.float32))
+        for poly_only in (False, True):
+            exp = w.detect_batch(item_id, t, poly_only=poly_only)
+            got = cde.detect_batch(item_id, t, poly_only=poly_only)
+            bad = np.nonzero(got != exp)[0]
+            assert len(bad) == 0, f"{name} item {item_id} poly_only={poly_only}: {len(bad)} mismatches, first {bad[:5]}"

@@ -613,6 +613,7 @@ k_s2_poly(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_
 
 }  // namespace jg
 #include "detect_grid.cuh"
+#include "collect_grid.cuh"
 namespace jg {
 
 // ---------------------------------------------------------------------------------------------------
@@ -631,13 +632,18 @@ static int persistent_grid(K kernel, int slot, int n_sms, size_t smem) {
 }
 
 // the per-(layout, filter) summary buffer: [kinds][GridDev]
-size_t detect_kinds_bytes(int n_nodes) { return kinds_bytes(n_nodes) + sizeof(GridDev); }
+size_t detect_kinds_bytes(int n_nodes) { return kinds_bytes(n_nodes) + ((sizeof(GridDev) + 15) & ~(size_t)15) + sizeof(GridCollect); }
+static const GridCollect* cgrid_of(const uint8_t* d_kinds, int n_nodes) {
+    return (const GridCollect*)(d_kinds + kinds_bytes(n_nodes) + ((sizeof(GridDev) + 15) & ~(size_t)15));
+}
 static const GridDev* grid_of(const uint8_t* d_kinds, int n_nodes) { return (const GridDev*)(d_kinds + kinds_bytes(n_nodes)); }
 
 cudaError_t launch_node_kinds(const DevLayout& L, int depth, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st) {
     cudaMemsetAsync(d_kinds, 0, kinds_bytes(L.n_nodes), st);
     k_node_kinds<<<(L.n_nodes + 255) / 256, 256, 0, st>>>(L, d_filt, d_kinds);
     k_grid_build<<<1, 1024, 0, st>>>(L, depth, d_kinds, (GridDev*)(d_kinds + kinds_bytes(L.n_nodes)));
+    if (!d_filt)  // the collect grid does not depend on a filter: built with the NoFilter summary only
+        k_cgrid_build<<<1, 1024, 0, st>>>(L, grid_of(d_kinds, L.n_nodes), (GridCollect*)cgrid_of(d_kinds, L.n_nodes));
     return cudaGetLastError();
 }
 // 1 when the grid kernels can serve this layout (k_grid_build's verdict); synchronises the stream
@@ -708,6 +714,22 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
                                                                         plan.gbits, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
     }
     if (n_launches) *n_launches += 2;
+    return cudaGetLastError();
+}
+
+// collect on the grid (k_collect_grid); d_kinds = the NoFilter summary buffer, d_next = a zeroed device int
+bool collect_grid_applicable(const DetectPlan& plan, const DevItem& it, int words) {
+    return plan.use_grid && it.n_piers == 0 && words <= CG_MAX_WORDS && it.n_poles * S2_MAX_GROUP <= 4096;
+}
+cudaError_t launch_collect_grid(const DevLayout& L, const DevItem& it, const uint8_t* d_kinds, const float4* d_xf, long long n, int mode,
+                                uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st, int* n_launches) {
+    cudaMemsetAsync(d_next, 0, sizeof(int), st);
+    const size_t smem = ((sizeof(GridDev) + 15) & ~(size_t)15) + S_WARPS * sizeof(CGSlots);
+    const int g = persistent_grid(k_collect_grid, 10, n_sms, smem);
+    const long long want = (n + S_WARPS * S2_MAX_GROUP - 1) / (S_WARPS * S2_MAX_GROUP);
+    k_collect_grid<<<(int)(want < g ? want : g), S_THREADS, smem, st>>>(L, it, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes), d_xf,
+                                                                        (int)n, mode, d_out_bits, words, d_next);
+    if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
 

@@ -795,8 +795,15 @@ int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms,
     const int group = e->collect_group ? e->collect_group : auto_group(it->n_verts);
     int launches = 0;
     JG_CUDA(e, cudaEventRecord(e->ev0, e->compute));
-    JG_CUDA(e, launch_collect(e->L, dev_item(e, *it), (const float4*)d_transforms, n, mode, d_out_bits, words, group,
-                              e->n_sms, e->compute, &launches));
+    const DevItem di = dev_item(e, *it);
+    if (!e->force_walk && n <= JG_MAX_LAUNCH_QUERIES && collect_grid_applicable(e->plan, di, words)) {
+        rc = ensure_ctx(e, e->main_ctx, 1, 0, false);  // the work counter lives in the scratch block
+        if (rc != JG_OK) return rc;
+        JG_CUDA(e, launch_collect_grid(e->L, di, e->d_kinds, (const float4*)d_transforms, n, mode, d_out_bits, words, &e->main_ctx.sc.ctl->s1_next,
+                                       e->n_sms, e->compute, &launches));
+    } else {
+        JG_CUDA(e, launch_collect(e->L, di, (const float4*)d_transforms, n, mode, d_out_bits, words, group, e->n_sms, e->compute, &launches));
+    }
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
     e->timing_valid = true;
     e->stat_launches += launches;
@@ -822,7 +829,11 @@ static int collect_host(JgEngine* e, int item_id, const float* transforms, int64
         if (rc != JG_OK) return rc;
         JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * off, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
         int launches = 0;
-        JG_CUDA(e, launch_collect(e->L, di, c.d_xf, m, mode, (uint32_t*)c.d_out, words, group, e->n_sms, c.st, &launches));
+        if (!e->force_walk && collect_grid_applicable(e->plan, di, words))
+            JG_CUDA(e, launch_collect_grid(e->L, di, e->d_kinds, c.d_xf, m, mode, (uint32_t*)c.d_out, words, &c.sc.ctl->s1_next, e->n_sms, c.st,
+                                           &launches));
+        else
+            JG_CUDA(e, launch_collect(e->L, di, c.d_xf, m, mode, (uint32_t*)c.d_out, words, group, e->n_sms, c.st, &launches));
         JG_CUDA(e, cudaMemcpyAsync((char*)out_bits + (size_t)off * out_per_q, c.d_out, (size_t)m * out_per_q, cudaMemcpyDeviceToHost, c.st));
         e->stat_launches += launches;
         e->stat_h2d += (uint64_t)m * sizeof(float4);

@@ -89,6 +89,9 @@ bool detect_fused_applicable(const DetectPlan& plan, const SegTable& tab, int mo
 cudaError_t launch_detect_fused(const DevLayout& L, const SegTable& tab, const XfSrc& d_xf, const uint32_t* d_filt,
                                 const uint8_t* d_kinds, uint8_t* d_out, const DetectScratch& sc, int n_sms, int avail_all,
                                 cudaStream_t st, int* n_launches);
+bool collect_grid_applicable(const DetectPlan& plan, const DevItem& it, int words);
+cudaError_t launch_collect_grid(const DevLayout& L, const DevItem& it, const uint8_t* d_kinds, const float4* d_xf, long long n, int mode,
+                                uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,
                            uint32_t* d_out_bits, int words, int group, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_fp32_nofma(float* d_out, int blocks, int iters, cudaStream_t st);

@@ -144,6 +144,13 @@ def test_grid_and_walk_paths_agree_with_oracle(jg, engines, name):
                 got = cde.detect_batch(item_id, t)
                 assert np.array_equal(got, exp), f"{name} item {item_id} walk={walk}: {(got != exp).sum()} mismatches"
                 assert np.array_equal(cde.detect_batch(item_id, t, poly_only=True), exp_p)
+                words = cde.collector_words()
+                tc = t[:1500]
+                gc = cde.collect_batch(item_id, tc, words)
+                ec = w.collect_batch(item_id, tc, words)
+                badc = np.nonzero((gc != ec).any(axis=1))[0]
+                assert len(badc) == 0, f"{name} item {item_id} walk={walk}: collect {len(badc)} mismatches, first {badc[:3]} got {gc[badc[:3]]} exp {ec[badc[:3]]}"
+                assert np.array_equal(cde.collect_batch(item_id, tc, words, poly_only=True), w.collect_batch(item_id, tc, words, poly_only=True))
     finally:
         cde.set_detect_path(False)
 
@@ -268,3 +275,6 @@ def test_queries_aligned_with_cell_boundaries(jg, engines, name):
             got = cde.detect_batch(item_id, t, poly_only=poly_only)
             bad = np.nonzero(got != exp)[0]
             assert len(bad) == 0, f"{name} item {item_id} poly_only={poly_only}: {len(bad)} mismatches, first {bad[:5]}"
+            words = cde.collector_words()
+            gc, ec = cde.collect_batch(item_id, t[:1000], words, poly_only=poly_only), w.collect_batch(item_id, t[:1000], words, poly_only=poly_only)
+            assert np.array_equal(gc, ec), f"{name} item {item_id} collect poly_only={poly_only}: {(gc != ec).any(axis=1).sum()} mismatches"

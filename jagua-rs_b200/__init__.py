@@ -518,4 +518,5 @@ class CDEngine:
         self._chk(self._lib.jg_flush_l2(self._eng))
 
 
+from . import workload  # noqa: E402
 from .workload import Workload, load_workload, build_engine, make_queries, make_queries_indexed, split_batch  # noqa: E402

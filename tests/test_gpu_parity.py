@@ -278,3 +278,113 @@ def test_queries_aligned_with_cell_boundaries(jg, engines, name):
             words = cde.collector_words()
             gc, ec = cde.collect_batch(item_id, t[:1000], words, poly_only=poly_only), w.collect_batch(item_id, t[:1000], words, poly_only=poly_only)
             assert np.array_equal(gc, ec), f"{name} item {item_id} collect poly_only={poly_only}: {(gc != ec).any(axis=1).sum()} mismatches"
+
+
+def test_quality_zone_filters_match_oracle(jg, engines):
+    """BASELINE.json config 4: bin with holes and inferior-quality zones; every item is queried under the
+    HazKeyFilter::from_irrelevant_qzones filter of its min_quality (hazards/filter.rs:21-41; callers
+    lbf_bpp.rs:125-127), on the grid and on the walk kernels. Verdict byte incl. the N3 status bit."""
+    wl, cde, w = engines("baldacci1_bin")
+    words = cde.collector_words()
+    filters = {}
+    for fid, q in enumerate((0, 1, 2, 5)):
+        bits = cde.filter_from_irrelevant_qzones(q)
+        assert np.array_equal(bits, w.filter_qzones(q, words))
+        cde.upload_filter(fid, bits)
+        filters[fid] = bits
+    n_filtered_diff = 0
+    try:
+        for walk in (False, True):
+            cde.set_detect_path(walk)
+            for item_id in range(0, len(wl.items), 3):
+                t = jg.make_queries(wl, item_id, 3000, seed=41)
+                base = w.detect_batch(item_id, t)
+                for fid, bits in filters.items():
+                    exp = w.detect_batch(item_id, t, filter_bits=bits)
+                    got = cde.detect_batch(item_id, t, filter_id=fid)
+                    assert np.array_equal(got, exp), f"item {item_id} filter {fid} walk={walk}: {(got != exp).sum()} mismatches"
+                    expp = w.detect_batch(item_id, t, filter_bits=bits, poly_only=True)
+                    gotp = cde.detect_batch(item_id, t, filter_id=fid, poly_only=True)
+                    assert np.array_equal(gotp, expp)
+                    n_filtered_diff += int((exp != base).sum())
+    finally:
+        cde.set_detect_path(False)
+    assert n_filtered_diff > 0  # the filters really change verdicts
+
+
+@pytest.mark.parametrize("name", ["swim_half", "shirts_full"])
+def test_self_key_filter_matches_oracle(jg, engines, name):
+    """`impl HazardFilter for HazKey` (filter.rs:70-76), used by Layout::is_feasible (layout.rs:128-136): a placed
+    item queried at (and around) its own placement with its own hazard filtered out."""
+    wl, cde, w = engines(name)
+    rng = np.random.default_rng(23)
+    placed = [(k, h) for k, h in zip(cde.hazard_keys, wl.hazards) if h.kind == 0]
+    n_free = 0
+    for fid, (key, h) in enumerate(placed[:6]):
+        bits = cde.filter_from_keys([key])
+        cde.upload_filter(100 + fid, bits)
+        item_id = h.id
+        it = wl.items[item_id]
+        # recover the placement: the hazard's vertices are the item's under one allowed rotation + a translation
+        best = None
+        for r in np.asarray(it.rotations, np.float32):
+            cs = jg.compose(np.array([[r, 0, 0]], np.float32))[0]
+            rx = cs[0] * it.verts[:, 0] - cs[1] * it.verts[:, 1]
+            ry = cs[1] * it.verts[:, 0] + cs[0] * it.verts[:, 1]
+            off = h.verts[0] - np.array([rx[0], ry[0]], np.float32)
+            res = float(np.abs(np.stack([rx, ry], 1) + off - h.verts).max()) if len(h.verts) == len(it.verts) else 1e30
+            if best is None or res < best[0]:
+                best = (res, r, off)
+        scale = float(wl.cde_bbox[2] - wl.cde_bbox[0])
+        assert best[0] < 1e-3 * scale, "placement not recovered"
+        n = 2000
+        rots = np.full(n, best[1], np.float32)
+        jitter = rng.normal(0, 2e-3 * scale, (n, 2))
+        jitter[: n // 4] = 0.0  # the exact placement (up to f32 rounding of the recovered offset)
+        jitter[n // 4: n // 2] *= 0.01
+        txy = (best[2][None, :] + jitter).astype(np.float32)
+        t = jg.compose(np.concatenate([rots[:, None], txy], 1).astype(np.float32))
+        exp = w.detect_batch(item_id, t, filter_bits=bits)
+        got = cde.detect_batch(item_id, t, filter_id=100 + fid)
+        assert np.array_equal(got, exp), f"{name} hazard {fid}: {(got != exp).sum()} mismatches"
+        n_free += int((exp == 0).sum())
+    assert n_free > 0
+
+
+def test_filtered_entire_hazard_reports_reference_panic(jg, orc):
+    """with the virtual root's Entire hazard filtered out and no edge hit, the reference reaches
+    `unreachable!` (cd_engine.rs:179); the verdict byte must carry the status bit, never a silent verdict.
+    Synthetic fixture: a square container whose left half is one inferior-quality zone, a small square item."""
+    def rect(x0, y0, x1, y1):
+        return np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], np.float32)
+
+    wl = jg.Workload("n3_synthetic", 5, 16, 2, 0, np.array([0, 0, 1024, 1024], np.float32))
+    wl.hazards.append(jg.workload.WHazard(1, 0, 0, 0, False, rect(0, 0, 1024, 1024), np.array([512, 512, 512], np.float32)))
+    wl.hazards.append(jg.workload.WHazard(3, 0, 3, 0, False, rect(0, 0, 512, 1024), np.array([256, 512, 256], np.float32)))
+    item = rect(-6, -6, 6, 6)
+    wl.items.append(jg.workload.WItem(item, np.array([0, 0, 6], np.float32), np.array([[0, 0, 6], [3, 3, 3]], np.float32),
+                                      np.zeros((0, 4), np.float32), np.array([0.0], np.float32), 5))
+    cde = jg.build_engine(wl, device=0)
+    w = oracle_world(orc, wl)
+    try:
+        zone_key = cde.hazard_keys[1]
+        bits = cde.filter_from_keys([zone_key])
+        assert np.array_equal(cde.filter_from_irrelevant_qzones(5), bits)  # quality 3 < required 5 -> irrelevant
+        cde.upload_filter(0, bits)
+        rng = np.random.default_rng(3)
+        n = 20000
+        txy = (rng.random((n, 2)) * 1024).astype(np.float32)
+        t = jg.compose(np.concatenate([np.zeros((n, 1), np.float32), txy], 1).astype(np.float32))
+        seen = 0
+        for walk in (False, True):
+            cde.set_detect_path(walk)
+            for poly_only in (False, True):
+                exp = w.detect_batch(0, t, filter_bits=bits, poly_only=poly_only)
+                got = cde.detect_batch(0, t, filter_id=0, poly_only=poly_only)
+                assert np.array_equal(got, exp), f"walk={walk} poly_only={poly_only}: {(got != exp).sum()} mismatches"
+                seen += int((exp == 0x80).sum())
+            # without the filter the zone is a plain collision
+            assert np.array_equal(cde.detect_batch(0, t), w.detect_batch(0, t))
+        assert seen > 0, "the fixture never reaches the reference's unreachable!()"
+    finally:
+        cde.close()

@@ -198,6 +198,15 @@ const char* jg_cde_last_error(const JgCde* c);
  * (kind, id, quality, pk). Returns the HazKey (slot index | version << 32) through *hkey. */
 int jg_cde_register_hazard(JgCde* c, int kind, int64_t id, int64_t quality, uint64_t pk, const float* verts_xy,
                            int n_verts, const float* poi_xy, int dynamic, uint64_t* hkey);
+/* Layout::place_item (entities/layout.rs:40-60) + PlacedItem::new (entities/placed_item.rs:27-36): the
+ * item's collision shape is cloned under the composed transformation (cos, sin, tx, ty) - every vertex
+ * and the poi centre by TRANSFORM_FORMULA (geometry/primitives/point.rs:26-31, three f32 roundings),
+ * bbox rebuilt by a min/max fold - and registered as a dynamic HazardEntity::PlacedItem{id = item_id, pk}.
+ * pk is the caller's PItemKey (slot index | version << 32 of its own placed-items SlotMap). */
+int jg_cde_place_item(JgCde* c, int64_t item_id, uint64_t pk, const float* item_verts_xy, int n_verts,
+                      const float* item_poi_xy, const float transform4[4], uint64_t* hkey);
+/* Layout::remove_item (entities/layout.rs:62-74): deregisters the PlacedItem hazard carrying `pk` */
+int jg_cde_remove_item(JgCde* c, uint64_t pk);
 /* CDEngine::deregister_hazard_by_key (cd_engine.rs:87-96) */
 int jg_cde_deregister_hazard(JgCde* c, uint64_t hkey);
 /* CDEngine::haz_key_from_pi_key (cd_engine.rs:333-341); *hkey = 0 when absent */

@@ -91,6 +91,8 @@ C_ABI = {
     "jg_cde_last_error": (C.c_char_p, [_vp]),
     "jg_cde_register_hazard": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64, _f32p, C.c_int, _f32p, C.c_int,
                                          C.POINTER(C.c_uint64)]),
+    "jg_cde_place_item": (C.c_int, [_vp, C.c_int64, C.c_uint64, _f32p, C.c_int, _f32p, _f32p, C.POINTER(C.c_uint64)]),
+    "jg_cde_remove_item": (C.c_int, [_vp, C.c_uint64]),
     "jg_cde_deregister_hazard": (C.c_int, [_vp, C.c_uint64]),
     "jg_cde_hkey_from_pk": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     "jg_cde_save": (C.c_int, [_vp, C.POINTER(C.c_int)]),
@@ -268,6 +270,25 @@ class CDEngine:
             raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
         self._dirty = True
         return int(key.value)
+
+    def place_item(self, item_id: int, shape: "ItemShape", transform4, pk: int) -> int:
+        """Layout::place_item (entities/layout.rs:40-60): registers the item's shape under the composed
+        transformation (cos, sin, tx, ty) as a PlacedItem hazard with PItemKey `pk`. Returns the HazKey."""
+        v = _f32(shape.verts).reshape(-1, 2)
+        key = C.c_uint64(0)
+        rc = self._lib.jg_cde_place_item(self._cde, int(item_id), int(pk), v, len(v), _f32(shape.poi)[:2].copy(),
+                                         _f32(transform4).reshape(4).copy(), C.byref(key))
+        if rc < 0:
+            raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
+        self._dirty = True
+        return int(key.value)
+
+    def remove_item(self, pk: int):
+        """Layout::remove_item (entities/layout.rs:62-74)."""
+        rc = self._lib.jg_cde_remove_item(self._cde, int(pk))
+        if rc < 0:
+            raise JaguaCudaError(rc, f"remove_item: no placed item with key {pk}")
+        self._dirty = True
 
     def deregister_hazard_by_key(self, hkey: int):
         rc = self._lib.jg_cde_deregister_hazard(self._cde, int(hkey))

@@ -28,6 +28,7 @@
 // Node arrays (meta, bbox, kind) are staged into shared memory once per CTA when they fit; entries, hazard
 // edges and hazard shapes are read through L1. If a stack could overflow (never seen; the capacity follows
 // the tree depth) the warp falls back to the register-only walk of kernels.cuh for that work item.
+#include <cstdlib>
 #include "kernels.cuh"
 #include "launch.hpp"
 
@@ -628,7 +629,9 @@ static int persistent_grid(K kernel, int slot, int n_sms, size_t smem) {
         g_occ[slot] = b < 1 ? 1 : b;
         g_occ_smem[slot] = smem;
     }
-    return n_sms * g_occ[slot];
+    static const int cap = [] { const char* v = getenv("JG_CTAS_PER_SM"); return v ? atoi(v) : 0; }();  // experiments
+    const int b = (cap > 0 && cap < g_occ[slot]) ? cap : g_occ[slot];
+    return n_sms * b;
 }
 
 // the per-(layout, filter) summary buffer: [kinds][GridDev]

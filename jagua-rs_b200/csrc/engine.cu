@@ -96,7 +96,26 @@ struct JgEngine {
     size_t flush_words = 0;
 
     uint64_t stat_launches = 0, stat_queries = 0, stat_h2d = 0, stat_d2h = 0, stat_uploads = 0;
+    // JG_TRACE=1: device timeline of the pieces of the last host batch, printed by jg_sync (debugging aid)
+    std::vector<cudaEvent_t> trace_ev;
+    std::vector<int64_t> trace_m;
+    size_t trace_used = 0;
+    double trace_host_t0 = 0.0;
 };
+static bool trace_on() {
+    static const bool on = getenv("JG_TRACE") != nullptr;
+    return on;
+}
+static cudaEvent_t trace_mark(JgEngine* e, cudaStream_t st) {
+    if (e->trace_used == e->trace_ev.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->trace_ev.push_back(ev);
+    }
+    cudaEvent_t ev = e->trace_ev[e->trace_used++];
+    cudaEventRecord(ev, st);
+    return ev;
+}
 
 #define JG_CUDA(e, call)                                                                             \
     do {                                                                                             \
@@ -257,6 +276,19 @@ int jg_sync(JgEngine* e) {
     for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
     if (e->st_copy) JG_CUDA(e, cudaStreamSynchronize(e->st_copy));
     JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    if (trace_on() && e->trace_used >= 5) {
+        fprintf(stderr, "[jg trace] piece: queries | t(start) t(h2d done) t(kernels done) t(d2h done)  [us since first mark]\n");
+        for (size_t i = 1; i + 3 < e->trace_used + 0 && (i - 1) / 4 < e->trace_m.size(); i += 4) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, e->trace_ev[0], e->trace_ev[i]);
+            cudaEventElapsedTime(&b, e->trace_ev[0], e->trace_ev[i + 1]);
+            cudaEventElapsedTime(&c, e->trace_ev[0], e->trace_ev[i + 2]);
+            cudaEventElapsedTime(&d, e->trace_ev[0], e->trace_ev[i + 3]);
+            fprintf(stderr, "[jg trace] %8lld | %8.1f %8.1f %8.1f %8.1f\n", (long long)e->trace_m[(i - 1) / 4], a * 1e3, b * 1e3, c * 1e3, d * 1e3);
+        }
+        e->trace_used = 0;
+        e->trace_m.clear();
+    }
     if (e->stream_pending) {
         e->stream_pending = false;
         if (*e->h_err) {
@@ -706,9 +738,16 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
         if (rem > 2 * taper_min) return (rem / 2 + 31) & ~(int64_t)31;
         return rem;
     };
+    const bool tr = trace_on();
+    if (tr) {
+        e->trace_used = 0;
+        e->trace_m.clear();
+        trace_mark(e, e->chunks[e->next_chunk % e->chunks.size()].st);
+    }
     while (next_piece(e, n_seg, items.data(), seg_offsets, piece_size(cur.q), cur, p)) {
         ChunkCtx& c = e->chunks[e->next_chunk++ % e->chunks.size()];
         JG_CUDA(e, cudaStreamSynchronize(c.st));  // buffers of this slot are free again
+        if (tr) trace_mark(e, c.st), e->trace_m.push_back(p.m);
         rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n), true);
         if (rc != JG_OK) return rc;
         XfSrc src{c.d_xf, nullptr, nullptr};
@@ -724,8 +763,11 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
             e->stat_h2d += (uint64_t)p.m * 9;
         }
         int launches = 0;
+        if (tr) trace_mark(e, c.st);
         JG_CUDA(e, launch_piece(e, p, src, d_filt, d_kinds, mode, c.d_out, c.sc, c.st, &launches));
+        if (tr) trace_mark(e, c.st);
         JG_CUDA(e, cudaMemcpyAsync(out + p.off, c.d_out, (size_t)p.m, cudaMemcpyDeviceToHost, c.st));
+        if (tr) trace_mark(e, c.st);
         e->stat_launches += launches;
         e->stat_d2h += (uint64_t)p.m;
     }
@@ -1063,6 +1105,33 @@ int jg_cde_register_hazard(JgCde* c, int kind, int64_t id, int64_t quality, uint
     const uint64_t k = cde.register_hazard(std::move(hz));
     if (hkey) *hkey = k;
     return cde.last_error.empty() ? JG_OK : JG_ERR_REFERENCE_PANIC;
+}
+int jg_cde_place_item(JgCde* c, int64_t item_id, uint64_t pk, const float* item_verts_xy, int n_verts,
+                      const float* item_poi_xy, const float transform4[4], uint64_t* hkey) {
+    if (!c || !item_verts_xy || n_verts < 3 || !item_poi_xy || !transform4) return JG_ERR_INVALID;
+    HostCDE& cde = ((JgCdeBox*)c)->cde;
+    const Xf xf{transform4[0], transform4[1], transform4[2], transform4[3]};
+    HostHazard hz;
+    hz.kind = JG_HAZ_PLACED_ITEM;
+    hz.id = item_id;
+    hz.quality = 0;
+    hz.pk = pk;
+    hz.dynamic = true;
+    hz.xy.resize(2 * (size_t)n_verts);
+    for (int i = 0; i < n_verts; i++)  // simple_polygon.rs:226-253 transform_from: vertex by vertex
+        xf_point(xf, item_verts_xy[2 * i], item_verts_xy[2 * i + 1], hz.xy[2 * i], hz.xy[2 * i + 1]);
+    xf_point(xf, item_poi_xy[0], item_poi_xy[1], hz.poi_x, hz.poi_y);  // circle.rs:79-85: centre moves, radius stays
+    cde.last_error.clear();
+    const uint64_t k = cde.register_hazard(std::move(hz));
+    if (hkey) *hkey = k;
+    return cde.last_error.empty() ? JG_OK : JG_ERR_REFERENCE_PANIC;
+}
+int jg_cde_remove_item(JgCde* c, uint64_t pk) {
+    if (!c) return JG_ERR_INVALID;
+    HostCDE& cde = ((JgCdeBox*)c)->cde;
+    const uint64_t k = cde.hkey_from_pk(pk);
+    if (k == 0) return JG_ERR_INVALID;
+    return cde.deregister_hazard(k) ? JG_OK : JG_ERR_INVALID;
 }
 int jg_cde_deregister_hazard(JgCde* c, uint64_t hkey) {
     if (!c) return JG_ERR_INVALID;

@@ -3,7 +3,7 @@ order-normalised hazard bitsets must be bit-identical for every query."""
 import numpy as np
 import pytest
 
-from helpers import ALL_WORKLOADS, oracle_world, verdict_summary
+from helpers import ALL_WORKLOADS, oracle_world, place_remove_sequence, verdict_summary
 
 pytestmark = pytest.mark.gpu
 
@@ -37,7 +37,9 @@ def test_detect_matches_oracle(jg, engines, name):
         assert len(bad) == 0, f"{name} item {item_id}: {len(bad)} mismatches, first {bad[:5]} got {got[bad[:5]]} exp {exp[bad[:5]]}"
         for k, v in verdict_summary(got).items():
             total[k] += v
-    assert total["free"] > 0 and total["poly"] > 0, total  # the batch exercises every stage
+    # the batch exercises every stage (uniform samples over the CDE square of a narrow, nearly full strip may hold
+    # no free placement at all: the synthesised multi-strip layouts only need the polygon stage to be reached)
+    assert total["poly"] > 0 and (total["free"] > 0 or "_ms" in name), total
 
 
 @pytest.mark.parametrize("name", ALL_WORKLOADS)
@@ -388,3 +390,27 @@ def test_filtered_entire_hazard_reports_reference_panic(jg, orc):
         assert seen > 0, "the fixture never reaches the reference's unreachable!()"
     finally:
         cde.close()
+
+
+@pytest.mark.parametrize("name", ["swim_half", "jakobs1_ms1", "albano_ms0", "baldacci1_bin"])
+def test_queries_follow_layout_updates(jg, orc, name):
+    """Layout::place_item / remove_item between batches (config 5's update cadence): after every few updates the
+    re-uploaded layout answers detect and collect batches exactly like the oracle's incrementally updated CDE."""
+    wl = jg.load_workload(name)
+    cde = jg.build_engine(wl, device=0)
+    w = oracle_world(orc, wl)
+    words_seen = set()
+
+    def check(op):
+        if op % 5 != 4:
+            return
+        words = cde.collector_words()
+        words_seen.add(words)
+        for item_id in (0, len(wl.items) // 2, len(wl.items) - 1):
+            t = jg.make_queries(wl, item_id, 3000, seed=100 + op)
+            assert np.array_equal(cde.detect_batch(item_id, t), w.detect_batch(item_id, t)), f"{name}: detect differs after update {op}"
+            assert np.array_equal(cde.collect_batch(item_id, t, words), w.collect_batch(item_id, t, words)), f"{name}: collect differs after update {op}"
+
+    left = place_remove_sequence(jg, wl, cde, w, n_ops=40, seed=11, after_each=check)
+    assert len(left) > 0 and cde.stats()["layout_uploads"] >= 8
+    cde.close()

@@ -6,7 +6,7 @@ import struct
 import numpy as np
 import pytest
 
-from helpers import ALL_WORKLOADS, oracle_world
+from helpers import ALL_WORKLOADS, oracle_world, place_remove_sequence
 
 
 @pytest.mark.parametrize("name", ALL_WORKLOADS)
@@ -60,6 +60,25 @@ def test_incremental_updates_match_oracle(jg, orc, name):
     same()
     assert w.matches_fresh() in (0, -1) or True  # (matches_fresh needs a Container; dumps already agree)
     assert cde.n_hazards() == len(w.hazards())
+    cde.close()
+
+
+@pytest.mark.parametrize("name", ["swim_half", "jakobs1_ms0", "albano_ms1", "baldacci1_bin", "gardeyn1c_half"])
+def test_place_and_remove_items_match_oracle(jg, orc, name):
+    """Layout::place_item / remove_item (entities/layout.rs:40-74) through jg_cde_place_item / jg_cde_remove_item:
+    the quadtree is the oracle's, word for word, after every operation."""
+    wl = jg.load_workload(name)
+    cde = jg.build_engine(wl, device=None)
+    w = oracle_world(orc, wl)
+
+    def same(op):
+        assert np.array_equal(cde.tree_dump(), w.tree_dump()), f"trees differ after operation {op}"
+        assert w.check_invariants() == 0
+
+    left = place_remove_sequence(jg, wl, cde, w, n_ops=30, seed=3, after_each=same)
+    assert cde.n_hazards() == len(w.hazards()) and len(left) > 0
+    with pytest.raises(jg.JaguaCudaError):
+        cde.remove_item(0x7777000000000001)  # unknown PItemKey
     cde.close()
 
 

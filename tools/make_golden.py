@@ -26,6 +26,8 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     for name in ALL_WORKLOADS:
+        if os.path.exists(os.path.join(out_dir, name + ".npz")) and "--all" not in sys.argv:
+            continue  # existing pins stay byte-identical; --all regenerates everything
         wl = jg.load_workload(name)
         w = oracle_world(orc, wl)
         words = max(1, (w.haz_capacity() + 31) // 32)

@@ -22,8 +22,8 @@ for i, m in enumerate(sizes):
     host_t.array[offs[i]:offs[i + 1]] = jg.make_queries(wl, i, m, seed=0)
 host_out = jg.PinnedBuffer((n,), np.uint8)
 ids = list(range(len(wl.items)))
-for chunk in (1 << 17, 1 << 18):
-    for streams in (4, 8):
+for chunk in (1 << 16, 1 << 17, 1 << 18):
+    for streams in (3, 6):
         cde.set_batching(chunk, streams)
         for _ in range(5):
             cde.detect_multi(ids, offs, host_t.array, out=host_out.array, wait=False)

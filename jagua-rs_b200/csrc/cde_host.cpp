@@ -2,6 +2,8 @@
 #include "cde_host.hpp"
 
 #include <algorithm>
+#include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <limits>
 
@@ -303,6 +305,57 @@ void HostCDE::filter_qzones(int required_quality, uint32_t* bits, int words) con
 // ---- flatten -------------------------------------------------------------------------------------
 static uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
+bool blob_grid_ok(const uint8_t* blob) {
+    JgLayoutHeader h;
+    std::memcpy(&h, blob, sizeof(h));
+    const int D = (int)h.root_level;
+    if (D < 0 || D > 5 || h.n_nodes == 0 || h.n_nodes > 0xFFFEu) return false;
+    const int G = 1 << D;
+    const int32_t* nm = (const int32_t*)(blob + h.off_node_meta);
+    const float* nb = (const float*)(blob + h.off_node_bbox);
+    float xs[33], ys[33];
+    xs[0] = nb[0], xs[G] = nb[2], ys[0] = nb[1], ys[G] = nb[3];
+    if (!(nb[2] > nb[0] && nb[3] > nb[1])) return false;
+    for (int step = G; step >= 2; step >>= 1)
+        for (int a = 0; a < G; a += step) {  // rect.rs:248-253 centroid, as k_grid_build nests it
+            xs[a + step / 2] = (xs[a] + xs[a + step]) / 2.0f;
+            ys[a + step / 2] = (ys[a] + ys[a + step]) / 2.0f;
+        }
+    const float inv_cw = (float)G / (nb[2] - nb[0]), inv_ch = (float)G / (nb[3] - nb[1]);
+    for (int k = 0; k <= G; k++) {  // premise of the one-correction cell lookup
+        const float fx = std::floor((xs[k] - xs[0]) * inv_cw), fy = std::floor((ys[k] - ys[0]) * inv_ch);
+        if (!(fx >= (float)(k - 1) && fx <= (float)k && fy >= (float)(k - 1) && fy <= (float)k)) return false;
+        if (k > 0 && !(xs[k] > xs[k - 1] && ys[k] > ys[k - 1])) return false;
+    }
+    std::vector<uint8_t> level(h.n_nodes, 0);
+    for (uint32_t n = 0; n < h.n_nodes; n++) {
+        int lv = 0, ci = 0, cj = 0;
+        uint32_t cur = n;
+        while (cur > 0 && lv <= D) {
+            const int q = (int)((cur - 1) & 3u);
+            ci |= ((q == 0 || q == 3) ? 1 : 0) << lv;
+            cj |= ((q == 0 || q == 1) ? 1 : 0) << lv;
+            lv++;
+            const int32_t par = nm[4 * cur + 3];
+            if (par < 0 || (uint32_t)par >= h.n_nodes || nm[4 * par] != (int32_t)(((cur - 1) & ~3u) + 1)) return false;
+            cur = (uint32_t)par;
+        }
+        if (lv > D || cur != 0) return false;
+        const int s = D - lv;
+        if (!(nb[4 * n] == xs[ci << s] && nb[4 * n + 2] == xs[(ci + 1) << s] && nb[4 * n + 1] == ys[cj << s] &&
+              nb[4 * n + 3] == ys[(cj + 1) << s]))
+            return false;
+        level[n] = (uint8_t)lv;
+        const int n_entire = nm[4 * n + 2] & 0xFFFF, n_partial = (nm[4 * n + 2] >> 16) & 0xFFFF;
+        const bool has_children = nm[4 * n] >= 0;
+        if (n_entire == 0 && n_partial > 0) {
+            if (!has_children && (lv != D || n_partial > 255 || nm[4 * n + 1] + n_entire >= (1 << 24))) return false;  // leaf record
+            if (has_children && lv >= D) return false;
+        }
+    }
+    return true;
+}
+
 std::vector<uint8_t> HostCDE::flatten() const {
     // breadth-first renumbering: flat index 0 = root, the 4 children of a node are contiguous
     std::vector<int> order{0};   // arena index by flat index
@@ -414,6 +467,9 @@ std::vector<uint8_t> HostCDE::flatten() const {
         std::memcpy(haz_verts + 2 * vi, hz.xy.data(), hz.xy.size() * sizeof(float));
         vi += (uint32_t)hz.n_verts();
     }
+    // the grid premise of the detect / collect grid kernels, evaluated here so that an upload needs no read-back
+    const uint32_t flags = JG_LAYOUT_FLAG_GRID_CHECKED | (blob_grid_ok(blob.data()) ? JG_LAYOUT_FLAG_GRID_OK : 0u);
+    std::memcpy(blob.data() + offsetof(JgLayoutHeader, flags), &flags, sizeof(flags));
     return blob;
 }
 

@@ -56,6 +56,10 @@ struct QNode {
     uint32_t n_active_edges = 0;
 };
 
+// The host twin of k_grid_build's validity verdict (csrc/detect_grid.cuh) for a NoFilter summary, evaluated on
+// a flattened blob: lets a layout upload choose the kernel path without reading anything back from the device.
+bool blob_grid_ok(const uint8_t* blob);
+
 class HostCDE {
 public:
     HostCDE(Rect bbox, JgConfig cfg);

@@ -649,6 +649,7 @@ cudaError_t launch_node_kinds(const DevLayout& L, int depth, const uint32_t* d_f
         k_cgrid_build<<<1, 1024, 0, st>>>(L, grid_of(d_kinds, L.n_nodes), (GridCollect*)cgrid_of(d_kinds, L.n_nodes));
     return cudaGetLastError();
 }
+const int* detect_grid_ok_ptr(const uint8_t* d_kinds, int n_nodes) { return &grid_of(d_kinds, n_nodes)->ok; }
 // 1 when the grid kernels can serve this layout (k_grid_build's verdict); synchronises the stream
 cudaError_t detect_grid_usable(const uint8_t* d_kinds, int n_nodes, cudaStream_t st, int* ok) {
     *ok = 0;

@@ -58,8 +58,25 @@ struct JgEngine {
     int n_sms = 148;
     std::string err;
 
-    void* d_blob = nullptr;
-    size_t blob_cap = 0;
+    // Two layout buffers: an upload fills the one that is not current on its own stream (st_up) while queries on
+    // the current one are still running; queries launched afterwards wait for `ready` on the device, never on the host.
+    struct LayoutBuf {
+        void* d_blob = nullptr;
+        size_t blob_cap = 0;
+        uint8_t* d_kinds = nullptr;  // node summary under NoFilter (+ GridDev + GridCollect)
+        size_t kinds_cap = 0;
+        void* h_stage = nullptr;     // pinned copy of the blob (the caller's buffer may be pageable / short-lived)
+        size_t stage_cap = 0;
+        cudaEvent_t ready = nullptr; // copy + summaries of the last upload into this buffer are done
+        std::vector<cudaEvent_t> marks;  // recorded on every query stream when this buffer became current
+        bool marks_valid = false;
+        int expect_grid = -1;        // host verdict to be confirmed by k_grid_build's (-1: nothing pending)
+    } bufs[2];
+    int cur = 0;
+    cudaStream_t st_up = nullptr;
+    int* h_grid_ok = nullptr;  // pinned, [2]: k_grid_build's verdict of the last upload into each buffer
+    int grid_ok_cur = 0;       // the grid premise holds for the current layout
+    void* d_blob = nullptr;    // = bufs[cur].d_blob
     JgLayoutHeader hdr{};
     DevLayout L{};
     bool has_layout = false;
@@ -68,8 +85,7 @@ struct JgEngine {
     DetectPlan plan{0, 0, 0, 0};
     bool force_walk = false;  // jg_engine_set_detect_path: keep the quadtree-walk kernels even when the grid applies
     bool use_fused = false;   // JG_PATH_FUSED: one fused, copy-following kernel per batch (experimental, slower)
-    uint8_t* d_kinds = nullptr;   // node summary under NoFilter
-    size_t kinds_cap = 0;
+    uint8_t* d_kinds = nullptr;   // = bufs[cur].d_kinds
 
     std::map<int, ItemDev> items;
     std::map<int, FilterDev> filters;
@@ -222,6 +238,14 @@ int jg_engine_create(int device, const JgConfig* cfg, JgEngine** out) {
     }
     e->h_err = e->h_avail + JG_STREAM_MAX_CHUNKS;
     *e->h_err = 0;
+    if (cudaStreamCreateWithFlags(&e->st_up, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void**)&e->h_grid_ok, 2 * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->bufs[0].ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->bufs[1].ready, cudaEventDisableTiming) != cudaSuccess) {
+        delete e;
+        return JG_ERR_CUDA;
+    }
+    e->h_grid_ok[0] = e->h_grid_ok[1] = 0;
     e->chunks.resize(3);
     for (ChunkCtx& c : e->chunks)
         if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) {
@@ -251,14 +275,20 @@ void jg_engine_destroy(JgEngine* e) {
     if (e->st_copy) cudaStreamDestroy(e->st_copy);
     if (e->ev_reset) cudaEventDestroy(e->ev_reset);
     if (e->h_avail) cudaFreeHost(e->h_avail);
-    if (e->d_kinds) cudaFree(e->d_kinds);
+    for (JgEngine::LayoutBuf& B : e->bufs) {
+        cudaFree(B.d_blob), cudaFree(B.d_kinds);
+        if (B.h_stage) cudaFreeHost(B.h_stage);
+        if (B.ready) cudaEventDestroy(B.ready);
+        for (cudaEvent_t ev : B.marks) cudaEventDestroy(ev);
+    }
+    if (e->st_up) cudaStreamDestroy(e->st_up);
+    if (e->h_grid_ok) cudaFreeHost(e->h_grid_ok);
     for (ChunkCtx& c : e->chunks) {
         cudaStream_t st = c.st;
         free_ctx(c);
         if (st) cudaStreamDestroy(st);
     }
     free_ctx(e->main_ctx);
-    if (e->d_blob) cudaFree(e->d_blob);
     if (e->d_flush) cudaFree(e->d_flush);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -275,7 +305,14 @@ int jg_sync(JgEngine* e) {
     JG_CUDA(e, cudaSetDevice(e->device));
     for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
     if (e->st_copy) JG_CUDA(e, cudaStreamSynchronize(e->st_copy));
+    if (e->st_up) JG_CUDA(e, cudaStreamSynchronize(e->st_up));
     JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    for (int b = 0; b < 2; b++)  // stream-ordered uploads: k_grid_build must have confirmed the host's verdict
+        if (e->bufs[b].expect_grid >= 0) {
+            const int want = e->bufs[b].expect_grid;
+            e->bufs[b].expect_grid = -1;
+            if (e->h_grid_ok[b] != want) return fail(e, JG_ERR_INVALID, "layout upload: host and device disagree on the grid premise");
+        }
     if (trace_on() && e->trace_used >= 5) {
         fprintf(stderr, "[jg trace] piece: queries | t(start) t(h2d done) t(kernels done) t(d2h done)  [us since first mark]\n");
         for (size_t i = 1; i + 3 < e->trace_used + 0 && (i - 1) / 4 < e->trace_m.size(); i += 4) {
@@ -371,35 +408,104 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
                 return fail(e, JG_ERR_INVALID, "layout blob: bad edge range");
         }
     }
-    rc = jg_sync(e);  // queries in flight finish on the old layout
-    if (rc != JG_OK) return rc;
-    if (e->blob_cap < h.total_bytes) {
-        if (e->d_blob) cudaFree(e->d_blob);
-        e->d_blob = nullptr;
-        e->blob_cap = 0;
+    // Which kernels serve this layout (grid or walk) is decided on the host: by the producer (flags) or here.
+    int host_grid = -1;  // -1 unknown (device blob of a foreign producer): read k_grid_build's verdict back
+    if (h.flags & JG_LAYOUT_FLAG_GRID_CHECKED) host_grid = (h.flags & JG_LAYOUT_FLAG_GRID_OK) ? 1 : 0;
+    else if (!src_on_device) host_grid = blob_grid_ok((const uint8_t*)src) ? 1 : 0;
+    static const bool force_sync = getenv("JG_SYNC_UPLOAD") != nullptr;
+    // stream-ordered path: needs a current layout to keep serving, a host verdict, and no per-filter summaries
+    // (those are rebuilt lazily on the compute stream and are not double-buffered)
+    const bool fast = !force_sync && e->has_layout && host_grid >= 0 && e->filters.empty();
+    const int nb = fast ? 1 - e->cur : e->cur;
+    JgEngine::LayoutBuf& B = e->bufs[nb];
+    const size_t kinds_need = detect_kinds_bytes((int)h.n_nodes);
+    const bool grow = B.blob_cap < h.total_bytes || B.kinds_cap < kinds_need || (fast && !src_on_device && B.stage_cap < h.total_bytes);
+    if (!fast || grow) {
+        rc = jg_sync(e);  // queries in flight finish on the old layout
+        if (rc != JG_OK) return rc;
+    }
+    if (B.blob_cap < h.total_bytes) {
+        if (B.d_blob) cudaFree(B.d_blob);
+        B.d_blob = nullptr;
+        B.blob_cap = 0;
         const size_t cap = (size_t)h.total_bytes * 2 + 4096;
-        JG_CUDA(e, cudaMalloc(&e->d_blob, cap));
-        e->blob_cap = cap;
+        JG_CUDA(e, cudaMalloc(&B.d_blob, cap));
+        B.blob_cap = cap;
     }
-    JG_CUDA(e, cudaMemcpyAsync(e->d_blob, src, h.total_bytes,
-                               src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->compute));
-    JG_CUDA(e, cudaStreamSynchronize(e->compute));
-    bind_layout(e, h);
-    e->layout_version++;
-    e->plan = make_detect_plan((int)h.n_nodes, (int)h.root_level);
-    if (e->kinds_cap < detect_kinds_bytes((int)h.n_nodes)) {
-        if (e->d_kinds) cudaFree(e->d_kinds);
-        e->d_kinds = nullptr;
-        e->kinds_cap = 0;
-        const size_t cap = detect_kinds_bytes((int)h.n_nodes) * 2;
-        JG_CUDA(e, cudaMalloc(&e->d_kinds, cap));
-        e->kinds_cap = cap;
+    if (B.kinds_cap < kinds_need) {
+        if (B.d_kinds) cudaFree(B.d_kinds);
+        B.d_kinds = nullptr;
+        B.kinds_cap = 0;
+        JG_CUDA(e, cudaMalloc(&B.d_kinds, kinds_need * 2));
+        B.kinds_cap = kinds_need * 2;
     }
-    JG_CUDA(e, launch_node_kinds(e->L, (int)h.root_level, nullptr, e->d_kinds, e->compute));
-    {
+    if (fast) {
+        std::vector<cudaStream_t> qs{e->compute, e->st_copy};
+        for (ChunkCtx& c : e->chunks) qs.push_back(c.st);
+        // readers of buffer nb were launched before the other buffer became current: its marks cover them
+        JgEngine::LayoutBuf& O = e->bufs[1 - nb];
+        if (O.marks_valid)
+            for (cudaEvent_t ev : O.marks) JG_CUDA(e, cudaStreamWaitEvent(e->st_up, ev, 0));
+        else
+            for (cudaStream_t st : qs) JG_CUDA(e, cudaStreamSynchronize(st));
+        if (!src_on_device) {
+            if (B.stage_cap < h.total_bytes) {
+                if (B.h_stage) cudaFreeHost(B.h_stage);
+                B.h_stage = nullptr;
+                B.stage_cap = 0;
+                JG_CUDA(e, cudaHostAlloc(&B.h_stage, (size_t)h.total_bytes * 2 + 4096, cudaHostAllocDefault));
+                B.stage_cap = (size_t)h.total_bytes * 2 + 4096;
+            }
+            JG_CUDA(e, cudaEventSynchronize(B.ready));  // the previous copy out of this staging buffer (two uploads ago)
+            std::memcpy(B.h_stage, src, h.total_bytes);
+            JG_CUDA(e, cudaMemcpyAsync(B.d_blob, B.h_stage, h.total_bytes, cudaMemcpyHostToDevice, e->st_up));
+        } else {
+            JG_CUDA(e, cudaMemcpyAsync(B.d_blob, src, h.total_bytes, cudaMemcpyDeviceToDevice, e->st_up));
+        }
+        e->cur = nb;
+        e->d_blob = B.d_blob;
+        e->d_kinds = B.d_kinds;
+        bind_layout(e, h);
+        e->layout_version++;
+        e->plan = make_detect_plan((int)h.n_nodes, (int)h.root_level);
+        JG_CUDA(e, launch_node_kinds(e->L, (int)h.root_level, nullptr, B.d_kinds, e->st_up));
+        JG_CUDA(e, cudaMemcpyAsync(&e->h_grid_ok[nb], detect_grid_ok_ptr(B.d_kinds, (int)h.n_nodes), sizeof(int), cudaMemcpyDeviceToHost, e->st_up));
+        JG_CUDA(e, cudaEventRecord(B.ready, e->st_up));
+        B.expect_grid = host_grid;
+        e->grid_ok_cur = host_grid;
+        e->plan.use_grid = (host_grid && !e->force_walk) ? 1 : 0;
+        // queries launched from now on read the new buffer: they wait for it on the device; the marks taken now
+        // cover every reader of the other buffer
+        if (B.marks.size() != qs.size()) {
+            for (cudaEvent_t ev : B.marks) cudaEventDestroy(ev);
+            B.marks.assign(qs.size(), nullptr);
+            for (cudaEvent_t& ev : B.marks) JG_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        }
+        for (size_t i = 0; i < qs.size(); i++) {
+            JG_CUDA(e, cudaEventRecord(B.marks[i], qs[i]));
+            JG_CUDA(e, cudaStreamWaitEvent(qs[i], B.ready, 0));
+        }
+        B.marks_valid = true;
+        if (src_on_device) JG_CUDA(e, cudaStreamSynchronize(e->st_up));  // the caller may reuse its buffer on return
+    } else {
+        JG_CUDA(e, cudaMemcpyAsync(B.d_blob, src, h.total_bytes,
+                                   src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->compute));
+        JG_CUDA(e, cudaStreamSynchronize(e->compute));
+        e->cur = nb;
+        e->d_blob = B.d_blob;
+        e->d_kinds = B.d_kinds;
+        bind_layout(e, h);
+        e->layout_version++;
+        e->plan = make_detect_plan((int)h.n_nodes, (int)h.root_level);
+        JG_CUDA(e, launch_node_kinds(e->L, (int)h.root_level, nullptr, B.d_kinds, e->compute));
         int ok = 0;
-        JG_CUDA(e, detect_grid_usable(e->d_kinds, (int)h.n_nodes, e->compute, &ok));
+        JG_CUDA(e, detect_grid_usable(B.d_kinds, (int)h.n_nodes, e->compute, &ok));
+        if (host_grid >= 0 && host_grid != ok)
+            return fail(e, JG_ERR_INVALID, "layout upload: host and device disagree on the grid premise");
+        e->grid_ok_cur = ok;
         e->plan.use_grid = (ok && !e->force_walk) ? 1 : 0;
+        B.expect_grid = -1;
+        e->bufs[0].marks_valid = e->bufs[1].marks_valid = false;  // everything was synchronised
     }
     e->stat_launches += 2;
     e->epoch = epoch;
@@ -942,6 +1048,7 @@ int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams) {
     int rc = jg_sync(e);
     if (rc != JG_OK) return rc;
     e->chunk_queries = chunk_queries;
+    e->bufs[0].marks_valid = e->bufs[1].marks_valid = false;  // the set of query streams changes
     while ((int)e->chunks.size() > n_streams) {
         cudaStream_t st = e->chunks.back().st;
         free_ctx(e->chunks.back());
@@ -975,12 +1082,7 @@ int jg_engine_set_detect_path(JgEngine* e, int path) {
     if (rcs != JG_OK) return rcs;
     e->force_walk = path == JG_PATH_WALK;
     e->use_fused = path == JG_PATH_FUSED;
-    if (e->has_layout && e->d_kinds) {
-        int ok = 0;
-        JG_CUDA(e, cudaSetDevice(e->device));
-        JG_CUDA(e, detect_grid_usable(e->d_kinds, (int)e->hdr.n_nodes, e->compute, &ok));
-        e->plan.use_grid = (ok && !e->force_walk) ? 1 : 0;
-    }
+    if (e->has_layout && e->d_kinds) e->plan.use_grid = (e->grid_ok_cur && !e->force_walk) ? 1 : 0;
     return JG_OK;
 }
 int jg_engine_detect_path(const JgEngine* e) { return e && e->plan.use_grid ? (e->use_fused ? 2 : 1) : 0; }

@@ -80,6 +80,7 @@ size_t detect_kinds_bytes(int n_nodes);
 // per-filter node summary read by the detect kernels; d_filt == nullptr is NoFilter
 cudaError_t launch_node_kinds(const DevLayout& L, int depth, const uint32_t* d_filt, uint8_t* d_kinds, cudaStream_t st);
 cudaError_t detect_grid_usable(const uint8_t* d_kinds, int n_nodes, cudaStream_t st, int* ok);
+const int* detect_grid_ok_ptr(const uint8_t* d_kinds, int n_nodes);  // device address of k_grid_build's verdict
 cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegTable& tab, const XfSrc& d_xf,
                           const uint32_t* d_filt, const uint8_t* d_kinds, int mode, uint8_t* d_out, const DetectScratch& sc,
                           int n_sms, cudaStream_t st, int* n_launches);

@@ -14,6 +14,10 @@
 
 #define JG_LAYOUT_MAGIC 0x4A47424Cu /* "JGBL" */
 #define JG_LAYOUT_VERSION 1u
+/* flags: the producer evaluated the grid premise of csrc/detect_grid.cuh on the host (GRID_CHECKED) and it holds
+ * (GRID_OK): depth <= 5, every node box equals the nested-midpoint grid bit for bit, leaf records fit. */
+#define JG_LAYOUT_FLAG_GRID_CHECKED 1u
+#define JG_LAYOUT_FLAG_GRID_OK 2u
 
 typedef struct JgLayoutHeader {
     uint32_t magic, version;
@@ -26,7 +30,7 @@ typedef struct JgLayoutHeader {
     uint32_t root_level;   // CDEConfig::quadtree_depth
     uint32_t cd_threshold;
     uint32_t exterior_slot;
-    uint32_t reserved0;
+    uint32_t flags;        // JG_LAYOUT_FLAG_*
     float cde_bbox[4];     // = node_bbox[0]
     // byte offsets from the start of the blob
     uint32_t off_node_meta;    // int4  {child_base | -1, entry_begin, n_entire | n_partial << 16, parent | -1}

@@ -150,9 +150,8 @@ def apply_update(b):
             cde.sync_layout()
     if world > 1:
         d_blob = multigpu.broadcast_blob(blob, dist, src=0, device=f"cuda:{local_rank}")
+        # stream-ordered on the engine's upload stream; returns once the receive buffer has been copied
         cdes[s].upload_layout_device(d_blob.data_ptr(), d_blob.numel(), epoch=b + 2)
-        # the receive buffer must outlive the upload copy
-        cdes[s].sync()
     update_s += time.perf_counter() - t0
 
 

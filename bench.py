@@ -9,8 +9,11 @@ A step = one pass of the hot path (detect_surrogate_collision + detect_poly_coll
 
 value      queries/s, inputs resident in HBM, CUDA events on the engine's compute stream, L2 flushed
            (untimed) before every step.
-e2e        queries/s through the public host-buffer API (CDEngine.detect_batch_async on pinned host
-           arrays + sync): H2D of the transforms and D2H of the verdicts inside the timed region.
+e2e        queries/s through the public host-buffer API (CDEngine.detect_multi on pinned host arrays, the
+           asynchronous form: K batches enqueued back to back, one sync at the end, so consecutive batches
+           overlap their copies and kernels on the engine's streams): H2D of every step's transforms and
+           D2H of every step's verdicts inside the timed region. e2e.one_batch_at_a_time is the same call
+           followed by a sync after every batch (the latency-bound figure).
 roofline   FP32 pipe without FMA (the kernels are compiled -fmad=false for bit-exactness): algorithmic
            flops counted by the instrumented oracle (workloads/swim_half.flops.json) / device time,
            against the peak measured live by jg_fp32_nofma_peak. The HBM view of the same step is
@@ -208,10 +211,6 @@ def main():
     def step_device():
         cde.detect_multi_device(item_ids, offs, dev_t.ptr, dev_out.ptr)
 
-    def step_e2e():
-        cde.detect_multi(item_ids, offs, host_t.array, out=host_out.array, wait=False)
-        cde.sync()
-
     # the same batch in the compact wire form (rotation index u8 + translation 2 x f32 = 9 B/query)
     host_ridx = jg.PinnedBuffer((n_q,), np.uint8)
     host_txy = jg.PinnedBuffer((n_q, 2), np.float32)
@@ -223,10 +222,6 @@ def main():
             r, t = jg.make_queries_indexed(wl, i, n, seed=rank)
             host_ridx.array[offs[i]:offs[i + 1]] = r
             host_txy.array[offs[i]:offs[i + 1]] = t
-
-    def step_e2e_indexed():
-        cde.detect_multi_indexed(item_ids, offs, host_ridx.array, host_txy.array, out=host_out_ix.array, wait=False)
-        cde.sync()
 
     def barrier():
         cde.sync()
@@ -255,35 +250,50 @@ def main():
     gpu_launches = cde.stats()["launches"] - launches0 - args.steps  # minus the untimed L2 flush fills
 
     # ---- e2e: host buffers through the public API, copies inside the timed region
-    for _ in range(max(args.warmup, 3)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_ix_s = 0.0
-    if indexed_ok:
-        for _ in range(max(args.warmup, 3)):
-            step_e2e_indexed()
+    # (a) one batch at a time: enqueue + sync per step, pieces of 256 Ki queries on 4 streams
+    # (b) batches in flight: K steps enqueued back to back (whole batch per stream, 3 streams), one sync at the end
+    ring = [host_out] + [jg.PinnedBuffer((n_q,), np.uint8) for _ in range(3)]
+    ring_ix = [host_out_ix] + [jg.PinnedBuffer((n_q,), np.uint8) for _ in range(3)]
+
+    def run_e2e(step_fn, pipelined):
+        cde.set_batching(1 << 20 if pipelined else 1 << 18, 3 if pipelined else 4)
+        for i in range(max(args.warmup, 3)):
+            step_fn(i)
+            cde.sync()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e_indexed()
+        for i in range(args.steps):
+            step_fn(i)
+            if not pipelined:
+                cde.sync()
         barrier()
-        e2e_ix_s = time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    def enq(i):
+        cde.detect_multi(item_ids, offs, host_t.array, out=ring[i % 4].array, wait=False)
+
+    def enq_ix(i):
+        cde.detect_multi_indexed(item_ids, offs, host_ridx.array, host_txy.array, out=ring_ix[i % 4].array, wait=False)
+
+    e2e_serial_s = run_e2e(enq, False)
+    e2e_s = run_e2e(enq, True)
+    e2e_ix_s = e2e_ix_serial_s = 0.0
+    if indexed_ok:
+        e2e_ix_serial_s = run_e2e(enq_ix, False)
+        e2e_ix_s = run_e2e(enq_ix, True)
     clocks = sampler.stop()
 
     if dist is not None:
         import torch
-        tt = torch.tensor([dev_ms, e2e_s, e2e_ix_s], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dev_ms, e2e_s, e2e_ix_s, e2e_serial_s, e2e_ix_serial_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, e2e_ix_s = float(tt[0]), float(tt[1]), float(tt[2])
+        dev_ms, e2e_s, e2e_ix_s, e2e_serial_s, e2e_ix_serial_s = (float(x) for x in tt)
 
     # verdicts of the last e2e step vs the device-resident path (same inputs -> identical)
-    same = np.array_equal(host_out.array, dev_out.download((n_q,), np.uint8))
-    same_ix = bool(indexed_ok and np.array_equal(host_out.array, host_out_ix.array))
+    dev_verdicts = dev_out.download((n_q,), np.uint8)
+    n_ring = min(4, args.steps)  # every in-flight result buffer the timed steps wrote
+    same = all(np.array_equal(ring[k].array, dev_verdicts) for k in range(n_ring))
+    same_ix = bool(indexed_ok and all(np.array_equal(ring_ix[k].array, dev_verdicts) for k in range(n_ring)))
 
     if rank == 0:
         total_q = args.queries * world
@@ -321,8 +331,16 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 16 * args.queries, "d2h_bytes_per_step": args.queries,
                         "ms_per_step": e2e_s / args.steps * 1e3, "same_verdicts_as_device_path": bool(same),
                         "input": "composed (cos, sin, tx, ty) f32 records, 16 B/query, pinned host memory",
+                        "mode": "detect_multi(wait=False) for all K steps back to back (4 rotating result buffers), one sync at the end: "
+                                "consecutive batches overlap on the engine's streams; every step's H2D and D2H is inside the timed region",
+                        "pcie_h2d_ceiling_queries_per_s": 53e9 / 16,
+                        "one_batch_at_a_time": {"value": total_q * args.steps / e2e_serial_s, "unit": UNIT,
+                                                "ms_per_step": e2e_serial_s / args.steps * 1e3,
+                                                "mode": "sync after every batch; pieces of 256 Ki queries on 4 streams"},
                         "compact_input": None if not indexed_ok else {
                             "value": total_q * args.steps / e2e_ix_s, "unit": UNIT, "ms_per_step": e2e_ix_s / args.steps * 1e3,
+                            "one_batch_at_a_time": {"value": total_q * args.steps / e2e_ix_serial_s, "unit": UNIT,
+                                                    "ms_per_step": e2e_ix_serial_s / args.steps * 1e3},
                             "h2d_bytes_per_step": 9 * args.queries, "d2h_bytes_per_step": args.queries,
                             "input": "jg_detect_multi_indexed: rotation index u8 + translation 2 x f32 = 9 B/query (items with discrete "
                                      "allowed orientations), same queries", "same_verdicts": same_ix}},

@@ -246,7 +246,7 @@ int jg_engine_create(int device, const JgConfig* cfg, JgEngine** out) {
         return JG_ERR_CUDA;
     }
     e->h_grid_ok[0] = e->h_grid_ok[1] = 0;
-    e->chunks.resize(3);
+    e->chunks.resize(4);  // in-flight pieces of host batches (tools/pipeline_probe.py: 4 x 256 Ki is the best default)
     for (ChunkCtx& c : e->chunks)
         if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) {
             delete e;

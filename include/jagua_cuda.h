@@ -185,6 +185,28 @@ int jg_fp32_nofma_peak(JgEngine* e, double* gflops, float* ms);
 int jg_flush_l2(JgEngine* e);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Item preparation (host, once per item type)                                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+/* SPSurrogateConfig (geometry/fail_fast/sp_surrogate.rs:120-131); LBF defaults (lbf/src/config.rs:33-41):
+ * n_pole_limits {100, 20, 10}, coverage_limits {0.0, 0.75, 0.90}, n_ff_poles 2, n_ff_piers 0 */
+typedef struct JgSurrogateConfig {
+    int n_pole_limits[3];
+    float coverage_limits[3];
+    int n_ff_poles;
+    int n_ff_piers;
+} JgSurrogateConfig;
+
+/* Importer::import_item for an ExtShape::SimplePolygon with shape modification disabled (io/import.rs:47-98,
+ * 198-260) + Item::new's surrogate (entities/item.rs:28-53, fail_fast/sp_surrogate.rs:33-61, fail_fast/pole.rs:12-135):
+ * cleans the vertex list (closing duplicate, approx-equal neighbours), orients it counter-clockwise, computes the
+ * pole of inaccessibility, centres the shape on its centroid (pre_transform = (0, -cx, -cy)) and generates the
+ * surrogate poles under the coverage limits. Outputs are what jg_item_upload takes. verts_xy must hold 2 * n_pts
+ * floats; poles beyond poles_cap are counted in *n_poles but not written. Piers (n_ff_piers > 0) are not generated. */
+int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
+                   float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2], float* area);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Host mirror of CDEngine's update path                                                       */
 /* ------------------------------------------------------------------------------------------ */
 

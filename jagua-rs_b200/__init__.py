@@ -86,6 +86,8 @@ C_ABI = {
     "jg_compose_batch": (None, [_f32p, C.c_int64, _f32p, C.c_int]),
     "jg_fp32_nofma_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "jg_flush_l2": (C.c_int, [_vp]),
+    "jg_item_import": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int, C.POINTER(C.c_int), _f32p,
+                                 C.POINTER(C.c_float)]),
     "jg_cde_create": (C.c_int, [_f32p, C.POINTER(JgConfig), C.POINTER(_vp)]),
     "jg_cde_destroy": (None, [_vp]),
     "jg_cde_last_error": (C.c_char_p, [_vp]),
@@ -150,6 +152,28 @@ class ItemShape:
     poi: np.ndarray              # (x, y[, r])
     poles: np.ndarray            # (P, 3) x, y, r
     piers: np.ndarray = None     # (Q, 4)
+
+
+class JgSurrogateConfig(C.Structure):
+    _fields_ = [("n_pole_limits", C.c_int * 3), ("coverage_limits", C.c_float * 3), ("n_ff_poles", C.c_int), ("n_ff_piers", C.c_int)]
+
+
+def import_item(points, n_pole_limits=((100, 0.0), (20, 0.75), (10, 0.90)), n_ff_poles: int = 2):
+    """Importer::import_item + Item::new's surrogate for a simple polygon (io/import.rs:47-98, fail_fast/pole.rs:12-135)
+    through jg_item_import: returns (ItemShape, pre_transform (tx, ty), area). Shape modification (simplification,
+    offsetting) is not applied; piers are not generated."""
+    lib = load_library()
+    pts = _f32(points).reshape(-1, 2)
+    cfg = JgSurrogateConfig((C.c_int * 3)(*[int(a) for a, _ in n_pole_limits]), (C.c_float * 3)(*[float(b) for _, b in n_pole_limits]),
+                            int(n_ff_poles), 0)
+    verts = np.zeros((len(pts), 2), np.float32)
+    poles = np.zeros((1000, 3), np.float32)
+    poi, pre = np.zeros(3, np.float32), np.zeros(2, np.float32)
+    nv, npol, area = C.c_int(0), C.c_int(0), C.c_float(0.0)
+    rc = lib.jg_item_import(pts, len(pts), C.addressof(cfg), verts, C.byref(nv), poi, poles, len(poles), C.byref(npol), pre, C.byref(area))
+    if rc != JG_OK:
+        raise JaguaCudaError(rc, "jg_item_import: degenerate polygon (fewer than 3 distinct vertices, duplicate points or no area)")
+    return ItemShape(verts[:nv.value].copy(), poi, poles[:npol.value].copy(), np.zeros((0, 4), np.float32)), pre, float(area.value)
 
 
 class PinnedBuffer:

@@ -160,6 +160,11 @@ def main():
         return
 
     import jagua_rs_b200 as jg
+    from jagua_rs_b200 import multigpu
+
+    # pinned staging buffers on the GPU's own socket (matters from 4 ranks up: every rank streams ~53 GB/s)
+    # (N = 1 keeps every core: the cpu_baseline leg below uses all of them)
+    numa = multigpu.bind_to_gpu_numa_node(local_rank) if world > 1 and not os.environ.get("JG_NO_NUMA_BIND") else {"why": "single rank or JG_NO_NUMA_BIND"}
 
     dist = None
     if world > 1:
@@ -344,7 +349,7 @@ def main():
                             "h2d_bytes_per_step": 9 * args.queries, "d2h_bytes_per_step": args.queries,
                             "input": "jg_detect_multi_indexed: rotation index u8 + translation 2 x f32 = 9 B/query (items with discrete "
                                      "allowed orientations), same queries", "same_verdicts": same_ix}},
-                "roofline": roofline, "layout_setup_ms": layout_setup_ms}
+                "roofline": roofline, "layout_setup_ms": layout_setup_ms, "numa_binding_rank0": numa}
         if world == 1 and not args.no_cpu_baseline:
             orc, oracle_world = load_oracle()
             w = oracle_world(orc, wl)

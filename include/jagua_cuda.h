@@ -206,6 +206,11 @@ typedef struct JgSurrogateConfig {
 int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
                    float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2], float* area);
 
+/* SPolygon::new for a shape that is registered as it is (container outer boundary, hole, quality zone;
+ * geometry/primitives/simple_polygon.rs:40-71): orientation normalised to counter-clockwise (written to
+ * verts_ccw_xy when non-null, 2 * n_pts floats) and the pole of inaccessibility jg_cde_register_hazard wants. */
+int jg_polygon_poi(const float* pts_xy, int n_pts, float poi_xyr[3], float* verts_ccw_xy);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Host mirror of CDEngine's update path                                                       */
 /* ------------------------------------------------------------------------------------------ */

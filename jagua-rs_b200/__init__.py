@@ -88,6 +88,7 @@ C_ABI = {
     "jg_flush_l2": (C.c_int, [_vp]),
     "jg_item_import": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int, C.POINTER(C.c_int), _f32p,
                                  C.POINTER(C.c_float)]),
+    "jg_polygon_poi": (C.c_int, [_f32p, C.c_int, _f32p, _vp]),
     "jg_cde_create": (C.c_int, [_f32p, C.POINTER(JgConfig), C.POINTER(_vp)]),
     "jg_cde_destroy": (None, [_vp]),
     "jg_cde_last_error": (C.c_char_p, [_vp]),
@@ -174,6 +175,18 @@ def import_item(points, n_pole_limits=((100, 0.0), (20, 0.75), (10, 0.90)), n_ff
     if rc != JG_OK:
         raise JaguaCudaError(rc, "jg_item_import: degenerate polygon (fewer than 3 distinct vertices, duplicate points or no area)")
     return ItemShape(verts[:nv.value].copy(), poi, poles[:npol.value].copy(), np.zeros((0, 4), np.float32)), pre, float(area.value)
+
+
+def polygon_poi(points):
+    """SPolygon::new for a shape registered as it is: (counter-clockwise vertices, poi (x, y, r))."""
+    lib = load_library()
+    pts = _f32(points).reshape(-1, 2)
+    poi = np.zeros(3, np.float32)
+    ccw = np.zeros_like(pts)
+    rc = lib.jg_polygon_poi(pts, len(pts), poi, ccw.ctypes.data)
+    if rc != JG_OK:
+        raise JaguaCudaError(rc, "jg_polygon_poi: degenerate polygon")
+    return ccw, poi
 
 
 class PinnedBuffer:

@@ -129,6 +129,30 @@ bool compute_pole(const Shape& sh, const std::vector<Pole>& poles, Pole& out) {
 
 using namespace jg;
 
+// SPolygon::new's pole of inaccessibility (simple_polygon.rs:40-71,151-171) for a shape that is used as it is
+// (container outer boundary, holes, zones): same cleaning-free path as the reference - the caller passes the
+// final vertex list; orientation is normalised to counter-clockwise first, as SPolygon::new does.
+extern "C" int jg_polygon_poi(const float* pts_xy, int n_pts, float poi_xyr[3], float* verts_ccw_xy) {
+    if (!pts_xy || n_pts < 3 || !poi_xyr) return JG_ERR_INVALID;
+    Shape sh;
+    sh.v.resize((size_t)n_pts);
+    for (int i = 0; i < n_pts; i++) sh.v[i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
+    sh.area = signed_area(sh.v);
+    if (sh.area == 0.0f) return JG_ERR_INVALID;
+    if (sh.area < 0.0f) {
+        std::vector<Pt> r(sh.v.rbegin(), sh.v.rend());
+        sh.v.swap(r);
+        sh.area = -sh.area;
+    }
+    sh.bbox = bbox_of(sh.v);
+    Pole poi;
+    if (!compute_pole(sh, {}, poi)) return JG_ERR_REFERENCE_PANIC;
+    poi_xyr[0] = poi.x, poi_xyr[1] = poi.y, poi_xyr[2] = poi.r;
+    if (verts_ccw_xy)
+        for (int i = 0; i < n_pts; i++) verts_ccw_xy[2 * i] = sh.v[i].x, verts_ccw_xy[2 * i + 1] = sh.v[i].y;
+    return JG_OK;
+}
+
 extern "C" int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
                               float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2],
                               float* area) {

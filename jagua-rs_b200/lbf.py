@@ -1,0 +1,261 @@
+"""Batched left-bottom-fill on top of the engine: the caller side of the hot path.
+
+Mirrors the reference's LBF strip-packing optimizer (lbf/src/opt/lbf_spp.rs:37-123, lbf/src/opt/search.rs:17-115,
+lbf/src/opt/loss.rs:12-52, lbf/src/samplers/{uniform_rect_sampler,ls_sampler}.rs) with one structural change: the
+reference evaluates its samples one by one, each decision (worth_testing, bbox tightening, mean shift) depending on
+the previous sample; here every decision point takes a whole BATCH of samples through `CDEngine.detect_batch`
+(surrogate + polygon stage on the GPU) and keeps the feasible sample of minimal loss. The sample order therefore
+differs from the reference and results are compared on solution quality (strip width / density, feasibility checked
+by the oracle in tests/), not bit for bit:
+
+  * uniform phase: `uniform_rounds` batches over the CDE bbox, the sampling box tightened to x_max <= cost / 10
+    after every round (LBFLoss::tighten_sample_bbox);
+  * local search: `ls_rounds` batches drawn from normal distributions around the best sample, the standard
+    deviations decaying from 1 % to 0.05 % of the bbox (translation) and 2 deg to 0.5 deg (continuous rotation)
+    along init * (end / init)^progress (LSSampler::decay_stddev), the mean shifted to every improvement;
+  * no feasible sample: the strip grows by 10 % (change_strip_width) - a new CDEngine, all placements re-registered;
+  * at the end the strip is fitted to the right-most item * 1.00001 (SPProblem::fit_strip).
+
+Items come from an instance file through jg_item_import (importer cleaning, centring, surrogate poles, product C++),
+placements go through jg_cde_place_item, layouts through the stream-ordered upload. Nothing here touches oracle/.
+"""
+from __future__ import annotations
+
+import json
+import time
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import HAZ_EXTERIOR, CDEngine, ItemShape, compose, import_item, polygon_poi
+
+X_MULTIPLIER = np.float32(10.0)  # lbf/src/opt/loss.rs:5
+
+
+@dataclass
+class LbfItem:
+    id: int
+    shape: ItemShape
+    rotations: Optional[np.ndarray]  # radians (f32); None = continuous; empty = no rotation
+    demand: int
+    area: float
+    diameter: float
+    pre_transform: np.ndarray
+
+
+@dataclass
+class Placement:
+    item_id: int
+    d_transf: np.ndarray  # (rotation, tx, ty) f32
+    pk: int
+
+
+@dataclass
+class LbfResult:
+    strip_width: float
+    strip_height: float
+    density: float
+    placements: List[Placement] = field(default_factory=list)
+    samples: int = 0
+    seconds: float = 0.0
+    strip_extensions: int = 0
+
+
+def load_items(instance: dict) -> List[LbfItem]:
+    """io/import.rs:47-98 for the simple-polygon items of an instance file (serde semantics: decimal -> f64 -> f32;
+    allowed_orientations in degrees -> f32::to_radians, io/import.rs:80-89)."""
+    items = []
+    for it in sorted(instance["items"], key=lambda it: it["id"]):
+        if it.get("demand", 1) <= 0:
+            continue
+        sh = it["shape"]
+        if sh["type"] == "simple_polygon":
+            pts = np.array(sh["data"], np.float64).astype(np.float32)
+        elif sh["type"] == "polygon":
+            pts = np.array(sh["data"]["outer"], np.float64).astype(np.float32)  # holes ignored, as the reference warns
+        elif sh["type"] == "rectangle":
+            d = sh["data"]
+            x0, y0 = np.float32(d["x_min"]), np.float32(d["y_min"])
+            x1, y1 = np.float32(x0 + np.float32(d["width"])), np.float32(y0 + np.float32(d["height"]))
+            pts = np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], np.float32)
+        else:
+            raise ValueError(f"unsupported shape type {sh['type']}")
+        shape, pre, area = import_item(pts)
+        ao = it.get("allowed_orientations")
+        if ao is None:
+            rots = None
+        elif len(ao) == 0 or (len(ao) == 1 and ao[0] == 0.0):
+            rots = np.zeros(0, np.float32)
+        else:
+            rots = (np.array(ao, np.float64).astype(np.float32) * (np.float32(np.pi) / np.float32(180.0))).astype(np.float32)
+        v = shape.verts.astype(np.float64)
+        diam = float(np.sqrt(((v[:, None, :] - v[None, :, :]) ** 2).sum(-1).max()))
+        items.append(LbfItem(len(items), shape, rots, int(it.get("demand", 1)), area, diam, pre))
+    return items
+
+
+class BatchedLBF:
+    def __init__(self, instance: dict, device: int = 0, quadtree_depth: int = 5, cd_threshold: int = 16, n_ff_poles: int = 2,
+                 seed: int = 0):
+        self.items = load_items(instance)
+        self.height = np.float32(instance["strip_height"])
+        area = np.float32(0.0)
+        for it in self.items:  # probs/spp/io/import.rs:40-48: f32 sum of area * demand
+            area = np.float32(area + np.float32(np.float32(it.area) * np.float32(it.demand)))
+        self.total_area = float(area)
+        self.width = np.float32(area / self.height)
+        self.cfg = dict(quadtree_depth=quadtree_depth, cd_threshold=cd_threshold, n_ff_poles=n_ff_poles, n_ff_piers=0)
+        self.device = device
+        self.rng = np.random.Generator(np.random.Philox(key=[seed, 0xF4]))
+        self.placements: List[Placement] = []
+        self.cde: Optional[CDEngine] = None
+        self.samples = 0
+        self.extensions = 0
+        self._next_pk = 1
+        self._build_engine()
+
+    # -- container (probs/spp/entities/strip.rs:44-61: rectangle (0, 0, width, height); CDE bbox = its square hull) ----
+    def _build_engine(self):
+        if self.cde is not None:
+            self.cde.close()
+        w, h = np.float32(self.width), self.height
+        rect = np.array([[0, 0], [w, 0], [w, h], [0, h]], np.float32)
+        dx = dy = np.float32(0.0)
+        if h < w:
+            dy = np.float32((w - h) / np.float32(2.0))
+        elif w < h:
+            dx = np.float32((h - w) / np.float32(2.0))
+        self.bbox = np.array([-dx, -dy, w + dx, h + dy], np.float32)  # rect.rs:93-109 inflate_to_square
+        self.cde = CDEngine(self.bbox, device=self.device, **self.cfg)
+        verts, poi = polygon_poi(rect)
+        self.cde.register_hazard(HAZ_EXTERIOR, verts, poi, dynamic=False)
+        for it in self.items:
+            self.cde.upload_item(it.id, it.shape)
+        for p in self.placements:  # Layout::swap_container re-registers every placed item
+            self.cde.place_item(p.item_id, self.items[p.item_id].shape, compose(p.d_transf.reshape(1, 3))[0], p.pk)
+
+    # -- samplers ------------------------------------------------------------------------------------------------
+    def _rotations(self, item: LbfItem, n: int) -> np.ndarray:
+        if item.rotations is None:
+            return (self.rng.random(n, dtype=np.float32) * np.float32(2.0 * np.pi)).astype(np.float32)
+        if len(item.rotations) == 0:
+            return np.zeros(n, np.float32)
+        return item.rotations[self.rng.integers(0, len(item.rotations), n)]
+
+    def _uniform(self, item: LbfItem, box: np.ndarray, n: int) -> np.ndarray:
+        u = self.rng.random((n, 2), dtype=np.float32)
+        x = (box[0] + (box[2] - box[0]) * u[:, 0]).astype(np.float32)
+        y = (box[1] + (box[3] - box[1]) * u[:, 1]).astype(np.float32)
+        return np.stack([self._rotations(item, n), x, y], 1).astype(np.float32)
+
+    def _normal(self, item: LbfItem, mean: np.ndarray, sd_t: float, sd_r: float, n: int) -> np.ndarray:
+        x = (mean[1] + sd_t * self.rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+        y = (mean[2] + sd_t * self.rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+        if item.rotations is None:  # NormalRotDistr: normal around the reference rotation
+            r = (mean[0] + sd_r * self.rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+        else:  # discrete / none: the rotation of the reference transformation is kept
+            r = np.full(n, mean[0], np.float32)
+        return np.stack([r, x, y], 1).astype(np.float32)
+
+    # -- one batch through the engine: feasible sample of minimal loss -----------------------------------------------
+    def _best_of(self, item: LbfItem, dts: np.ndarray, below: Optional[float]):
+        t4 = compose(dts)
+        verdicts = self.cde.detect_batch(item.id, t4)
+        self.samples += len(dts)
+        free = np.nonzero(verdicts == 0)[0]
+        if len(free) == 0:
+            return None
+        v = item.shape.verts
+        c, s, tx, ty = (t4[free, k][:, None] for k in range(4))
+        # the transformed shape's bbox (SPolygon::transform_from + generate_bounding_box), f32 like the kernels
+        x = (c * v[None, :, 0] + (-s) * v[None, :, 1]).astype(np.float32) + tx
+        y = (s * v[None, :, 0] + c * v[None, :, 1]).astype(np.float32) + ty
+        cost = x.max(1) * X_MULTIPLIER + y.max(1)  # LBFLoss::cost
+        k = int(np.argmin(cost))
+        if below is not None and not cost[k] < below:
+            return None
+        return dts[free[k]].copy(), float(cost[k])
+
+    def search(self, item: LbfItem, n_samples: int, ls_frac: float, uniform_rounds: int, ls_rounds: int):
+        """search.rs:17-106 with batches at the decision points."""
+        n_ls = int(n_samples * ls_frac)
+        n_uni = n_samples - n_ls
+        box = self.bbox.copy()
+        best = None
+        per = max(n_uni // uniform_rounds, 1)
+        for _ in range(uniform_rounds):
+            got = self._best_of(item, self._uniform(item, box, per), None if best is None else best[1])
+            if got is not None:
+                best = got
+                box[2] = min(box[2], np.float32(best[1]) / X_MULTIPLIER)  # tighten_sample_bbox
+                if not box[2] > box[0]:
+                    break
+        if best is None:
+            return None
+        max_dim = float(max(self.bbox[2] - self.bbox[0], self.bbox[3] - self.bbox[1]))
+        sd_t0, sd_t1 = 0.01 * max_dim, 0.0005 * max_dim  # ls_sampler.rs:12-16
+        sd_r0, sd_r1 = 2.0 * np.pi / 180.0, 0.5 * np.pi / 180.0
+        per = max(n_ls // max(ls_rounds, 1), 1)
+        for r in range(ls_rounds):
+            pct = r / max(ls_rounds, 1)
+            sd_t, sd_r = sd_t0 * (sd_t1 / sd_t0) ** pct, sd_r0 * (sd_r1 / sd_r0) ** pct
+            got = self._best_of(item, self._normal(item, best[0], sd_t, sd_r, per), best[1])
+            if got is not None:
+                best = got
+        return best
+
+    def solve(self, n_samples: int = 5000, ls_frac: float = 0.2, uniform_rounds: int = 4, ls_rounds: int = 8,
+              max_items: int = 1 << 30) -> LbfResult:
+        t0 = time.perf_counter()
+        order = sorted(self.items, key=lambda it: -it.diameter)  # search.rs:108-115 item_placement_order
+        placed = 0
+        for item in order:
+            demand = item.demand
+            guard = 0
+            while demand > 0 and placed < max_items:
+                got = self.search(item, n_samples, ls_frac, uniform_rounds, ls_rounds)
+                if got is None:
+                    guard += 1
+                    if guard > 100:
+                        raise RuntimeError("strip width is running away: does every item fit in the strip's height?")
+                    self.width = np.float32(self.width * np.float32(1.1))
+                    self.extensions += 1
+                    self._build_engine()
+                    continue
+                dt = got[0]
+                pk = self._next_pk
+                self._next_pk += 1
+                self.cde.place_item(item.id, item.shape, compose(dt.reshape(1, 3))[0], pk)
+                self.placements.append(Placement(item.id, dt, pk))
+                demand -= 1
+                placed += 1
+        # problem.rs:39-57 fit_strip
+        x_max = -np.inf
+        for p in self.placements:
+            t4 = compose(p.d_transf.reshape(1, 3))[0]
+            v = self.items[p.item_id].shape.verts
+            x = (t4[0] * v[:, 0] + (-t4[1]) * v[:, 1]).astype(np.float32) + t4[2]
+            x_max = max(x_max, float(x.max()))
+        if self.placements:
+            self.width = np.float32(np.float32(x_max) * np.float32(1.00001))
+            self._build_engine()
+        used = sum(self.items[p.item_id].area for p in self.placements)
+        return LbfResult(float(self.width), float(self.height), used / float(self.width * self.height), list(self.placements),
+                         self.samples, time.perf_counter() - t0, self.extensions)
+
+    def close(self):
+        if self.cde is not None:
+            self.cde.close()
+            self.cde = None
+
+
+def solve_file(path: str, **kw) -> LbfResult:
+    with open(path) as f:
+        inst = json.load(f)
+    solve_kw = {k: kw.pop(k) for k in list(kw) if k in ("n_samples", "ls_frac", "uniform_rounds", "ls_rounds", "max_items")}
+    lbf = BatchedLBF(inst, **kw)
+    try:
+        return lbf.solve(**solve_kw)
+    finally:
+        lbf.close()

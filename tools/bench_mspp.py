@@ -39,13 +39,14 @@ args = ap.parse_args()
 rank = int(os.environ.get("RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+from jagua_rs_b200 import multigpu  # noqa: E402
+numa = multigpu.bind_to_gpu_numa_node(local_rank) if world > 1 else None
 dist = None
 if world > 1:
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from jagua_rs_b200 import multigpu
 
 strips = []
 k = 0

@@ -308,12 +308,22 @@ def main():
         flops_per_q = flops_info["detect_flops_per_query"] if args.queries == flops_info["queries"] else None
         roofline = None
         traffic = None
+        issue = None
+        clocks_mhz_guess = clocks.get("sm_mhz") or 1965.0
         try:  # DRAM bytes of the two kernels from the committed ncu capture of this same step
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tr = json.load(f)
             if cde.detect_path() == "grid" and args.queries == TOTAL_QUERIES:
                 traffic = {"bytes_per_step": tr["k_s1_grid"] + tr["k_s2_grid"], "algorithmic_bytes_per_step": ALG_BYTES_PER_QUERY * args.queries,
                            "source": tr["source"]}
+                wi = tr.get("warp_instructions")
+                if wi:  # what actually bounds these kernels: warp instructions issued vs the SMs' issue slots
+                    n_wi = wi["k_s1_grid"] + wi["k_s2_grid"]
+                    peak_issue = 148 * 4 * clocks_mhz_guess * 1e6
+                    issue = {"warp_instructions_per_step": n_wi, "achieved": n_wi / (ms_per_step * 1e-3) / 1e9,
+                             "peak": peak_issue / 1e9, "unit": "G warp-instructions/s", "frac": n_wi / (ms_per_step * 1e-3) / peak_issue,
+                             "peak_source": "148 SMs x 4 schedulers x 1 instruction/clk x the SM clock sampled during the run",
+                             "source": wi["source"]}
         except (OSError, KeyError, ValueError):
             pass
         if flops_per_q:
@@ -321,7 +331,7 @@ def main():
             roofline = {"bound": "fp32_nofma", "achieved": ach, "peak": peak_gflops / 1e3, "unit": "TFLOP/s",
                         "frac": ach / (peak_gflops / 1e3), "traffic": traffic,
                         "peak_source": "measured live: jg_fp32_nofma_peak (independent FADD/FMUL chains)",
-                        "flops_per_query": flops_per_q, "kernels": f"{cde.detect_path()} path: " + ("k_s1_grid + k_s2_grid" if cde.detect_path() == "grid" else "k_s1_surr + k_s2_poly") + ", one launch pair for the 10 item segments",
+                        "issue": issue, "flops_per_query": flops_per_q, "kernels": f"{cde.detect_path()} path: " + ("k_s1_grid + k_s2_grid" if cde.detect_path() == "grid" else "k_s1_surr + k_s2_poly") + ", one launch pair for the 10 item segments",
                         "hbm": {"achieved": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9, "peak": 6555.2,
                                 "unit": "GB/s", "frac": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9 / 6555.2,
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}

@@ -210,6 +210,9 @@ int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg
  * geometry/primitives/simple_polygon.rs:40-71): orientation normalised to counter-clockwise (written to
  * verts_ccw_xy when non-null, 2 * n_pts floats) and the pole of inaccessibility jg_cde_register_hazard wants. */
 int jg_polygon_poi(const float* pts_xy, int n_pts, float poi_xyr[3], float* verts_ccw_xy);
+/* import_simple_polygon + SPolygon::new for a container boundary, hole or quality zone (io/import.rs:100-195,
+ * 198-211): vertex cleaning as in jg_item_import, then jg_polygon_poi. verts_xy must hold 2 * n_pts floats. */
+int jg_shape_import(const float* pts_xy, int n_pts, float* verts_xy, int* n_verts, float poi_xyr[3]);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Host mirror of CDEngine's update path                                                       */

@@ -89,6 +89,7 @@ C_ABI = {
     "jg_item_import": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int, C.POINTER(C.c_int), _f32p,
                                  C.POINTER(C.c_float)]),
     "jg_polygon_poi": (C.c_int, [_f32p, C.c_int, _f32p, _vp]),
+    "jg_shape_import": (C.c_int, [_f32p, C.c_int, _f32p, C.POINTER(C.c_int), _f32p]),
     "jg_cde_create": (C.c_int, [_f32p, C.POINTER(JgConfig), C.POINTER(_vp)]),
     "jg_cde_destroy": (None, [_vp]),
     "jg_cde_last_error": (C.c_char_p, [_vp]),
@@ -187,6 +188,19 @@ def polygon_poi(points):
     if rc != JG_OK:
         raise JaguaCudaError(rc, "jg_polygon_poi: degenerate polygon")
     return ccw, poi
+
+
+def import_shape(points):
+    """import_simple_polygon + SPolygon::new for a container boundary / hole / quality zone: (vertices, poi)."""
+    lib = load_library()
+    pts = _f32(points).reshape(-1, 2)
+    verts = np.zeros_like(pts)
+    poi = np.zeros(3, np.float32)
+    nv = C.c_int(0)
+    rc = lib.jg_shape_import(pts, len(pts), verts, C.byref(nv), poi)
+    if rc != JG_OK:
+        raise JaguaCudaError(rc, "jg_shape_import: degenerate polygon")
+    return verts[:nv.value].copy(), poi
 
 
 class PinnedBuffer:
@@ -576,5 +590,6 @@ class CDEngine:
         self._chk(self._lib.jg_flush_l2(self._eng))
 
 
+from . import instance  # noqa: E402
 from . import workload  # noqa: E402
 from .workload import Workload, load_workload, build_engine, make_queries, make_queries_indexed, split_batch  # noqa: E402

@@ -509,7 +509,13 @@ __device__ __forceinline__ void g1_phase_b(const GCtx& c, G1Warp& w, int lane) {
 }
 
 template <bool FILT>
-__global__ void __launch_bounds__(S_THREADS)
+#ifndef G1_MIN_BLOCKS
+#define G1_MIN_BLOCKS 1
+#endif
+#ifndef G2_MIN_BLOCKS
+#define G2_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(S_THREADS, G1_MIN_BLOCKS)
 k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
           const XfSrc xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
           DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
@@ -920,7 +926,7 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
 }
 
 template <bool FILT>
-__global__ void __launch_bounds__(S_THREADS)
+__global__ void __launch_bounds__(S_THREADS, G2_MIN_BLOCKS)
 k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
           const uint8_t* __restrict__ g_kinds, const XfSrc xforms, const uint32_t* __restrict__ filt,
           uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {

@@ -153,28 +153,45 @@ extern "C" int jg_polygon_poi(const float* pts_xy, int n_pts, float poi_xyr[3], 
     return JG_OK;
 }
 
+// io/import.rs:198-211,236-260 import_simple_polygon: strips a closing duplicate and approx-equal consecutive vertices;
+// false when fewer than 3 vertices remain or a non-consecutive duplicate exists (the reference bails)
+static bool clean_points(std::vector<Pt>& p) {
+    if (p.size() > 1 && p.front().x == p.back().x && p.front().y == p.back().y) p.pop_back();
+    std::vector<size_t> drop;
+    const size_t n = p.size();
+    for (size_t i = 0; i < n; i++) {
+        const size_t j = (i + 1) % n;
+        if (approx_eq(p[i].x, p[j].x) && approx_eq(p[i].y, p[j].y)) drop.push_back(i);
+    }
+    for (size_t k = drop.size(); k-- > 0;)  // io/import.rs:250-259: descending index order
+        if (drop[k] < p.size()) p.erase(p.begin() + (long)drop[k]);
+    if (p.size() < 3) return false;
+    for (size_t i = 0; i < p.size(); i++)  // simple_polygon.rs:45-47: no duplicate points
+        for (size_t j = i + 1; j < p.size(); j++)
+            if (p[i].x == p[j].x && p[i].y == p[j].y) return false;
+    return true;
+}
+
+// import_simple_polygon + SPolygon::new for a container boundary, hole or quality zone (io/import.rs:100-195: their
+// pre-transform is empty and shape modification is disabled): cleaned, counter-clockwise vertices + poi.
+extern "C" int jg_shape_import(const float* pts_xy, int n_pts, float* verts_xy, int* n_verts, float poi_xyr[3]) {
+    if (!pts_xy || n_pts < 3 || !verts_xy || !n_verts || !poi_xyr) return JG_ERR_INVALID;
+    std::vector<Pt> p((size_t)n_pts);
+    for (int i = 0; i < n_pts; i++) p[i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
+    if (!clean_points(p)) return JG_ERR_INVALID;
+    std::vector<float> flat(2 * p.size());
+    for (size_t i = 0; i < p.size(); i++) flat[2 * i] = p[i].x, flat[2 * i + 1] = p[i].y;
+    *n_verts = (int)p.size();
+    return jg_polygon_poi(flat.data(), (int)p.size(), poi_xyr, verts_xy);
+}
+
 extern "C" int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
                               float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2],
                               float* area) {
     if (!pts_xy || n_pts < 3 || !scfg || !verts_xy || !n_verts || !poi_xyr || !n_poles || !pre_transform_xy) return JG_ERR_INVALID;
     std::vector<Pt> p((size_t)n_pts);
     for (int i = 0; i < n_pts; i++) p[i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
-    // io/import.rs:198-211: drop a closing duplicate, then approx-equal consecutive vertices
-    if (p.size() > 1 && p.front().x == p.back().x && p.front().y == p.back().y) p.pop_back();
-    {
-        std::vector<size_t> drop;
-        const size_t n = p.size();
-        for (size_t i = 0; i < n; i++) {
-            const size_t j = (i + 1) % n;
-            if (approx_eq(p[i].x, p[j].x) && approx_eq(p[i].y, p[j].y)) drop.push_back(i);
-        }
-        for (size_t k = drop.size(); k-- > 0;)  // io/import.rs:250-259: descending index order
-            if (drop[k] < p.size()) p.erase(p.begin() + (long)drop[k]);
-    }
-    if (p.size() < 3) return JG_ERR_INVALID;
-    for (size_t i = 0; i < p.size(); i++)  // simple_polygon.rs:45-47: no duplicate points
-        for (size_t j = i + 1; j < p.size(); j++)
-            if (p[i].x == p[j].x && p[i].y == p[j].y) return JG_ERR_INVALID;
+    if (!clean_points(p)) return JG_ERR_INVALID;
     Shape sh;
     sh.v = p;
     sh.area = signed_area(sh.v);

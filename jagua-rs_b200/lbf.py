@@ -28,20 +28,10 @@ from typing import List, Optional
 
 import numpy as np
 
-from . import HAZ_EXTERIOR, CDEngine, ItemShape, compose, import_item, polygon_poi
+from . import HAZ_EXTERIOR, CDEngine, compose, polygon_poi
+from .instance import InstItem as LbfItem, import_items
 
 X_MULTIPLIER = np.float32(10.0)  # lbf/src/opt/loss.rs:5
-
-
-@dataclass
-class LbfItem:
-    id: int
-    shape: ItemShape
-    rotations: Optional[np.ndarray]  # radians (f32); None = continuous; empty = no rotation
-    demand: int
-    area: float
-    diameter: float
-    pre_transform: np.ndarray
 
 
 @dataclass
@@ -62,43 +52,10 @@ class LbfResult:
     strip_extensions: int = 0
 
 
-def load_items(instance: dict) -> List[LbfItem]:
-    """io/import.rs:47-98 for the simple-polygon items of an instance file (serde semantics: decimal -> f64 -> f32;
-    allowed_orientations in degrees -> f32::to_radians, io/import.rs:80-89)."""
-    items = []
-    for it in sorted(instance["items"], key=lambda it: it["id"]):
-        if it.get("demand", 1) <= 0:
-            continue
-        sh = it["shape"]
-        if sh["type"] == "simple_polygon":
-            pts = np.array(sh["data"], np.float64).astype(np.float32)
-        elif sh["type"] == "polygon":
-            pts = np.array(sh["data"]["outer"], np.float64).astype(np.float32)  # holes ignored, as the reference warns
-        elif sh["type"] == "rectangle":
-            d = sh["data"]
-            x0, y0 = np.float32(d["x_min"]), np.float32(d["y_min"])
-            x1, y1 = np.float32(x0 + np.float32(d["width"])), np.float32(y0 + np.float32(d["height"]))
-            pts = np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], np.float32)
-        else:
-            raise ValueError(f"unsupported shape type {sh['type']}")
-        shape, pre, area = import_item(pts)
-        ao = it.get("allowed_orientations")
-        if ao is None:
-            rots = None
-        elif len(ao) == 0 or (len(ao) == 1 and ao[0] == 0.0):
-            rots = np.zeros(0, np.float32)
-        else:
-            rots = (np.array(ao, np.float64).astype(np.float32) * (np.float32(np.pi) / np.float32(180.0))).astype(np.float32)
-        v = shape.verts.astype(np.float64)
-        diam = float(np.sqrt(((v[:, None, :] - v[None, :, :]) ** 2).sum(-1).max()))
-        items.append(LbfItem(len(items), shape, rots, int(it.get("demand", 1)), area, diam, pre))
-    return items
-
-
 class BatchedLBF:
     def __init__(self, instance: dict, device: int = 0, quadtree_depth: int = 5, cd_threshold: int = 16, n_ff_poles: int = 2,
                  seed: int = 0):
-        self.items = load_items(instance)
+        self.items = import_items(instance["items"])
         self.height = np.float32(instance["strip_height"])
         area = np.float32(0.0)
         for it in self.items:  # probs/spp/io/import.rs:40-48: f32 sum of area * demand

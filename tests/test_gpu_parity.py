@@ -414,3 +414,30 @@ def test_queries_follow_layout_updates(jg, orc, name):
     left = place_remove_sequence(jg, wl, cde, w, n_ops=40, seed=11, after_each=check)
     assert len(left) > 0 and cde.stats()["layout_uploads"] >= 8
     cde.close()
+
+
+@pytest.mark.parametrize("asset,samples", [("jakobs1.json", 3000), ("swim.json", 4000)])
+def test_batched_lbf_solution_is_feasible(jg, orc, asset, samples):
+    """the batched LBF search on the engine (jagua-rs_b200/lbf.py). Judged on the solution, not bit
+    for bit: every item is placed, the oracle's Layout::is_feasible accepts the layout, and the strip is not much wider than
+    what the sequential CPU restatement of lbf_spp.rs reaches with the same sample budget."""
+    import json
+    import os
+
+    from jagua_rs_b200 import lbf
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets", asset)
+    with open(path) as f:
+        inst = json.load(f)
+    solver = lbf.BatchedLBF(inst, device=0, seed=1)
+    res = solver.solve(n_samples=samples)
+    solver.close()
+    assert len(res.placements) == sum(it.get("demand", 1) for it in inst["items"])
+    w = orc.world_from_instance(inst)
+    w.change_strip_width(res.strip_width)
+    for p in res.placements:
+        w.place_item(p.item_id, float(p.d_transf[0]), float(p.d_transf[1]), float(p.d_transf[2]))
+    assert w.is_feasible()
+    w2 = orc.world_from_instance(inst)
+    w2.lbf_solve_spp(samples, 0.2, 1)
+    assert res.strip_width < 1.25 * w2.strip_width(), (res.strip_width, w2.strip_width())

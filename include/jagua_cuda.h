@@ -134,6 +134,36 @@ int jg_collect_batch_async(JgEngine* e, int item_id, const float* transforms, in
 int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int mode,
                             uint32_t* d_out_bits, int words);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Batched placement search rounds                                                             */
+/* ------------------------------------------------------------------------------------------ */
+
+/* One decision point of lbf::opt::search (lbf/src/opt/search.rs:17-106) as a batch: n samples are DRAWN ON THE DEVICE
+ * (mode 0: UniformRectSampler over `box`, rotation uniform over the item's allowed set or fixed to rot_idx >= 0,
+ * uniform_rect_sampler.rs:18-45; mode 1: LSSampler, normal(mean, sd) translations around the reference transformation
+ * with its rotation rot_idx, ls_sampler.rs:34-120), resolved by the detect kernels (surrogate + polygon stage, under
+ * filter_id), and reduced to the free sample of minimal LBFLoss::cost (x_max * 10 + y_max of the placed shape's bbox,
+ * lbf/src/opt/loss.rs:12-35). Items need jg_item_set_rotations (a single (cos, sin) = (1, 0) entry if they do not
+ * rotate); continuous rotations are not drawn here (their (cos, sin) must come from the host libm). Synchronous; the
+ * samples are a pure function of (seed, counter, sample index) - Philox4x32-10, not the reference's SmallRng stream. */
+typedef struct JgSearchRound {
+    int mode;      /* 0 uniform, 1 normal */
+    int rot_idx;   /* fixed rotation index; -1 (mode 0 only): uniform over the allowed rotations */
+    float box[4];  /* mode 0: x_min, y_min, x_max, y_max of the sampling box */
+    float mean[2]; /* mode 1: reference translation */
+    float sd;      /* mode 1: standard deviation of both translation components */
+    uint64_t seed, counter;
+} JgSearchRound;
+typedef struct JgSearchBest {
+    int64_t n_free; /* samples without a collision */
+    int64_t index;  /* sample index of the best free sample, -1 if none */
+    float loss, tx, ty;
+    int rot_idx;
+} JgSearchBest;
+int jg_search_round(JgEngine* e, int item_id, const JgSearchRound* round, int64_t n, int filter_id, JgSearchBest* best);
+/* the samples and verdict bytes of the last jg_search_round (tests, debugging): n must match; null pointers are skipped */
+int jg_search_samples(JgEngine* e, int64_t n, uint8_t* rot_idx, float* txy, uint8_t* verdicts);
+
 int jg_sync(JgEngine* e);
 
 /* Counters since engine creation: [0] kernel launches, [1] queries resolved, [2] H2D bytes,

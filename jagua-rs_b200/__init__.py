@@ -68,6 +68,8 @@ C_ABI = {
     "jg_detect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "jg_collect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
     "jg_collect_batch_device": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
+    "jg_search_round": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp]),
+    "jg_search_samples": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
     "jg_sync": (C.c_int, [_vp]),
     "jg_engine_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "jg_engine_last_kernel_ms": (C.c_float, [_vp]),
@@ -154,6 +156,16 @@ class ItemShape:
     poi: np.ndarray              # (x, y[, r])
     poles: np.ndarray            # (P, 3) x, y, r
     piers: np.ndarray = None     # (Q, 4)
+
+
+class JgSearchRound(C.Structure):
+    _fields_ = [("mode", C.c_int), ("rot_idx", C.c_int), ("box", C.c_float * 4), ("mean", C.c_float * 2), ("sd", C.c_float),
+                ("seed", C.c_uint64), ("counter", C.c_uint64)]
+
+
+class JgSearchBest(C.Structure):
+    _fields_ = [("n_free", C.c_int64), ("index", C.c_int64), ("loss", C.c_float), ("tx", C.c_float), ("ty", C.c_float),
+                ("rot_idx", C.c_int)]
 
 
 class JgSurrogateConfig(C.Structure):
@@ -545,6 +557,31 @@ class CDEngine:
         self.sync_layout()
         self._chk(self._lib.jg_collect_batch_device(self._eng, int(item_id), int(d_transforms), int(n),
                                                     MODE_POLY_ONLY if poly_only else MODE_DEFAULT, int(d_out_bits), int(words)))
+
+    def search_round(self, item_id: int, n: int, *, box=None, mean=None, sd: float = 0.0, rot_idx: int = -1, seed: int = 0,
+                     counter: int = 0, filter_id: int = -1):
+        """One batched decision point of the LBF search, samples drawn on the device (jg_search_round): uniform over `box`
+        when `mean` is None, else normal(mean, sd) around the reference translation with rotation `rot_idx`. Returns
+        dict(n_free, index, loss, rot_idx, tx, ty); index == -1 when no sample is free."""
+        self.sync_layout()
+        r = JgSearchRound()
+        r.mode = 0 if mean is None else 1
+        r.rot_idx = int(rot_idx)
+        if box is not None:
+            r.box = (C.c_float * 4)(*[float(v) for v in box])
+        if mean is not None:
+            r.mean = (C.c_float * 2)(float(mean[0]), float(mean[1]))
+        r.sd = float(sd)
+        r.seed, r.counter = int(seed), int(counter)
+        b = JgSearchBest()
+        self._chk(self._lib.jg_search_round(self._eng, int(item_id), C.addressof(r), int(n), int(filter_id), C.addressof(b)))
+        return dict(n_free=int(b.n_free), index=int(b.index), loss=float(b.loss), rot_idx=int(b.rot_idx), tx=float(b.tx), ty=float(b.ty))
+
+    def search_samples(self, n: int):
+        """(rot_idx u8, txy (n, 2) f32, verdict bytes) of the last search_round (tests)."""
+        ridx, txy, v = np.zeros(n, np.uint8), np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)
+        self._chk(self._lib.jg_search_samples(self._eng, int(n), ridx.ctypes.data, txy.ctypes.data, v.ctypes.data))
+        return ridx, txy, v
 
     def sync(self):
         self._need_engine()

@@ -31,6 +31,8 @@ struct ItemDev {
     int n_piers = 0;
     float2* rots = nullptr;  // (cos, sin) per allowed rotation (jg_item_set_rotations)
     int n_rots = 0;
+    float2* rot_ext = nullptr;     // per allowed rotation: (x_max, y_max) of the rotated, untranslated shape (search rounds)
+    std::vector<float> h_verts;    // host copy of the vertices (extents are computed on the host)
 };
 struct FilterDev {
     uint32_t* bits = nullptr;
@@ -111,6 +113,9 @@ struct JgEngine {
     uint32_t* d_flush = nullptr;
     size_t flush_words = 0;
 
+    unsigned long long* d_search = nullptr;  // search rounds: {min key, n_free, best txy bits, best rot idx}
+    unsigned long long* h_search = nullptr;  // pinned copy
+    int64_t search_last_n = 0;
     uint64_t stat_launches = 0, stat_queries = 0, stat_h2d = 0, stat_d2h = 0, stat_uploads = 0;
     // JG_TRACE=1: device timeline of the pieces of the last host batch, printed by jg_sync (debugging aid)
     std::vector<cudaEvent_t> trace_ev;
@@ -265,6 +270,7 @@ void jg_engine_destroy(JgEngine* e) {
         cudaFree(kv.second.poles);
         cudaFree(kv.second.piers);
         cudaFree(kv.second.rots);
+        cudaFree(kv.second.rot_ext);
     }
     for (auto& kv : e->filters) cudaFree(kv.second.bits), cudaFree(kv.second.kinds);
     {
@@ -281,6 +287,8 @@ void jg_engine_destroy(JgEngine* e) {
         if (B.ready) cudaEventDestroy(B.ready);
         for (cudaEvent_t ev : B.marks) cudaEventDestroy(ev);
     }
+    if (e->d_search) cudaFree(e->d_search);
+    if (e->h_search) cudaFreeHost(e->h_search);
     if (e->st_up) cudaStreamDestroy(e->st_up);
     if (e->h_grid_ok) cudaFreeHost(e->h_grid_ok);
     for (ChunkCtx& c : e->chunks) {
@@ -534,8 +542,10 @@ int jg_item_upload(JgEngine* e, int item_id, const float* verts_xy, int n_verts,
     cudaFree(it.poles);
     cudaFree(it.piers);
     cudaFree(it.rots);
+    cudaFree(it.rot_ext);
     it = ItemDev{};
     it.n_verts = n_verts;
+    it.h_verts.assign(verts_xy, verts_xy + 2 * (size_t)n_verts);
     it.poi_x = poi_xy[0];
     it.poi_y = poi_xy[1];
     it.n_poles = n_poles;
@@ -570,6 +580,24 @@ int jg_item_set_rotations(JgEngine* e, int item_id, const float* rot_cos_sin, in
     JG_CUDA(e, cudaMalloc(&it.rots, (size_t)n_rot * sizeof(float2)));
     JG_CUDA(e, cudaMemcpy(it.rots, rot_cos_sin, (size_t)n_rot * sizeof(float2), cudaMemcpyHostToDevice));
     it.n_rots = n_rot;
+    // extents of the rotated shape, with xf_point's own arithmetic (two products, one sum, no contraction): the bbox
+    // of the placed shape is (ext + translation) by monotonicity of the final rounding
+    std::vector<float2> ext((size_t)n_rot);
+    for (int r = 0; r < n_rot; r++) {
+        const Xf xf{rot_cos_sin[2 * r], rot_cos_sin[2 * r + 1], 0.0f, 0.0f};
+        const float m01 = -xf.s;
+        float xm = -3.402823466e+38f, ym = -3.402823466e+38f;
+        for (int i = 0; i < it.n_verts; i++) {
+            const float x = it.h_verts[2 * i], y = it.h_verts[2 * i + 1];
+            xm = fmaxf(xm, xf.c * x + m01 * y);
+            ym = fmaxf(ym, xf.s * x + xf.c * y);
+        }
+        ext[r] = make_float2(xm, ym);
+    }
+    cudaFree(it.rot_ext);
+    it.rot_ext = nullptr;
+    JG_CUDA(e, cudaMalloc(&it.rot_ext, (size_t)n_rot * sizeof(float2)));
+    JG_CUDA(e, cudaMemcpy(it.rot_ext, ext.data(), (size_t)n_rot * sizeof(float2), cudaMemcpyHostToDevice));
     return JG_OK;
 }
 
@@ -1040,6 +1068,96 @@ int jg_timer_stop(JgEngine* e, float* ms) {
     JG_CUDA(e, cudaEventRecord(e->tm1, e->compute));
     JG_CUDA(e, cudaEventSynchronize(e->tm1));
     JG_CUDA(e, cudaEventElapsedTime(ms, e->tm0, e->tm1));
+    return JG_OK;
+}
+
+// ---- batched placement search rounds (search.cu) -------------------------------------------------------
+__global__ void k_search_fetch(unsigned long long* best, const uint8_t* ridx, const float2* txy) {
+    const unsigned long long key = best[0];
+    if (key == ~0ull) return;
+    const uint32_t q = (uint32_t)key;
+    const float2 t = txy[q];
+    best[2] = ((unsigned long long)__float_as_uint(t.y) << 32) | __float_as_uint(t.x);
+    best[3] = ridx[q];
+}
+
+int jg_search_round(JgEngine* e, int item_id, const JgSearchRound* round, int64_t n, int filter_id, JgSearchBest* best) {
+    int rc = check_ready(e);
+    if (rc != JG_OK) return rc;
+    if (!round || !best || n <= 0 || n > JG_MAX_LAUNCH_QUERIES || (round->mode != 0 && round->mode != 1)) return JG_ERR_INVALID;
+    const int ids[1] = {item_id};
+    const int64_t offs[2] = {0, n};
+    std::vector<const ItemDev*> items;
+    rc = resolve_segments(e, 1, ids, offs, items);
+    if (rc != JG_OK) return rc;
+    const ItemDev& it = *items[0];
+    if (it.n_rots == 0 || !it.rot_ext) return fail(e, JG_ERR_INVALID, "search rounds need jg_item_set_rotations (a single (1, 0) entry for items that do not rotate)");
+    if (round->rot_idx >= it.n_rots || (round->mode == 1 && round->rot_idx < 0)) return fail(e, JG_ERR_INVALID, "search round: bad rotation index");
+    const uint32_t* d_filt;
+    const uint8_t* d_kinds;
+    rc = find_filter(e, filter_id, &d_filt, &d_kinds);
+    if (rc != JG_OK) return rc;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    if (!e->d_search) {
+        JG_CUDA(e, cudaMalloc(&e->d_search, 4 * sizeof(unsigned long long)));
+        JG_CUDA(e, cudaHostAlloc((void**)&e->h_search, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    }
+    ChunkCtx& c = e->main_ctx;
+    rc = ensure_ctx(e, c, (size_t)n, (size_t)n, true);
+    if (rc != JG_OK) return rc;
+    float2* d_txy = (float2*)c.d_xf;
+    uint8_t* d_ridx = (uint8_t*)(d_txy + n);
+    SearchRound sr;
+    sr.mode = round->mode;
+    sr.rot_idx = round->rot_idx;
+    sr.n_rots = it.n_rots;
+    sr.sd = round->sd;
+    for (int k = 0; k < 4; k++) sr.box[k] = round->box[k];
+    sr.mean[0] = round->mean[0], sr.mean[1] = round->mean[1];
+    sr.seed = round->seed, sr.counter = round->counter;
+    cudaStream_t st = e->compute;
+    JG_CUDA(e, cudaMemsetAsync(e->d_search, 0xFF, sizeof(unsigned long long), st));
+    JG_CUDA(e, cudaMemsetAsync(e->d_search + 1, 0, 3 * sizeof(unsigned long long), st));
+    JG_CUDA(e, launch_search_sample(sr, n, d_ridx, d_txy, e->n_sms, st));
+    int launches = 3;
+    PieceCursor cur;
+    Piece p;
+    if (!next_piece(e, 1, items.data(), offs, JG_MAX_LAUNCH_QUERIES, cur, p) || p.m != n) return fail(e, JG_ERR_CAPACITY, "search round: batch does not fit one launch");
+    JG_CUDA(e, launch_piece(e, p, XfSrc{nullptr, d_ridx, d_txy}, d_filt, d_kinds, JG_MODE_DEFAULT, c.d_out, c.sc, st, &launches));
+    JG_CUDA(e, launch_search_reduce(n, c.d_out, d_ridx, d_txy, it.rot_ext, it.n_rots, e->d_search, e->n_sms, st));
+    k_search_fetch<<<1, 1, 0, st>>>(e->d_search, d_ridx, d_txy);
+    JG_CUDA(e, cudaMemcpyAsync(e->h_search, e->d_search, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    JG_CUDA(e, cudaStreamSynchronize(st));
+    e->stat_launches += launches;
+    e->stat_queries += (uint64_t)n;
+    e->stat_d2h += 32;
+    e->search_last_n = n;
+    best->n_free = (int64_t)e->h_search[1];
+    best->index = -1;
+    best->loss = 0.0f, best->tx = 0.0f, best->ty = 0.0f, best->rot_idx = -1;
+    if (e->h_search[0] != ~0ull) {
+        uint32_t kb = (uint32_t)(e->h_search[0] >> 32);
+        kb = (kb & 0x80000000u) ? (kb & 0x7FFFFFFFu) : ~kb;  // inverse of order_key
+        std::memcpy(&best->loss, &kb, 4);
+        best->index = (int64_t)(uint32_t)e->h_search[0];
+        const uint32_t bx = (uint32_t)e->h_search[2], by = (uint32_t)(e->h_search[2] >> 32);
+        std::memcpy(&best->tx, &bx, 4);
+        std::memcpy(&best->ty, &by, 4);
+        best->rot_idx = (int)e->h_search[3];
+    }
+    return JG_OK;
+}
+
+int jg_search_samples(JgEngine* e, int64_t n, uint8_t* rot_idx, float* txy, uint8_t* verdicts) {
+    if (!e || n <= 0 || n != e->search_last_n) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    ChunkCtx& c = e->main_ctx;
+    const float2* d_txy = (const float2*)c.d_xf;
+    const uint8_t* d_ridx = (const uint8_t*)(d_txy + n);
+    JG_CUDA(e, cudaStreamSynchronize(e->compute));
+    if (txy) JG_CUDA(e, cudaMemcpy(txy, d_txy, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost));
+    if (rot_idx) JG_CUDA(e, cudaMemcpy(rot_idx, d_ridx, (size_t)n, cudaMemcpyDeviceToHost));
+    if (verdicts) JG_CUDA(e, cudaMemcpy(verdicts, c.d_out, (size_t)n, cudaMemcpyDeviceToHost));
     return JG_OK;
 }
 

@@ -95,6 +95,19 @@ cudaError_t launch_collect_grid(const DevLayout& L, const DevItem& it, const uin
                                 uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st, int* n_launches);
 cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,
                            uint32_t* d_out_bits, int words, int group, int n_sms, cudaStream_t st, int* n_launches);
+// one round of a batched placement search (search.cu)
+struct SearchRound {
+    int mode;      // 0 uniform over box, 1 normal around mean
+    int rot_idx;   // fixed rotation index, or -1 (uniform mode): uniform over the item's n_rots rotations
+    int n_rots;
+    float sd;
+    float box[4];
+    float mean[2];
+    unsigned long long seed, counter;
+};
+cudaError_t launch_search_sample(const SearchRound& r, long long n, uint8_t* d_ridx, float2* d_txy, int n_sms, cudaStream_t st);
+cudaError_t launch_search_reduce(long long n, const uint8_t* d_verdicts, const uint8_t* d_ridx, const float2* d_txy, const float2* d_rot_ext,
+                                 int n_rots, unsigned long long* d_best, int n_sms, cudaStream_t st);
 cudaError_t launch_fp32_nofma(float* d_out, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_fill(uint32_t* p, size_t n_words, uint32_t v, int n_sms, cudaStream_t st);
 

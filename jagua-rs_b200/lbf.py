@@ -13,6 +13,10 @@ by the oracle in tests/), not bit for bit:
   * local search: `ls_rounds` batches drawn from normal distributions around the best sample, the standard
     deviations decaying from 1 % to 0.05 % of the bbox (translation) and 2 deg to 0.5 deg (continuous rotation)
     along init * (end / init)^progress (LSSampler::decay_stddev), the mean shifted to every improvement;
+  * items with a discrete set of allowed rotations (or none) run every round entirely on the device
+    (`CDEngine.search_round`: Philox sampling kernel, detect kernels, loss reduction kernel; 32 bytes come back per
+    round); items that rotate continuously are sampled on the host, because their (cos, sin) must come from the host
+    libm to stay bit-compatible with the reference's `Transformation`s;
   * no feasible sample: the strip grows by 10 % (change_strip_width) - a new CDEngine, all placements re-registered;
   * at the end the strip is fitted to the right-most item * 1.00001 (SPProblem::fit_strip).
 
@@ -54,7 +58,7 @@ class LbfResult:
 
 class BatchedLBF:
     def __init__(self, instance: dict, device: int = 0, quadtree_depth: int = 5, cd_threshold: int = 16, n_ff_poles: int = 2,
-                 seed: int = 0):
+                 seed: int = 0, device_sampling: bool = True):
         self.items = import_items(instance["items"])
         self.height = np.float32(instance["strip_height"])
         area = np.float32(0.0)
@@ -65,6 +69,9 @@ class BatchedLBF:
         self.cfg = dict(quadtree_depth=quadtree_depth, cd_threshold=cd_threshold, n_ff_poles=n_ff_poles, n_ff_piers=0)
         self.device = device
         self.rng = np.random.Generator(np.random.Philox(key=[seed, 0xF4]))
+        self.seed = int(seed)
+        self.device_sampling = device_sampling
+        self._round = 0
         self.placements: List[Placement] = []
         self.cde: Optional[CDEngine] = None
         self.samples = 0
@@ -89,6 +96,8 @@ class BatchedLBF:
         self.cde.register_hazard(HAZ_EXTERIOR, verts, poi, dynamic=False)
         for it in self.items:
             self.cde.upload_item(it.id, it.shape)
+            if it.rotations is not None:  # discrete / none: search rounds can run on the device
+                self.cde.set_item_rotations(it.id, it.rotations if len(it.rotations) else np.zeros(1, np.float32))
         for p in self.placements:  # Layout::swap_container re-registers every placed item
             self.cde.place_item(p.item_id, self.items[p.item_id].shape, compose(p.d_transf.reshape(1, 3))[0], p.pk)
 
@@ -134,10 +143,45 @@ class BatchedLBF:
             return None
         return dts[free[k]].copy(), float(cost[k])
 
+    def _search_on_device(self, item: LbfItem, n_uni: int, n_ls: int, uniform_rounds: int, ls_rounds: int):
+        rots = item.rotations if len(item.rotations) else np.zeros(1, np.float32)
+        box = self.bbox.copy()
+        best = None  # (d_transf, loss, rotation index)
+
+        def take(got):
+            nonlocal best
+            if got["index"] >= 0 and (best is None or got["loss"] < best[1]):
+                best = (np.array([rots[got["rot_idx"]], got["tx"], got["ty"]], np.float32), got["loss"], got["rot_idx"])
+                return True
+            return False
+
+        per = max(n_uni // uniform_rounds, 1)
+        for _ in range(uniform_rounds):
+            self._round += 1
+            self.samples += per
+            if take(self.cde.search_round(item.id, per, box=box, seed=self.seed, counter=self._round)):
+                box[2] = min(box[2], np.float32(best[1]) / X_MULTIPLIER)  # tighten_sample_bbox
+                if not box[2] > box[0]:
+                    break
+        if best is None:
+            return None
+        max_dim = float(max(self.bbox[2] - self.bbox[0], self.bbox[3] - self.bbox[1]))
+        sd0, sd1 = 0.01 * max_dim, 0.0005 * max_dim  # ls_sampler.rs:12-16
+        per = max(n_ls // max(ls_rounds, 1), 1)
+        for r in range(ls_rounds):
+            self._round += 1
+            self.samples += per
+            sd = sd0 * (sd1 / sd0) ** (r / max(ls_rounds, 1))
+            take(self.cde.search_round(item.id, per, mean=(best[0][1], best[0][2]), sd=sd, rot_idx=best[2], seed=self.seed,
+                                       counter=self._round))
+        return best[0], best[1]
+
     def search(self, item: LbfItem, n_samples: int, ls_frac: float, uniform_rounds: int, ls_rounds: int):
         """search.rs:17-106 with batches at the decision points."""
         n_ls = int(n_samples * ls_frac)
         n_uni = n_samples - n_ls
+        if self.device_sampling and item.rotations is not None:
+            return self._search_on_device(item, n_uni, n_ls, uniform_rounds, ls_rounds)
         box = self.bbox.copy()
         best = None
         per = max(n_uni // uniform_rounds, 1)

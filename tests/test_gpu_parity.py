@@ -441,3 +441,50 @@ def test_batched_lbf_solution_is_feasible(jg, orc, asset, samples):
     w2 = orc.world_from_instance(inst)
     w2.lbf_solve_spp(samples, 0.2, 1)
     assert res.strip_width < 1.25 * w2.strip_width(), (res.strip_width, w2.strip_width())
+
+
+@pytest.mark.parametrize("name", ["swim_half", "shirts_full"])
+def test_search_round_matches_host_evaluation(jg, engines, name):
+    """jg_search_round (samples drawn on the device, detect kernels, loss reduction on the device) against the same
+    round evaluated through the ordinary path: the device's samples are fetched, composed on the host, resolved by
+    detect_batch AND by the oracle, and the minimal LBF loss over the free ones is recomputed in f32 on the host."""
+    wl, cde, w = engines(name)
+    b = wl.cde_bbox
+    for item_id in (0, len(wl.items) - 1):
+        it = wl.items[item_id]
+        rots = it.rotations if it.rotations is not None and len(it.rotations) else np.zeros(1, np.float32)
+        cde.set_item_rotations(item_id, rots)
+        cs = jg.compose(np.stack([rots, np.zeros_like(rots), np.zeros_like(rots)], 1))[:, :2]
+        n = 100_000
+        rounds = [dict(box=b, seed=5, counter=1), dict(box=[b[0], b[1], (b[0] + b[2]) / 2, b[3]], seed=5, counter=2, rot_idx=0)]
+        first = cde.search_round(item_id, n, **rounds[0])
+        if first["index"] >= 0:
+            rounds.append(dict(mean=(first["tx"], first["ty"]), sd=0.01 * float(b[2] - b[0]), rot_idx=first["rot_idx"], seed=5, counter=3))
+        for kw in rounds:
+            got = cde.search_round(item_id, n, **kw)
+            ridx, txy, verdicts = cde.search_samples(n)
+            assert ridx.max() < len(rots)
+            if "box" in kw:
+                bx = kw["box"]
+                assert txy[:, 0].min() >= bx[0] and txy[:, 0].max() <= bx[2] and txy[:, 1].min() >= bx[1] and txy[:, 1].max() <= bx[3]
+                if kw.get("rot_idx", -1) < 0 and len(rots) > 1:
+                    assert len(np.unique(ridx)) == len(rots)
+            else:
+                assert np.all(ridx == kw["rot_idx"]) and abs(float(txy[:, 0].mean()) - kw["mean"][0]) < 0.05 * kw["sd"] * 10
+            t4 = np.ascontiguousarray(np.concatenate([cs[ridx], txy], 1).astype(np.float32))
+            assert np.array_equal(verdicts, cde.detect_batch(item_id, t4))
+            assert np.array_equal(verdicts, w.detect_batch(item_id, t4))
+            free = np.nonzero(verdicts == 0)[0]
+            assert got["n_free"] == len(free)
+            if len(free) == 0:
+                assert got["index"] == -1
+                continue
+            v = it.verts
+            c, s = t4[free, 0][:, None], t4[free, 1][:, None]
+            x = ((c * v[None, :, 0] + (-s) * v[None, :, 1]).astype(np.float32) + t4[free, 2][:, None]).max(1)
+            y = ((s * v[None, :, 0] + c * v[None, :, 1]).astype(np.float32) + t4[free, 3][:, None]).max(1)
+            cost = (x * np.float32(10.0) + y).astype(np.float32)
+            assert np.float32(got["loss"]) == cost.min()
+            k = got["index"]
+            assert verdicts[k] == 0 and cost[np.searchsorted(free, k)] == cost.min()
+            assert (got["rot_idx"], np.float32(got["tx"]), np.float32(got["ty"])) == (int(ridx[k]), txy[k, 0], txy[k, 1])

@@ -510,10 +510,10 @@ __device__ __forceinline__ void g1_phase_b(const GCtx& c, G1Warp& w, int lane) {
 
 template <bool FILT>
 #ifndef G1_MIN_BLOCKS
-#define G1_MIN_BLOCKS 1
+#define G1_MIN_BLOCKS 4
 #endif
 #ifndef G2_MIN_BLOCKS
-#define G2_MIN_BLOCKS 1
+#define G2_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(S_THREADS, G1_MIN_BLOCKS)
 k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,

@@ -182,6 +182,9 @@ int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams);
 /* Lanes per query (0 = choose from the item's vertex count, else 4, 8, 16 or 32) of the detect
  * stage-2 and collect kernels. A tuning knob; results do not depend on it. */
 int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group);
+/* Launches of at least min_queries queries run detect_containment_collision (cd_engine.rs:231-255) in a kernel of its
+ * own after the edge tests (default 2^21; 0 = always, a huge value = never). Results do not depend on it. */
+int jg_engine_set_split_min(JgEngine* e, int64_t min_queries);
 /* Which detect kernels serve the next layout uploads: JG_PATH_AUTO (grid kernels when the quadtree is at
  * most 5 deep and the batch has no surrogate piers, else the quadtree-walk kernels) or JG_PATH_WALK (always
  * the walk kernels). Takes effect immediately for the current layout. Results do not depend on it. */

@@ -77,6 +77,7 @@ C_ABI = {
     "jg_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "jg_engine_set_batching": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "jg_engine_set_groups": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "jg_engine_set_split_min": (C.c_int, [_vp, C.c_int64]),
     "jg_engine_set_detect_path": (C.c_int, [_vp, C.c_int]),
     "jg_engine_detect_path": (C.c_int, [_vp]),
     "jg_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
@@ -606,6 +607,10 @@ class CDEngine:
 
     def set_batching(self, chunk_queries: int, n_streams: int):
         self._chk(self._lib.jg_engine_set_batching(self._eng, int(chunk_queries), int(n_streams)))
+
+    def set_split_min(self, min_queries: int):
+        """Launch size from which the containment tests run in their own kernel (0 = always)."""
+        self._chk(self._lib.jg_engine_set_split_min(self._eng, int(min_queries)))
 
     def set_groups(self, detect_group: int = 0, collect_group: int = 0):
         self._chk(self._lib.jg_engine_set_groups(self._eng, int(detect_group), int(collect_group)))

@@ -332,6 +332,9 @@ struct GCtx {
     uint8_t* out;
     DetectCtl* ctl;
     int* sv_entry;
+    int4* ct_meta = nullptr;   // containment list (k_s2_grid -> k_s2_contain): {query | segment, first entry, n_partial, -}
+    float4* ct_bb = nullptr;   // ... the transformed shape's bbox
+    float4* ct_xf = nullptr;   // ... and the query's transformation
 };
 struct G1Warp {  // stage-1 state of a warp (shared memory + two counters)
     float4* s_circ;    // phase B: the current pole of each lane's query
@@ -670,7 +673,7 @@ __device__ __forceinline__ bool path_reaches(const GridDev& g, const Seg& sg, in
 
 // one group of `ng` survivors (ents[0 .. ng): survivor-list entries in global memory, or in the warp's own shared
 // memory when LOCAL) resolved by a warp; GS = slots in use (>= ng)
-template <bool FILT, bool LOCAL>
+template <bool FILT, bool LOCAL, bool SPLIT>
 __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* ents, int ng, int GS, int lane) {
     const int D = c.g.D, G = c.g.G;
     if (lane < ng) {
@@ -891,6 +894,40 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
     }
     __syncwarp();
     const unsigned hm = *(volatile unsigned*)&W.hit;
+    if (SPLIT) {
+        // cd_engine.rs:174-193 continues in k_s2_contain: survivors without an edge hit whose virtual root holds Partial
+        // hazards are handed over (their verdict stays 0 unless a containment collision is found there). Keeping the
+        // containment code out of this kernel takes a fifth off its instruction-cache footprint.
+        bool handover = false;
+        int ct_entries = 0;  // first entry of the virtual root (all Partial: n_entire == 0)
+        if (lane < ng && verdict < 0) {
+            if ((hm >> lane) & 1u) {
+                verdict = JG_VERDICT_POLY;
+            } else {
+                const int4 m = __ldg(&c.L.node_meta[W.vnode[lane]]);
+                const int n_partial = (m.z >> 16) & 0xFFFF;
+                if ((m.z & 0xFFFF) > 0) verdict = JG_VERDICT_REF_PANIC;  // cd_engine.rs:179
+                else {
+                    verdict = 0;
+                    handover = n_partial > 0;
+                    ct_entries = m.y;
+                    W.q_ne[lane] = n_partial;  // (the edge list is done with: the slot carries the entry count now)
+                }
+            }
+        }
+        const unsigned hv = __ballot_sync(FULL, handover);
+        if (hv) {
+            int cb = 0;
+            if (lane == 0) cb = atomicAdd(&c.ctl->n_ct, __popc(hv));
+            cb = __shfl_sync(FULL, cb, 0);
+            if (handover) {
+                const int k = cb + __popc(hv & lanemask_lt());
+                c.ct_meta[k] = make_int4(sv_pack(W.q[lane], W.seg[lane]), ct_entries, W.q_ne[lane], 0);
+                c.ct_bb[k] = W.bb[lane];
+                c.ct_xf[k] = W.xf[lane];
+            }
+        }
+    } else {
     // cd_engine.rs:174-193: survivors without an edge hit -> `unreachable!` or containment tests
     for (int s = 0; s < ng; s++) {
         if (__shfl_sync(FULL, verdict, s) >= 0) continue;
@@ -921,22 +958,24 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
         }
         if (lane == s) verdict = v;
     }
+    }
     if (lane < ng) c.out[W.q[lane]] = (uint8_t)verdict;
     __syncwarp();
 }
 
-template <bool FILT>
+template <bool FILT, bool SPLIT>
 __global__ void __launch_bounds__(S_THREADS, G2_MIN_BLOCKS)
 k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
           const uint8_t* __restrict__ g_kinds, const XfSrc xforms, const uint32_t* __restrict__ filt,
-          uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
+          uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry,
+          int4* __restrict__ ct_meta, float4* __restrict__ ct_bb, float4* __restrict__ ct_xf) {
     extern __shared__ __align__(16) unsigned char smem[];
     SegTable* t = (SegTable*)smem;
     for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
     unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
     const GridDev& g = *stage_grid(p, ggrid);
     __syncthreads();
-    const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry};
+    const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry, ct_meta, ct_bb, ct_xf};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     G2Slots& W = *(G2Slots*)(p + (size_t)warp * sizeof(G2Slots));
     const int total = ctl->n_surv;
@@ -949,7 +988,118 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
         if (lane == 0) gbase = atomicAdd(&ctl->s2_next, GS);
         gbase = __shfl_sync(FULL, gbase, 0);
         if (gbase >= total) break;
-        g2_group<FILT, false>(c, W, sv_entry + gbase, (total - gbase) < GS ? (total - gbase) : GS, GS, lane);
+        g2_group<FILT, false, SPLIT>(c, W, sv_entry + gbase, (total - gbase) < GS ? (total - gbase) : GS, GS, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// containment pass: CDEngine::detect_containment_collision (cd_engine.rs:231-255) against every relevant Partial
+// hazard of the virtual root (cd_engine.rs:182-192), for the survivors k_s2_grid handed over. A team of four lanes owns
+// one survivor (8 survivors per warp, all teams in lockstep): the team's lanes take the hazards four at a time for the
+// bbox relation (rect.rs:70-89), and walk a polygon with stride 4 for the rare point-in-polygon tests
+// (simple_polygon.rs:255-292; the crossing count of a task is the popcount of its team's ballot bits). The verdict of a
+// survivor is an OR over its hazards, so the order is free.
+// ---------------------------------------------------------------------------------------------------
+#define CT_GROUP 8
+template <bool FILT>
+__global__ void __launch_bounds__(S_THREADS)
+k_s2_contain(const DevLayout L, const __grid_constant__ SegTable gtab, const uint32_t* __restrict__ filt,
+             uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, const int4* __restrict__ ct_meta,
+             const float4* __restrict__ ct_bb, const float4* __restrict__ ct_xf) {
+    const int total = ctl->n_ct;
+    if (total == 0) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    SegTable* t = (SegTable*)smem;
+    for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
+    __syncthreads();
+    const SegTable& tab = *t;
+    const int lane = threadIdx.x & 31, team = lane >> 2, sub = lane & 3;
+    const unsigned team_bits = 0xFu << (team * 4);
+    for (;;) {
+        int gbase = 0;
+        if (lane == 0) gbase = atomicAdd(&ctl->ct_next, CT_GROUP);
+        gbase = __shfl_sync(FULL, gbase, 0);
+        if (gbase >= total) break;
+        const bool valid = gbase + team < total;
+        int q = 0, np = 0, eb = 0;
+        const SegDesc* sd = &tab.seg[0];
+        Xf xf{1.0f, 0.0f, 0.0f, 0.0f};
+        Rect sb{0.0f, 0.0f, 0.0f, 0.0f};
+        if (valid) {
+            const int4 cm = __ldcg(&ct_meta[gbase + team]);
+            const float4 t4 = __ldcg(&ct_xf[gbase + team]), b4 = __ldcg(&ct_bb[gbase + team]);
+            q = cm.x & 0x3FFFFFF;
+            sd = &tab.seg[(unsigned)cm.x >> 26];
+            xf = Xf{t4.x, t4.y, t4.z, t4.w};
+            sb = Rect{b4.x, b4.y, b4.z, b4.w};
+            eb = cm.y;  // n_entire == 0 here (k_s2_grid reports the other case itself): Partial entries start the node's list
+            np = cm.z;
+        }
+        bool collided = false;
+        const int max_np = __reduce_max_sync(FULL, np);
+        for (int j0 = 0; j0 < max_np; j0 += 4) {
+            const int j = j0 + sub;
+            int hs = -1, rel = REL_DISJOINT, scope_interior = 1;
+            if (j < np && !collided) {
+                hs = __ldg(&L.entry_meta[eb + j]).x;
+                if (FILT && filt_bit(filt, hs)) hs = -1;
+            }
+            if (hs >= 0) {
+                scope_interior = __ldg(&L.haz_meta[hs]).x == 1 ? 1 : 0;
+                rel = rect_almost_relation(ld_rect(&L.haz_bbox[hs]), sb);
+            }
+            const bool pip = hs >= 0 && (rel == REL_SURROUNDING || rel == REL_ENCLOSED);
+            // no point-in-polygon needed: contained = false -> collision iff the hazard's scope is Exterior (hazard.rs:55-62)
+            const unsigned quick = __ballot_sync(FULL, hs >= 0 && !pip && !scope_interior);
+            if (quick & team_bits) collided = true;
+            const unsigned pips = __ballot_sync(FULL, pip);
+            for (int k = 0; k < 4; k++) {
+                if (!(pips & (0x11111111u << k))) continue;  // no team has a task in this position
+                const int owner = team * 4 + k;
+                const int h = __shfl_sync(FULL, hs, owner), r = __shfl_sync(FULL, rel, owner), si = __shfl_sync(FULL, scope_interior, owner);
+                const bool act = ((pips >> owner) & 1u) && !collided;
+                const float2* verts = nullptr;
+                int n = 0;
+                bool use_xf = false;
+                Rect pb{0.0f, 0.0f, 0.0f, 0.0f};
+                float px = 0.0f, py = 0.0f;
+                if (act) {
+                    if (r == REL_SURROUNDING) {  // the hazard's shape against the item's (transformed) poi
+                        const int4 hmeta = __ldg(&L.haz_meta[h]);
+                        verts = L.haz_verts + hmeta.y, n = hmeta.z;
+                        pb = ld_rect(&L.haz_bbox[h]);
+                        xf_point(xf, sd->poi_x, sd->poi_y, px, py);
+                    } else {  // the item's transformed shape against the hazard's poi
+                        const float4 hp = __ldg(&L.haz_poi[h]);
+                        verts = sd->verts, n = sd->n_verts, use_xf = true;
+                        pb = sb;
+                        px = hp.x, py = hp.y;
+                    }
+                    if (!rect_point(pb, px, py)) n = 0;  // outside the bbox: not contained (simple_polygon.rs:258-262)
+                }
+                const Seg ray{px, py, pb.x_max + (pb.x_max - pb.x_min), py};
+                const int trips = __reduce_max_sync(FULL, act ? (n + 3) >> 2 : 0);
+                int n_int = 0;
+                for (int b = 0; b < trips; b++) {
+                    const int i = b * 4 + sub;
+                    bool cross = false;
+                    if (act && i < n) {
+                        const float2 a = __ldg(&verts[i]), bb2 = __ldg(&verts[i == n - 1 ? 0 : i + 1]);
+                        float sx = a.x, sy = a.y, ex = bb2.x, ey = bb2.y;
+                        if (use_xf) {
+                            xf_point(xf, a.x, a.y, sx, sy);
+                            xf_point(xf, bb2.x, bb2.y, ex, ey);
+                        }
+                        if ((approx_eq(sy, py) && fpa_gt(sx, px)) || (approx_eq(ey, py) && fpa_gt(ex, px))) cross = fpa_lt(sy, py) || fpa_lt(ey, py);
+                        else cross = seg_seg(ray, Seg{sx, sy, ex, ey});
+                    }
+                    n_int += __popc(__ballot_sync(FULL, cross) & team_bits);
+                }
+                const bool contained = (n_int & 1) == 1;
+                if (act && (si ? contained : !contained)) collided = true;
+            }
+        }
+        if (valid && sub == 0 && collided) out[q] = (uint8_t)JG_VERDICT_POLY;
     }
 }
 
@@ -1058,7 +1208,7 @@ k_detect_fused(const DevLayout L, const __grid_constant__ SegTable gtab, const G
             grp_off = 0;
         }
         if (grp_off >= 0) {
-            g2_group<FILT, true>(c, W, w.s_surv + grp_off, grp_n, GS, lane);
+            g2_group<FILT, true, false>(c, W, w.s_surv + grp_off, grp_n, GS, lane);
             idle_since = -1;
         } else if (run_b) {
             g1_phase_b<FILT, true>(c, w, lane);

@@ -47,7 +47,7 @@ struct ChunkCtx {
     float4* d_xf = nullptr;
     uint8_t* d_out = nullptr;  // verdict bytes or collector words
     size_t cap_q = 0, cap_out = 0;
-    DetectScratch sc{nullptr, nullptr};
+    DetectScratch sc{nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap_sv = 0;
     cudaEvent_t done = nullptr;  // join point of device-resident batches spread over the chunk streams
 };
@@ -84,7 +84,8 @@ struct JgEngine {
     bool has_layout = false;
     uint64_t epoch = 0;
     uint64_t layout_version = 0;  // bumped by every upload; per-filter node summaries are keyed on it
-    DetectPlan plan{0, 0, 0, 0};
+    DetectPlan plan{0, 0, 0, 0, 1 << 21};
+    long long split_min = -1;  // jg_engine_set_split_min override (-1: the default of make_detect_plan)
     bool force_walk = false;  // jg_engine_set_detect_path: keep the quadtree-walk kernels even when the grid applies
     bool use_fused = false;   // JG_PATH_FUSED: one fused, copy-following kernel per batch (experimental, slower)
     uint8_t* d_kinds = nullptr;   // = bufs[cur].d_kinds
@@ -173,13 +174,22 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
     }
     if (c.cap_sv < n_q) {
         cudaFree(c.sc.sv_entry);
+        cudaFree(c.sc.ct_meta);
+        cudaFree(c.sc.ct_bb);
+        cudaFree(c.sc.ct_xf);
         c.sc.sv_entry = nullptr;
+        c.sc.ct_meta = nullptr;
+        c.sc.ct_bb = nullptr;
+        c.sc.ct_xf = nullptr;
         c.cap_sv = 0;
         if (!c.sc.ctl) {
             JG_CUDA(e, cudaMalloc(&c.sc.ctl, sizeof(DetectCtl)));
             JG_CUDA(e, cudaMemset(c.sc.ctl, 0, sizeof(DetectCtl)));
         }
         JG_CUDA(e, cudaMalloc(&c.sc.sv_entry, n_q * sizeof(int)));
+        JG_CUDA(e, cudaMalloc(&c.sc.ct_meta, n_q * sizeof(int4)));
+        JG_CUDA(e, cudaMalloc(&c.sc.ct_bb, n_q * sizeof(float4)));
+        JG_CUDA(e, cudaMalloc(&c.sc.ct_xf, n_q * sizeof(float4)));
         c.cap_sv = n_q;
     }
     return JG_OK;
@@ -187,7 +197,7 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
 
 static void free_ctx(ChunkCtx& c) {
     cudaFree(c.d_xf), cudaFree(c.d_out);
-    cudaFree(c.sc.ctl), cudaFree(c.sc.sv_entry);
+    cudaFree(c.sc.ctl), cudaFree(c.sc.sv_entry), cudaFree(c.sc.ct_meta), cudaFree(c.sc.ct_bb), cudaFree(c.sc.ct_xf);
     if (c.done) cudaEventDestroy(c.done);
     c = ChunkCtx{};
 }
@@ -476,6 +486,7 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
         bind_layout(e, h);
         e->layout_version++;
         e->plan = make_detect_plan((int)h.n_nodes, (int)h.root_level);
+        if (e->split_min >= 0) e->plan.split_min = e->split_min;
         JG_CUDA(e, launch_node_kinds(e->L, (int)h.root_level, nullptr, B.d_kinds, e->st_up));
         JG_CUDA(e, cudaMemcpyAsync(&e->h_grid_ok[nb], detect_grid_ok_ptr(B.d_kinds, (int)h.n_nodes), sizeof(int), cudaMemcpyDeviceToHost, e->st_up));
         JG_CUDA(e, cudaEventRecord(B.ready, e->st_up));
@@ -505,6 +516,7 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
         bind_layout(e, h);
         e->layout_version++;
         e->plan = make_detect_plan((int)h.n_nodes, (int)h.root_level);
+        if (e->split_min >= 0) e->plan.split_min = e->split_min;
         JG_CUDA(e, launch_node_kinds(e->L, (int)h.root_level, nullptr, B.d_kinds, e->compute));
         int ok = 0;
         JG_CUDA(e, detect_grid_usable(B.d_kinds, (int)h.n_nodes, e->compute, &ok));
@@ -1183,6 +1195,13 @@ int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams) {
         free_ctx(c);
         c.st = st;
     }
+    return JG_OK;
+}
+
+int jg_engine_set_split_min(JgEngine* e, int64_t min_queries) {
+    if (!e || min_queries < 0) return JG_ERR_INVALID;
+    e->split_min = min_queries;
+    e->plan.split_min = min_queries;
     return JG_OK;
 }
 

@@ -57,6 +57,10 @@ struct DetectCtl {
     int done_warps;  // warps that have finished all their stage-1 work
     int avail;       // queries whose transforms have arrived in device memory (streamed batches)
     int error;       // 1: a warp gave up waiting (lost copy); the results are incomplete
+    // containment pass (k_s2_contain): survivors without an edge hit whose virtual root holds Partial hazards
+    int n_ct;        // entries in the containment list
+    int ct_next;     // next unclaimed entry
+    int pad[2];
 };
 #define JG_MAX_LAUNCH_QUERIES (1 << 26)  // survivor entries keep the query index in 26 bits
 #define JG_MAX_NODES (1 << 20)           // stage-2 pair words keep the node index in >= 20 bits
@@ -66,6 +70,10 @@ struct DetectCtl {
 struct DetectScratch {
     DetectCtl* ctl;
     int* sv_entry;  // survivors of stage 1: query index within the batch (low 26 bits) | segment (high 6 bits)
+    // containment list written by k_s2_grid: survivor entry + virtual root node, and the transformed shape's bbox
+    int4* ct_meta;
+    float4* ct_bb;
+    float4* ct_xf;
 };
 // Per-layout launch parameters (make_detect_plan).
 struct DetectPlan {
@@ -73,6 +81,7 @@ struct DetectPlan {
     int cap_in;         // capacity of a warp's inner-pair stack
     int gbits;          // log2 of the survivors a stage-2 warp resolves together
     int use_grid;       // depth <= 5 and the node boxes match the nested-midpoint grid: k_s1_grid / k_s2_grid
+    long long split_min;  // launches of at least this many queries run the containment tests in k_s2_contain
 };
 DetectPlan make_detect_plan(int n_nodes, int depth);
 size_t detect_kinds_bytes(int n_nodes);

@@ -488,3 +488,25 @@ def test_search_round_matches_host_evaluation(jg, engines, name):
             k = got["index"]
             assert verdicts[k] == 0 and cost[np.searchsorted(free, k)] == cost.min()
             assert (got["rot_idx"], np.float32(got["tx"]), np.float32(got["ty"])) == (int(ridx[k]), txy[k, 0], txy[k, 1])
+
+
+@pytest.mark.parametrize("name", ["swim_half", "baldacci1_bin", "gardeyn1c_half", "albano_ms0"])
+def test_split_containment_kernel_matches_inline_path(jg, engines, name):
+    """Large launches run detect_containment_collision in k_s2_contain (teams of four lanes per survivor) instead of
+    inside k_s2_grid; forced here for small batches: same verdicts as the oracle, with and without filters."""
+    wl, cde, w = engines(name)
+    fbits = cde.filter_from_irrelevant_qzones(2)
+    cde.upload_filter(7, fbits)
+    try:
+        cde.set_split_min(0)
+        n_contained = 0
+        for item_id in range(0, len(wl.items), max(1, len(wl.items) // 4)):
+            t = jg.make_queries(wl, item_id, 6000, seed=77)
+            exp = w.detect_batch(item_id, t)
+            assert np.array_equal(cde.detect_batch(item_id, t), exp)
+            assert np.array_equal(cde.detect_batch(item_id, t, poly_only=True), w.detect_batch(item_id, t, poly_only=True))
+            assert np.array_equal(cde.detect_batch(item_id, t, filter_id=7), w.detect_batch(item_id, t, filter_bits=fbits))
+            n_contained += int((exp == 0).sum())
+        assert n_contained > 0 or name == "baldacci1_bin"  # (uniform samples over that bin are almost never free)
+    finally:
+        cde.set_split_min(1 << 21)

@@ -890,6 +890,14 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
         e->trace_m.clear();
         trace_mark(e, e->chunks[e->next_chunk % e->chunks.size()].st);
     }
+    // size every piece slot now (no-ops once they are): a slot that first grows in the middle of a run of batches would
+    // stall that batch by several milliseconds of cudaMalloc
+    for (ChunkCtx& c : e->chunks)
+        if (c.cap_q < (size_t)(chunk < n ? chunk : n) || c.cap_sv < (size_t)(chunk < n ? chunk : n) || c.cap_out < (size_t)(chunk < n ? chunk : n)) {
+            JG_CUDA(e, cudaStreamSynchronize(c.st));
+            rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n), true);
+            if (rc != JG_OK) return rc;
+        }
     while (next_piece(e, n_seg, items.data(), seg_offsets, piece_size(cur.q), cur, p)) {
         ChunkCtx& c = e->chunks[e->next_chunk++ % e->chunks.size()];
         JG_CUDA(e, cudaStreamSynchronize(c.st));  // buffers of this slot are free again

@@ -186,83 +186,6 @@ __device__ __forceinline__ bool leaf_cell_collides(const DevLayout& L, uint32_t 
     return false;
 }
 
-// ---- flat leaf tests ---------------------------------------------------------------------------------
-// QTHazPartial::collides_with (qt_partial_hazard.rs:67-72) for up to 32 (entity, leaf cell) pairs at once, one
-// pair per lane, with the hazard edges of all pairs spread evenly over the lanes: per round e every pair looks
-// at its e-th relevant Partial entry (filter, entity-vs-ff_bbox), the surviving (pair, entry) ranges are laid
-// end to end by a warp scan, and lane t of every 32-wide chunk tests edge t of that flat list. The verdict of a
-// pair is an OR over its (entry, edge) tests, so the order is free; a pair stops contributing once it has a hit.
-struct FlatScratch {
-    float4 ent[32];  // entity of the r-th contributing pair of the round
-    int4 own[32];    // its {first flat index, first edge, owner lane, -}
-    unsigned hit;    // bit l: the pair of lane l has a hit
-    unsigned pad[3];
-};
-__device__ __forceinline__ unsigned lanemask_le_() {
-    unsigned m;
-    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
-    return m;
-}
-template <class Ent>
-__device__ __forceinline__ Ent ent_of(const float4& v);
-template <>
-__device__ __forceinline__ Circ ent_of<Circ>(const float4& v) { return Circ{v.x, v.y, v.z}; }
-template <>
-__device__ __forceinline__ Seg ent_of<Seg>(const float4& v) { return Seg{v.x, v.y, v.z, v.w}; }
-
-// lane: entity e4 and leaf record rec (first Partial entry << 8 | n_partial; 0 = no pair). Returns, per lane,
-// whether its pair collides. All 32 lanes must call.
-template <class Ent, bool FILT>
-__device__ __forceinline__ bool flat_leaf_pairs(const DevLayout& L, const uint32_t* filt, FlatScratch& S, const float4 e4,
-                                                const uint32_t rec, const int lane) {
-    const int e0 = (int)(rec >> 8), np = (int)(rec & 255u);
-    const int maxp = __reduce_max_sync(FULL, np);
-    if (maxp == 0) return false;
-    const Ent ent = ent_of<Ent>(e4);
-    if (lane == 0) S.hit = 0u;
-    bool mine = false;
-    __syncwarp();
-    for (int e = 0; e < maxp; e++) {
-        int cnt = 0, ebeg = 0;
-        if (e < np && !mine) {
-            const int4 em = __ldg(&L.entry_meta[e0 + e]);
-            if (!(FILT && filt_bit(filt, em.x)) && ent_rect(ent, ld_rect(&L.entry_ff[e0 + e]))) cnt = em.z, ebeg = em.y;
-        }
-        const unsigned ne = __ballot_sync(FULL, cnt > 0);
-        if (!ne) continue;
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int T = __shfl_sync(FULL, incl, 31), excl = incl - cnt;
-        if (cnt > 0) {
-            const int r = __popc(ne & lanemask_lt());
-            S.ent[r] = e4;
-            S.own[r] = make_int4(excl, ebeg, lane, 0);
-        }
-        __syncwarp();
-        for (int t0 = 0; t0 < T; t0 += 32) {
-            // owners (contributing pairs) whose flat range starts inside this chunk / before it
-            const unsigned starts = __reduce_or_sync(FULL, (cnt > 0 && excl >= t0 && excl < t0 + 32) ? 1u << (excl - t0) : 0u);
-            const int before = __popc(__ballot_sync(FULL, cnt > 0 && excl < t0));
-            const int t = t0 + lane;
-            if (t < T) {
-                const int4 ow = S.own[before + __popc(starts & lanemask_le_()) - 1];
-                if (!((*(volatile unsigned*)&S.hit >> ow.z) & 1u)) {
-                    const float4 oe = S.ent[before + __popc(starts & lanemask_le_()) - 1];
-                    if (ent_seg(ent_of<Ent>(oe), ld_seg(&L.edges[ow.y + (t - ow.x)]))) atomicOr(&S.hit, 1u << ow.z);
-                }
-            }
-        }
-        __syncwarp();
-        mine = (*(volatile unsigned*)&S.hit >> lane) & 1u;
-        __syncwarp();  // the next round rewrites S.ent / S.own
-    }
-    return mine;
-}
-
 // Does the circle pass circ_rect (circle.rs:115-128) for some Entire-flagged finest cell? Rows of the
 // conservative window; per row the flagged cells nearest to the centre's column on either side.
 __device__ __forceinline__ bool circ_touches_entire(const GridDev& g, const Circ& c, int i0, int i1, int j0, int j1) {
@@ -291,11 +214,7 @@ __device__ __forceinline__ bool circ_touches_entire(const GridDev& g, const Circ
 #define G1_PAIR_CAP 192  // leaf pairs waiting per warp: drained below 32 before every push round of <= 4 per lane
 #define G1_PUSH 4
 #define G1_SURV_CAP 40  // local survivors: fewer than 8 left over + up to 32 new ones
-#ifdef G1_FLAT
-#define G1_WARP_BYTES (32 * sizeof(float4) + (G1_PAIR_CAP + 64 + 4 + G1_SURV_CAP) * sizeof(uint32_t) + sizeof(FlatScratch))
-#else
 #define G1_WARP_BYTES (32 * sizeof(float4) + (G1_PAIR_CAP + 64 + 4 + G1_SURV_CAP) * sizeof(uint32_t))
-#endif
 #define GF_WARP_BYTES (G1_WARP_BYTES + ((sizeof(G2Slots) + 15) & ~(size_t)15))
 
 // ---------------------------------------------------------------------------------------------------
@@ -343,7 +262,6 @@ struct G1Warp {  // stage-1 state of a warp (shared memory + two counters)
     unsigned* s_hit;
     int* s_cnt;
     int* s_surv;       // fused kernel: this warp's survivors waiting for stage 2
-    FlatScratch* flat;
     int n_pend, seg_hint, n_sv;
     __device__ __forceinline__ void bind(unsigned char* wp) {
         s_circ = (float4*)wp;
@@ -352,7 +270,6 @@ struct G1Warp {  // stage-1 state of a warp (shared memory + two counters)
         s_hit = (unsigned*)(s_pend + 64);
         s_cnt = (int*)(s_hit + 1);
         s_surv = s_cnt + 3;
-        flat = (FlatScratch*)(s_surv + G1_SURV_CAP);
         n_pend = 0, seg_hint = 0, n_sv = 0;
     }
 };
@@ -479,11 +396,7 @@ __device__ __forceinline__ void g1_phase_b(const GCtx& c, G1Warp& w, int lane) {
                         rec = c.g.cell_leaf[pr >> 5];
                     }
                 }
-#ifdef G1_FLAT
-                const bool lanehit = flat_leaf_pairs<Circ, FILT>(c.L, c.filt, *w.flat, e4, rec, lane);
-#else
                 const bool lanehit = rec != 0u && leaf_cell_collides<Circ, FILT>(c.L, rec, Circ{e4.x, e4.y, e4.z}, c.filt);
-#endif
                 if (lanehit) atomicOr(w.s_hit, 1u << ol);
                 __syncwarp();
             }
@@ -624,9 +537,6 @@ struct G2Slots {  // per-warp state of the survivors of the current group
     int pad[2];
     int q_verdict[S2_MAX_GROUP];  // classification of each survivor (-1 = undecided) and its edge count
     int q_ne[S2_MAX_GROUP];
-#ifdef G2_FLAT
-    FlatScratch flat;
-#endif
 };
 
 // CDEngine::get_virtual_root (cd_engine.rs:314-327) on the grid: at each level the FIRST child (NE, NW, SW,
@@ -836,33 +746,6 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
         // rounds: every lane scans on to its next would-be hit (an Entire cell, or a leaf cell whose edge
         // tests succeed), then the lanes that found one verify together that the reference reaches it
         for (;;) {
-#ifdef G2_FLAT
-            // every scanning lane steps to its next candidate cell; the leaf cells of the round are tested together
-            int ci = -1;
-            uint32_t rec = 0u;
-            bool would = false;
-            while (scanning) {
-                if (!bits) {
-                    if (j >= j1) { scanning = false; break; }
-                    j++;
-                    er = c.g.ent_rows[j] & cm;
-                    bits = er | (c.g.leaf_rows[j] & cm);
-                    continue;
-                }
-                ci = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if ((er >> ci) & 1u) would = true;
-                else rec = c.g.cell_leaf[j * GRID_G + ci];
-                break;
-            }
-            if (!__any_sync(FULL, ci >= 0)) break;
-            would = flat_leaf_pairs<Seg, FILT>(c.L, c.filt, W.flat, make_float4(sg.sx, sg.sy, sg.ex, sg.ey), rec, lane) || would;
-            const int hi = would ? ci : -1;
-            if (!__any_sync(FULL, hi >= 0)) {
-                if ((*(volatile unsigned*)&W.hit >> slot) & 1u) scanning = false;
-                continue;
-            }
-#else
             int hi = -1;
             while (scanning) {
                 if (!bits) {
@@ -877,7 +760,6 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
                 if (((er >> i) & 1u) || leaf_cell_collides<Seg, FILT>(c.L, c.g.cell_leaf[j * GRID_G + i], sg, c.filt)) { hi = i; break; }
             }
             if (!__any_sync(FULL, hi >= 0)) break;
-#endif
             bool lanehit = false;
             if (hi >= 0) {
                 // a finest cell that holds an endpoint is flagged at every level (qt_traits.rs:36-44: not range-

@@ -1,10 +1,12 @@
+"""Enqueue / sync time of one detect_multi call per strip engine, repeated (found a first-use allocation stall of the
+piece slots: every slot is now sized on first use). Usage: python tools/mspp_probe.py jakobs1"""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import jagua_rs_b200 as jg
 inst = sys.argv[1]
 strips=[]; k=0
-while os.path.exists(f"/root/repo/workloads/{inst}_ms{k}.npz"):
+while os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "workloads", f"{inst}_ms{k}.npz")):
     strips.append(jg.load_workload(f"{inst}_ms{k}")); k+=1
 S=len(strips); n_items=len(strips[0].items)
 cdes=[jg.build_engine(wl, device=0) for wl in strips]

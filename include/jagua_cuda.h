@@ -165,6 +165,11 @@ int jg_search_round(JgEngine* e, int item_id, const JgSearchRound* round, int64_
 int jg_search_samples(JgEngine* e, int64_t n, uint8_t* rot_idx, float* txy, uint8_t* verdicts);
 
 int jg_sync(JgEngine* e);
+/* Finer than jg_sync: jg_fence_record marks everything enqueued on this engine so far, jg_fence_wait blocks until that
+ * much has completed (later batches keep running). Fences are recycled after 32 newer ones (then a wait degrades to
+ * jg_sync). */
+int jg_fence_record(JgEngine* e, uint64_t* fence);
+int jg_fence_wait(JgEngine* e, uint64_t fence);
 
 /* Counters since engine creation: [0] kernel launches, [1] queries resolved, [2] H2D bytes,
  * [3] D2H bytes, [4] layout uploads, [5] survivors of the surrogate stage and [6] work items that

@@ -71,6 +71,8 @@ C_ABI = {
     "jg_search_round": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp]),
     "jg_search_samples": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
     "jg_sync": (C.c_int, [_vp]),
+    "jg_fence_record": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "jg_fence_wait": (C.c_int, [_vp, C.c_uint64]),
     "jg_engine_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "jg_engine_last_kernel_ms": (C.c_float, [_vp]),
     "jg_timer_start": (C.c_int, [_vp]),
@@ -583,6 +585,15 @@ class CDEngine:
         ridx, txy, v = np.zeros(n, np.uint8), np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)
         self._chk(self._lib.jg_search_samples(self._eng, int(n), ridx.ctypes.data, txy.ctypes.data, v.ctypes.data))
         return ridx, txy, v
+
+    def fence(self) -> int:
+        """Marks everything enqueued so far; wait_fence(token) blocks until that much is done (later batches keep running)."""
+        tok = C.c_uint64(0)
+        self._chk(self._lib.jg_fence_record(self._eng, C.byref(tok)))
+        return int(tok.value)
+
+    def wait_fence(self, token: int):
+        self._chk(self._lib.jg_fence_wait(self._eng, int(token)))
 
     def sync(self):
         self._need_engine()

@@ -114,6 +114,13 @@ struct JgEngine {
     uint32_t* d_flush = nullptr;
     size_t flush_words = 0;
 
+    // fences: completion points of everything enqueued so far (one event per query stream), a small ring
+    struct Fence {
+        std::vector<cudaEvent_t> ev;
+        uint64_t id = 0;
+    };
+    std::vector<Fence> fences;
+    uint64_t next_fence = 1;
     unsigned long long* d_search = nullptr;  // search rounds: {min key, n_free, best txy bits, best rot idx}
     unsigned long long* h_search = nullptr;  // pinned copy
     int64_t search_last_n = 0;
@@ -297,6 +304,8 @@ void jg_engine_destroy(JgEngine* e) {
         if (B.ready) cudaEventDestroy(B.ready);
         for (cudaEvent_t ev : B.marks) cudaEventDestroy(ev);
     }
+    for (JgEngine::Fence& f : e->fences)
+        for (cudaEvent_t ev : f.ev) cudaEventDestroy(ev);
     if (e->d_search) cudaFree(e->d_search);
     if (e->h_search) cudaFreeHost(e->h_search);
     if (e->st_up) cudaStreamDestroy(e->st_up);
@@ -1203,6 +1212,35 @@ int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams) {
         free_ctx(c);
         c.st = st;
     }
+    return JG_OK;
+}
+
+// Completion point of everything enqueued on this engine so far (the *_async entry points return after enqueueing;
+// jg_sync waits for all of it, a fence only for what preceded it). Fences live in a ring of 32.
+int jg_fence_record(JgEngine* e, uint64_t* fence) {
+    if (!e || !fence) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    if (e->fences.empty()) e->fences.resize(32);
+    JgEngine::Fence& f = e->fences[e->next_fence % e->fences.size()];
+    std::vector<cudaStream_t> qs{e->compute, e->st_copy};
+    for (ChunkCtx& c : e->chunks) qs.push_back(c.st);
+    while (f.ev.size() < qs.size()) {
+        cudaEvent_t ev;
+        JG_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        f.ev.push_back(ev);
+    }
+    for (size_t i = 0; i < qs.size(); i++) JG_CUDA(e, cudaEventRecord(f.ev[i], qs[i]));
+    for (size_t i = qs.size(); i < f.ev.size(); i++) JG_CUDA(e, cudaEventRecord(f.ev[i], e->compute));
+    f.id = e->next_fence++;
+    *fence = f.id;
+    return JG_OK;
+}
+int jg_fence_wait(JgEngine* e, uint64_t fence) {
+    if (!e || fence == 0 || fence >= e->next_fence) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    JgEngine::Fence& f = e->fences[fence % e->fences.size()];
+    if (f.id != fence) return jg_sync(e);  // recycled: everything that old is covered by a full sync
+    for (cudaEvent_t ev : f.ev) JG_CUDA(e, cudaEventSynchronize(ev));
     return JG_OK;
 }
 

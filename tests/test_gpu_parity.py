@@ -510,3 +510,46 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
         assert n_contained > 0 or name == "baldacci1_bin"  # (uniform samples over that bin are almost never free)
     finally:
         cde.set_split_min(1 << 21)
+
+
+@pytest.mark.parametrize("name", ["swim_half", "jakobs1_ms1"])
+def test_layout_update_behind_batches_in_flight(jg, orc, name):
+    """Stream-ordered layout uploads: a batch enqueued before an update is resolved on the old layout, a batch enqueued
+    after it on the new one, with no host synchronisation in between (fences only order the host's reads)."""
+    wl = jg.load_workload(name)
+    cde = jg.build_engine(wl, device=0)
+    w = oracle_world(orc, wl)
+    cde.sync_layout()
+    n_items = len(wl.items)
+    n = 40_000
+    sizes = jg.split_batch(n, n_items)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    ids = list(range(n_items))
+    t = jg.PinnedBuffer((n, 4), np.float32)
+    for i, m in enumerate(sizes):
+        t.array[offs[i]:offs[i + 1]] = jg.make_queries(wl, i, m, seed=9)
+    outs = [jg.PinnedBuffer((n,), np.uint8) for _ in range(8)]
+    rng = np.random.default_rng(4)
+    b = wl.cde_bbox
+    expected, fences = [], []
+    uploads0 = cde.stats()["layout_uploads"]
+    for step in range(8):
+        cde.detect_multi(ids, offs, t.array, out=outs[step].array, wait=False)  # in flight while the layout changes
+        fences.append(cde.fence())
+        expected.append(np.concatenate([w.detect_batch(i, np.ascontiguousarray(t.array[offs[i]:offs[i + 1]])) for i in range(n_items)]))
+        i = int(rng.integers(n_items))
+        it = wl.items[i]
+        rot = 0.0 if it.rotations is None or len(it.rotations) == 0 else float(it.rotations[0])
+        dt = np.array([[rot, b[0] + (b[2] - b[0]) * rng.random(), b[1] + (b[3] - b[1]) * rng.random()]], np.float32)
+        pk = w.place_item(i, float(dt[0, 0]), float(dt[0, 1]), float(dt[0, 2]))
+        cde.place_item(i, jg.ItemShape(it.verts, it.poi, it.poles, it.piers), jg.compose(dt)[0], pk)
+        cde.sync_layout()  # returns without waiting for the batch above
+    for step in (3, 0, 7):  # fences can be waited for in any order
+        cde.wait_fence(fences[step])
+        assert np.array_equal(outs[step].array, expected[step]), f"step {step}"
+    cde.sync()
+    for step in range(8):
+        assert np.array_equal(outs[step].array, expected[step]), f"step {step}"
+    assert len({e.tobytes() for e in expected}) > 1  # the updates really changed verdicts
+    assert cde.stats()["layout_uploads"] - uploads0 == 8
+    cde.close()

@@ -34,6 +34,9 @@ ap.add_argument("--instance", default="jakobs1")
 ap.add_argument("--queries-per-gpu", type=int, default=12_500_000)
 ap.add_argument("--sub-batch", type=int, default=1 << 20)
 ap.add_argument("--no-check", action="store_true")
+ap.add_argument("--lookahead", type=int, default=0, choices=[0, 1],
+                help="1: the update before sub-batch b is decided from the verdicts of sub-batch b-2 (waited for through a "
+                     "fence), so rank 0 never waits for the sub-batch in flight; 0: from sub-batch b-1 (fully dependent)")
 args = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0"))
@@ -102,9 +105,14 @@ def barrier():
         torch.cuda.synchronize()
 
 
+fences = {}  # (sub-batch, strip) -> fence token of that strip's engine (rank 0, lookahead mode)
+
+
 def run_sub(b, out_slot):
     for s in range(S):
         cdes[s].detect_multi(ids, offs, host_t[s][b % N_SETS].array, out=host_out[s][out_slot].array, wait=False)
+        if args.lookahead and rank == 0:
+            fences[(b, s)] = cdes[s].fence()
 
 
 rng = np.random.default_rng(7)
@@ -123,8 +131,19 @@ def apply_update(b):
     blob = None
     if rank == 0:
         cde = cdes[s]
-        cde.sync()  # the previous sub-batch's verdicts for this strip are final
-        prev = host_out[s][(b - 1) if keep else (b - 1) % 2].array
+        src_b = b - 1 - args.lookahead  # the sub-batch whose verdicts steer this update
+        if src_b < 0:
+            update_s += time.perf_counter() - t0
+            if world > 1:  # nothing to decide yet, but every rank takes part in the broadcast
+                d_blob = multigpu.broadcast_blob(cde.flatten(), dist, src=0, device=f"cuda:{local_rank}")
+                cdes[s].upload_layout_device(d_blob.data_ptr(), d_blob.numel(), epoch=b + 2)
+            return
+        if args.lookahead:
+            cde.wait_fence(fences.pop((src_b, s)))  # that sub-batch is done; the one in flight keeps running
+        else:
+            cde.sync()  # the previous sub-batch's verdicts for this strip are final
+        assert keep or not args.lookahead, "--lookahead keeps every sub-batch's verdicts (rank 0 checks them)"
+        prev = host_out[s][src_b if keep else src_b % 2].array
         did = False
         if placed[s] and rng.random() < 0.4:
             pk = placed[s].pop(int(rng.integers(len(placed[s]))))
@@ -136,7 +155,7 @@ def apply_update(b):
             if len(free):
                 q = int(free[int(rng.integers(len(free)))])
                 item = int(np.searchsorted(offs, q, side="right") - 1)
-                t4 = host_t[s][(b - 1) % N_SETS].array[q].copy()
+                t4 = host_t[s][src_b % N_SETS].array[q].copy()
                 pk = next_pk
                 next_pk += 1
                 cde.place_item(item, shapes[item], t4, pk)
@@ -182,7 +201,7 @@ if rank == 0:
             "config": {"workload": f"{args.instance}: {S} strips with minimum separation (workloads/{args.instance}_ms*.npz), "
                                    f"{n_items} item types, host buffers (16 B in, 1 B out per query), one layout update + blob "
                                    "broadcast before every sub-batch", "hazards_per_strip": [len(w.hazards) for w in strips]},
-            "layout_updates": n_updates, "update_seconds_rank0": update_s,
+            "lookahead": args.lookahead, "layout_updates": n_updates, "update_seconds_rank0": update_s,
             "update_ms_each": update_s / max(n_sub - 1, 1) * 1e3}
     if keep:
         for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):

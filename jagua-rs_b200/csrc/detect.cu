@@ -689,7 +689,7 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
         // Large launches hand the containment tests to their own kernel (k_s2_contain): stage 2 is bound by instruction
         // fetch and runs 17 % faster without that code, which pays for the third launch (~25 us) from ~2 M queries on
         // (4 M queries: 706 -> 670 us); smaller launches keep the containment tests inline.
-        const bool split = (long long)n >= plan.split_min;
+        const bool split = (long long)n >= plan.split_min && sc.ct_meta != nullptr;
         const size_t gs3 = ((sizeof(SegTable) + 15) & ~(size_t)15) + 16;
         const int want3 = (n + S_WARPS * CT_GROUP - 1) / (S_WARPS * CT_GROUP);
 #define JG_LAUNCH_S2(FILT_, SPLIT_, SLOT_)                                                                                     \

@@ -48,7 +48,7 @@ struct ChunkCtx {
     uint8_t* d_out = nullptr;  // verdict bytes or collector words
     size_t cap_q = 0, cap_out = 0;
     DetectScratch sc{nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap_sv = 0;
+    size_t cap_sv = 0, cap_ct = 0;
     cudaEvent_t done = nullptr;  // join point of device-resident batches spread over the chunk streams
 };
 
@@ -181,23 +181,26 @@ static int ensure_ctx(JgEngine* e, ChunkCtx& c, size_t n_q, size_t out_bytes, bo
     }
     if (c.cap_sv < n_q) {
         cudaFree(c.sc.sv_entry);
-        cudaFree(c.sc.ct_meta);
-        cudaFree(c.sc.ct_bb);
-        cudaFree(c.sc.ct_xf);
         c.sc.sv_entry = nullptr;
-        c.sc.ct_meta = nullptr;
-        c.sc.ct_bb = nullptr;
-        c.sc.ct_xf = nullptr;
         c.cap_sv = 0;
         if (!c.sc.ctl) {
             JG_CUDA(e, cudaMalloc(&c.sc.ctl, sizeof(DetectCtl)));
             JG_CUDA(e, cudaMemset(c.sc.ctl, 0, sizeof(DetectCtl)));
         }
         JG_CUDA(e, cudaMalloc(&c.sc.sv_entry, n_q * sizeof(int)));
-        JG_CUDA(e, cudaMalloc(&c.sc.ct_meta, n_q * sizeof(int4)));
-        JG_CUDA(e, cudaMalloc(&c.sc.ct_bb, n_q * sizeof(float4)));
-        JG_CUDA(e, cudaMalloc(&c.sc.ct_xf, n_q * sizeof(float4)));
         c.cap_sv = n_q;
+    }
+    // the hand-over list of the containment kernel: only slots that can see a launch large enough to use it (48 B/query)
+    if ((long long)c.cap_sv >= e->plan.split_min && c.cap_ct < c.cap_sv) {
+        cudaFree(c.sc.ct_meta);
+        cudaFree(c.sc.ct_bb);
+        cudaFree(c.sc.ct_xf);
+        c.sc.ct_meta = nullptr, c.sc.ct_bb = nullptr, c.sc.ct_xf = nullptr;
+        c.cap_ct = 0;
+        JG_CUDA(e, cudaMalloc(&c.sc.ct_meta, c.cap_sv * sizeof(int4)));
+        JG_CUDA(e, cudaMalloc(&c.sc.ct_bb, c.cap_sv * sizeof(float4)));
+        JG_CUDA(e, cudaMalloc(&c.sc.ct_xf, c.cap_sv * sizeof(float4)));
+        c.cap_ct = c.cap_sv;
     }
     return JG_OK;
 }

@@ -499,6 +499,9 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
     cde.upload_filter(7, fbits)
     try:
         cde.set_split_min(0)
+        l0 = cde.stats()["launches"]
+        cde.detect_batch(0, jg.make_queries(wl, 0, 1000, seed=1))
+        assert cde.stats()["launches"] - l0 == 3  # k_s1_grid, k_s2_grid<split>, k_s2_contain
         n_contained = 0
         for item_id in range(0, len(wl.items), max(1, len(wl.items) // 4)):
             t = jg.make_queries(wl, item_id, 6000, seed=77)

@@ -77,6 +77,7 @@ class BatchedLBF:
         self.samples = 0
         self.extensions = 0
         self._next_pk = 1
+        self.filter_id = -1  # HazardFilter of the current search (-1 = NoFilter)
         self._build_engine()
 
     # -- container (probs/spp/entities/strip.rs:44-61: rectangle (0, 0, width, height); CDE bbox = its square hull) ----
@@ -127,7 +128,7 @@ class BatchedLBF:
     # -- one batch through the engine: feasible sample of minimal loss -----------------------------------------------
     def _best_of(self, item: LbfItem, dts: np.ndarray, below: Optional[float]):
         t4 = compose(dts)
-        verdicts = self.cde.detect_batch(item.id, t4)
+        verdicts = self.cde.detect_batch(item.id, t4, filter_id=self.filter_id)
         self.samples += len(dts)
         free = np.nonzero(verdicts == 0)[0]
         if len(free) == 0:
@@ -159,7 +160,7 @@ class BatchedLBF:
         for _ in range(uniform_rounds):
             self._round += 1
             self.samples += per
-            if take(self.cde.search_round(item.id, per, box=box, seed=self.seed, counter=self._round)):
+            if take(self.cde.search_round(item.id, per, box=box, seed=self.seed, counter=self._round, filter_id=self.filter_id)):
                 box[2] = min(box[2], np.float32(best[1]) / X_MULTIPLIER)  # tighten_sample_bbox
                 if not box[2] > box[0]:
                     break
@@ -173,7 +174,7 @@ class BatchedLBF:
             self.samples += per
             sd = sd0 * (sd1 / sd0) ** (r / max(ls_rounds, 1))
             take(self.cde.search_round(item.id, per, mean=(best[0][1], best[0][2]), sd=sd, rot_idx=best[2], seed=self.seed,
-                                       counter=self._round))
+                                       counter=self._round, filter_id=self.filter_id))
         return best[0], best[1]
 
     def search(self, item: LbfItem, n_samples: int, ls_frac: float, uniform_rounds: int, ls_rounds: int):
@@ -249,6 +250,115 @@ class BatchedLBF:
         if self.cde is not None:
             self.cde.close()
             self.cde = None
+
+
+@dataclass
+class BinLayout:
+    bin_id: int
+    cde: CDEngine
+    bbox: np.ndarray
+    placements: List[Placement] = field(default_factory=list)
+
+
+@dataclass
+class BinResult:
+    layouts: List[BinLayout]
+    placed: int
+    unplaced: int
+    samples: int
+    seconds: float
+
+
+class BatchedLBFBins(BatchedLBF):
+    """lbf_bpp.rs:39-137 on the engine: items by descending diameter; every copy is searched for in the open layouts in
+    the order they were opened, then in the first closed bin type that still has stock (a layout is opened only when a
+    placement is found there). Items with a min_quality are searched under HazKeyFilter::from_irrelevant_qzones
+    (filter.rs:21-41), one filter id per quality, uploaded per layout."""
+
+    def __init__(self, instance: dict, device: int = 0, quadtree_depth: int = 5, cd_threshold: int = 16, n_ff_poles: int = 2,
+                 seed: int = 0, device_sampling: bool = True):
+        from .instance import load_instance
+
+        self.inst = load_instance(instance)
+        self.items = self.inst.items
+        self.cfg = dict(quadtree_depth=quadtree_depth, cd_threshold=cd_threshold, n_ff_poles=n_ff_poles, n_ff_piers=0)
+        self.device = device
+        self.rng = np.random.Generator(np.random.Philox(key=[seed, 0xB1]))
+        self.seed = int(seed)
+        self.device_sampling = device_sampling
+        self._round = 0
+        self.samples = 0
+        self._next_pk = 1
+        self.filter_id = -1
+        self.cde = None
+        self.bbox = None
+        self.layouts: List[BinLayout] = []
+        self.stock = [int(b.get("stock", 1)) for b in self.inst.bins]
+        self.qualities = sorted({it.min_quality for it in self.items if it.min_quality is not None})
+
+    def _open(self, bin_id: int) -> BinLayout:
+        from .instance import container_engine, container_hazards
+
+        cde = container_engine(self.inst, bin_id, device=self.device, **self.cfg)
+        bbox, _ = container_hazards(self.inst.bins[bin_id])
+        for it in self.items:
+            if it.rotations is not None:
+                cde.set_item_rotations(it.id, it.rotations if len(it.rotations) else np.zeros(1, np.float32))
+        for q in self.qualities:  # padded so that the bitset keeps covering the slot map as items are placed
+            bits = np.zeros(64, np.uint32)
+            fb = cde.filter_from_irrelevant_qzones(q)
+            bits[:len(fb)] = fb
+            cde.upload_filter(int(q), bits)
+        return BinLayout(bin_id, cde, bbox)
+
+    def _search_in(self, lay: BinLayout, item, n_samples, ls_frac, uniform_rounds, ls_rounds):
+        self.cde, self.bbox = lay.cde, lay.bbox
+        self.filter_id = -1 if item.min_quality is None else int(item.min_quality)
+        return self.search(item, n_samples, ls_frac, uniform_rounds, ls_rounds)
+
+    def solve(self, n_samples: int = 5000, ls_frac: float = 0.2, uniform_rounds: int = 4, ls_rounds: int = 8,
+              max_items: int = 1 << 30) -> BinResult:
+        t0 = time.perf_counter()
+        placed = unplaced = 0
+        for item in sorted(self.items, key=lambda it: -it.diameter):
+            demand = item.demand
+            while demand > 0 and placed < max_items:
+                where = None
+                for lay in self.layouts:  # open layouts first
+                    got = self._search_in(lay, item, n_samples, ls_frac, uniform_rounds, ls_rounds)
+                    if got is not None:
+                        where = (lay, got)
+                        break
+                if where is None:
+                    for bin_id, qty in enumerate(self.stock):  # then closed bins with stock
+                        if qty <= 0:
+                            continue
+                        lay = self._open(bin_id)
+                        got = self._search_in(lay, item, n_samples, ls_frac, uniform_rounds, ls_rounds)
+                        if got is not None:
+                            self.stock[bin_id] -= 1
+                            self.layouts.append(lay)
+                            where = (lay, got)
+                            break
+                        lay.cde.close()
+                if where is None:
+                    unplaced += demand  # items of this type do not fit anywhere (lbf_bpp.rs:70)
+                    break
+                lay, (dt, _) = where
+                pk = self._next_pk
+                self._next_pk += 1
+                lay.cde.place_item(item.id, item.shape, compose(dt.reshape(1, 3))[0], pk)
+                lay.placements.append(Placement(item.id, dt, pk))
+                demand -= 1
+                placed += 1
+        self.cde = None
+        return BinResult(self.layouts, placed, unplaced, self.samples, time.perf_counter() - t0)
+
+    def close(self):
+        for lay in self.layouts:
+            lay.cde.close()
+        self.layouts = []
+        self.cde = None
 
 
 def solve_file(path: str, **kw) -> LbfResult:

@@ -556,3 +556,27 @@ def test_layout_update_behind_batches_in_flight(jg, orc, name):
     assert len({e.tobytes() for e in expected}) > 1  # the updates really changed verdicts
     assert cde.stats()["layout_uploads"] - uploads0 == 8
     cde.close()
+
+
+def test_batched_lbf_bins_solution_is_feasible(jg, orc):
+    """lbf_bpp.rs on the engine (bins with holes and quality zones, items searched under the from_irrelevant_qzones
+    filter of their min_quality): every layout is re-placed in an oracle layout of the same bin and must be feasible
+    (Layout::is_feasible checks every placed item against holes, zones below its min_quality and the other items)."""
+    import json
+    import os
+
+    from jagua_rs_b200 import lbf
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets", "baldacci1.json")
+    with open(path) as f:
+        inst = json.load(f)
+    solver = lbf.BatchedLBFBins(inst, device=0, seed=2)
+    res = solver.solve(n_samples=4000, max_items=30)
+    assert res.placed == 30 and len(res.layouts) >= 2
+    assert any(solver.items[p.item_id].min_quality is not None for lay in res.layouts for p in lay.placements)
+    for lay in res.layouts:
+        w = orc.world_from_instance(inst, bin_index=lay.bin_id)
+        for p in lay.placements:
+            w.place_item(p.item_id, float(p.d_transf[0]), float(p.d_transf[1]), float(p.d_transf[2]))
+        assert w.is_feasible(), f"bin {lay.bin_id}"
+    solver.close()

@@ -580,3 +580,26 @@ def test_batched_lbf_bins_solution_is_feasible(jg, orc):
             w.place_item(p.item_id, float(p.d_transf[0]), float(p.d_transf[1]), float(p.d_transf[2]))
         assert w.is_feasible(), f"bin {lay.bin_id}"
     solver.close()
+
+
+@pytest.mark.parametrize("name", ["swim_half", "shirts_full_d10"])
+def test_non_finite_queries_terminate_and_do_not_disturb_others(jg, engines, name):
+    """The reference cannot even build such a Transformation (NotNan panics); the engine must still terminate on them and
+    every ordinary query of the same batch must keep its verdict and hazard set (grid and walk kernels)."""
+    wl, cde, w = engines(name)
+    words = cde.collector_words()
+    for item_id in (0, len(wl.items) - 1):
+        t = jg.make_queries(wl, item_id, 4096, seed=123)
+        exp = w.detect_batch(item_id, t)
+        expc = w.collect_batch(item_id, t, words)
+        bad = t.copy()
+        rows = np.arange(0, len(t), 7)
+        vals = [np.nan, np.inf, -np.inf, 3.0e38, -3.0e38, 1.0e-45]
+        for k, r in enumerate(rows):
+            bad[r, (k // len(vals)) % 4] = vals[k % len(vals)]
+        keep = np.ones(len(t), bool)
+        keep[rows] = False
+        got = cde.detect_batch(item_id, bad)
+        assert np.array_equal(got[keep], exp[keep])
+        gotc = cde.collect_batch(item_id, bad, words)
+        assert np.array_equal(gotc[keep], expc[keep])

@@ -15,8 +15,10 @@ by the oracle in tests/), not bit for bit:
     along init * (end / init)^progress (LSSampler::decay_stddev), the mean shifted to every improvement;
   * items with a discrete set of allowed rotations (or none) run every round entirely on the device
     (`CDEngine.search_round`: Philox sampling kernel, detect kernels, loss reduction kernel; 32 bytes come back per
-    round); items that rotate continuously are sampled on the host, because their (cos, sin) must come from the host
-    libm to stay bit-compatible with the reference's `Transformation`s;
+    round); the (cos, sin) of a sample must come from the host libm to stay bit-compatible with the reference's
+    `Transformation`s, so items that rotate continuously are searched on a lattice of `rotation_lattice` (256) evenly
+    spaced angles composed once on the host - every sample is still an exact transformation, only the sampling
+    distribution of the rotation is discretised - or, with `rotation_lattice=0`, sampled on the host as before;
   * no feasible sample: the strip grows by 10 % (change_strip_width) - a new CDEngine, all placements re-registered;
   * at the end the strip is fitted to the right-most item * 1.00001 (SPProblem::fit_strip).
 
@@ -58,7 +60,8 @@ class LbfResult:
 
 class BatchedLBF:
     def __init__(self, instance: dict, device: int = 0, quadtree_depth: int = 5, cd_threshold: int = 16, n_ff_poles: int = 2,
-                 seed: int = 0, device_sampling: bool = True):
+                 seed: int = 0, device_sampling: bool = True, rotation_lattice: int = 256):
+        self.rotation_lattice = int(rotation_lattice)
         self.items = import_items(instance["items"])
         self.height = np.float32(instance["strip_height"])
         area = np.float32(0.0)
@@ -97,10 +100,20 @@ class BatchedLBF:
         self.cde.register_hazard(HAZ_EXTERIOR, verts, poi, dynamic=False)
         for it in self.items:
             self.cde.upload_item(it.id, it.shape)
-            if it.rotations is not None:  # discrete / none: search rounds can run on the device
-                self.cde.set_item_rotations(it.id, it.rotations if len(it.rotations) else np.zeros(1, np.float32))
+            rots = self._device_rotations(it)
+            if rots is not None:  # search rounds can run on the device
+                self.cde.set_item_rotations(it.id, rots)
         for p in self.placements:  # Layout::swap_container re-registers every placed item
             self.cde.place_item(p.item_id, self.items[p.item_id].shape, compose(p.d_transf.reshape(1, 3))[0], p.pk)
+
+    def _device_rotations(self, item):
+        """The rotation set registered with the engine for device-side search rounds (None: host sampling)."""
+        if item.rotations is not None:
+            return item.rotations if len(item.rotations) else np.zeros(1, np.float32)
+        if self.rotation_lattice > 0:
+            n = min(self.rotation_lattice, 256)
+            return (np.arange(n, dtype=np.float64) * (2.0 * np.pi / n)).astype(np.float32)
+        return None
 
     # -- samplers ------------------------------------------------------------------------------------------------
     def _rotations(self, item: LbfItem, n: int) -> np.ndarray:
@@ -145,7 +158,7 @@ class BatchedLBF:
         return dts[free[k]].copy(), float(cost[k])
 
     def _search_on_device(self, item: LbfItem, n_uni: int, n_ls: int, uniform_rounds: int, ls_rounds: int):
-        rots = item.rotations if len(item.rotations) else np.zeros(1, np.float32)
+        rots = self._device_rotations(item)
         box = self.bbox.copy()
         best = None  # (d_transf, loss, rotation index)
 
@@ -173,7 +186,9 @@ class BatchedLBF:
             self._round += 1
             self.samples += per
             sd = sd0 * (sd1 / sd0) ** (r / max(ls_rounds, 1))
-            take(self.cde.search_round(item.id, per, mean=(best[0][1], best[0][2]), sd=sd, rot_idx=best[2], seed=self.seed,
+            # items on a rotation lattice also try the neighbouring angles (the reference's LSSampler perturbs the rotation)
+            ri = best[2] if item.rotations is not None else (best[2] + (0, 1, -1)[r % 3]) % len(rots)
+            take(self.cde.search_round(item.id, per, mean=(best[0][1], best[0][2]), sd=sd, rot_idx=ri, seed=self.seed,
                                        counter=self._round, filter_id=self.filter_id))
         return best[0], best[1]
 
@@ -181,7 +196,7 @@ class BatchedLBF:
         """search.rs:17-106 with batches at the decision points."""
         n_ls = int(n_samples * ls_frac)
         n_uni = n_samples - n_ls
-        if self.device_sampling and item.rotations is not None:
+        if self.device_sampling and self._device_rotations(item) is not None:
             return self._search_on_device(item, n_uni, n_ls, uniform_rounds, ls_rounds)
         box = self.bbox.copy()
         best = None
@@ -276,8 +291,10 @@ class BatchedLBFBins(BatchedLBF):
     (filter.rs:21-41), one filter id per quality, uploaded per layout."""
 
     def __init__(self, instance: dict, device: int = 0, quadtree_depth: int = 5, cd_threshold: int = 16, n_ff_poles: int = 2,
-                 seed: int = 0, device_sampling: bool = True):
+                 seed: int = 0, device_sampling: bool = True, rotation_lattice: int = 256):
         from .instance import load_instance
+
+        self.rotation_lattice = int(rotation_lattice)
 
         self.inst = load_instance(instance)
         self.items = self.inst.items
@@ -302,8 +319,9 @@ class BatchedLBFBins(BatchedLBF):
         cde = container_engine(self.inst, bin_id, device=self.device, **self.cfg)
         bbox, _ = container_hazards(self.inst.bins[bin_id])
         for it in self.items:
-            if it.rotations is not None:
-                cde.set_item_rotations(it.id, it.rotations if len(it.rotations) else np.zeros(1, np.float32))
+            rots = self._device_rotations(it)
+            if rots is not None:
+                cde.set_item_rotations(it.id, rots)
         for q in self.qualities:  # padded so that the bitset keeps covering the slot map as items are placed
             bits = np.zeros(64, np.uint32)
             fb = cde.filter_from_irrelevant_qzones(q)

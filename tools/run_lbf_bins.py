@@ -20,10 +20,11 @@ ap.add_argument("instance", nargs="?", default=os.path.join(ROOT, "assets", "bal
 ap.add_argument("--samples", type=int, default=20000)
 ap.add_argument("--seed", type=int, default=0)
 ap.add_argument("--no-check", action="store_true")
+ap.add_argument("--rotation-lattice", type=int, default=256, help="angles of the device-side lattice for items that rotate continuously (0: sample them on the host)")
 args = ap.parse_args()
 with open(args.instance) as f:
     inst = json.load(f)
-solver = lbf.BatchedLBFBins(inst, device=0, seed=args.seed)
+solver = lbf.BatchedLBFBins(inst, device=0, seed=args.seed, rotation_lattice=args.rotation_lattice)
 res = solver.solve(n_samples=args.samples)
 line = {"instance": os.path.basename(args.instance), "n_samples_per_search": args.samples, "placed": res.placed, "unplaced": res.unplaced,
         "bins_used": [lay.bin_id for lay in res.layouts], "items_per_bin": [len(lay.placements) for lay in res.layouts],

@@ -244,6 +244,17 @@ typedef struct JgSurrogateConfig {
 int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
                    float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2], float* area);
 
+/* The same with Importer's poly_simpl_tolerance (io/import.rs:31-45, geometry/original_shape.rs:33-45): the centred shape
+ * goes through simplify_shape in Inflate mode (geometry/shape_modification.rs:48-144) and SPolygon::new again before the
+ * surrogate is generated; *area stays the original shape's. narrow_concavity_cutoff_ratio is not applied. */
+int jg_item_import_simplified(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float simplify_tolerance,
+                              float* verts_xy, int* n_verts, float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles,
+                              float pre_transform_xy[2], float* area);
+/* simplify_shape (geometry/shape_modification.rs:48-144) on a clean counter-clockwise vertex list; mode 0 Inflate (result
+ * is a superset: items, holes, zones), 1 Deflate (subset: container boundaries); followed by SPolygon::new (poi). */
+int jg_shape_simplify(const float* pts_xy, int n_pts, int mode, float max_area_change_ratio, float* verts_xy, int* n_verts,
+                      float poi_xyr[3]);
+
 /* SPolygon::new for a shape that is registered as it is (container outer boundary, hole, quality zone;
  * geometry/primitives/simple_polygon.rs:40-71): orientation normalised to counter-clockwise (written to
  * verts_ccw_xy when non-null, 2 * n_pts floats) and the pole of inaccessibility jg_cde_register_hazard wants. */

@@ -9,9 +9,11 @@
 //                                              are the "next" row f3 of SURVEY section 8)
 //   geometry/fail_fast/pole.rs:12-135          generate_surrogate_poles, compute_pole, POINode
 //   geometry/fail_fast/sp_surrogate.rs:33-61   SPSurrogate::new (poles; piers only when n_ff_piers > 0: not generated here)
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <deque>
+#include <utility>
 #include <vector>
 
 #include "../../include/jagua_cuda.h"
@@ -129,6 +131,149 @@ bool compute_pole(const Shape& sh, const std::vector<Pole>& poles, Pole& out) {
 
 using namespace jg;
 
+// ---- geometry/shape_modification.rs:48-330 simplify_shape --------------------------------------------------------
+// Removes one vertex (concave / collinear corner) or replaces two consecutive convex corners by the intersection of
+// their outer edges, always the valid candidate of least area change, until the accumulated area change would exceed
+// max_ratio of the original area or fewer than 4 vertices remain. Inflate: the result is a superset of the input;
+// Deflate: a subset (corners are walked in reverse and flipped).
+enum CornerKind { CK_CONCAVE, CK_CONVEX, CK_COLLINEAR };
+struct Corner3 {
+    int a, b, c;  // left-hand side of a -> b -> c
+};
+struct Cand {
+    int kind;     // 0 concave, 1 convex-convex, 2 collinear
+    Corner3 c1, c2;
+};
+
+static CornerKind corner_kind(const std::vector<Pt>& p, const Corner3& c) {  // shape_modification.rs:312-329
+    const Pt p1 = p[c.a], p2 = p[c.b], p3 = p[c.c];
+    const float ux = p2.x - p1.x, uy = p2.y - p1.y, vx = p3.x - p1.x, vy = p3.y - p1.y;
+    const float cross = ux * vy - uy * vx;
+    return cross < 0.0f ? CK_CONCAVE : (cross == 0.0f ? CK_COLLINEAR : CK_CONVEX);
+}
+
+// shape_modification.rs:249-280 calculate_intersection_in_front
+static bool intersection_in_front(const Pt& a1, const Pt& a2, const Pt& b1, const Pt& b2, Pt& out) {
+    const float x1 = a1.x, y1 = a1.y, x2 = a2.x, y2 = a2.y, x3 = b1.x, y3 = b1.y, x4 = b2.x, y4 = b2.y;
+    const float t_nom = (x2 - x4) * (y4 - y3) - (y2 - y4) * (x4 - x3);
+    const float t_denom = (x2 - x1) * (y4 - y3) - (y2 - y1) * (x4 - x3);
+    const float u_nom = (x2 - x4) * (y2 - y1) - (y2 - y4) * (x2 - x1);
+    const float u_denom = (x2 - x1) * (y4 - y3) - (y2 - y1) * (x4 - x3);
+    const float t = t_denom != 0.0f ? t_nom / t_denom : 0.0f;
+    const float u = u_denom != 0.0f ? u_nom / u_denom : 0.0f;
+    if (t < 0.0f && u < 0.0f) {
+        out = Pt{x2 + t * (x1 - x2), y2 + t * (y1 - y2)};
+        return true;
+    }
+    return false;
+}
+// shape_modification.rs:236-247: edge_prev = c1.a -> c1.b, edge_next = c2.c -> c2.b
+static bool replacing_vertex(const std::vector<Pt>& p, const Corner3& c1, const Corner3& c2, Pt& out) {
+    return intersection_in_front(p[c1.a], p[c1.b], p[c2.c], p[c2.b], out);
+}
+static float tri_area_abs(const Pt& p0, const Pt& p1, const Pt& p2) {  // shape_modification.rs:155,168
+    const float a = (p0.x * p1.y + p1.x * p2.y + p2.x * p0.y - p0.x * p2.y - p1.x * p0.y - p2.x * p1.y) / 2.0f;
+    return fabsf(a);
+}
+static float cand_area_delta(const std::vector<Pt>& p, const Cand& c) {  // :146-174; infinity for an invalid candidate
+    if (c.kind == 2) return 0.0f;
+    if (c.kind == 0) return tri_area_abs(p[c.c1.a], p[c.c1.b], p[c.c1.c]);
+    Pt r;
+    if (!replacing_vertex(p, c.c1, c.c2, r)) return INFINITY;
+    return tri_area_abs(p[c.c1.b], r, p[c.c2.b]);
+}
+static bool same_pt(const Pt& a, const Pt& b) { return a.x == b.x && a.y == b.y; }
+static bool edge_hits(const Pt& s, const Pt& e, const Pt& ns, const Pt& ne) {  // Edge::collides_with(Edge), edge.rs:162-170
+    return seg_seg(Seg{s.x, s.y, e.x, e.y}, Seg{ns.x, ns.y, ne.x, ne.y});
+}
+// shape_modification.rs:176-208; *panic = the reference would unwrap a degenerate Edge
+static bool cand_valid(const std::vector<Pt>& p, const Cand& c, bool* panic) {
+    const size_t n = p.size();
+    if (c.kind == 2) return true;
+    if (c.kind == 0) {
+        const Pt ns = p[c.c1.a], ne = p[c.c1.c];
+        if (same_pt(ns, ne)) { *panic = true; return false; }
+        const Pt aff[3] = {p[c.c1.a], p[c.c1.b], p[c.c1.c]};
+        for (size_t i = 0; i < n; i++) {
+            const Pt s = p[i], e = p[(i + 1) % n];
+            bool skip = false;
+            for (const Pt& a : aff) skip = skip || same_pt(a, s) || same_pt(a, e);
+            if (!skip && edge_hits(s, e, ns, ne)) return false;
+        }
+        return true;
+    }
+    Pt r;
+    if (!replacing_vertex(p, c.c1, c.c2, r)) return false;
+    if (same_pt(p[c.c1.a], r) || same_pt(r, p[c.c2.c])) { *panic = true; return false; }
+    const Pt aff[4] = {p[c.c1.b], p[c.c1.a], p[c.c2.b], p[c.c2.c]};
+    for (size_t i = 0; i < n; i++) {
+        const Pt s = p[i], e = p[(i + 1) % n];
+        bool skip = false;
+        for (const Pt& a : aff) skip = skip || same_pt(a, s) || same_pt(a, e);
+        if (!skip && (edge_hits(s, e, p[c.c1.a], r) || edge_hits(s, e, r, p[c.c2.c]))) return false;
+    }
+    return true;
+}
+static std::vector<Pt> cand_execute(const std::vector<Pt>& p, const Cand& c) {  // :218-234
+    std::vector<Pt> q = p;
+    if (c.kind != 1) {
+        q.erase(q.begin() + c.c1.b);
+        return q;
+    }
+    Pt r;
+    replacing_vertex(p, c.c1, c.c2, r);
+    q.erase(q.begin() + c.c1.b);
+    const int other = c.c1.b < c.c2.b ? c.c2.b - 1 : c.c2.b;
+    q.erase(q.begin() + other);
+    q.insert(q.begin() + other, r);
+    return q;
+}
+// returns false when the reference would panic (degenerate replacement edge)
+static bool simplify_points(std::vector<Pt>& pts, float original_area, bool deflate, float max_ratio) {
+    const size_t rounds = pts.size();
+    for (size_t round = 0; round < rounds; round++) {
+        const int n = (int)pts.size();
+        if (n < 4) break;
+        std::vector<Corner3> corners((size_t)n);
+        for (int i = 0; i < n; i++) corners[(size_t)i] = Corner3{(i - 1 + n) % n, i, (i + 1) % n};
+        if (deflate) {
+            std::reverse(corners.begin(), corners.end());
+            for (Corner3& c : corners) std::swap(c.a, c.c);
+        }
+        std::vector<Cand> cands;
+        Corner3 prev = corners.back();
+        CornerKind prev_kind = corner_kind(pts, prev);
+        for (const Corner3& c : corners) {
+            const CornerKind k = corner_kind(pts, c);
+            if (k == CK_CONCAVE) cands.push_back(Cand{0, c, c});
+            else if (k == CK_COLLINEAR) cands.push_back(Cand{2, c, c});
+            else if (prev_kind == CK_CONVEX) cands.push_back(Cand{1, prev, c});
+            prev = c;
+            prev_kind = k;
+        }
+        // stable sort by area change (OrderedFloat: NaN last), first valid candidate wins
+        std::vector<std::pair<float, size_t>> order;
+        for (size_t i = 0; i < cands.size(); i++) order.push_back({cand_area_delta(pts, cands[i]), i});
+        std::stable_sort(order.begin(), order.end(), [](const std::pair<float, size_t>& a, const std::pair<float, size_t>& b) {
+            const bool an = a.first != a.first, bn = b.first != b.first;
+            if (an || bn) return !an && bn;
+            return a.first < b.first;
+        });
+        const Cand* best = nullptr;
+        for (const auto& o : order) {
+            bool panic = false;
+            if (cand_valid(pts, cands[o.second], &panic)) { best = &cands[o.second]; break; }
+            if (panic) return false;
+        }
+        if (!best) break;
+        std::vector<Pt> next = cand_execute(pts, *best);
+        const float delta = fabsf(signed_area(next) - original_area) / original_area;
+        if (!(delta <= max_ratio)) break;  // area change too significant
+        pts.swap(next);
+    }
+    return true;
+}
+
 // SPolygon::new's pole of inaccessibility (simple_polygon.rs:40-71,151-171) for a shape that is used as it is
 // (container outer boundary, holes, zones): same cleaning-free path as the reference - the caller passes the
 // final vertex list; orientation is normalised to counter-clockwise first, as SPolygon::new does.
@@ -185,9 +330,25 @@ extern "C" int jg_shape_import(const float* pts_xy, int n_pts, float* verts_xy, 
     return jg_polygon_poi(flat.data(), (int)p.size(), poi_xyr, verts_xy);
 }
 
-extern "C" int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
-                              float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2],
-                              float* area) {
+// simplify_shape (geometry/shape_modification.rs:48-144) on a clean counter-clockwise vertex list: mode 0 = Inflate (items,
+// holes, zones), 1 = Deflate (container boundaries). The result goes through SPolygon::new again (orientation, poi).
+extern "C" int jg_shape_simplify(const float* pts_xy, int n_pts, int mode, float max_area_change_ratio, float* verts_xy, int* n_verts,
+                                 float poi_xyr[3]) {
+    if (!pts_xy || n_pts < 3 || !verts_xy || !n_verts || !poi_xyr || (mode != 0 && mode != 1)) return JG_ERR_INVALID;
+    std::vector<Pt> p((size_t)n_pts);
+    for (int i = 0; i < n_pts; i++) p[i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
+    const float area = signed_area(p);
+    if (!(area > 0.0f)) return JG_ERR_INVALID;  // SPolygon vertices are counter-clockwise
+    if (!simplify_points(p, area, mode == 1, max_area_change_ratio)) return JG_ERR_REFERENCE_PANIC;
+    std::vector<float> flat(2 * p.size());
+    for (size_t i = 0; i < p.size(); i++) flat[2 * i] = p[i].x, flat[2 * i + 1] = p[i].y;
+    *n_verts = (int)p.size();
+    return jg_polygon_poi(flat.data(), (int)p.size(), poi_xyr, verts_xy);
+}
+
+static int item_import_impl(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
+                            float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2],
+                            float* area, float simplify_tolerance) {
     if (!pts_xy || n_pts < 3 || !scfg || !verts_xy || !n_verts || !poi_xyr || !n_poles || !pre_transform_xy) return JG_ERR_INVALID;
     std::vector<Pt> p((size_t)n_pts);
     for (int i = 0; i < n_pts; i++) p[i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
@@ -220,6 +381,16 @@ extern "C" int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateC
     for (Pt& q : sh.v) xf_point(pre, q.x, q.y, q.x, q.y);
     xf_point(pre, poi.x, poi.y, poi.x, poi.y);
     sh.bbox = bbox_of(sh.v);
+    const float area_orig = sh.area;  // Item::area() stays the original shape's
+    if (simplify_tolerance >= 0.0f) {
+        // original_shape.rs:33-45: simplify the transformed shape (Inflate for items); simplify_shape ends in
+        // SPolygon::new, so area, bbox and the pole of inaccessibility are recomputed from the resulting points
+        if (!simplify_points(sh.v, sh.area, false, simplify_tolerance)) return JG_ERR_REFERENCE_PANIC;
+        sh.area = signed_area(sh.v);
+        if (!(sh.area > 0.0f)) return JG_ERR_REFERENCE_PANIC;
+        sh.bbox = bbox_of(sh.v);
+        if (!compute_pole(sh, {}, poi)) return JG_ERR_REFERENCE_PANIC;
+    }
     // pole.rs:12-47 generate_surrogate_poles
     std::vector<Pole> poles{poi};
     const float PI_F = 3.14159265358979323846f;
@@ -236,14 +407,29 @@ extern "C" int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateC
         if (limit >= 0 && (int)poles.size() >= limit) break;
         if (poles.size() >= 1000) return JG_ERR_REFERENCE_PANIC;  // pole.rs:40-43 assert
     }
-    *n_verts = (int)nv;
-    for (size_t i = 0; i < nv; i++) verts_xy[2 * i] = sh.v[i].x, verts_xy[2 * i + 1] = sh.v[i].y;
+    *n_verts = (int)sh.v.size();
+    for (size_t i = 0; i < sh.v.size(); i++) verts_xy[2 * i] = sh.v[i].x, verts_xy[2 * i + 1] = sh.v[i].y;
     poi_xyr[0] = poi.x, poi_xyr[1] = poi.y, poi_xyr[2] = poi.r;
     *n_poles = (int)poles.size();
     if (poles_xyr)
         for (int i = 0; i < (int)poles.size() && i < poles_cap; i++)
             poles_xyr[3 * i] = poles[i].x, poles_xyr[3 * i + 1] = poles[i].y, poles_xyr[3 * i + 2] = poles[i].r;
     pre_transform_xy[0] = -cx, pre_transform_xy[1] = -cy;
-    if (area) *area = sh.area;
+    if (area) *area = area_orig;
     return JG_OK;
+}
+
+extern "C" int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
+                              float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2],
+                              float* area) {
+    return item_import_impl(pts_xy, n_pts, scfg, verts_xy, n_verts, poi_xyr, poles_xyr, poles_cap, n_poles, pre_transform_xy, area, -1.0f);
+}
+// ... with Importer's poly_simpl_tolerance (io/import.rs:31-45; lbf default 0.001): the centred shape is simplified in
+// Inflate mode before the surrogate is generated. narrow_concavity_cutoff_ratio is not applied.
+extern "C" int jg_item_import_simplified(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float simplify_tolerance,
+                                         float* verts_xy, int* n_verts, float poi_xyr[3], float* poles_xyr, int poles_cap,
+                                         int* n_poles, float pre_transform_xy[2], float* area) {
+    if (!(simplify_tolerance >= 0.0f)) return JG_ERR_INVALID;
+    return item_import_impl(pts_xy, n_pts, scfg, verts_xy, n_verts, poi_xyr, poles_xyr, poles_cap, n_poles, pre_transform_xy, area,
+                            simplify_tolerance);
 }

@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE - the checker for jg_shape_simplify / jg_item_import_simplified, never imported by the product.
+
+A restatement of the reference's polygon simplification in numpy float32 scalars (every operation rounds to f32, no
+fused multiply-add), written from the reference source and independent of the product's C++:
+
+    jagua-rs/src/geometry/shape_modification.rs:48-144   simplify_shape
+    :146-174 calculate_area_delta   :176-208 candidate_is_valid   :218-234 execute_candidate
+    :236-280 replacing_vertex_convex_convex_candidate, calculate_intersection_in_front   :293-329 Corner, CornerType
+    jagua-rs/src/geometry/primitives/edge.rs:180-228     edge_intersection (Edge: CollidesWith<Edge>)
+    jagua-rs/src/geometry/primitives/simple_polygon.rs:135-149 calculate_area
+
+Parity status: unpinned against the Rust crate (no toolchain here); it pins the product against an independent second
+reading of the same source.
+"""
+import numpy as np
+
+F = np.float32
+ZERO, ONE, TWO = F(0.0), F(1.0), F(2.0)
+
+
+def area(pts):
+    """simple_polygon.rs:135-149 (shoelace, counter-clockwise positive)"""
+    sigma = ZERO
+    n = len(pts)
+    for i in range(n):
+        j = (i + 1) % n
+        (xi, yi), (xj, yj) = pts[i], pts[j]
+        sigma = F(sigma + F(F(yi + yj) * F(xi - xj)))
+    return F(F(0.5) * sigma)
+
+
+def edges_collide(e1, e2):
+    """edge.rs:180-228 with calc_loc = false"""
+    (x1, y1), (x2, y2) = e1
+    (x3, y3), (x4, y4) = e2
+    if max(min(x1, x2), min(x3, x4)) > min(max(x1, x2), max(x3, x4)):
+        return False
+    if max(min(y1, y2), min(y3, y4)) > min(max(y1, y2), max(y3, y4)):
+        return False
+    t_nom = F(F(F(x2 - x4) * F(y4 - y3)) - F(F(y2 - y4) * F(x4 - x3)))
+    t_den = F(F(F(x2 - x1) * F(y4 - y3)) - F(F(y2 - y1) * F(x4 - x3)))
+    u_nom = F(F(F(x2 - x4) * F(y2 - y1)) - F(F(y2 - y4) * F(x2 - x1)))
+    u_den = t_den
+    if t_den == ZERO or u_den == ZERO:
+        return False
+    with np.errstate(all="ignore"):
+        t, u = F(t_nom / t_den), F(u_nom / u_den)
+    return bool(ZERO <= t <= ONE and ZERO <= u <= ONE)
+
+
+def intersection_in_front(l1, l2):
+    """shape_modification.rs:249-280"""
+    (x1, y1), (x2, y2) = l1
+    (x3, y3), (x4, y4) = l2
+    t_nom = F(F(F(x2 - x4) * F(y4 - y3)) - F(F(y2 - y4) * F(x4 - x3)))
+    t_den = F(F(F(x2 - x1) * F(y4 - y3)) - F(F(y2 - y1) * F(x4 - x3)))
+    u_nom = F(F(F(x2 - x4) * F(y2 - y1)) - F(F(y2 - y4) * F(x2 - x1)))
+    u_den = F(F(F(x2 - x1) * F(y4 - y3)) - F(F(y2 - y1) * F(x4 - x3)))
+    with np.errstate(all="ignore"):
+        t = F(t_nom / t_den) if t_den != ZERO else ZERO
+        u = F(u_nom / u_den) if u_den != ZERO else ZERO
+    if t < ZERO and u < ZERO:
+        return (F(x2 + F(t * F(x1 - x2))), F(y2 + F(t * F(y1 - y2))))
+    return None
+
+
+def corner_type(p1, p2, p3):
+    """shape_modification.rs:312-329: left-hand side of p1 -> p2 -> p3"""
+    ax, ay = F(p2[0] - p1[0]), F(p2[1] - p1[1])
+    bx, by = F(p3[0] - p1[0]), F(p3[1] - p1[1])
+    cross = F(F(ax * by) - F(ay * bx))
+    return "concave" if cross < ZERO else ("collinear" if cross == ZERO else "convex")
+
+
+def replacing_vertex(shape, c1, c2):
+    """shape_modification.rs:236-247"""
+    assert c1[2] == c2[1] and c1[1] == c2[0]
+    return intersection_in_front((shape[c1[0]], shape[c1[1]]), (shape[c2[2]], shape[c2[1]]))
+
+
+def tri(p0, p1, p2):
+    (x0, y0), (x1, y1), (x2, y2) = p0, p1, p2
+    a = F(x0 * y1)
+    a = F(a + F(x1 * y2))
+    a = F(a + F(x2 * y0))
+    a = F(a - F(x0 * y2))
+    a = F(a - F(x1 * y0))
+    a = F(a - F(x2 * y1))
+    return abs(F(a / TWO))
+
+
+def area_delta(shape, cand):
+    """shape_modification.rs:146-174 (None = InvalidCandidate)"""
+    kind = cand[0]
+    if kind == "collinear":
+        return ZERO
+    if kind == "concave":
+        c = cand[1]
+        return tri(shape[c[0]], shape[c[1]], shape[c[2]])
+    c1, c2 = cand[1], cand[2]
+    r = replacing_vertex(shape, c1, c2)
+    if r is None:
+        return None
+    return tri(shape[c1[1]], r, shape[c2[1]])
+
+
+def edge_list(points):
+    n = len(points)
+    return [(points[i], points[(i + 1) % n]) for i in range(n)]
+
+
+def is_valid(shape, cand):
+    """shape_modification.rs:176-208 (raises where the reference unwraps a degenerate Edge)"""
+    kind = cand[0]
+    if kind == "collinear":
+        return True
+    if kind == "concave":
+        c = cand[1]
+        if shape[c[0]] == shape[c[2]]:
+            raise ValueError("degenerate edge")
+        new_edge = (shape[c[0]], shape[c[2]])
+        affected = [shape[c[0]], shape[c[1]], shape[c[2]]]
+        return all(not edges_collide(l, new_edge) for l in edge_list(shape) if l[0] not in affected and l[1] not in affected)
+    c1, c2 = cand[1], cand[2]
+    r = replacing_vertex(shape, c1, c2)
+    if r is None:
+        return False
+    if shape[c1[0]] == r or r == shape[c2[2]]:
+        raise ValueError("degenerate edge")
+    e1, e2 = (shape[c1[0]], r), (r, shape[c2[2]])
+    affected = [shape[c1[1]], shape[c1[0]], shape[c2[1]], shape[c2[2]]]
+    return all(not edges_collide(l, e1) and not edges_collide(l, e2)
+               for l in edge_list(shape) if l[0] not in affected and l[1] not in affected)
+
+
+def execute(shape, cand):
+    """shape_modification.rs:218-234"""
+    pts = list(shape)
+    if cand[0] in ("collinear", "concave"):
+        del pts[cand[1][1]]
+        return pts
+    c1, c2 = cand[1], cand[2]
+    r = replacing_vertex(shape, c1, c2)
+    del pts[c1[1]]
+    other = c2[1] - 1 if c1[1] < c2[1] else c2[1]
+    del pts[other]
+    pts.insert(other, r)
+    return pts
+
+
+def simplify(points, mode="inflate", max_area_change_ratio=0.001):
+    """shape_modification.rs:48-144 up to (not including) the final SPolygon::new. points: counter-clockwise (x, y)."""
+    ref = [(F(x), F(y)) for x, y in np.asarray(points, np.float32)]
+    original_area = area(ref)
+    max_ratio = F(max_area_change_ratio)
+    for _ in range(len(ref)):
+        n = len(ref)
+        if n < 4:
+            break
+        corners = [((i - 1) % n, i, (i + 1) % n) for i in range(n)]
+        if mode == "deflate":
+            corners = [(c[2], c[1], c[0]) for c in reversed(corners)]
+        cands = []
+        prev = corners[-1]
+        prev_type = corner_type(*[ref[k] for k in prev])
+        for c in corners:
+            ct = corner_type(*[ref[k] for k in c])
+            if ct == "concave":
+                cands.append(("concave", c))
+            elif ct == "collinear":
+                cands.append(("collinear", c))
+            elif prev_type == "convex":
+                cands.append(("convex_convex", prev, c))
+            prev, prev_type = c, ct
+        keyed = []
+        for c in cands:
+            d = area_delta(ref, c)
+            keyed.append(float("inf") if d is None else float(d))
+        order = sorted(range(len(cands)), key=lambda k: (np.isnan(keyed[k]), keyed[k]))  # stable; OrderedFloat puts NaN last
+        best = next((cands[k] for k in order if is_valid(ref, cands[k])), None)
+        if best is None:
+            break
+        new = execute(ref, best)
+        with np.errstate(all="ignore"):
+            delta = F(abs(F(area(new) - original_area)) / original_area)
+        if delta <= max_ratio:
+            ref = new
+        else:
+            break
+    return np.array(ref, np.float32).reshape(-1, 2)

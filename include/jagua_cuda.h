@@ -246,10 +246,14 @@ int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg
 
 /* The same with Importer's poly_simpl_tolerance (io/import.rs:31-45, geometry/original_shape.rs:33-45): the centred shape
  * goes through simplify_shape in Inflate mode (geometry/shape_modification.rs:48-144) and SPolygon::new again before the
- * surrogate is generated; *area stays the original shape's. narrow_concavity_cutoff_ratio is not applied. */
+ * surrogate is generated; *area stays the original shape's. narrow_concavity_cutoff_ratio >= 0 (lbf default 0.01) adds
+ * close_narrow_concavities (shape_modification.rs:374-502) and the second simplification with tolerance / 10; < 0 = None. */
 int jg_item_import_simplified(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float simplify_tolerance,
-                              float* verts_xy, int* n_verts, float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles,
-                              float pre_transform_xy[2], float* area);
+                              float narrow_concavity_cutoff_ratio, float* verts_xy, int* n_verts, float poi_xyr[3],
+                              float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2], float* area);
+/* close_narrow_concavities (geometry/shape_modification.rs:374-502) on a clean counter-clockwise vertex list + SPolygon::new */
+int jg_shape_close_concavities(const float* pts_xy, int n_pts, int mode, float max_distance_ratio, float* verts_xy, int* n_verts,
+                               float poi_xyr[3]);
 /* simplify_shape (geometry/shape_modification.rs:48-144) on a clean counter-clockwise vertex list; mode 0 Inflate (result
  * is a superset: items, holes, zones), 1 Deflate (subset: container boundaries); followed by SPolygon::new (poi). */
 int jg_shape_simplify(const float* pts_xy, int n_pts, int mode, float max_area_change_ratio, float* verts_xy, int* n_verts,

@@ -93,8 +93,9 @@ C_ABI = {
     "jg_flush_l2": (C.c_int, [_vp]),
     "jg_item_import": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int, C.POINTER(C.c_int), _f32p,
                                  C.POINTER(C.c_float)]),
-    "jg_item_import_simplified": (C.c_int, [_f32p, C.c_int, _vp, C.c_float, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int,
+    "jg_item_import_simplified": (C.c_int, [_f32p, C.c_int, _vp, C.c_float, C.c_float, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int,
                                             C.POINTER(C.c_int), _f32p, C.POINTER(C.c_float)]),
+    "jg_shape_close_concavities": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_float, _f32p, C.POINTER(C.c_int), _f32p]),
     "jg_shape_simplify": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_float, _f32p, C.POINTER(C.c_int), _f32p]),
     "jg_polygon_poi": (C.c_int, [_f32p, C.c_int, _f32p, _vp]),
     "jg_shape_import": (C.c_int, [_f32p, C.c_int, _f32p, C.POINTER(C.c_int), _f32p]),
@@ -191,7 +192,21 @@ def simplify_shape(points, mode: str = "inflate", max_area_change_ratio: float =
     return verts[:nv.value].copy(), poi
 
 
-def import_item(points, n_pole_limits=((100, 0.0), (20, 0.75), (10, 0.90)), n_ff_poles: int = 2, simplify_tolerance=None):
+def close_narrow_concavities(points, mode: str = "inflate", max_distance_ratio: float = 0.01):
+    """close_narrow_concavities (geometry/shape_modification.rs:374-502) on a clean counter-clockwise vertex list."""
+    lib = load_library()
+    pts = _f32(points).reshape(-1, 2)
+    verts = np.zeros_like(pts)
+    poi = np.zeros(3, np.float32)
+    nv = C.c_int(0)
+    rc = lib.jg_shape_close_concavities(pts, len(pts), {"inflate": 0, "deflate": 1}[mode], float(max_distance_ratio), verts, C.byref(nv), poi)
+    if rc != JG_OK:
+        raise JaguaCudaError(rc, "jg_shape_close_concavities: bad input or a degenerate shape (the reference panics)")
+    return verts[:nv.value].copy(), poi
+
+
+def import_item(points, n_pole_limits=((100, 0.0), (20, 0.75), (10, 0.90)), n_ff_poles: int = 2, simplify_tolerance=None,
+                narrow_concavity_cutoff_ratio=None):
     """Importer::import_item + Item::new's surrogate for a simple polygon (io/import.rs:47-98, fail_fast/pole.rs:12-135)
     through jg_item_import: returns (ItemShape, pre_transform (tx, ty), area). Shape modification (simplification,
     offsetting) is not applied; piers are not generated."""
@@ -206,8 +221,9 @@ def import_item(points, n_pole_limits=((100, 0.0), (20, 0.75), (10, 0.90)), n_ff
     if simplify_tolerance is None:
         rc = lib.jg_item_import(pts, len(pts), C.addressof(cfg), verts, C.byref(nv), poi, poles, len(poles), C.byref(npol), pre, C.byref(area))
     else:  # Importer's poly_simpl_tolerance (lbf default 0.001)
-        rc = lib.jg_item_import_simplified(pts, len(pts), C.addressof(cfg), float(simplify_tolerance), verts, C.byref(nv), poi, poles,
-                                           len(poles), C.byref(npol), pre, C.byref(area))
+        rc = lib.jg_item_import_simplified(pts, len(pts), C.addressof(cfg), float(simplify_tolerance),
+                                           -1.0 if narrow_concavity_cutoff_ratio is None else float(narrow_concavity_cutoff_ratio),
+                                           verts, C.byref(nv), poi, poles, len(poles), C.byref(npol), pre, C.byref(area))
     if rc != JG_OK:
         raise JaguaCudaError(rc, "jg_item_import: degenerate polygon (fewer than 3 distinct vertices, duplicate points or no area)")
     return ItemShape(verts[:nv.value].copy(), poi, poles[:npol.value].copy(), np.zeros((0, 4), np.float32)), pre, float(area.value)

@@ -274,6 +274,94 @@ static bool simplify_points(std::vector<Pt>& pts, float original_area, bool defl
     return true;
 }
 
+// ---- geometry/convex_hull.rs:30-63 + simple_polygon.rs:105-120 calculate_diameter ---------------------------------
+static float hull_cross(const Pt& a, const Pt& b, const Pt& c) { return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x); }
+static void hull_grow(std::vector<Pt>& h, const Pt& next) {
+    while (h.size() >= 2 && hull_cross(h[h.size() - 2], h[h.size() - 1], next) <= 0.0f) h.pop_back();
+    h.push_back(next);
+}
+static float polygon_diameter(std::vector<Pt> pts) {
+    std::stable_sort(pts.begin(), pts.end(), [](const Pt& a, const Pt& b) { return a.x < b.x; });  // sort_by_key(OrderedFloat(x))
+    std::vector<Pt> lower, upper;
+    for (size_t i = 0; i < pts.size(); i++) hull_grow(lower, pts[i]);
+    for (size_t i = pts.size(); i-- > 0;) hull_grow(upper, pts[i]);
+    upper.pop_back();
+    lower.pop_back();
+    lower.insert(lower.end(), upper.begin(), upper.end());
+    float best = -1.0f;
+    for (size_t i = 0; i < lower.size(); i++)
+        for (size_t j = i + 1; j < lower.size(); j++) {
+            const float dx = lower[i].x - lower[j].x, dy = lower[i].y - lower[j].y;
+            best = fmaxf(best, dx * dx + dy * dy);
+        }
+    return sqrtf(best);
+}
+
+// ---- geometry/shape_modification.rs:374-502 close_narrow_concavities -----------------------------------------------
+// Replaces a concavity whose mouth (v[i] -> v[j], shrunk by 0.9999) is shorter than max_ratio x the diameter by that
+// straight edge, always the valid candidate that eliminates most vertices, until none is left.
+static bool close_concavities(std::vector<Pt>& v, bool deflate, float max_ratio) {
+    const size_t rounds = v.size();
+    for (size_t round = 0; round < rounds; round++) {
+        const int n = (int)v.size();
+        Shape sh;
+        sh.v = v;
+        sh.bbox = bbox_of(v);
+        sh.area = signed_area(v);
+        const float diameter = polygon_diameter(v);
+        auto elim = [&](int i, int j) { return j > i ? j - i - 1 : n - i + j - 1; };
+        auto inside = [&](float x, float y) { return poly_point<false>(&sh.v[0].x, n, sh.bbox, x, y, Xf{1.0f, 0.0f, 0.0f, 0.0f}); };
+        int bi = -1, bj = -1;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                if (i == j || (i + 1) % n == j || (j + 1) % n == i) continue;  // adjacent points
+                if (same_pt(v[i], v[j])) return false;                          // Edge::try_new would fail
+                // Edge::scale(0.9999) (edge.rs:39-46)
+                const float factor = 0.9999f;
+                const float dx = v[j].x - v[i].x, dy = v[j].y - v[i].y;
+                float sx = v[i].x, sy = v[i].y, ex = v[j].x, ey = v[j].y;
+                sx -= dx * (factor - 1.0f) / 2.0f;
+                sy -= dy * (factor - 1.0f) / 2.0f;
+                ex += dx * (factor - 1.0f) / 2.0f;
+                ey += dy * (factor - 1.0f) / 2.0f;
+                const float lx = sx - ex, ly = sy - ey;
+                if (sqrtf(lx * lx + ly * ly) > max_ratio * diameter) continue;  // mouth too wide
+                const bool s_in = inside(sx, sy), e_in = inside(ex, ey);
+                if (!deflate && (s_in || e_in)) continue;
+                if (deflate && !(s_in && e_in)) continue;
+                bool hits = false;
+                for (int k = 0; k < n && !hits; k++) hits = edge_hits(v[k], v[(k + 1) % n], Pt{sx, sy}, Pt{ex, ey});
+                if (hits) continue;
+                std::vector<Pt> sub;
+                if (j > i) sub.assign(v.begin() + i, v.begin() + j);
+                else {
+                    sub.assign(v.begin() + i, v.end());
+                    sub.insert(sub.end(), v.begin(), v.begin() + j);
+                }
+                if (signed_area(sub) >= 0.0f) continue;
+                if (bi < 0 || elim(i, j) > elim(bi, bj)) bi = i, bj = j;
+            }
+        if (bi < 0) break;
+        std::vector<Pt> next;
+        if (bi + 1 <= bj - 1) {  // j does not wrap around
+            for (int k = 0; k < n; k++)
+                if (k < bi + 1 || k > bj - 1) next.push_back(v[k]);
+        } else {
+            for (int k = 0; k < n; k++) {
+                const bool drop = (bi + 1 < n && k >= bi + 1) || (bj - 1 >= 0 && k <= bj - 1);
+                if (!drop) next.push_back(v[k]);
+            }
+        }
+        // SPolygon::new (simple_polygon.rs:40-71)
+        if (next.size() < 3) return false;
+        const float a = signed_area(next);
+        if (a == 0.0f) return false;
+        if (a < 0.0f) std::reverse(next.begin(), next.end());
+        v.swap(next);
+    }
+    return true;
+}
+
 // SPolygon::new's pole of inaccessibility (simple_polygon.rs:40-71,151-171) for a shape that is used as it is
 // (container outer boundary, holes, zones): same cleaning-free path as the reference - the caller passes the
 // final vertex list; orientation is normalised to counter-clockwise first, as SPolygon::new does.
@@ -346,9 +434,24 @@ extern "C" int jg_shape_simplify(const float* pts_xy, int n_pts, int mode, float
     return jg_polygon_poi(flat.data(), (int)p.size(), poi_xyr, verts_xy);
 }
 
+// close_narrow_concavities (geometry/shape_modification.rs:374-502) on a clean counter-clockwise vertex list, followed by
+// SPolygon::new (poi). mode 0 Inflate, 1 Deflate.
+extern "C" int jg_shape_close_concavities(const float* pts_xy, int n_pts, int mode, float max_distance_ratio, float* verts_xy,
+                                          int* n_verts, float poi_xyr[3]) {
+    if (!pts_xy || n_pts < 3 || !verts_xy || !n_verts || !poi_xyr || (mode != 0 && mode != 1)) return JG_ERR_INVALID;
+    std::vector<Pt> p((size_t)n_pts);
+    for (int i = 0; i < n_pts; i++) p[i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
+    if (!(signed_area(p) > 0.0f)) return JG_ERR_INVALID;
+    if (!close_concavities(p, mode == 1, max_distance_ratio)) return JG_ERR_REFERENCE_PANIC;
+    std::vector<float> flat(2 * p.size());
+    for (size_t i = 0; i < p.size(); i++) flat[2 * i] = p[i].x, flat[2 * i + 1] = p[i].y;
+    *n_verts = (int)p.size();
+    return jg_polygon_poi(flat.data(), (int)p.size(), poi_xyr, verts_xy);
+}
+
 static int item_import_impl(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
                             float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2],
-                            float* area, float simplify_tolerance) {
+                            float* area, float simplify_tolerance, float concavity_ratio) {
     if (!pts_xy || n_pts < 3 || !scfg || !verts_xy || !n_verts || !poi_xyr || !n_poles || !pre_transform_xy) return JG_ERR_INVALID;
     std::vector<Pt> p((size_t)n_pts);
     for (int i = 0; i < n_pts; i++) p[i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
@@ -386,6 +489,13 @@ static int item_import_impl(const float* pts_xy, int n_pts, const JgSurrogateCon
         // original_shape.rs:33-45: simplify the transformed shape (Inflate for items); simplify_shape ends in
         // SPolygon::new, so area, bbox and the pole of inaccessibility are recomputed from the resulting points
         if (!simplify_points(sh.v, sh.area, false, simplify_tolerance)) return JG_ERR_REFERENCE_PANIC;
+        if (concavity_ratio >= 0.0f) {
+            // original_shape.rs:38-44: close narrow concavities, then simplify once more with a tenth of the tolerance
+            // (each step ends in SPolygon::new: the second simplification measures against the area at its start)
+            if (!close_concavities(sh.v, false, concavity_ratio)) return JG_ERR_REFERENCE_PANIC;
+            const float a2 = signed_area(sh.v);
+            if (!(a2 > 0.0f) || !simplify_points(sh.v, a2, false, simplify_tolerance / 10.0f)) return JG_ERR_REFERENCE_PANIC;
+        }
         sh.area = signed_area(sh.v);
         if (!(sh.area > 0.0f)) return JG_ERR_REFERENCE_PANIC;
         sh.bbox = bbox_of(sh.v);
@@ -422,14 +532,15 @@ static int item_import_impl(const float* pts_xy, int n_pts, const JgSurrogateCon
 extern "C" int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
                               float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2],
                               float* area) {
-    return item_import_impl(pts_xy, n_pts, scfg, verts_xy, n_verts, poi_xyr, poles_xyr, poles_cap, n_poles, pre_transform_xy, area, -1.0f);
+    return item_import_impl(pts_xy, n_pts, scfg, verts_xy, n_verts, poi_xyr, poles_xyr, poles_cap, n_poles, pre_transform_xy, area, -1.0f, -1.0f);
 }
 // ... with Importer's poly_simpl_tolerance (io/import.rs:31-45; lbf default 0.001): the centred shape is simplified in
-// Inflate mode before the surrogate is generated. narrow_concavity_cutoff_ratio is not applied.
+// Inflate mode before the surrogate is generated; narrow_concavity_cutoff_ratio >= 0 (lbf default 0.01) adds
+// close_narrow_concavities and the second simplification pass (original_shape.rs:38-44); < 0 = None.
 extern "C" int jg_item_import_simplified(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float simplify_tolerance,
-                                         float* verts_xy, int* n_verts, float poi_xyr[3], float* poles_xyr, int poles_cap,
-                                         int* n_poles, float pre_transform_xy[2], float* area) {
+                                         float narrow_concavity_cutoff_ratio, float* verts_xy, int* n_verts, float poi_xyr[3],
+                                         float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2], float* area) {
     if (!(simplify_tolerance >= 0.0f)) return JG_ERR_INVALID;
     return item_import_impl(pts_xy, n_pts, scfg, verts_xy, n_verts, poi_xyr, poles_xyr, poles_cap, n_poles, pre_transform_xy, area,
-                            simplify_tolerance);
+                            simplify_tolerance, narrow_concavity_cutoff_ratio);
 }

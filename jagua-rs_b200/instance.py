@@ -1,9 +1,10 @@
 """Instance files of the reference (io/ext_repr.rs:6-121, probs/{spp,bpp}/io/ext_repr.rs) on the product side: what the
 importer turns them into before any collision query runs (io/import.rs:47-195, entities/container.rs:28-133).
 
-Shapes are parsed with serde's f32 semantics (decimal -> f64 -> f32). Items go through jg_item_import, container
-boundaries / holes / quality zones through jg_shape_import (product C++); shape modification (simplification,
-offsetting) is not applied. `container_engine` registers the static hazards in the order
+Shapes are parsed with serde's f32 semantics (decimal -> f64 -> f32). Items go through jg_item_import[_simplified],
+container boundaries / holes / quality zones through jg_shape_import (product C++). Item simplification and narrow-
+concavity closing (geometry/shape_modification.rs) are optional, as in the reference's Importer; offsetting (geo-buffer)
+and the containers' own modification are not applied. `container_engine` registers the static hazards in the order
 Container::new does - Exterior, then per quality 0..9 the zones in input order, the holes of a `polygon` outer shape
 appended to quality 0 (io/import.rs:166-167) - so HazKeys (slot numbers) match the reference's.
 """
@@ -53,8 +54,9 @@ def shape_points(shape: dict):
     raise ValueError(f"unsupported shape type {t}")
 
 
-def import_items(records) -> List[InstItem]:
-    """Importer::import_item for every record with demand > 0, ids renumbered densely in id order."""
+def import_items(records, simplify_tolerance=None, narrow_concavity_cutoff_ratio=None) -> List[InstItem]:
+    """Importer::import_item for every record with demand > 0, ids renumbered densely in id order. simplify_tolerance /
+    narrow_concavity_cutoff_ratio = Importer's shape modification (lbf defaults 0.001 / 0.01; None = unmodified shapes)."""
     from . import import_item
 
     items = []
@@ -62,7 +64,7 @@ def import_items(records) -> List[InstItem]:
         if it.get("demand", 1) <= 0:
             continue
         pts, _ = shape_points(it["shape"])  # holes of a `polygon` item are ignored, as the reference warns
-        shape, pre, area = import_item(pts)
+        shape, pre, area = import_item(pts, simplify_tolerance=simplify_tolerance, narrow_concavity_cutoff_ratio=narrow_concavity_cutoff_ratio)
         ao = it.get("allowed_orientations")
         if ao is None:
             rots = None  # RotationRange::Continuous
@@ -76,13 +78,13 @@ def import_items(records) -> List[InstItem]:
     return items
 
 
-def load_instance(path_or_dict) -> Instance:
+def load_instance(path_or_dict, simplify_tolerance=None, narrow_concavity_cutoff_ratio=None) -> Instance:
     if isinstance(path_or_dict, dict):
         d = path_or_dict
     else:
         with open(path_or_dict) as f:
             d = json.load(f)
-    inst = Instance(str(d.get("name", "")), import_items(d["items"]))
+    inst = Instance(str(d.get("name", "")), import_items(d["items"], simplify_tolerance, narrow_concavity_cutoff_ratio))
     if "strip_height" in d:
         inst.strip_height = float(np.float32(d["strip_height"]))
     inst.bins = sorted(d.get("bins", []), key=lambda b: b["id"])

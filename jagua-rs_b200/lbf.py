@@ -60,9 +60,10 @@ class LbfResult:
 
 class BatchedLBF:
     def __init__(self, instance: dict, device: int = 0, quadtree_depth: int = 5, cd_threshold: int = 16, n_ff_poles: int = 2,
-                 seed: int = 0, device_sampling: bool = True, rotation_lattice: int = 256):
+                 seed: int = 0, device_sampling: bool = True, rotation_lattice: int = 256, simplify_tolerance=None,
+                 narrow_concavity_cutoff_ratio=None):
         self.rotation_lattice = int(rotation_lattice)
-        self.items = import_items(instance["items"])
+        self.items = import_items(instance["items"], simplify_tolerance, narrow_concavity_cutoff_ratio)
         self.height = np.float32(instance["strip_height"])
         area = np.float32(0.0)
         for it in self.items:  # probs/spp/io/import.rs:40-48: f32 sum of area * demand

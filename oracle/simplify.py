@@ -188,3 +188,123 @@ def simplify(points, mode="inflate", max_area_change_ratio=0.001):
         else:
             break
     return np.array(ref, np.float32).reshape(-1, 2)
+
+
+# ---- close_narrow_concavities (shape_modification.rs:374-502) and what it needs ------------------------------------------
+def approx_eq(a, b):
+    """util/fpa.rs over float-cmp 0.10 approx_eq!(f32): epsilon = f32::EPSILON, ulps = 4"""
+    a, b = F(a), F(b)
+    if a == b:
+        return True
+    with np.errstate(all="ignore"):
+        if abs(F(a - b)) <= F(1.1920929e-07):
+            return True
+    ia, ib = int(np.array(a).view(np.int32)), int(np.array(b).view(np.int32))
+    d = (ia - ib + 2 ** 31) % 2 ** 32 - 2 ** 31  # wrapping_sub on the i32 views
+    ad = (2 ** 31 - 1) if d == -2 ** 31 else abs(d)
+    return ad <= 4
+
+
+def point_in_polygon(pts, p):
+    """simple_polygon.rs:255-292 (ray casting with the FPA vertex rule)"""
+    xs, ys = [q[0] for q in pts], [q[1] for q in pts]
+    x_min, x_max, y_min, y_max = min(xs), max(xs), min(ys), max(ys)
+    px, py = p
+    if not (x_min <= px <= x_max and y_min <= py <= y_max):
+        return False
+    ray = ((px, py), (F(x_max + F(x_max - x_min)), py))
+    n = 0
+    for s, e in edge_list(pts):
+        def gt(a, b):
+            return (not approx_eq(a, b)) and a > b
+
+        def lt(a, b):
+            return (not approx_eq(a, b)) and a < b
+        if (approx_eq(s[1], py) and gt(s[0], px)) or (approx_eq(e[1], py) and gt(e[0], px)):
+            if lt(s[1], py) or lt(e[1], py):
+                n += 1
+        elif edges_collide(ray, (s, e)):
+            n += 1
+    return n % 2 == 1
+
+
+def diameter(pts):
+    """simple_polygon.rs:105-120 over convex_hull.rs:30-63 (monotone chain on the points sorted by x, stable)"""
+    def cross(a, b, c):
+        return F(F(F(b[0] - a[0]) * F(c[1] - a[1])) - F(F(b[1] - a[1]) * F(c[0] - a[0])))
+
+    def grow(h, nxt):
+        while len(h) >= 2 and cross(h[-2], h[-1], nxt) <= ZERO:
+            h.pop()
+        h.append(nxt)
+        return h
+    srt = sorted(pts, key=lambda q: q[0])
+    lower, upper = [], []
+    for q in srt:
+        grow(lower, q)
+    for q in reversed(srt):
+        grow(upper, q)
+    hull = lower[:-1] + upper[:-1]
+    best = F(-1.0)
+    for i in range(len(hull)):
+        for j in range(i + 1, len(hull)):
+            dx, dy = F(hull[i][0] - hull[j][0]), F(hull[i][1] - hull[j][1])
+            best = max(best, F(F(dx * dx) + F(dy * dy)))
+    return F(np.sqrt(best))
+
+
+def close_narrow_concavities(points, mode="inflate", max_distance_ratio=0.01):
+    """shape_modification.rs:374-502 (each round ends in SPolygon::new: orientation normalised)"""
+    v = [(F(x), F(y)) for x, y in np.asarray(points, np.float32)]
+    ratio = F(max_distance_ratio)
+    factor = F(0.9999)
+    for _ in range(len(v)):
+        n = len(v)
+        diam = diameter(v)
+
+        def elim(i, j):
+            return j - i - 1 if j > i else n - i + j - 1
+        best = None
+        for i in range(n):
+            for j in range(n):
+                if i == j or (i + 1) % n == j or (j + 1) % n == i:
+                    continue
+                (sx, sy), (ex, ey) = v[i], v[j]
+                dx, dy = F(ex - sx), F(ey - sy)
+                fm1 = F(factor - ONE)
+                sx = F(sx - F(F(dx * fm1) / TWO))
+                sy = F(sy - F(F(dy * fm1) / TWO))
+                ex = F(ex + F(F(dx * fm1) / TWO))
+                ey = F(ey + F(F(dy * fm1) / TWO))
+                lx, ly = F(sx - ex), F(sy - ey)
+                if F(np.sqrt(F(F(lx * lx) + F(ly * ly)))) > F(ratio * diam):
+                    continue
+                s_in, e_in = point_in_polygon(v, (sx, sy)), point_in_polygon(v, (ex, ey))
+                if mode == "inflate" and (s_in or e_in):
+                    continue
+                if mode == "deflate" and not (s_in and e_in):
+                    continue
+                c_edge = ((sx, sy), (ex, ey))
+                if any(edges_collide(e, c_edge) for e in edge_list(v)):
+                    continue
+                sub = v[i:j] if j > i else v[i:] + v[:j]
+                if area(sub) >= ZERO:
+                    continue
+                if best is None or elim(i, j) > elim(*best):
+                    best = (i, j)
+        if best is None:
+            break
+        i, j = best
+        start, end = i + 1, j - 1
+        ref = list(v)
+        if start <= end:
+            del ref[start:end + 1]
+        else:
+            if start < n:
+                del ref[start:]
+            if end >= 0:
+                del ref[0:end + 1]
+        if area(ref) < ZERO:
+            ref.reverse()
+        v = ref
+    return np.array(v, np.float32).reshape(-1, 2)

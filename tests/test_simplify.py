@@ -79,3 +79,66 @@ def test_containers_deflate_like_the_oracle(jg):
 def test_simplify_rejects_bad_input(jg):
     with pytest.raises(jg.JaguaCudaError):
         jg.simplify_shape(np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))  # clockwise: not an SPolygon vertex list
+
+
+def _comb(n_teeth=5, gap=0.02, depth=1.0, width=1.0):
+    """a comb: n_teeth teeth separated by narrow slots (concavities `gap` wide, `depth` deep), counter-clockwise"""
+    pts = [(0.0, 0.0)]
+    x = 0.0
+    for k in range(n_teeth):
+        pts += [(x + width, 0.0)] if k == n_teeth - 1 else [(x + width, 0.0), (x + width, depth * 0.9), (x + width + gap, depth * 0.9), (x + width + gap, 0.0)]
+        x += width + gap
+    pts = [(0.0, -1.0), (x, -1.0)] + [(px, py) for px, py in reversed([(p[0], -p[1]) for p in pts[1:]])]
+    v = np.array(pts, np.float32)
+    if np.sum(v[:, 0] * np.roll(v[:, 1], -1) - np.roll(v[:, 0], -1) * v[:, 1]) < 0:
+        v = v[::-1].copy()
+    return v
+
+
+def test_close_narrow_concavities_like_the_oracle(jg):
+    import simplify as osimp
+
+    comb = _comb()
+    base, _ = jg.import_shape(comb)
+    got, _ = jg.close_narrow_concavities(base, "inflate", 0.05)
+    exp = osimp.close_narrow_concavities(base, "inflate", 0.05)
+    assert np.array_equal(got, exp)
+    assert len(got) < len(base) and shoelace(got) > shoelace(base)  # slots closed: fewer vertices, larger area
+    same, _ = jg.close_narrow_concavities(base, "inflate", 0.001)      # mouths wider than the cutoff: untouched
+    assert np.array_equal(same, base) and np.array_equal(osimp.close_narrow_concavities(base, "inflate", 0.001), base)
+    # items of the instance files with the lbf default (narrow_concavity_cutoff_ratio 0.01)
+    n = 0
+    for name in ("swim.json", "trousers.json", "jakobs1.json"):
+        with open(os.path.join(ROOT, "assets", name)) as f:
+            inst = json.load(f)
+        for it in inst["items"]:
+            pts, _ = jg.instance.shape_points(it["shape"])
+            b, _, _ = jg.import_item(pts)
+            if len(b.verts) > 24:
+                continue
+            g, _ = jg.close_narrow_concavities(b.verts, "inflate", 0.01)
+            assert np.array_equal(g, osimp.close_narrow_concavities(b.verts, "inflate", 0.01))
+            n += 1
+    assert n >= 10
+
+
+def test_default_lbf_preprocessing_pipeline(jg):
+    """original_shape.rs:23-51 with the lbf defaults: simplify(0.001) -> close_narrow_concavities(0.01) -> simplify(0.0001),
+    each step through SPolygon::new; the importer entry point must equal the three calls chained by hand."""
+    import simplify as osimp
+
+    with open(os.path.join(ROOT, "assets", "swim.json")) as f:
+        inst = json.load(f)
+    for it in inst["items"]:
+        pts, _ = jg.instance.shape_points(it["shape"])
+        base, pre, area = jg.import_item(pts)
+        full, pre2, area2 = jg.import_item(pts, simplify_tolerance=0.001, narrow_concavity_cutoff_ratio=0.01)
+        v1, _ = jg.simplify_shape(base.verts, "inflate", 0.001)
+        v2, _ = jg.close_narrow_concavities(v1, "inflate", 0.01)
+        v3, poi3 = jg.simplify_shape(v2, "inflate", np.float32(0.001) / np.float32(10.0))
+        assert np.array_equal(full.verts, v3) and np.array_equal(full.poi, poi3)
+        assert np.array_equal(pre, pre2) and area == area2 and len(full.verts) <= len(base.verts)
+        if len(base.verts) <= 40:
+            o = osimp.simplify(osimp.close_narrow_concavities(osimp.simplify(base.verts, "inflate", 0.001), "inflate", 0.01),
+                               "inflate", np.float32(0.001) / np.float32(10.0))
+            assert np.array_equal(full.verts, o)

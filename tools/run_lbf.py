@@ -23,17 +23,20 @@ ap.add_argument("--samples", type=int, default=5000)
 ap.add_argument("--ls-frac", type=float, default=0.2)
 ap.add_argument("--seed", type=int, default=0)
 ap.add_argument("--no-check", action="store_true")
+ap.add_argument("--shape-defaults", action="store_true", help="the lbf defaults for item shapes: poly_simpl_tolerance 0.001, narrow_concavity_cutoff_ratio 0.01")
 ap.add_argument("--rotation-lattice", type=int, default=256, help="angles of the device-side lattice for items that rotate continuously (0: sample them on the host)")
 ap.add_argument("--host-sampling", action="store_true", help="draw the samples with numpy on the host instead of on the device")
 args = ap.parse_args()
 
 with open(args.instance) as f:
     inst = json.load(f)
-solver = lbf.BatchedLBF(inst, device=0, seed=args.seed, device_sampling=not args.host_sampling, rotation_lattice=args.rotation_lattice)
+solver = lbf.BatchedLBF(inst, device=0, seed=args.seed, device_sampling=not args.host_sampling, rotation_lattice=args.rotation_lattice,
+                        simplify_tolerance=0.001 if args.shape_defaults else None,
+                        narrow_concavity_cutoff_ratio=0.01 if args.shape_defaults else None)
 res = solver.solve(n_samples=args.samples, ls_frac=args.ls_frac)
 stats = solver.cde.stats()
 line = {"instance": os.path.basename(args.instance), "n_samples_per_placement": args.samples, "placed": len(res.placements),
-        "strip_width": res.strip_width, "strip_height": res.strip_height, "density": res.density, "seconds": res.seconds,
+        "item_vertices": int(sum(len(it.shape.verts) for it in solver.items)), "strip_width": res.strip_width, "strip_height": res.strip_height, "density": res.density, "seconds": res.seconds,
         "samples_evaluated": res.samples, "strip_extensions": res.strip_extensions,
         "samples_per_second": res.samples / res.seconds,
         "sampling": "host (numpy Philox)" if args.host_sampling else "device (k_search_sample) for items with discrete rotations"}

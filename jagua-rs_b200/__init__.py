@@ -80,6 +80,8 @@ C_ABI = {
     "jg_engine_set_batching": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "jg_engine_set_groups": (C.c_int, [_vp, C.c_int, C.c_int]),
     "jg_engine_set_split_min": (C.c_int, [_vp, C.c_int64]),
+    "jg_set_dependent_launch": (C.c_int, [C.c_int]),
+    "jg_dependent_launch": (C.c_int, []),
     "jg_engine_set_detect_path": (C.c_int, [_vp, C.c_int]),
     "jg_engine_detect_path": (C.c_int, [_vp]),
     "jg_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
@@ -658,6 +660,10 @@ class CDEngine:
     def set_split_min(self, min_queries: int):
         """Launch size from which the containment tests run in their own kernel (0 = always)."""
         self._chk(self._lib.jg_engine_set_split_min(self._eng, int(min_queries)))
+
+    def set_dependent_launch(self, on: bool):
+        """Stage 2 of the grid path as a programmatic dependent launch behind stage 1 (process-wide)."""
+        self._chk(self._lib.jg_set_dependent_launch(1 if on else 0))
 
     def set_groups(self, detect_group: int = 0, collect_group: int = 0):
         self._chk(self._lib.jg_engine_set_groups(self._eng, int(detect_group), int(collect_group)))

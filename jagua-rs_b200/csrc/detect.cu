@@ -621,6 +621,10 @@ namespace jg {
 // ---------------------------------------------------------------------------------------------------
 static int g_occ[16];
 static size_t g_occ_smem[16];
+// jg_set_dependent_launch / JG_PDL: stage 2 of the grid path launched with programmatic stream serialization
+static int g_dependent_launch = [] { const char* v = getenv("JG_PDL"); return v ? atoi(v) : 1; }();
+void set_dependent_launch(int on) { g_dependent_launch = on ? 1 : 0; }
+int dependent_launch() { return g_dependent_launch; }
 template <class K>
 static int persistent_grid(K kernel, int slot, int n_sms, size_t smem) {
     if (g_occ[slot] == 0 || g_occ_smem[slot] != smem) {
@@ -695,8 +699,25 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
 #define JG_LAUNCH_S2(FILT_, SPLIT_, SLOT_)                                                                                     \
     {                                                                                                                          \
         const int g = persistent_grid(k_s2_grid<FILT_, SPLIT_>, SLOT_, n_sms, gs2);                                            \
-        k_s2_grid<FILT_, SPLIT_><<<want2g < g ? want2g : g, S_THREADS, gs2, st>>>(L, tab, gd, d_kinds, d_xf, d_filt, d_out, sc.ctl,   \
-                                                                                 sc.sv_entry, sc.ct_meta, sc.ct_bb, sc.ct_xf); \
+        if (g_dependent_launch && !(mode & JG_MODE_POLY_ONLY)) {                                                               \
+            /* programmatic dependent launch: k_s1_grid releases its dependents at once (griddepcontrol.launch_dependents), */ \
+            /* so stage-2 CTAs move in while stage 1 drains, stage their tables and wait in griddepcontrol.wait */             \
+            cudaLaunchConfig_t lc = {};                                                                                        \
+            lc.gridDim = dim3((unsigned)(want2g < g ? want2g : g));                                                            \
+            lc.blockDim = dim3(S_THREADS);                                                                                     \
+            lc.dynamicSmemBytes = gs2;                                                                                         \
+            lc.stream = st;                                                                                                    \
+            cudaLaunchAttribute at[1];                                                                                         \
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                     \
+            at[0].val.programmaticStreamSerializationAllowed = 1;                                                              \
+            lc.attrs = at;                                                                                                     \
+            lc.numAttrs = 1;                                                                                                   \
+            cudaLaunchKernelEx(&lc, k_s2_grid<FILT_, SPLIT_>, L, tab, gd, d_kinds, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry,   \
+                               sc.ct_meta, sc.ct_bb, sc.ct_xf);                                                                \
+        } else                                                                                                                 \
+            k_s2_grid<FILT_, SPLIT_><<<want2g < g ? want2g : g, S_THREADS, gs2, st>>>(L, tab, gd, d_kinds, d_xf, d_filt, d_out, \
+                                                                                     sc.ctl, sc.sv_entry, sc.ct_meta,          \
+                                                                                     sc.ct_bb, sc.ct_xf);                      \
     }
         if (d_filt && split) JG_LAUNCH_S2(true, true, 6)
         else if (d_filt) JG_LAUNCH_S2(true, false, 14)

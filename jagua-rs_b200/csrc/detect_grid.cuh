@@ -435,6 +435,10 @@ __global__ void __launch_bounds__(S_THREADS, G1_MIN_BLOCKS)
 k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
           const XfSrc xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
           DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry) {
+    // a stage-2 grid launched with programmatic stream serialization may take the SM slots this grid's CTAs free as they
+    // exit (every CTA of this persistent grid is resident from the start, so nothing of it can be locked out); it reads
+    // nothing of ours before its griddepcontrol.wait. A no-op for ordinary launches.
+    asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ __align__(16) unsigned char smem[];
     SegTable* t = (SegTable*)smem;
     for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
@@ -857,6 +861,9 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
     unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
     const GridDev& g = *stage_grid(p, ggrid);
     __syncthreads();
+    // dependent launch: everything above reads launch parameters and the grid summary of an earlier upload; the survivor
+    // list, its count and the verdict bytes belong to stage 1, complete and visible only after this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry, ct_meta, ct_bb, ct_xf};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     G2Slots& W = *(G2Slots*)(p + (size_t)warp * sizeof(G2Slots));

@@ -1254,6 +1254,12 @@ int jg_engine_set_split_min(JgEngine* e, int64_t min_queries) {
     return JG_OK;
 }
 
+int jg_set_dependent_launch(int on) {
+    jg::set_dependent_launch(on);
+    return JG_OK;
+}
+int jg_dependent_launch(void) { return jg::dependent_launch(); }
+
 int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group) {
     auto ok = [](int g) { return g == 0 || g == 4 || g == 8 || g == 16 || g == 32; };
     if (!e || !ok(detect_group) || !ok(collect_group)) return JG_ERR_INVALID;

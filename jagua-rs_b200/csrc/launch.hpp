@@ -84,6 +84,9 @@ struct DetectPlan {
     long long split_min;  // launches of at least this many queries run the containment tests in k_s2_contain
 };
 DetectPlan make_detect_plan(int n_nodes, int depth);
+// stage 2 of the grid path as a programmatic dependent launch behind stage 1 (process-wide; default from JG_PDL)
+void set_dependent_launch(int on);
+int dependent_launch();
 size_t detect_kinds_bytes(int n_nodes);
 
 // per-filter node summary read by the detect kernels; d_filt == nullptr is NoFilter

@@ -515,6 +515,40 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
         cde.set_split_min(1 << 21)
 
 
+@pytest.mark.parametrize("name", ["swim_half", "baldacci1_bin", "shirts_full"])
+def test_dependent_launch_matches_stream_order(jg, engines, name):
+    """Stage 2 launched with programmatic stream serialization (its CTAs move in while stage 1 drains and wait in
+    griddepcontrol.wait): same verdicts as the oracle and as the ordinary stream order, single batches, multi-segment
+    batches through host buffers (pieces on several streams) and the split containment path."""
+    wl, cde, w = engines(name)
+    fbits = cde.filter_from_irrelevant_qzones(2)
+    cde.upload_filter(7, fbits)
+    was = cde._lib.jg_dependent_launch()
+    try:
+        cde.set_dependent_launch(True)
+        assert cde._lib.jg_dependent_launch() == 1
+        for item_id in range(0, len(wl.items), max(1, len(wl.items) // 3)):
+            for n in (1, 33, 20000):
+                t = jg.make_queries(wl, item_id, n, seed=5 + n)
+                exp = w.detect_batch(item_id, t)
+                assert np.array_equal(cde.detect_batch(item_id, t), exp)
+                assert np.array_equal(cde.detect_batch(item_id, t, filter_id=7), w.detect_batch(item_id, t, filter_bits=fbits))
+        ids = list(range(len(wl.items)))
+        ts = [jg.make_queries(wl, i, 30000, seed=900 + i) for i in ids]
+        exp = np.concatenate([w.detect_batch(i, t) for i, t in zip(ids, ts)])
+        offs = np.arange(len(ids) + 1, dtype=np.int64) * 30000
+        tall = np.ascontiguousarray(np.concatenate(ts))
+        for rep in range(3):
+            assert np.array_equal(cde.detect_multi(ids, offs, tall), exp)
+        cde.set_split_min(0)
+        assert np.array_equal(cde.detect_multi(ids, offs, tall), exp)
+        cde.set_dependent_launch(False)
+        assert np.array_equal(cde.detect_multi(ids, offs, tall), exp)
+    finally:
+        cde.set_split_min(1 << 21)
+        cde.set_dependent_launch(bool(was))
+
+
 @pytest.mark.parametrize("name", ["swim_half", "jakobs1_ms1"])
 def test_layout_update_behind_batches_in_flight(jg, orc, name):
     """Stream-ordered layout uploads: a batch enqueued before an update is resolved on the old layout, a batch enqueued

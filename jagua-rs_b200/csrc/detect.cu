@@ -621,6 +621,14 @@ namespace jg {
 // ---------------------------------------------------------------------------------------------------
 static int g_occ[16];
 static size_t g_occ_smem[16];
+#ifdef JG_DIVCOUNT
+extern "C" int jg_debug_divcount(unsigned long long out[4], int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_divcount, sizeof(unsigned long long) * 4);
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_divcount, z, sizeof(z)); }
+    return 0;
+}
+#endif
 // jg_set_dependent_launch / JG_PDL: stage 2 of the grid path launched with programmatic stream serialization
 static int g_dependent_launch = [] { const char* v = getenv("JG_PDL"); return v ? atoi(v) : 1; }();
 void set_dependent_launch(int on) { g_dependent_launch = on ? 1 : 0; }

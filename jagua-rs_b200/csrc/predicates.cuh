@@ -129,6 +129,14 @@ JG_HD bool rect_seg(const Rect& r, const Seg& e) {
 // The IEEE division itself is needed only on rare branches (and expands to ~20 instructions wherever it is
 // inlined): on the device it lives out of line, which takes ~550 instructions out of the stage-2 kernel, whose
 // speed is set by instruction fetch (3.6 K SASS instructions against a 32 KB L1.5 instruction cache).
+#if defined(JG_DIVCOUNT) && defined(__CUDACC__)
+static __device__ unsigned long long g_divcount[4];  // experiments (-DJG_DIVCOUNT): thread-level divisions per site class, per translation unit
+#endif
+#if defined(JG_DIVCOUNT) && defined(__CUDA_ARCH__)
+#define JG_DIV_SITE(k) atomicAdd(&g_divcount[k], 1ull)
+#else
+#define JG_DIV_SITE(k) ((void)0)
+#endif
 #if defined(__CUDA_ARCH__)
 static __device__ __noinline__ float div_rare(float a, float d) { return a / d; }
 #else
@@ -137,12 +145,14 @@ static inline float div_rare(float a, float d) { return a / d; }
 JG_HD bool unit_quotient(float a, float d) {
     const float aa = fabsf(a), ad = fabsf(d);
     if (!(ad <= 3.402823466e+38f)) {  // infinite / NaN divisor (coordinates overflowed): no shortcut
+        JG_DIV_SITE(0);
         const float q = div_rare(a, d);
         return q >= 0.0f && q <= 1.0f;
     }
     if (!(aa <= ad)) return false;  // also NaN / infinite numerators
     if (a == 0.0f || (a < 0.0f) == (d < 0.0f)) return true;
     if (aa < ad * 1e-30f) {
+        JG_DIV_SITE(1);
         const float q = div_rare(a, d);
         return q >= 0.0f && q <= 1.0f;
     }
@@ -174,6 +184,7 @@ JG_HD int seg_seg_half(const Seg& e1, const Seg& e2) {
     const float u_nom = (x2 - x4) * (y2 - y1) - (y2 - y4) * (x2 - x1);
     if (denom == 0.0f) return 0;
     if (!(unit_quotient(t_nom, denom) && unit_quotient(u_nom, denom))) return 0;
+    JG_DIV_SITE(2);
     const float u = div_rare(u_nom, denom);  // the half is decided on the rounded quotient, as in the reference
     return u > 0.5f ? 1 : (u < 0.5f ? 2 : 3);
 }

@@ -18,19 +18,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "jagua-rs_b200", "libjagua_cuda.so")
 
 
-def line_map(kernel_mangled_sub):
-    """offset -> (file, line) for the first function whose mangled name contains the substring."""
+def line_maps(kernel_mangled_sub):
+    """{function: {offset: ((file, line), sass)}} for every function whose mangled name contains the substring
+    (template instantiations are separate functions, each with offsets from 0)."""
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", SO], cwd=tmp, capture_output=True)
+    maps = {}
     for f in sorted(os.listdir(tmp)):
         if not f.endswith(".cubin") or "sm_100" not in f:
             continue
         txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-        cur_fn, cur_line, m = None, None, {}
+        cur_fn, cur_line = None, None
         for ln in txt.splitlines():
             s = ln.strip()
             if s.startswith(".text.") and s.endswith(":"):
                 cur_fn = s[6:-1]
+                cur_line = None
                 continue
             g = re.match(r'//## File "(.*)", line (\d+)', s)
             if g:
@@ -38,10 +41,22 @@ def line_map(kernel_mangled_sub):
                 continue
             g = re.match(r"/\*([0-9a-f]{4,})\*/\s+(.*)", s)
             if g and cur_fn and kernel_mangled_sub in cur_fn:
-                m[int(g.group(1), 16)] = (cur_line, g.group(2))
-        if m:
-            return m
-    return {}
+                maps.setdefault(cur_fn, {})[int(g.group(1), 16)] = (cur_line, g.group(2))
+    return maps
+
+
+def pick_map(maps, offsets_ops):
+    """The instantiation that was profiled: same instruction count and the most matching opcodes."""
+    best, best_score = {}, -1
+    for fn, m in maps.items():
+        if len(m) != len(offsets_ops):
+            continue
+        score = sum(1 for off, op in offsets_ops if off in m and m[off][1].replace("@", " ").split()[-0:1] and op in m[off][1])
+        if score > best_score:
+            best, best_score = m, score
+    if best_score < 0 and maps:
+        best = next(iter(maps.values()))
+    return best
 
 
 def main():
@@ -61,7 +76,15 @@ def main():
     hdr = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}
     sub = re.search(r"(k_[a-z0-9_]+)", name).group(1)
-    lm = line_map(sub)
+    srows = [r for r in rows[1:] if len(r) >= len(hdr) and r[0].startswith("0x")]
+    base0 = int(srows[0][0], 16)
+
+    def opcode(text):
+        toks = text.split()
+        toks = [t for t in toks if not t.startswith("@")]
+        return toks[0] if toks else ""
+
+    lm = pick_map(line_maps(sub), [(int(r[0], 16) - base0, opcode(r[ix["Source"]])) for r in srows])
     base = None
     agg = defaultdict(lambda: [0.0, 0.0, 0.0])
     tot = [0.0, 0.0, 0.0]

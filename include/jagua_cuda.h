@@ -241,12 +241,26 @@ typedef struct JgSurrogateConfig {
     int n_ff_piers;
 } JgSurrogateConfig;
 
+/* generate_piers (geometry/fail_fast/piers.rs:25-226) as SPSurrogate::new calls it (sp_surrogate.rs:40-44): n_piers
+ * segments inside the shape covering what the given poles (the first n_ff_poles surrogate poles) leave unrepresented.
+ * verts_xy: the item's imported, counter-clockwise vertices (output of jg_item_import*); piers_xyxy: 4 * n_piers floats
+ * (sx, sy, ex, ey), the form jg_item_upload takes. cfg == NULL or zero fields: the reference's release constants
+ * (200 rays per angle, 90 angles, 100 grid points per dimension; its debug build uses 10 / 4 / 10). The reference's
+ * panics (a ray end inside the shape, a NaN loss, no clipped ray) return JG_ERR_REFERENCE_PANIC. */
+typedef struct JgPierConfig {
+    int rays_per_angle;
+    int n_angles;
+    int n_points_per_dimension;
+} JgPierConfig;
+int jg_item_generate_piers(const float* verts_xy, int n_verts, const float* poles_xyr, int n_poles, int n_piers,
+                           const JgPierConfig* cfg, float* piers_xyxy);
+
 /* Importer::import_item for an ExtShape::SimplePolygon with shape modification disabled (io/import.rs:47-98,
  * 198-260) + Item::new's surrogate (entities/item.rs:28-53, fail_fast/sp_surrogate.rs:33-61, fail_fast/pole.rs:12-135):
  * cleans the vertex list (closing duplicate, approx-equal neighbours), orients it counter-clockwise, computes the
  * pole of inaccessibility, centres the shape on its centroid (pre_transform = (0, -cx, -cy)) and generates the
  * surrogate poles under the coverage limits. Outputs are what jg_item_upload takes. verts_xy must hold 2 * n_pts
- * floats; poles beyond poles_cap are counted in *n_poles but not written. Piers (n_ff_piers > 0) are not generated. */
+ * floats; poles beyond poles_cap are counted in *n_poles but not written. Piers: jg_item_generate_piers. */
 int jg_item_import(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
                    float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2], float* area);
 

@@ -93,6 +93,7 @@ C_ABI = {
     "jg_compose_batch": (None, [_f32p, C.c_int64, _f32p, C.c_int]),
     "jg_fp32_nofma_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "jg_flush_l2": (C.c_int, [_vp]),
+    "jg_item_generate_piers": (C.c_int, [_f32p, C.c_int, _vp, C.c_int, C.c_int, _vp, _f32p]),
     "jg_item_import": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int, C.POINTER(C.c_int), _f32p,
                                  C.POINTER(C.c_float)]),
     "jg_item_import_simplified": (C.c_int, [_f32p, C.c_int, _vp, C.c_float, C.c_float, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int,
@@ -207,11 +208,30 @@ def close_narrow_concavities(points, mode: str = "inflate", max_distance_ratio: 
     return verts[:nv.value].copy(), poi
 
 
+class JgPierConfig(C.Structure):
+    _fields_ = [("rays_per_angle", C.c_int), ("n_angles", C.c_int), ("n_points_per_dimension", C.c_int)]
+
+
+def generate_piers(verts, poles, n_piers: int, rays_per_angle: int = 0, n_angles: int = 0, n_points_per_dimension: int = 0):
+    """generate_piers (geometry/fail_fast/piers.rs:25-226): n_piers segments (sx, sy, ex, ey) inside the imported shape
+    `verts` that cover what `poles` (the fail-fast poles: sp_surrogate.rs:40-44) leave unrepresented. Zero sizes select
+    the reference's release constants (200 rays per angle, 90 angles, 100 x 100 grid points)."""
+    lib = load_library()
+    v = _f32(verts).reshape(-1, 2)
+    pl = _f32(poles).reshape(-1, 3)
+    out = np.zeros((int(n_piers), 4), np.float32)
+    cfg = JgPierConfig(int(rays_per_angle), int(n_angles), int(n_points_per_dimension))
+    rc = lib.jg_item_generate_piers(v, len(v), pl.ctypes.data if len(pl) else None, len(pl), int(n_piers), C.addressof(cfg), out)
+    if rc != JG_OK:
+        raise JaguaCudaError(rc, "jg_item_generate_piers: bad input, or a state in which the reference panics")
+    return out
+
+
 def import_item(points, n_pole_limits=((100, 0.0), (20, 0.75), (10, 0.90)), n_ff_poles: int = 2, simplify_tolerance=None,
-                narrow_concavity_cutoff_ratio=None):
+                narrow_concavity_cutoff_ratio=None, n_ff_piers: int = 0):
     """Importer::import_item + Item::new's surrogate for a simple polygon (io/import.rs:47-98, fail_fast/pole.rs:12-135)
-    through jg_item_import: returns (ItemShape, pre_transform (tx, ty), area). Shape modification (simplification,
-    offsetting) is not applied; piers are not generated."""
+    through jg_item_import: returns (ItemShape, pre_transform (tx, ty), area). Offsetting is not applied; n_ff_piers > 0
+    adds generate_piers against the first n_ff_poles poles (sp_surrogate.rs:40-44)."""
     lib = load_library()
     pts = _f32(points).reshape(-1, 2)
     cfg = JgSurrogateConfig((C.c_int * 3)(*[int(a) for a, _ in n_pole_limits]), (C.c_float * 3)(*[float(b) for _, b in n_pole_limits]),
@@ -228,7 +248,10 @@ def import_item(points, n_pole_limits=((100, 0.0), (20, 0.75), (10, 0.90)), n_ff
                                            verts, C.byref(nv), poi, poles, len(poles), C.byref(npol), pre, C.byref(area))
     if rc != JG_OK:
         raise JaguaCudaError(rc, "jg_item_import: degenerate polygon (fewer than 3 distinct vertices, duplicate points or no area)")
-    return ItemShape(verts[:nv.value].copy(), poi, poles[:npol.value].copy(), np.zeros((0, 4), np.float32)), pre, float(area.value)
+    piers = np.zeros((0, 4), np.float32)
+    if n_ff_piers > 0:
+        piers = generate_piers(verts[:nv.value], poles[:min(int(n_ff_poles), npol.value)], n_ff_piers)
+    return ItemShape(verts[:nv.value].copy(), poi, poles[:npol.value].copy(), piers), pre, float(area.value)
 
 
 def polygon_poi(points):

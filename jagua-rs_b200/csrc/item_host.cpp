@@ -8,7 +8,8 @@
 //   geometry/original_shape.rs:23-51           convert_to_internal with shape modification disabled (offset / simplification
 //                                              are the "next" row f3 of SURVEY section 8)
 //   geometry/fail_fast/pole.rs:12-135          generate_surrogate_poles, compute_pole, POINode
-//   geometry/fail_fast/sp_surrogate.rs:33-61   SPSurrogate::new (poles; piers only when n_ff_piers > 0: not generated here)
+//   geometry/fail_fast/sp_surrogate.rs:33-61   SPSurrogate::new (poles; piers: jg_item_generate_piers, on request)
+//   geometry/fail_fast/piers.rs:25-226         generate_piers
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -526,6 +527,200 @@ static int item_import_impl(const float* pts_xy, int n_pts, const JgSurrogateCon
             poles_xyr[3 * i] = poles[i].x, poles_xyr[3 * i + 1] = poles[i].y, poles_xyr[3 * i + 2] = poles[i].r;
     pre_transform_xy[0] = -cx, pre_transform_xy[1] = -cy;
     if (area) *area = area_orig;
+    return JG_OK;
+}
+
+// ---- geometry/fail_fast/piers.rs:25-226 generate_piers ------------------------------------------------------------
+// Piers are segments inside the shape that cover what the fail-fast poles leave unrepresented. A fan of rays (a
+// vertical segment through the centroid, translated along x and rotated about the origin) is clipped to the shape;
+// n times over, the clipped ray that minimises the summed squared distance of the unrepresented grid points to their
+// nearest pole / selected pier / the candidate is selected. f32 throughout, every loop in the reference's order
+// (the sums are sequential folds, min_by_key keeps the first minimum, sorted_by_key is stable).
+// Third-party arithmetic: ndarray 0.17 `Array::linspace(a, b, n)` is restated as a + ((b - a) / (n - 1)) * i (unpinned,
+// like float-cmp); `f32::sin_cos` is glibc sinf / cosf.
+namespace jg {
+namespace {
+struct M3 {
+    float m[3][3];
+};
+M3 dot_prod(const M3& l, const M3& r) {  // transformation.rs:150-172
+    M3 o;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) o.m[i][j] = l.m[i][0] * r.m[0][j] + l.m[i][1] * r.m[1][j] + l.m[i][2] * r.m[2][j];
+    return o;
+}
+Pt m3_point(const M3& t, const Pt& p) {  // point.rs:10-31 TRANSFORM_FORMULA
+    return Pt{t.m[0][0] * p.x + t.m[0][1] * p.y + t.m[0][2] * 1.0f, t.m[1][0] * p.x + t.m[1][1] * p.y + t.m[1][2] * 1.0f};
+}
+struct SegPt {
+    Pt s, e;
+};
+// edge.rs:180-228 edge_intersection(e1, e2, true): the location is x2 + t * (x1 - x2) on e1
+bool edge_collides_at(const SegPt& e1, const SegPt& e2, Pt& out) {
+    const float x1 = e1.s.x, y1 = e1.s.y, x2 = e1.e.x, y2 = e1.e.y;
+    const float x3 = e2.s.x, y3 = e2.s.y, x4 = e2.e.x, y4 = e2.e.y;
+    if (fmaxf(fminf(x1, x2), fminf(x3, x4)) > fminf(fmaxf(x1, x2), fmaxf(x3, x4))) return false;
+    if (fmaxf(fminf(y1, y2), fminf(y3, y4)) > fminf(fmaxf(y1, y2), fmaxf(y3, y4))) return false;
+    const float t_nom = (x2 - x4) * (y4 - y3) - (y2 - y4) * (x4 - x3);
+    const float denom = (x2 - x1) * (y4 - y3) - (y2 - y1) * (x4 - x3);
+    const float u_nom = (x2 - x4) * (y2 - y1) - (y2 - y4) * (x2 - x1);
+    if (denom == 0.0f) return false;
+    const float t = t_nom / denom, u = u_nom / denom;
+    if (!(t >= 0.0f && t <= 1.0f && u >= 0.0f && u <= 1.0f)) return false;
+    out = Pt{x2 + t * (x1 - x2), y2 + t * (y1 - y2)};
+    return true;
+}
+float pt_distance(const Pt& a, const Pt& b) {  // point.rs:43-47
+    const float dx = a.x - b.x, dy = a.y - b.y;
+    return sqrtf(dx * dx + dy * dy);
+}
+float circle_distance(const Pole& c, const Pt& p) {  // circle.rs:136-147
+    const float dx = p.x - c.x, dy = p.y - c.y;
+    const float sq = dx * dx + dy * dy;
+    return sq < c.r * c.r ? 0.0f : sqrtf(sq) - c.r;
+}
+std::vector<float> linspace(float a, float b, int n) {
+    std::vector<float> v((size_t)n);
+    const float step = n > 1 ? (b - a) / (float)(n - 1) : 0.0f;
+    for (int i = 0; i < n; i++) v[(size_t)i] = a + step * (float)i;
+    return v;
+}
+}  // namespace
+}  // namespace jg
+
+extern "C" int jg_item_generate_piers(const float* verts_xy, int n_verts, const float* poles_xyr, int n_poles, int n_piers,
+                                      const JgPierConfig* cfg, float* piers_xyxy) {
+    if (!verts_xy || n_verts < 3 || n_piers < 0 || n_poles < 0 || (n_poles > 0 && !poles_xyr) || (n_piers > 0 && !piers_xyxy))
+        return JG_ERR_INVALID;
+    if (n_piers == 0) return JG_OK;  // piers.rs:26-28
+    const int rays_per_angle = cfg && cfg->rays_per_angle > 0 ? cfg->rays_per_angle : 200;  // piers.rs:16-18, release values
+    const int n_angles = cfg && cfg->n_angles > 0 ? cfg->n_angles : 90;
+    const int n_grid = cfg && cfg->n_points_per_dimension > 0 ? cfg->n_points_per_dimension : 100;
+    const float CLIPPING_TRIM = 0.999f, ACTION_RADIUS_RATIO = 0.10f;
+    Shape sh;
+    sh.v.resize((size_t)n_verts);
+    for (int i = 0; i < n_verts; i++) sh.v[(size_t)i] = Pt{verts_xy[2 * i], verts_xy[2 * i + 1]};
+    sh.area = signed_area(sh.v);
+    if (!(sh.area > 0.0f)) return JG_ERR_INVALID;  // SPolygon::new keeps the vertices counter-clockwise
+    sh.bbox = bbox_of(sh.v);
+    std::vector<Pole> poles((size_t)n_poles);
+    for (int i = 0; i < n_poles; i++) poles[(size_t)i] = Pole{poles_xyr[3 * i], poles_xyr[3 * i + 1], poles_xyr[3 * i + 2]};
+    const size_t nv = sh.v.size();
+    const Rect bbox = sh.bbox;
+    Rect sq = bbox;  // rect.rs:93-109 inflate_to_square
+    {
+        const float w = sq.x_max - sq.x_min, h = sq.y_max - sq.y_min;
+        float dx = 0.0f, dy = 0.0f;
+        if (h < w) dy = (w - h) / 2.0f;
+        else if (w < h) dx = (h - w) / 2.0f;
+        sq = Rect{sq.x_min - dx, sq.y_min - dy, sq.x_max + dx, sq.y_max + dy};
+    }
+    const float sq_w = sq.x_max - sq.x_min, sq_h = sq.y_max - sq.y_min;
+    float cx = 0.0f, cy = 0.0f;  // simple_polygon.rs:173-192 centroid
+    for (size_t i = 0; i < nv; i++) {
+        const size_t j = i + 1 == nv ? 0 : i + 1;
+        const float cr = sh.v[i].x * sh.v[j].y - sh.v[j].x * sh.v[i].y;
+        cx += (sh.v[i].x + sh.v[j].x) * cr;
+        cy += (sh.v[i].y + sh.v[j].y) * cr;
+    }
+    cx /= 6.0f * sh.area;
+    cy /= 6.0f * sh.area;
+    const SegPt base_ray{Pt{cx, cy - 2.0f * sq_h}, Pt{cx, cy + 2.0f * sq_h}};  // piers.rs:36-40
+    if (base_ray.s.x == base_ray.e.x && base_ray.s.y == base_ray.e.y) return JG_ERR_REFERENCE_PANIC;  // Edge::try_new
+    // piers.rs:101-127 generate_ray_transformations: translation (x, 0), then rotation (angle-major order)
+    const float dx_ray = sq_w / (float)rays_per_angle;
+    const std::vector<float> angles = linspace(0.0f, 3.14159265358979323846f, n_angles + 1);
+    std::vector<SegPt> clipped;
+    std::vector<std::pair<float, Pt>> hits;
+    for (int a = 0; a < n_angles; a++) {
+        const float sn = sinf(angles[(size_t)a]), cs = cosf(angles[(size_t)a]);
+        const M3 rot{{{cs, -sn, 0.0f}, {sn, cs, 0.0f}, {0.0f, 0.0f, 1.0f}}};
+        for (int i = 0; i < rays_per_angle; i++) {
+            const float x = sq.x_min + dx_ray * (float)i;
+            const M3 tr{{{1.0f, 0.0f, x}, {0.0f, 1.0f, 0.0f}, {0.0f, 0.0f, 1.0f}}};
+            const M3 t = dot_prod(rot, tr);  // Transformation::rotate (transformation.rs:36-39)
+            const SegPt ray{m3_point(t, base_ray.s), m3_point(t, base_ray.e)};
+            // piers.rs:130-157 clip
+            const Xf id{1.0f, 0.0f, 0.0f, 0.0f};
+            if (poly_point<false>(&sh.v[0].x, (int)nv, sh.bbox, ray.s.x, ray.s.y, id) ||
+                poly_point<false>(&sh.v[0].x, (int)nv, sh.bbox, ray.e.x, ray.e.y, id))
+                return JG_ERR_REFERENCE_PANIC;  // piers.rs:132 assert!
+            hits.clear();
+            for (size_t k = 0; k < nv; k++) {
+                const SegPt edge{sh.v[k], sh.v[k + 1 == nv ? 0 : k + 1]};
+                Pt at;
+                if (edge_collides_at(edge, ray, at)) hits.push_back({pt_distance(ray.s, at), at});
+            }
+            for (const auto& h : hits)
+                if (h.first != h.first) return JG_ERR_REFERENCE_PANIC;  // NotNan::new(..).unwrap()
+            std::stable_sort(hits.begin(), hits.end(), [](const std::pair<float, Pt>& l, const std::pair<float, Pt>& r) { return l.first < r.first; });
+            for (size_t k = 0; k + 1 < hits.size(); k += 2) {
+                const Pt s = hits[k].second, e = hits[k + 1].second;
+                if (s.x == e.x && s.y == e.y) continue;
+                // Edge::scale (edge.rs:38-45)
+                const float ddx = e.x - s.x, ddy = e.y - s.y;
+                const float f1 = CLIPPING_TRIM - 1.0f;
+                SegPt c{s, e};
+                c.s.x -= ddx * f1 / 2.0f;
+                c.s.y -= ddy * f1 / 2.0f;
+                c.e.x += ddx * f1 / 2.0f;
+                c.e.y += ddy * f1 / 2.0f;
+                clipped.push_back(c);
+            }
+        }
+    }
+    // piers.rs:159-178 generate_unrepresented_point_grid (x-major)
+    std::vector<Pt> grid;
+    {
+        const std::vector<float> xr = linspace(sq.x_min, sq.x_max, n_grid), yr = linspace(sq.y_min, sq.y_max, n_grid);
+        const Xf id{1.0f, 0.0f, 0.0f, 0.0f};
+        for (float x : xr)
+            for (float y : yr) {
+                if (!poly_point<false>(&sh.v[0].x, (int)nv, sh.bbox, x, y, id)) continue;
+                bool in_pole = false;
+                for (const Pole& c : poles) {  // circle.rs:130-134
+                    const float ddx = x - c.x, ddy = y - c.y;
+                    if (ddx * ddx + ddy * ddy <= c.r * c.r) { in_pole = true; break; }
+                }
+                if (!in_pole) grid.push_back(Pt{x, y});
+            }
+    }
+    const float radius_of_ray_influence = ACTION_RADIUS_RATIO * sq_w;
+    const float bw = bbox.x_max - bbox.x_min, bh = bbox.y_max - bbox.y_min;
+    const float forfeit = sqrtf((bw * bw) * (bh * bh));  // piers.rs:58 (sic: a product)
+    std::vector<float> d_poles(grid.size()), d_rays(grid.size());
+    for (size_t g = 0; g < grid.size(); g++) {  // piers.rs:216-226
+        float m = forfeit;
+        for (const Pole& c : poles) m = fminf(m, circle_distance(c, grid[g]));
+        d_poles[g] = m;
+    }
+    std::vector<SegPt> selected;
+    for (int it = 0; it < n_piers; it++) {
+        for (size_t g = 0; g < grid.size(); g++) {  // piers.rs:204-214
+            float m = forfeit;
+            for (const SegPt& r : selected) m = fminf(m, edge_distance(r.s, r.e, grid[g].x, grid[g].y));
+            d_rays[g] = m;
+        }
+        if (clipped.empty()) return JG_ERR_REFERENCE_PANIC;  // piers.rs:92 bail!("no ray found")
+        size_t best = 0;
+        float best_loss = 0.0f;
+        for (size_t r = 0; r < clipped.size(); r++) {  // piers.rs:180-202 loss_function
+            float loss = 0.0f;
+            for (size_t g = 0; g < grid.size(); g++) {
+                const float dn = edge_distance(clipped[r].s, clipped[r].e, grid[g].x, grid[g].y);
+                const float dr = fminf(d_rays[g], dn);
+                const float d = dr < radius_of_ray_influence ? fminf(d_poles[g], dr) : d_poles[g];
+                loss += d * d;
+            }
+            if (loss != loss) return JG_ERR_REFERENCE_PANIC;  // NotNan::new(x).unwrap()
+            if (r == 0 || loss < best_loss) best = r, best_loss = loss;  // min_by_key: the first minimum
+        }
+        selected.push_back(clipped[best]);
+    }
+    for (int i = 0; i < n_piers; i++) {
+        piers_xyxy[4 * i] = selected[(size_t)i].s.x, piers_xyxy[4 * i + 1] = selected[(size_t)i].s.y;
+        piers_xyxy[4 * i + 2] = selected[(size_t)i].e.x, piers_xyxy[4 * i + 3] = selected[(size_t)i].e.y;
+    }
     return JG_OK;
 }
 

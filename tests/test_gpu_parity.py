@@ -515,6 +515,42 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
         cde.set_split_min(1 << 21)
 
 
+@pytest.mark.parametrize("name", ["swim_half", "trousers_full"])
+def test_generated_piers_on_the_fail_fast_path(jg, orc, name):
+    """Items whose surrogate carries piers generated by jg_item_generate_piers (fail_fast/piers.rs; n_ff_piers = 2):
+    detect_surrogate_collision tests the poles, then the piers (cd_engine.rs:204-223), collect_surrogate_collisions
+    likewise (cd_engine.rs:296-310). Batches with piers are served by the quadtree-walk kernels. Verdict bytes and hazard
+    sets against the oracle; a query the pole-only surrogate reports colliding stays colliding, and piers move queries
+    from the polygon stage to the surrogate stage."""
+    import dataclasses
+
+    wl = jg.load_workload(name)
+    base_cde = jg.build_engine(wl, device=0)
+    items = []
+    for it in wl.items:
+        piers = jg.generate_piers(it.verts, it.poles[:wl.n_ff_poles], 2, 24, 10, 24)
+        items.append(dataclasses.replace(it, piers=piers))
+    wlp = dataclasses.replace(wl, items=items, n_ff_piers=2)
+    cde = jg.build_engine(wlp, device=0)
+    w = oracle_world(orc, wlp)
+    try:
+        words = cde.collector_words()
+        moved = 0
+        for item_id in range(0, len(wlp.items), max(1, len(wlp.items) // 5)):
+            t = jg.make_queries(wlp, item_id, 20000, seed=31)
+            got, exp = cde.detect_batch(item_id, t), w.detect_batch(item_id, t)
+            assert np.array_equal(got, exp), f"{name} item {item_id}: {(got != exp).sum()} mismatches"
+            plain = base_cde.detect_batch(item_id, t)
+            assert not ((plain != 0) & (got == 0)).any() and not ((got == 2) & (plain == 1)).any()
+            moved += int(((got == 1) & (plain == 2)).sum())
+            gc, ec = cde.collect_batch(item_id, t[:4000], words), w.collect_batch(item_id, t[:4000], words)
+            assert np.array_equal(gc, ec)
+        assert moved > 0  # the piers caught collisions the two poles missed
+    finally:
+        cde.close()
+        base_cde.close()
+
+
 @pytest.mark.parametrize("name", ["swim_half", "baldacci1_bin", "shirts_full"])
 def test_dependent_launch_matches_stream_order(jg, engines, name):
     """Stage 2 launched with programmatic stream serialization (its CTAs move in while stage 1 drains and wait in

@@ -709,5 +709,6 @@ class CDEngine:
 
 
 from . import instance  # noqa: E402
+from . import export  # noqa: E402
 from . import workload  # noqa: E402
 from .workload import Workload, load_workload, build_engine, make_queries, make_queries_indexed, split_batch  # noqa: E402

@@ -329,7 +329,8 @@ def main():
         if flops_per_q:
             ach = flops_per_q * args.queries / (ms_per_step * 1e-3) / 1e12  # per GPU
             roofline = {"bound": "fp32_nofma", "achieved": ach, "peak": peak_gflops / 1e3, "unit": "TFLOP/s",
-                        "frac": ach / (peak_gflops / 1e3), "traffic": traffic,
+                        "frac": ach / (peak_gflops / 1e3), "traffic": traffic["bytes_per_step"] if traffic else None,
+                        "traffic_detail": traffic,
                         "peak_source": "measured live: jg_fp32_nofma_peak (independent FADD/FMUL chains)",
                         "issue": issue, "flops_per_query": flops_per_q, "kernels": f"{cde.detect_path()} path: " + ("k_s1_grid + k_s2_grid" if cde.detect_path() == "grid" else "k_s1_surr + k_s2_poly") + ", one launch pair for the 10 item segments",
                         "hbm": {"achieved": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9, "peak": 6555.2,

@@ -2,7 +2,7 @@
 jagua-rs_b200/lbf.py, next to the CPU restatement of the reference's sequential LBF (oracle/, same sample budget) and
 an oracle feasibility check of the GPU solution (every placed item re-placed in an oracle layout, Layout::is_feasible).
 
-    python tools/run_lbf.py [assets/swim.json] [--samples 5000] [--no-check]
+    python tools/run_lbf.py [assets/swim.json] [--samples 5000] [--no-check] [--solution out.json]
 """
 import argparse
 import json
@@ -23,6 +23,7 @@ ap.add_argument("--samples", type=int, default=5000)
 ap.add_argument("--ls-frac", type=float, default=0.2)
 ap.add_argument("--seed", type=int, default=0)
 ap.add_argument("--no-check", action="store_true")
+ap.add_argument("--solution", default=None, help="write the solution as the reference's ExtSPSolution JSON (probs/spp/io/ext_repr.rs)")
 ap.add_argument("--shape-defaults", action="store_true", help="the lbf defaults for item shapes: poly_simpl_tolerance 0.001, narrow_concavity_cutoff_ratio 0.01")
 ap.add_argument("--rotation-lattice", type=int, default=256, help="angles of the device-side lattice for items that rotate continuously (0: sample them on the host)")
 ap.add_argument("--host-sampling", action="store_true", help="draw the samples with numpy on the host instead of on the device")
@@ -56,5 +57,9 @@ if not args.no_check:
     dt = time.perf_counter() - t0
     line["cpu_lbf"] = {"placed": int(n), "strip_width": w2.strip_width(), "seconds": dt, "kind": "port (sequential search.rs restatement, 1 thread)",
                        "density": solver.total_area / (w2.strip_width() * float(res.strip_height))}
+if args.solution:
+    with open(args.solution, "w") as f:
+        json.dump(jg.export.export_spp_solution(res, solver.items), f, indent=1)
+    line["solution_file"] = args.solution
 print(json.dumps(line))
 solver.close()

@@ -62,11 +62,12 @@ JG_HD bool approx_eq(float a, float b) {
     int32_t ad = d < 0 ? (d == INT32_MIN ? INT32_MAX : -d) : d;
     return ad <= 4;
 }
-// util/fpa.rs:24-31: Equal when approx-equal, otherwise the exact ordering
-JG_HD bool fpa_le(float a, float b) { return approx_eq(a, b) || a < b; }
-JG_HD bool fpa_ge(float a, float b) { return approx_eq(a, b) || a > b; }
-JG_HD bool fpa_lt(float a, float b) { return !approx_eq(a, b) && a < b; }
-JG_HD bool fpa_gt(float a, float b) { return !approx_eq(a, b) && a > b; }
+// util/fpa.rs:24-31: Equal when approx-equal, otherwise the exact ordering. approx_eq is a pure function, so the cheap
+// exact comparison goes first (the same boolean, most calls never reach the ulp arithmetic).
+JG_HD bool fpa_le(float a, float b) { return a <= b || approx_eq(a, b); }
+JG_HD bool fpa_ge(float a, float b) { return a >= b || approx_eq(a, b); }
+JG_HD bool fpa_lt(float a, float b) { return a < b && !approx_eq(a, b); }
+JG_HD bool fpa_gt(float a, float b) { return a > b && !approx_eq(a, b); }
 
 // primitives/rect.rs:266-272
 JG_HD bool rect_rect(const Rect& a, const Rect& b) {

@@ -279,10 +279,24 @@ int jg_shape_close_concavities(const float* pts_xy, int n_pts, int mode, float m
 int jg_shape_simplify(const float* pts_xy, int n_pts, int mode, float max_area_change_ratio, float* verts_xy, int* n_verts,
                       float poi_xyr[3]);
 
+/* ... with the whole ShapeModifyConfig (geometry/shape_modification.rs:22-46, original_shape.rs:23-51): offset > 0 inflates
+ * the centred shape first (jg_shape_offset: the repo's own offsetter, not bit-equal to geo-buffer), then simplification /
+ * concavity closing as in jg_item_import_simplified (negative = None). verts_xy must hold verts_cap >= 2 * n_pts vertices. */
+int jg_item_import_modified(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float offset, float simplify_tolerance,
+                            float narrow_concavity_cutoff_ratio, float* verts_xy, int verts_cap, int* n_verts, float poi_xyr[3],
+                            float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2], float* area);
 /* SPolygon::new for a shape that is registered as it is (container outer boundary, hole, quality zone;
  * geometry/primitives/simple_polygon.rs:40-71): orientation normalised to counter-clockwise (written to
  * verts_ccw_xy when non-null, 2 * n_pts floats) and the pole of inaccessibility jg_cde_register_hazard wants. */
 int jg_polygon_poi(const float* pts_xy, int n_pts, float poi_xyr[3], float* verts_ccw_xy);
+/* offset_shape (geometry/shape_modification.rs:330-372; ShapeModifyConfig::offset = half the minimum separation): mode 0
+ * Inflate (items, holes, zones), 1 Deflate (container boundaries), distance >= 0. The repo's own offsetter - miter joins,
+ * corners beyond miter_limit * distance (default 2) cut on the tangents of the round join - NOT geo-buffer: an inflated
+ * shape contains the reference's rounded one but is not bit-equal to it. pts: clean counter-clockwise vertices; the result
+ * passes through the importer's cleaning and SPolygon::new (poi). At most 2 * n_pts vertices (verts_cap).
+ * JG_ERR_REFERENCE_PANIC: the offset polygon intersects itself (separation too large for the shape). */
+int jg_shape_offset(const float* pts_xy, int n_pts, int mode, float distance, float miter_limit, float* verts_xy, int verts_cap,
+                    int* n_verts, float poi_xyr[3]);
 /* import_simple_polygon + SPolygon::new for a container boundary, hole or quality zone (io/import.rs:100-195,
  * 198-211): vertex cleaning as in jg_item_import, then jg_polygon_poi. verts_xy must hold 2 * n_pts floats. */
 int jg_shape_import(const float* pts_xy, int n_pts, float* verts_xy, int* n_verts, float poi_xyr[3]);

@@ -93,6 +93,9 @@ C_ABI = {
     "jg_compose_batch": (None, [_f32p, C.c_int64, _f32p, C.c_int]),
     "jg_fp32_nofma_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "jg_flush_l2": (C.c_int, [_vp]),
+    "jg_item_import_modified": (C.c_int, [_f32p, C.c_int, _vp, C.c_float, C.c_float, C.c_float, _f32p, C.c_int, C.POINTER(C.c_int), _f32p,
+                                          _f32p, C.c_int, C.POINTER(C.c_int), _f32p, C.POINTER(C.c_float)]),
+    "jg_shape_offset": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_float, C.c_float, _f32p, C.c_int, C.POINTER(C.c_int), _f32p]),
     "jg_item_generate_piers": (C.c_int, [_f32p, C.c_int, _vp, C.c_int, C.c_int, _vp, _f32p]),
     "jg_item_import": (C.c_int, [_f32p, C.c_int, _vp, _f32p, C.POINTER(C.c_int), _f32p, _f32p, C.c_int, C.POINTER(C.c_int), _f32p,
                                  C.POINTER(C.c_float)]),
@@ -208,6 +211,21 @@ def close_narrow_concavities(points, mode: str = "inflate", max_distance_ratio: 
     return verts[:nv.value].copy(), poi
 
 
+def offset_shape(points, mode: str = "inflate", distance: float = 0.0, miter_limit: float = 2.0):
+    """offset_shape (geometry/shape_modification.rs:330-372) with the repo's own miter offsetter (not geo-buffer: not
+    bit-equal to the reference): (vertices, poi) of the clean counter-clockwise polygon moved by `distance`."""
+    lib = load_library()
+    pts = _f32(points).reshape(-1, 2)
+    verts = np.zeros((2 * len(pts), 2), np.float32)
+    poi = np.zeros(3, np.float32)
+    nv = C.c_int(0)
+    rc = lib.jg_shape_offset(pts, len(pts), {"inflate": 0, "deflate": 1}[mode], float(distance), float(miter_limit), verts, len(verts),
+                             C.byref(nv), poi)
+    if rc != JG_OK:
+        raise JaguaCudaError(rc, "jg_shape_offset: bad input, or the offset polygon intersects itself (reduce the separation)")
+    return verts[:nv.value].copy(), poi
+
+
 class JgPierConfig(C.Structure):
     _fields_ = [("rays_per_angle", C.c_int), ("n_angles", C.c_int), ("n_points_per_dimension", C.c_int)]
 
@@ -228,19 +246,25 @@ def generate_piers(verts, poles, n_piers: int, rays_per_angle: int = 0, n_angles
 
 
 def import_item(points, n_pole_limits=((100, 0.0), (20, 0.75), (10, 0.90)), n_ff_poles: int = 2, simplify_tolerance=None,
-                narrow_concavity_cutoff_ratio=None, n_ff_piers: int = 0):
+                narrow_concavity_cutoff_ratio=None, n_ff_piers: int = 0, offset: float = 0.0):
     """Importer::import_item + Item::new's surrogate for a simple polygon (io/import.rs:47-98, fail_fast/pole.rs:12-135)
-    through jg_item_import: returns (ItemShape, pre_transform (tx, ty), area). Offsetting is not applied; n_ff_piers > 0
-    adds generate_piers against the first n_ff_poles poles (sp_surrogate.rs:40-44)."""
+    through jg_item_import: returns (ItemShape, pre_transform (tx, ty), area). offset > 0 = ShapeModifyConfig::offset (half
+    the minimum separation; the repo's own offsetter, not bit-equal to geo-buffer); n_ff_piers > 0 adds generate_piers against
+    the first n_ff_poles poles (sp_surrogate.rs:40-44)."""
     lib = load_library()
     pts = _f32(points).reshape(-1, 2)
     cfg = JgSurrogateConfig((C.c_int * 3)(*[int(a) for a, _ in n_pole_limits]), (C.c_float * 3)(*[float(b) for _, b in n_pole_limits]),
                             int(n_ff_poles), 0)
-    verts = np.zeros((len(pts), 2), np.float32)
+    verts = np.zeros((2 * len(pts), 2), np.float32)
     poles = np.zeros((1000, 3), np.float32)
     poi, pre = np.zeros(3, np.float32), np.zeros(2, np.float32)
     nv, npol, area = C.c_int(0), C.c_int(0), C.c_float(0.0)
-    if simplify_tolerance is None:
+    if offset > 0.0:
+        rc = lib.jg_item_import_modified(pts, len(pts), C.addressof(cfg), float(offset),
+                                         -1.0 if simplify_tolerance is None else float(simplify_tolerance),
+                                         -1.0 if narrow_concavity_cutoff_ratio is None else float(narrow_concavity_cutoff_ratio),
+                                         verts, len(verts), C.byref(nv), poi, poles, len(poles), C.byref(npol), pre, C.byref(area))
+    elif simplify_tolerance is None:
         rc = lib.jg_item_import(pts, len(pts), C.addressof(cfg), verts, C.byref(nv), poi, poles, len(poles), C.byref(npol), pre, C.byref(area))
     else:  # Importer's poly_simpl_tolerance (lbf default 0.001)
         rc = lib.jg_item_import_simplified(pts, len(pts), C.addressof(cfg), float(simplify_tolerance),

@@ -450,9 +450,77 @@ extern "C" int jg_shape_close_concavities(const float* pts_xy, int n_pts, int mo
     return jg_polygon_poi(flat.data(), (int)p.size(), poi_xyr, verts_xy);
 }
 
+// offset_shape (geometry/shape_modification.rs:330-372) - the repo's OWN offsetter, not geo-buffer 0.2 (a third-party crate
+// that is not in the reference tree): results are NOT bit-equal to the reference's, and every consumer records the offset
+// polygons it used. The reference buffers with round joins; here every edge of the counter-clockwise polygon moves by d along
+// its outward normal (mode 0 Inflate: outwards, 1 Deflate: inwards), consecutive offset edges meet at their intersection
+// (miter), and corners whose miter would reach further than miter_limit * |d| from the vertex are cut by two points on the
+// tangents of the round join - so an inflated shape contains the reference's rounded one. Double arithmetic like the
+// reference's call (f32 -> f64 -> f32). Self-intersecting results are refused (JG_ERR_REFERENCE_PANIC): the separation is too
+// large for the shape's concavities. The result goes through the importer's cleaning and SPolygon::new like the reference's.
+extern "C" int jg_shape_offset(const float* pts_xy, int n_pts, int mode, float distance, float miter_limit, float* verts_xy,
+                               int verts_cap, int* n_verts, float poi_xyr[3]) {
+    if (!pts_xy || n_pts < 3 || !verts_xy || !n_verts || !poi_xyr || (mode != 0 && mode != 1) || !(distance >= 0.0f)) return JG_ERR_INVALID;
+    if (!(miter_limit > 1.0f)) miter_limit = 2.0f;
+    std::vector<Pt> p0((size_t)n_pts);
+    for (int i = 0; i < n_pts; i++) p0[(size_t)i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
+    if (!(signed_area(p0) > 0.0f)) return JG_ERR_INVALID;
+    const double d = mode == 1 ? -(double)distance : (double)distance;
+    const int n = n_pts;
+    std::vector<double> ox, oy;
+    std::vector<int> first((size_t)n), last((size_t)n);  // the offset points of corner i
+    for (int i = 0; i < n; i++) {
+        first[(size_t)i] = (int)ox.size();
+        if (i > 0) last[(size_t)(i - 1)] = (int)ox.size() - 1;
+        const Pt a = p0[(size_t)((i + n - 1) % n)], b = p0[(size_t)i], c = p0[(size_t)((i + 1) % n)];
+        double e0x = (double)b.x - a.x, e0y = (double)b.y - a.y, e1x = (double)c.x - b.x, e1y = (double)c.y - b.y;
+        const double l0 = std::sqrt(e0x * e0x + e0y * e0y), l1 = std::sqrt(e1x * e1x + e1y * e1y);
+        if (!(l0 > 0.0) || !(l1 > 0.0)) return JG_ERR_INVALID;
+        e0x /= l0, e0y /= l0, e1x /= l1, e1y /= l1;
+        const double n0x = e0y, n0y = -e0x, n1x = e1y, n1y = -e1x;  // outward normals of a counter-clockwise polygon
+        const double dotn = n0x * n1x + n0y * n1y;
+        const double denom = 1.0 + dotn;
+        if (denom < 1e-9) {  // a spike: the two offset edges are anti-parallel
+            ox.push_back(b.x + d * n0x), oy.push_back(b.y + d * n0y);
+            ox.push_back(b.x + d * n1x), oy.push_back(b.y + d * n1y);
+            continue;
+        }
+        const double mx = (n0x + n1x) / denom, my = (n0y + n1y) / denom;  // b + d * m: intersection of the offset lines
+        if (std::sqrt(mx * mx + my * my) > (double)miter_limit) {
+            const double t = std::tan(0.25 * std::acos(std::min(1.0, std::max(-1.0, dotn))));
+            ox.push_back(b.x + d * (n0x + e0x * t)), oy.push_back(b.y + d * (n0y + e0y * t));
+            ox.push_back(b.x + d * (n1x - e1x * t)), oy.push_back(b.y + d * (n1y - e1y * t));
+        } else {
+            ox.push_back(b.x + d * mx), oy.push_back(b.y + d * my);
+        }
+    }
+    const int m = (int)ox.size();
+    last[(size_t)(n - 1)] = m - 1;
+    for (int i = 0; i < n; i++) {  // every original edge must survive with its direction (else d exceeds the local feature size)
+        const int u = last[(size_t)i], w = first[(size_t)((i + 1) % n)];
+        const Pt b = p0[(size_t)i], c = p0[(size_t)((i + 1) % n)];
+        if (!((ox[(size_t)w] - ox[(size_t)u]) * ((double)c.x - b.x) + (oy[(size_t)w] - oy[(size_t)u]) * ((double)c.y - b.y) > 0.0))
+            return JG_ERR_REFERENCE_PANIC;
+    }
+    auto ccw = [&](int a, int b, int c) { return (oy[c] - oy[a]) * (ox[b] - ox[a]) - (oy[b] - oy[a]) * (ox[c] - ox[a]); };
+    for (int i = 0; i < m; i++)
+        for (int j = i + 2; j < m; j++) {
+            if (i == 0 && j == m - 1) continue;
+            const int i1 = (i + 1) % m, j1 = (j + 1) % m;
+            if (ccw(i, i1, j) * ccw(i, i1, j1) < 0.0 && ccw(j, j1, i) * ccw(j, j1, i1) < 0.0) return JG_ERR_REFERENCE_PANIC;
+        }
+    double a2 = 0.0;  // an offset that turns the polygon inside out (deflated past its width) has no proper crossing
+    for (int i = 0; i < m; i++) a2 += ox[(size_t)i] * oy[(size_t)((i + 1) % m)] - ox[(size_t)((i + 1) % m)] * oy[(size_t)i];
+    if (!(a2 > 0.0)) return JG_ERR_REFERENCE_PANIC;  // "Offset resulted in an empty polygon" (shape_modification.rs:351)
+    std::vector<float> flat((size_t)(2 * m));
+    for (int i = 0; i < m; i++) flat[(size_t)(2 * i)] = (float)ox[(size_t)i], flat[(size_t)(2 * i + 1)] = (float)oy[(size_t)i];
+    if (m > verts_cap) return JG_ERR_INVALID;
+    return jg_shape_import(flat.data(), m, verts_xy, n_verts, poi_xyr);  // import_simple_polygon + SPolygon::new
+}
+
 static int item_import_impl(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float* verts_xy, int* n_verts,
                             float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles, float pre_transform_xy[2],
-                            float* area, float simplify_tolerance, float concavity_ratio) {
+                            float* area, float simplify_tolerance, float concavity_ratio, float offset = 0.0f) {
     if (!pts_xy || n_pts < 3 || !scfg || !verts_xy || !n_verts || !poi_xyr || !n_poles || !pre_transform_xy) return JG_ERR_INVALID;
     std::vector<Pt> p((size_t)n_pts);
     for (int i = 0; i < n_pts; i++) p[i] = Pt{pts_xy[2 * i], pts_xy[2 * i + 1]};
@@ -486,6 +554,22 @@ static int item_import_impl(const float* pts_xy, int n_pts, const JgSurrogateCon
     xf_point(pre, poi.x, poi.y, poi.x, poi.y);
     sh.bbox = bbox_of(sh.v);
     const float area_orig = sh.area;  // Item::area() stays the original shape's
+    if (offset > 0.0f) {
+        // original_shape.rs:27-32: offset_shape in Inflate mode (ShapeModifyConfig::offset, half the minimum separation),
+        // with the repo's own offsetter (jg_shape_offset: not geo-buffer, not bit-equal to the reference)
+        std::vector<float> in(2 * sh.v.size()), outv(4 * sh.v.size());
+        for (size_t i = 0; i < sh.v.size(); i++) in[2 * i] = sh.v[i].x, in[2 * i + 1] = sh.v[i].y;
+        int nv2 = 0;
+        float poi2[3];
+        const int rc = jg_shape_offset(in.data(), (int)sh.v.size(), 0, offset, 2.0f, outv.data(), (int)(2 * sh.v.size()), &nv2, poi2);
+        if (rc != JG_OK) return rc;
+        sh.v.resize((size_t)nv2);
+        for (int i = 0; i < nv2; i++) sh.v[(size_t)i] = Pt{outv[(size_t)(2 * i)], outv[(size_t)(2 * i + 1)]};
+        sh.area = signed_area(sh.v);
+        if (!(sh.area > 0.0f)) return JG_ERR_REFERENCE_PANIC;
+        sh.bbox = bbox_of(sh.v);
+        poi = Pole{poi2[0], poi2[1], poi2[2]};
+    }
     if (simplify_tolerance >= 0.0f) {
         // original_shape.rs:33-45: simplify the transformed shape (Inflate for items); simplify_shape ends in
         // SPolygon::new, so area, bbox and the pole of inaccessibility are recomputed from the resulting points
@@ -738,4 +822,14 @@ extern "C" int jg_item_import_simplified(const float* pts_xy, int n_pts, const J
     if (!(simplify_tolerance >= 0.0f)) return JG_ERR_INVALID;
     return item_import_impl(pts_xy, n_pts, scfg, verts_xy, n_verts, poi_xyr, poles_xyr, poles_cap, n_poles, pre_transform_xy, area,
                             simplify_tolerance, narrow_concavity_cutoff_ratio);
+}
+// ... with the whole ShapeModifyConfig (geometry/shape_modification.rs:22-46): offset > 0 inflates the centred shape first
+// (jg_shape_offset), simplify_tolerance >= 0 / narrow_concavity_cutoff_ratio >= 0 as above (< 0 = None).
+extern "C" int jg_item_import_modified(const float* pts_xy, int n_pts, const JgSurrogateConfig* scfg, float offset,
+                                       float simplify_tolerance, float narrow_concavity_cutoff_ratio, float* verts_xy, int verts_cap,
+                                       int* n_verts, float poi_xyr[3], float* poles_xyr, int poles_cap, int* n_poles,
+                                       float pre_transform_xy[2], float* area) {
+    if (!(offset >= 0.0f) || verts_cap < 2 * n_pts) return JG_ERR_INVALID;
+    return item_import_impl(pts_xy, n_pts, scfg, verts_xy, n_verts, poi_xyr, poles_xyr, poles_cap, n_poles, pre_transform_xy, area,
+                            simplify_tolerance, narrow_concavity_cutoff_ratio, offset);
 }

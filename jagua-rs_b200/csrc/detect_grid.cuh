@@ -724,7 +724,10 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
         int l0 = 0, j = 0, j1 = -1;
         uint32_t cm = 0u, bits = 0u, er = 0u;
         if (f < E) {
-            for (int jj = 1; jj < GS; jj++) slot += (W.ebeg[jj] <= f) ? 1 : 0;
+            // the last slot whose first edge is <= f: ebeg[0 .. 8] is non-decreasing (slots beyond ng hold E)
+            if (W.ebeg[4] <= f) slot = 4;
+            if (W.ebeg[slot + 2] <= f) slot += 2;
+            if (W.ebeg[slot + 1] <= f) slot += 1;
             if (!((hm0 >> slot) & 1u)) {
                 const float4 t4 = W.xf[slot];
                 sg = item_edge(c.tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, f - W.ebeg[slot]);

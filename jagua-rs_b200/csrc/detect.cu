@@ -732,15 +732,28 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
         else if (split) JG_LAUNCH_S2(false, true, 7)
         else JG_LAUNCH_S2(false, false, 15)
 #undef JG_LAUNCH_S2
+#define JG_LAUNCH_S3(FILT_, SLOT_)                                                                                             \
+    {                                                                                                                          \
+        const int g3 = persistent_grid(k_s2_contain<FILT_>, SLOT_, n_sms, gs3);                                                \
+        cudaLaunchConfig_t lc = {};                                                                                            \
+        lc.gridDim = dim3((unsigned)(want3 < g3 ? want3 : g3));                                                                \
+        lc.blockDim = dim3(S_THREADS);                                                                                         \
+        lc.dynamicSmemBytes = gs3;                                                                                             \
+        lc.stream = st;                                                                                                        \
+        cudaLaunchAttribute at[1];                                                                                             \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                         \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                                  \
+        lc.attrs = at;                                                                                                         \
+        lc.numAttrs = g_dependent_launch ? 1 : 0;                                                                              \
+        const int4* cm_ = sc.ct_meta;                                                                                          \
+        const float4 *cb_ = sc.ct_bb, *cx_ = sc.ct_xf;                                                                         \
+        cudaLaunchKernelEx(&lc, k_s2_contain<FILT_>, L, tab, d_filt, d_out, sc.ctl, cm_, cb_, cx_);                            \
+    }
         if (split) {
-            if (d_filt) {
-                const int g3 = persistent_grid(k_s2_contain<true>, 12, n_sms, gs3);
-                k_s2_contain<true><<<want3 < g3 ? want3 : g3, S_THREADS, gs3, st>>>(L, tab, d_filt, d_out, sc.ctl, sc.ct_meta, sc.ct_bb, sc.ct_xf);
-            } else {
-                const int g3 = persistent_grid(k_s2_contain<false>, 13, n_sms, gs3);
-                k_s2_contain<false><<<want3 < g3 ? want3 : g3, S_THREADS, gs3, st>>>(L, tab, d_filt, d_out, sc.ctl, sc.ct_meta, sc.ct_bb, sc.ct_xf);
-            }
+            if (d_filt) JG_LAUNCH_S3(true, 12)
+            else JG_LAUNCH_S3(false, 13)
         }
+#undef JG_LAUNCH_S3
         if (n_launches) *n_launches += split ? 3 : 2;
         return cudaGetLastError();
     }

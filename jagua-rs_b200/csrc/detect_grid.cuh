@@ -867,6 +867,8 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
     // dependent launch: everything above reads launch parameters and the grid summary of an earlier upload; the survivor
     // list, its count and the verdict bytes belong to stage 1, complete and visible only after this wait
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ... and k_s2_contain, when it follows as a dependent launch, may move in as this (fully resident) grid drains
+    if (SPLIT) asm volatile("griddepcontrol.launch_dependents;");
     const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry, ct_meta, ct_bb, ct_xf};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     G2Slots& W = *(G2Slots*)(p + (size_t)warp * sizeof(G2Slots));
@@ -898,12 +900,14 @@ __global__ void __launch_bounds__(S_THREADS)
 k_s2_contain(const DevLayout L, const __grid_constant__ SegTable gtab, const uint32_t* __restrict__ filt,
              uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, const int4* __restrict__ ct_meta,
              const float4* __restrict__ ct_bb, const float4* __restrict__ ct_xf) {
-    const int total = ctl->n_ct;
-    if (total == 0) return;
     extern __shared__ __align__(16) unsigned char smem[];
     SegTable* t = (SegTable*)smem;
     for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
     __syncthreads();
+    // dependent launch behind k_s2_grid<.., true>: the hand-over list and its count are complete after this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int total = ctl->n_ct;
+    if (total == 0) return;
     const SegTable& tab = *t;
     const int lane = threadIdx.x & 31, team = lane >> 2, sub = lane & 3;
     const unsigned team_bits = 0xFu << (team * 4);

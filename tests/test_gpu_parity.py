@@ -499,6 +499,7 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
     cde.upload_filter(7, fbits)
     try:
         cde.set_split_min(0)
+        cde.detect_batch(0, jg.make_queries(wl, 0, 1000, seed=1))  # (a fresh engine's first call also uploads the layout)
         l0 = cde.stats()["launches"]
         cde.detect_batch(0, jg.make_queries(wl, 0, 1000, seed=1))
         assert cde.stats()["launches"] - l0 == 3  # k_s1_grid, k_s2_grid<split>, k_s2_contain

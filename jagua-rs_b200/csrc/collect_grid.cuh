@@ -22,13 +22,15 @@ namespace jg {
 struct GridCollect {
     int ok, pad[3];
     uint32_t rows[GRID_G];                 // finest cells whose collect terminal holds at least one hazard entry
+    uint32_t colfirst[GRID_G];             // ... cells in the first column / the first row of their terminal: a window visits a
+    uint32_t rowfirst[GRID_G];             //     terminal at its first cell inside the window, found with row-mask arithmetic
     uint16_t cell_node[GRID_G * GRID_G];   // collect terminal covering the cell
     uint8_t cell_level[GRID_G * GRID_G];   // ... and its level
 };
 
 __global__ void __launch_bounds__(1024) k_cgrid_build(const DevLayout L, const GridDev* __restrict__ g, GridCollect* __restrict__ cg) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < GRID_G; i += blockDim.x) cg->rows[i] = 0u;
+    for (int i = tid; i < GRID_G; i += blockDim.x) cg->rows[i] = 0u, cg->colfirst[i] = 0u, cg->rowfirst[i] = 0u;
     __syncthreads();
     if (!g->ok) {
         if (tid == 0) cg->ok = 0;
@@ -50,6 +52,9 @@ __global__ void __launch_bounds__(1024) k_cgrid_build(const DevLayout L, const G
         cg->cell_node[j * GRID_G + i] = (uint16_t)node;
         cg->cell_level[j * GRID_G + i] = (uint8_t)level;
         if ((m.z & 0xFFFF) + ((m.z >> 16) & 0xFFFF) > 0) atomicOr(&cg->rows[j], 1u << i);
+        const int sh = D - level;
+        if (((i >> sh) << sh) == i) atomicOr(&cg->colfirst[j], 1u << i);
+        if (((j >> sh) << sh) == j) atomicOr(&cg->rowfirst[j], 1u << i);
     }
     if (tid == 0) cg->ok = 1;
 }
@@ -158,13 +163,15 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
                     const PoleWin w = pole_window(g, c);
                     const uint32_t cm = col_mask(w.i0, w.i1);
                     for (int j = w.j0; j <= w.j1; j++) {
-                        uint32_t bits = cg->rows[j] & cm;
+                        // one visit per terminal and circle: at the terminal's first cell inside the window, i.e. the cells
+                        // with (i == ti || i == i0) && (j == tj || j == j0)
+                        uint32_t bits = cg->rows[j] & cm & (cg->colfirst[j] | (1u << w.i0));
+                        if (j != w.j0) bits &= cg->rowfirst[j];
                         while (bits) {
                             const int i = __ffs(bits) - 1;
                             bits &= bits - 1;
                             const int lt = cg->cell_level[j * GRID_G + i], sh = D - lt;
                             const int ti = (i >> sh) << sh, tj = (j >> sh) << sh;  // first finest cell of the terminal
-                            if (i != max(ti, w.i0) || j != max(tj, w.j0)) continue;  // one visit per terminal and circle
                             const Rect tb{g.xs[ti], g.ys[tj], g.xs[ti + (1 << sh)], g.ys[tj + (1 << sh)]};
                             if (!circ_rect(c, tb)) continue;  // circle.rs:115-128: reached iff its own bbox passes
                             cg_terminal<Circ>(L, cg->cell_node[j * GRID_G + i], c, W.bits[s], [] { return true; });
@@ -264,13 +271,14 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
                     j0 = max(j0, vj0), j1 = min(j1, vj0 + (1 << s0) - 1);
                     const uint32_t cm = col_mask(i0, i1);
                     for (int j = j0; j <= j1; j++) {
-                        uint32_t rb = cg->rows[j] & cm;
+                        // one visit per terminal and edge (see the poles above)
+                        uint32_t rb = cm ? cg->rows[j] & cm & (cg->colfirst[j] | (1u << i0)) : 0u;
+                        if (j != j0) rb &= cg->rowfirst[j];
                         while (rb) {
                             const int i = __ffs(rb) - 1;
                             rb &= rb - 1;
                             const int lt = cg->cell_level[j * GRID_G + i], sh = D - lt;
                             const int ti = (i >> sh) << sh, tj = (j >> sh) << sh;
-                            if (i != max(ti, i0) || j != max(tj, j0)) continue;  // one visit per terminal and edge
                             const Rect tb{g.xs[ti], g.ys[tj], g.xs[ti + (1 << sh)], g.ys[tj + (1 << sh)]};
                             cg_terminal<Seg>(L, cg->cell_node[j * GRID_G + i], sg, bits, [&] {
                                 return rect_point(tb, sg.sx, sg.sy) || rect_point(tb, sg.ex, sg.ey) || path_reaches(g, sg, l0, lt, i, j);

@@ -136,6 +136,8 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     CGSlots& W = *(CGSlots*)(p + (size_t)warp * sizeof(CGSlots));
     const int D = g.D, G = g.G, GS = S2_MAX_GROUP, V = it.n_verts;
+    const float inv_v = 1.0f / (float)V;  // f / V for f < 8 V without the integer division: (f + 0.5) / V is >= 0.5 / V away
+                                          // from an integer, far beyond the rounding of two f32 operations on values < 2^17
     const int qs = lane >> 2, sub = lane & 3;
 
     for (;;) {
@@ -246,7 +248,7 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
         for (int f0 = 0; f0 < E; f0 += 32) {
             const int f = f0 + lane;
             if (f < E) {
-                const int s = f / V, e = f - s * V;
+                const int s = (int)(((float)f + 0.5f) * inv_v), e = f - s * V;
                 const float4 t4 = W.xf[s];
                 const Xf xf{t4.x, t4.y, t4.z, t4.w};
                 const float2 a = __ldg(&it.verts[e]), b = __ldg(&it.verts[e == V - 1 ? 0 : e + 1]);

@@ -279,10 +279,11 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
                         while (rb) {
                             const int i = __ffs(rb) - 1;
                             rb &= rb - 1;
-                            const int lt = cg->cell_level[j * GRID_G + i], sh = D - lt;
-                            const int ti = (i >> sh) << sh, tj = (j >> sh) << sh;
-                            const Rect tb{g.xs[ti], g.ys[tj], g.xs[ti + (1 << sh)], g.ys[tj + (1 << sh)]};
                             cg_terminal<Seg>(L, cg->cell_node[j * GRID_G + i], sg, bits, [&] {
+                                // only asked once an entry of the terminal is hit: its level and box are not needed before
+                                const int lt = cg->cell_level[j * GRID_G + i], sh = D - lt;
+                                const int ti = (i >> sh) << sh, tj = (j >> sh) << sh;
+                                const Rect tb{g.xs[ti], g.ys[tj], g.xs[ti + (1 << sh)], g.ys[tj + (1 << sh)]};
                                 return rect_point(tb, sg.sx, sg.sy) || rect_point(tb, sg.ex, sg.ey) || path_reaches(g, sg, l0, lt, i, j);
                             });
                         }

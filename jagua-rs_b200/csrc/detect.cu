@@ -619,8 +619,8 @@ k_s2_poly(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_
 namespace jg {
 
 // ---------------------------------------------------------------------------------------------------
-static int g_occ[16];
-static size_t g_occ_smem[16];
+static int g_occ[24];
+static size_t g_occ_smem[24];
 #ifdef JG_DIVCOUNT
 extern "C" int jg_debug_divcount(unsigned long long out[4], int reset) {
     cudaDeviceSynchronize();
@@ -680,8 +680,9 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
     const size_t smem1 = common + S_WARPS * (32 * sizeof(float4) + ((size_t)plan.cap_in + LEAF_CAP + 4) * sizeof(uint32_t));
     const size_t smem2 = common + S_WARPS * (sizeof(S2Slots) + ((size_t)plan.cap_in + LEAF_CAP) * sizeof(uint32_t));
     const int want1 = (n + S_THREADS - 1) / S_THREADS;                               // 32 queries per warp batch
-    bool grid = plan.use_grid != 0;
-    for (int k = 0; k < tab.n_seg; k++) grid = grid && tab.seg[k].n_piers == 0;
+    const bool grid = plan.use_grid != 0;
+    bool piers = false;  // items whose surrogate carries piers: k_s1_grid<.., true> tests them after the poles
+    for (int k = 0; k < tab.n_seg; k++) piers = piers || tab.seg[k].n_piers != 0;
     if (grid) {
         const GridDev* gd = grid_of(d_kinds, L.n_nodes);
         const size_t gcommon = ((sizeof(SegTable) + 15) & ~(size_t)15) + ((sizeof(GridDev) + 15) & ~(size_t)15);
@@ -691,6 +692,12 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
         if (mode & JG_MODE_POLY_ONLY) {
             const int gs = want1 < n_sms * 8 ? want1 : n_sms * 8;
             k_s1_all_survive<<<gs, S_THREADS, 0, st>>>(tab, sc.ctl, sc.sv_entry);
+        } else if (piers && d_filt) {
+            const int g = persistent_grid(k_s1_grid<true, true>, 16, n_sms, gs1);
+            k_s1_grid<true, true><<<want1 < g ? want1 : g, S_THREADS, gs1, st>>>(L, tab, gd, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
+        } else if (piers) {
+            const int g = persistent_grid(k_s1_grid<false, true>, 17, n_sms, gs1);
+            k_s1_grid<false, true><<<want1 < g ? want1 : g, S_THREADS, gs1, st>>>(L, tab, gd, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
         } else if (d_filt) {
             const int g = persistent_grid(k_s1_grid<true>, 4, n_sms, gs1);
             k_s1_grid<true><<<want1 < g ? want1 : g, S_THREADS, gs1, st>>>(L, tab, gd, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);

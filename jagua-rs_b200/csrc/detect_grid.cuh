@@ -304,8 +304,13 @@ __device__ __forceinline__ void g1_phase_a(const GCtx& c, G1Warp& w, int base, i
     __syncwarp();
 }
 
-// phase B on up to 32 queued queries; survivors go to the survivor list (FUSED: published in order)
-template <bool FILT, bool FUSED>
+// Surrogate piers on the grid (cd_engine.rs:216-221: after the poles, from the ROOT): defined next to path_reaches below.
+template <bool FILT>
+__device__ bool seg_collides_from_root(const GCtx& c, const Seg& sg);
+
+// phase B on up to 32 queued queries; survivors go to the survivor list (FUSED: published in order). PIERS: items whose
+// surrogate carries piers test them after the poles, lane = query (piers are few and off in the reference's defaults).
+template <bool FILT, bool FUSED, bool PIERS = false>
 __device__ __forceinline__ void g1_phase_b(const GCtx& c, G1Warp& w, int lane) {
     const int take = w.n_pend < 32 ? w.n_pend : 32;
     w.n_pend -= take;
@@ -408,6 +413,17 @@ __device__ __forceinline__ void g1_phase_b(const GCtx& c, G1Warp& w, int lane) {
         }
         __syncwarp();
     }
+    if (PIERS && valid && !hit) {
+        const SegDesc& sd = c.tab.seg[k];
+        for (int j = 0; j < sd.n_piers && !hit; j++) {  // edge.rs:126-144: both end points transformed
+            const float4 pr = __ldg(&sd.piers[j]);
+            Seg sg;
+            xf_point(xf, pr.x, pr.y, sg.sx, sg.sy);
+            xf_point(xf, pr.z, pr.w, sg.ex, sg.ey);
+            hit = seg_collides_from_root<FILT>(c, sg);
+        }
+    }
+    __syncwarp();
     if (valid) c.out[q] = hit ? (uint8_t)JG_VERDICT_SURROGATE : (uint8_t)0;
     const unsigned sm = __ballot_sync(FULL, valid && !hit);
     if (sm) {
@@ -424,13 +440,13 @@ __device__ __forceinline__ void g1_phase_b(const GCtx& c, G1Warp& w, int lane) {
     __syncwarp();
 }
 
-template <bool FILT>
 #ifndef G1_MIN_BLOCKS
 #define G1_MIN_BLOCKS 4
 #endif
 #ifndef G2_MIN_BLOCKS
 #define G2_MIN_BLOCKS 4
 #endif
+template <bool FILT, bool PIERS = false>
 __global__ void __launch_bounds__(S_THREADS, G1_MIN_BLOCKS)
 k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
           const XfSrc xforms, const uint32_t* __restrict__ filt, uint8_t* __restrict__ out,
@@ -461,7 +477,7 @@ k_s1_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
             continue;
         }
         if (w.n_pend == 0) break;
-        g1_phase_b<FILT, false>(c, w, lane);
+        g1_phase_b<FILT, false, PIERS>(c, w, lane);
     }
 }
 
@@ -583,6 +599,36 @@ __device__ __forceinline__ bool path_reaches(const GridDev& g, const Seg& sg, in
         if (!((mask >> qd) & 1u)) return false;
     }
     return true;
+}
+
+// QTNode::collides (qt_node.rs:99-147) for an edge entity from the root, on the grid: the candidate cells of the edge's
+// window, would-be hits (Entire cells, leaf cells whose edge tests succeed) verified against the reference's descent - the
+// scheme of stage 2 (section 4.1 of DESIGN.md) with the root as the starting node. One lane, one edge.
+template <bool FILT>
+__device__ bool seg_collides_from_root(const GCtx& c, const Seg& sg) {
+    const GridDev& g = c.g;
+    const int G = g.G;
+    // the superset argument scales with the coordinates involved (a pier may stick out of the CDE's box)
+    const float amax = fmaxf(fmaxf(fabsf(sg.sx), fabsf(sg.ex)), fmaxf(fabsf(sg.sy), fabsf(sg.ey)));
+    const float delta = fmaxf(g.delta, amax * (1.0f / 8192.0f));
+    const int i0 = cell_lo(g.xs, G, fminf(sg.sx, sg.ex) - delta, g.x0, g.inv_cw);
+    const int i1 = cell_hi(g.xs, G, fmaxf(sg.sx, sg.ex) + delta, g.x0, g.inv_cw);
+    const int j0 = cell_lo(g.ys, G, fminf(sg.sy, sg.ey) - delta, g.y0, g.inv_ch);
+    const int j1 = cell_hi(g.ys, G, fmaxf(sg.sy, sg.ey) + delta, g.y0, g.inv_ch);
+    const uint32_t cm = col_mask(i0, i1);
+    for (int j = j0; j <= j1; j++) {
+        const uint32_t er = g.ent_rows[j] & cm;
+        uint32_t bits = er | (g.leaf_rows[j] & cm);
+        while (bits) {
+            const int i = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (!(((er >> i) & 1u) || leaf_cell_collides<Seg, FILT>(c.L, g.cell_leaf[j * GRID_G + i], sg, c.filt))) continue;
+            const Rect cb{g.xs[i], g.ys[j], g.xs[i + 1], g.ys[j + 1]};
+            if (rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) || path_reaches(g, sg, 0, g.cell_level[j * GRID_G + i], i, j))
+                return true;
+        }
+    }
+    return false;
 }
 
 // one group of `ng` survivors (ents[0 .. ng): survivor-list entries in global memory, or in the warp's own shared

@@ -520,9 +520,10 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
 def test_generated_piers_on_the_fail_fast_path(jg, orc, name):
     """Items whose surrogate carries piers generated by jg_item_generate_piers (fail_fast/piers.rs; n_ff_piers = 2):
     detect_surrogate_collision tests the poles, then the piers (cd_engine.rs:204-223), collect_surrogate_collisions
-    likewise (cd_engine.rs:296-310). Batches with piers are served by the quadtree-walk kernels. Verdict bytes and hazard
-    sets against the oracle; a query the pole-only surrogate reports colliding stays colliding, and piers move queries
-    from the polygon stage to the surrogate stage."""
+    likewise (cd_engine.rs:296-310). Detect batches with piers stay on the grid kernels (k_s1_grid<.., PIERS>: an edge
+    entity from the root), collect batches with piers use the walk kernel; the walk detect kernels are checked beside them.
+    Verdict bytes and hazard sets against the oracle; a query the pole-only surrogate reports colliding stays colliding,
+    and piers move queries from the polygon stage to the surrogate stage."""
     import dataclasses
 
     wl = jg.load_workload(name)
@@ -540,7 +541,16 @@ def test_generated_piers_on_the_fail_fast_path(jg, orc, name):
         for item_id in range(0, len(wlp.items), max(1, len(wlp.items) // 5)):
             t = jg.make_queries(wlp, item_id, 20000, seed=31)
             got, exp = cde.detect_batch(item_id, t), w.detect_batch(item_id, t)
+            assert cde.detect_path() == "grid"
             assert np.array_equal(got, exp), f"{name} item {item_id}: {(got != exp).sum()} mismatches"
+            fb = cde.filter_from_irrelevant_qzones(2)
+            cde.upload_filter(3, fb)
+            assert np.array_equal(cde.detect_batch(item_id, t, filter_id=3), w.detect_batch(item_id, t, filter_bits=fb))
+            cde.set_detect_path(True)
+            try:
+                assert np.array_equal(cde.detect_batch(item_id, t), exp)
+            finally:
+                cde.set_detect_path(False)
             plain = base_cde.detect_batch(item_id, t)
             assert not ((plain != 0) & (got == 0)).any() and not ((got == 2) & (plain == 1)).any()
             moved += int(((got == 1) & (plain == 2)).sum())

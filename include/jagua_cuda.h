@@ -197,7 +197,7 @@ int jg_engine_set_split_min(JgEngine* e, int64_t min_queries);
 int jg_set_dependent_launch(int on);
 int jg_dependent_launch(void);
 /* Which detect kernels serve the next layout uploads: JG_PATH_AUTO (grid kernels when the quadtree is at
- * most 5 deep - collect batches of items with surrogate piers excepted -, else the quadtree-walk kernels) or JG_PATH_WALK (always
+ * most 5 deep, else the quadtree-walk kernels) or JG_PATH_WALK (always
  * the walk kernels). Takes effect immediately for the current layout. Results do not depend on it. */
 #define JG_PATH_AUTO 0
 #define JG_PATH_WALK 1

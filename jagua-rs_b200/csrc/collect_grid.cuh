@@ -126,6 +126,9 @@ __device__ __forceinline__ unsigned containment_mask_warp(const DevLayout& L, co
     return res;
 }
 
+// PIERS: the pier stage is compiled in only for items that carry piers (the kernel is sensitive to its code size: with the
+// stage compiled in and unused, the shirts batch ran 8 % slower)
+template <bool PIERS>
 __global__ void __launch_bounds__(S_THREADS)
 k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ ggrid, const GridCollect* __restrict__ cg,
                const float4* __restrict__ xforms, int n, int mode, uint32_t* __restrict__ out_bits, int words, int* __restrict__ next) {
@@ -177,6 +180,44 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
                             const Rect tb{g.xs[ti], g.ys[tj], g.xs[ti + (1 << sh)], g.ys[tj + (1 << sh)]};
                             if (!circ_rect(c, tb)) continue;  // circle.rs:115-128: reached iff its own bbox passes
                             cg_terminal<Circ>(L, cg->cell_node[j * GRID_G + i], c, W.bits[s], [] { return true; });
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- surrogate piers from the root (cd_engine.rs:305-308), after the poles: lane = (query, pier), an edge entity
+            // whose walk starts at the root: the window is not clipped and the path is verified from level 0
+            const int n_pent = PIERS ? ng * it.n_piers : 0;
+            for (int e0 = 0; e0 < n_pent; e0 += 32) {
+                const int e = e0 + lane;
+                if (e < n_pent) {
+                    const int s = e / it.n_piers, pj = e - s * it.n_piers;
+                    const float4 t4 = W.xf[s];
+                    const Xf xf{t4.x, t4.y, t4.z, t4.w};
+                    const float4 pr = __ldg(&it.piers[pj]);
+                    Seg sg;
+                    xf_point(xf, pr.x, pr.y, sg.sx, sg.sy);
+                    xf_point(xf, pr.z, pr.w, sg.ex, sg.ey);
+                    uint32_t* bits = W.bits[s];
+                    const float amax = fmaxf(fmaxf(fabsf(sg.sx), fabsf(sg.ex)), fmaxf(fabsf(sg.sy), fabsf(sg.ey)));
+                    const float delta = fmaxf(g.delta, amax * (1.0f / 8192.0f));
+                    const int i0 = cell_lo(g.xs, G, fminf(sg.sx, sg.ex) - delta, g.x0, g.inv_cw);
+                    const int i1 = cell_hi(g.xs, G, fmaxf(sg.sx, sg.ex) + delta, g.x0, g.inv_cw);
+                    const int j0 = cell_lo(g.ys, G, fminf(sg.sy, sg.ey) - delta, g.y0, g.inv_ch);
+                    const int j1 = cell_hi(g.ys, G, fmaxf(sg.sy, sg.ey) + delta, g.y0, g.inv_ch);
+                    const uint32_t cm = col_mask(i0, i1);
+                    for (int j = j0; j <= j1; j++) {
+                        uint32_t rb = cm ? cg->rows[j] & cm & (cg->colfirst[j] | (1u << i0)) : 0u;
+                        if (j != j0) rb &= cg->rowfirst[j];
+                        while (rb) {
+                            const int i = __ffs(rb) - 1;
+                            rb &= rb - 1;
+                            cg_terminal<Seg>(L, cg->cell_node[j * GRID_G + i], sg, bits, [&] {
+                                const int lt = cg->cell_level[j * GRID_G + i], sh = D - lt;
+                                const int ti = (i >> sh) << sh, tj = (j >> sh) << sh;
+                                const Rect tb{g.xs[ti], g.ys[tj], g.xs[ti + (1 << sh)], g.ys[tj + (1 << sh)]};
+                                return rect_point(tb, sg.sx, sg.sy) || rect_point(tb, sg.ex, sg.ey) || path_reaches(g, sg, 0, lt, i, j);
+                            });
                         }
                     }
                 }

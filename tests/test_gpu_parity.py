@@ -520,8 +520,8 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
 def test_generated_piers_on_the_fail_fast_path(jg, orc, name):
     """Items whose surrogate carries piers generated by jg_item_generate_piers (fail_fast/piers.rs; n_ff_piers = 2):
     detect_surrogate_collision tests the poles, then the piers (cd_engine.rs:204-223), collect_surrogate_collisions
-    likewise (cd_engine.rs:296-310). Detect batches with piers stay on the grid kernels (k_s1_grid<.., PIERS>: an edge
-    entity from the root), collect batches with piers use the walk kernel; the walk detect kernels are checked beside them.
+    likewise (cd_engine.rs:296-310). Batches with piers stay on the grid kernels (k_s1_grid<.., PIERS> and the pier stage
+    of k_collect_grid: an edge entity from the root); the walk kernels are checked beside them.
     Verdict bytes and hazard sets against the oracle; a query the pole-only surrogate reports colliding stays colliding,
     and piers move queries from the polygon stage to the surrogate stage."""
     import dataclasses
@@ -549,6 +549,7 @@ def test_generated_piers_on_the_fail_fast_path(jg, orc, name):
             cde.set_detect_path(True)
             try:
                 assert np.array_equal(cde.detect_batch(item_id, t), exp)
+                assert np.array_equal(cde.collect_batch(item_id, t[:4000], words), w.collect_batch(item_id, t[:4000], words))
             finally:
                 cde.set_detect_path(False)
             plain = base_cde.detect_batch(item_id, t)

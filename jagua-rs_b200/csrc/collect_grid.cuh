@@ -60,15 +60,16 @@ __global__ void __launch_bounds__(1024) k_cgrid_build(const DevLayout L, const G
 }
 
 #define CG_MAX_WORDS 8
+#ifndef CG_GROUP
+#define CG_GROUP 16  // queries a warp resolves together: two poles per query fill the 32 lanes of the pole stage
+#endif
 struct CGSlots {  // per-warp state of the queries of the current group
-    float4 xf[S2_MAX_GROUP];
-    float4 bb[S2_MAX_GROUP];
-    int vnode[S2_MAX_GROUP];
-    int vcell[S2_MAX_GROUP];  // level << 16 | row << 8 | column of the virtual root at its level
-    int vterm[S2_MAX_GROUP];  // 1: the virtual root itself is the collect terminal of everything below it
-    int ebeg[S2_MAX_GROUP + 1];
-    int pad[3];
-    uint32_t bits[S2_MAX_GROUP][CG_MAX_WORDS];
+    float4 xf[CG_GROUP];
+    float4 bb[CG_GROUP];
+    int vnode[CG_GROUP];
+    int vcell[CG_GROUP];  // level << 16 | row << 8 | column of the virtual root at its level
+    int vterm[CG_GROUP];  // 1: the virtual root itself is the collect terminal of everything below it
+    uint32_t bits[CG_GROUP][CG_MAX_WORDS];
 };
 
 __device__ __forceinline__ bool cg_has(const uint32_t* bits, int slot) { return (((volatile const uint32_t*)bits)[slot >> 5] >> (slot & 31)) & 1u; }
@@ -138,10 +139,10 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     CGSlots& W = *(CGSlots*)(p + (size_t)warp * sizeof(CGSlots));
-    const int D = g.D, G = g.G, GS = S2_MAX_GROUP, V = it.n_verts;
-    const float inv_v = 1.0f / (float)V;  // f / V for f < 8 V without the integer division: (f + 0.5) / V is >= 0.5 / V away
+    const int D = g.D, G = g.G, GS = CG_GROUP, V = it.n_verts;
+    const float inv_v = 1.0f / (float)V;  // f / V for f < 16 V without the integer division: (f + 0.5) / V is >= 0.5 / V away
                                           // from an integer, far beyond the rounding of two f32 operations on values < 2^17
-    const int qs = lane >> 2, sub = lane & 3;
+    const int quad = lane >> 2, sub = lane & 3;
 
     for (;;) {
         int qbase = 0;
@@ -225,8 +226,9 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
             __syncwarp();
         }
 
-        // ---- polygon: bbox (quad = query), Exterior rule, virtual root
-        {
+        // ---- polygon: bbox (quad = query, eight queries per pass), Exterior rule, virtual root
+        for (int half = 0; half < ng; half += 8) {
+            const int qs = half + quad;
             float x0 = 3.402823466e+38f, y0 = 3.402823466e+38f, x1 = -3.402823466e+38f, y1 = -3.402823466e+38f;
             if (qs < ng) {
                 const float4 t4 = W.xf[qs];
@@ -262,7 +264,7 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
                 }
                 const unsigned all = __ballot_sync(FULL, sur);
                 if (!all) break;
-                const unsigned mine = (all >> (qs * 4)) & 0xFu;
+                const unsigned mine = (all >> (quad * 4)) & 0xFu;
                 if (mine) {
                     const int found = __ffs(mine) - 1;
                     ci = 2 * ci + ((found == 0 || found == 3) ? 1 : 0);
@@ -279,8 +281,6 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
                 const int sh = D - level;
                 W.vterm[qs] = cg->cell_level[(cj << sh) * GRID_G + (ci << sh)] <= level ? 1 : 0;
             }
-            if (lane < GS) W.ebeg[lane + 1] = (lane < ng ? lane + 1 : ng) * V;
-            if (lane == 0) W.ebeg[0] = 0;
         }
         __syncwarp();
 

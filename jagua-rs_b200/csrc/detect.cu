@@ -792,13 +792,13 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
 
 // collect on the grid (k_collect_grid); d_kinds = the NoFilter summary buffer, d_next = a zeroed device int
 bool collect_grid_applicable(const DetectPlan& plan, const DevItem& it, int words) {
-    return plan.use_grid && words <= CG_MAX_WORDS && it.n_poles * S2_MAX_GROUP <= 4096 && it.n_piers * S2_MAX_GROUP <= 4096;
+    return plan.use_grid && words <= CG_MAX_WORDS && it.n_poles * CG_GROUP <= 4096 && it.n_piers * CG_GROUP <= 4096;
 }
 cudaError_t launch_collect_grid(const DevLayout& L, const DevItem& it, const uint8_t* d_kinds, const float4* d_xf, long long n, int mode,
                                 uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st, int* n_launches) {
     cudaMemsetAsync(d_next, 0, sizeof(int), st);
     const size_t smem = ((sizeof(GridDev) + 15) & ~(size_t)15) + S_WARPS * sizeof(CGSlots);
-    const long long want = (n + S_WARPS * S2_MAX_GROUP - 1) / (S_WARPS * S2_MAX_GROUP);
+    const long long want = (n + S_WARPS * CG_GROUP - 1) / (S_WARPS * CG_GROUP);
     if (it.n_piers > 0) {
         const int g = persistent_grid(k_collect_grid<true>, 11, n_sms, smem);
         k_collect_grid<true><<<(int)(want < g ? want : g), S_THREADS, smem, st>>>(L, it, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes),

@@ -139,7 +139,11 @@ k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ 
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     CGSlots& W = *(CGSlots*)(p + (size_t)warp * sizeof(CGSlots));
-    const int D = g.D, G = g.G, GS = CG_GROUP, V = it.n_verts;
+    const int D = g.D, G = g.G, V = it.n_verts;
+    // queries per group: 16 when every warp has several groups to do (best lane use); fewer for small launches, where the
+    // length of a warp's dependent chain through one group, not the issue rate, sets the kernel's duration
+    const int per_warp = n / (int)(gridDim.x * S_WARPS * CG_GROUP);
+    const int GS = per_warp >= 4 ? CG_GROUP : per_warp >= 1 ? CG_GROUP / 2 : CG_GROUP / 4;
     const float inv_v = 1.0f / (float)V;  // f / V for f < 16 V without the integer division: (f + 0.5) / V is >= 0.5 / V away
                                           // from an integer, far beyond the rounding of two f32 operations on values < 2^17
     const int quad = lane >> 2, sub = lane & 3;

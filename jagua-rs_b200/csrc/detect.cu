@@ -798,7 +798,7 @@ cudaError_t launch_collect_grid(const DevLayout& L, const DevItem& it, const uin
                                 uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st, int* n_launches) {
     cudaMemsetAsync(d_next, 0, sizeof(int), st);
     const size_t smem = ((sizeof(GridDev) + 15) & ~(size_t)15) + S_WARPS * sizeof(CGSlots);
-    const long long want = (n + S_WARPS * CG_GROUP - 1) / (S_WARPS * CG_GROUP);
+    const long long want = (n + S_WARPS * (CG_GROUP / 4) - 1) / (S_WARPS * (CG_GROUP / 4));  // (small launches use groups of 4)
     if (it.n_piers > 0) {
         const int g = persistent_grid(k_collect_grid<true>, 11, n_sms, smem);
         k_collect_grid<true><<<(int)(want < g ? want : g), S_THREADS, smem, st>>>(L, it, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes),

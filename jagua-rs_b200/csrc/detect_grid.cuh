@@ -441,7 +441,7 @@ __device__ __forceinline__ void g1_phase_b(const GCtx& c, G1Warp& w, int lane) {
 }
 
 #ifndef G1_MIN_BLOCKS
-#define G1_MIN_BLOCKS 4
+#define G1_MIN_BLOCKS 5  // 48 registers: 40 resident warps per SM for the latency-bound stage 1 (4 CTAs: 214 us per 1M queries, 5: 212, 6: 226)
 #endif
 #ifndef G2_MIN_BLOCKS
 #define G2_MIN_BLOCKS 4

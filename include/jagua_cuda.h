@@ -188,7 +188,7 @@ int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams);
  * stage-2 and collect kernels. A tuning knob; results do not depend on it. */
 int jg_engine_set_groups(JgEngine* e, int detect_group, int collect_group);
 /* Launches of at least min_queries queries run detect_containment_collision (cd_engine.rs:231-255) in a kernel of its
- * own after the edge tests (default 2^21; 0 = always, a huge value = never). Results do not depend on it. */
+ * own after the edge tests (default 1.5 * 2^20; 0 = always, a huge value = never). Results do not depend on it. */
 int jg_engine_set_split_min(JgEngine* e, int64_t min_queries);
 /* Stage 2 of the grid detect path as a programmatic dependent launch behind stage 1: its CTAs take the SM slots stage 1
  * frees while it drains, stage their tables and wait for stage 1's completion on the device (griddepcontrol.wait).

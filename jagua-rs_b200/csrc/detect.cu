@@ -39,7 +39,7 @@ namespace jg {
 #define LEAF_CAP 160  // a leaf step runs as soon as 32 pairs wait; one inner step adds at most 128
 #define FULL 0xFFFFFFFFu
 #define S2_MAX_GROUP 8
-#define JG_SPLIT_MIN_QUERIES (1 << 21)  // launches from this size on run the containment tests in k_s2_contain
+#define JG_SPLIT_MIN_QUERIES (3 << 19)  // launches from this size on (1.5 M; tools/split_probe.py) run the containment tests in k_s2_contain
 
 enum : int { KIND_NONE = 0, KIND_INNER = 1, KIND_ENTIRE = 2, KIND_LEAF = 3 };
 enum : int { CH_DEAD = 0, CH_HIT = 1, CH_LEAF = 2, CH_INNER = 3 };
@@ -706,7 +706,7 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
             k_s1_grid<false><<<want1 < g ? want1 : g, S_THREADS, gs1, st>>>(L, tab, gd, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
         }
         // Large launches hand the containment tests to their own kernel (k_s2_contain): stage 2 is bound by instruction
-        // fetch and runs 17 % faster without that code, which pays for the third launch (~25 us) from ~2 M queries on
+        // fetch and runs 17 % faster without that code, which pays for the third launch (a dependent launch) from ~1.5 M queries on
         // (4 M queries: 706 -> 670 us); smaller launches keep the containment tests inline.
         const bool split = (long long)n >= plan.split_min && sc.ct_meta != nullptr;
         const size_t gs3 = ((sizeof(SegTable) + 15) & ~(size_t)15) + 16;

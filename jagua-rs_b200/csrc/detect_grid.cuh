@@ -899,7 +899,9 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
 }
 
 template <bool FILT, bool SPLIT>
-__global__ void __launch_bounds__(S_THREADS, G2_MIN_BLOCKS)
+// (the split variant, without the containment code, gains from a fifth CTA per SM at 48 registers - 4M queries 646 -> 637 us;
+// the inline variant loses: 1M queries 212 -> 222 us)
+__global__ void __launch_bounds__(S_THREADS, SPLIT ? G2_MIN_BLOCKS + 1 : G2_MIN_BLOCKS)
 k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
           const uint8_t* __restrict__ g_kinds, const XfSrc xforms, const uint32_t* __restrict__ filt,
           uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry,

@@ -943,8 +943,11 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
 // survivor is an OR over its hazards, so the order is free.
 // ---------------------------------------------------------------------------------------------------
 #define CT_GROUP 8
+#ifndef CT_MIN_BLOCKS
+#define CT_MIN_BLOCKS 4
+#endif
 template <bool FILT>
-__global__ void __launch_bounds__(S_THREADS)
+__global__ void __launch_bounds__(S_THREADS, CT_MIN_BLOCKS)
 k_s2_contain(const DevLayout L, const __grid_constant__ SegTable gtab, const uint32_t* __restrict__ filt,
              uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, const int4* __restrict__ ct_meta,
              const float4* __restrict__ ct_bb, const float4* __restrict__ ct_xf) {

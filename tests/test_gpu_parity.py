@@ -516,6 +516,22 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
         cde.set_split_min(3 << 19)
 
 
+@pytest.mark.parametrize("n", [3000, 200_000, 1_300_000])
+def test_collect_group_sizes_match_oracle(jg, engines, n):
+    """k_collect_grid resolves 4, 8 or 16 queries per warp group depending on the launch size (small launches are bound by
+    a warp's chain through one group): the three regimes against the oracle, on the layout with the most hazards."""
+    import os
+
+    wl, cde, w = engines("shirts_full")
+    words = cde.collector_words()
+    item_id = len(wl.items) - 1
+    t = jg.make_queries(wl, item_id, n, seed=123)
+    got = cde.collect_batch(item_id, t, words)
+    exp = w.collect_batch(item_id, t, words, nthreads=min(16, os.cpu_count() or 1))
+    bad = np.nonzero((got != exp).any(axis=1))[0]
+    assert len(bad) == 0, f"n={n}: {len(bad)} hazard-set mismatches, first {bad[:3]}"
+
+
 @pytest.mark.parametrize("name", ["swim_half", "trousers_full"])
 def test_generated_piers_on_the_fail_fast_path(jg, orc, name):
     """Items whose surrogate carries piers generated by jg_item_generate_piers (fail_fast/piers.rs; n_ff_piers = 2):

@@ -1,6 +1,14 @@
-import os, sys, dataclasses
+"""Detect throughput with two generated piers per item (fail_fast/piers.rs) on the grid and on the walk kernels.
+
+    python tools/pier_probe.py
+"""
+import dataclasses
+import os
+import sys
+
 import numpy as np
-sys.path.insert(0, "/root/repo")
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import jagua_rs_b200 as jg
 wl = jg.load_workload("swim_half")
 items = [dataclasses.replace(it, piers=jg.generate_piers(it.verts, it.poles[:wl.n_ff_poles], 2, 24, 10, 24)) for it in wl.items]

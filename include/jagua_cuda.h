@@ -79,6 +79,25 @@ int jg_layout_upload(JgEngine* e, const void* blob, size_t bytes, uint64_t epoch
 int jg_layout_upload_device(JgEngine* e, const void* d_blob, size_t bytes, uint64_t epoch);
 uint64_t jg_engine_layout_epoch(const JgEngine* e);
 
+/* Layout updates over NCCL (BASELINE north_star: "the layout is small, so it is replicated on every GPU ... NCCL over
+ * NVLink is used only to broadcast layout updates"): one engine per rank (process or thread), jg_nccl_unique_id on one
+ * rank, the 128 id bytes handed to every rank by whatever the host has (torch.distributed, MPI, a pipe),
+ * jg_engine_comm_init on every rank. max_blob_bytes is the capacity of the exchange buffer (0: 1 MiB); every update
+ * broadcasts exactly that many bytes, because receivers learn a blob's size only from its header. NCCL is loaded at run
+ * time (dlopen "libnccl.so.2": the copy a process already holds - torch's - is shared); engines that never call
+ * jg_engine_comm_init do not need it.
+ * jg_layout_broadcast is a collective: every rank calls it, in the same order. The root passes the flattened layout (host
+ * pointer) and gets it by the ordinary stream-ordered upload; the other ranks pass blob = NULL, wait ONCE for the
+ * arrival (the header and the device-side structural check come back together) and bind the blob from device memory.
+ * Replaces what Layout::place_item / remove_item / restore do to the CDE (entities/layout.rs:52-100) on the other GPUs.
+ * Queries in flight on any rank finish on the old layout. jg_cde_broadcast = flatten on the root + jg_layout_broadcast
+ * (c may be NULL on the other ranks). */
+int jg_nccl_unique_id(uint8_t id[128]);
+int jg_engine_comm_init(JgEngine* e, const uint8_t id[128], int rank, int world, size_t max_blob_bytes);
+int jg_engine_comm_destroy(JgEngine* e);
+int jg_layout_broadcast(JgEngine* e, int root, const void* blob, size_t bytes, uint64_t epoch);
+int jg_cde_broadcast(JgCde* c, JgEngine* e, int root, uint64_t* epoch);
+
 /* An item's collision shape: SPolygon.vertices (x,y pairs, CCW, already centred), SPolygon.poi
  * centre (simple_polygon.rs:24-37), SPSurrogate.poles (x,y,r) and piers (sx,sy,ex,ey)
  * (sp_surrogate.rs:17-30). The first min(n_ff_poles, n_poles) poles and all piers are tested. */
@@ -86,8 +105,16 @@ int jg_item_upload(JgEngine* e, int item_id, const float* verts_xy, int n_verts,
                    const float* poles_xyr, int n_poles, const float* piers, int n_piers);
 
 /* HazardFilter (hazards/filter.rs:7-76) as a bitset over hazard slot indices: bit set = the hazard
- * is irrelevant. NoFilter = filter_id -1 in the query calls. */
+ * is irrelevant. NoFilter = filter_id -1 in the query calls. A collector used as a filter (the blanket impl,
+ * filter.rs:67-76) is its bitset uploaded here. A slot bitset does not carry HazKey versions: the hazard SlotMap
+ * reuses slots (LIFO), so a bitset filter describes ONE layout - after any register / deregister upload it again,
+ * or use jg_filter_upload_keys, which the engine re-derives against every layout it receives. */
 int jg_filter_upload(JgEngine* e, int filter_id, const uint32_t* bits, int words);
+/* HazKeyFilter (hazards/filter.rs:12-58) by versioned keys (slot index | version << 32, as jg_cde_register_hazard returns
+ * them): a key matches a slot only while that slot still holds that version, exactly like the reference's SecondaryMap
+ * lookup - a stale key never hides the hazard that reuses its slot. The bitset is rebuilt from the keys against the slot
+ * versions of every layout upload (layout blob section haz_version). n_keys may be 0 (an empty filter). */
+int jg_filter_upload_keys(JgEngine* e, int filter_id, const uint64_t* hkeys, int n_keys);
 
 /* detect_surrogate_collision + detect_poly_collision for n transformations of one item.
  * transforms: n x (cos, sin, tx, ty) — the meaningful entries of `Transformation`
@@ -124,6 +151,21 @@ int jg_detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const in
 int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int filter_id,
                            int mode, uint8_t* d_out);
 
+/* Lattice query form for samplers that draw translations from a regular lattice over their sampling box (a
+ * UniformRectSampler, lbf/src/samplers/uniform_rect_sampler.rs:18-45, quantised to 65536 steps per axis): a query is
+ * (index of the rotation: 1 byte, lattice coordinates i, j: 2 x u16) = 5 B instead of 16 B over PCIe. Its translation is
+ * tx = x0 + (float)i * dx, ty = y0 + (float)j * dy, every product and sum rounded once in f32 (no FMA) - jg_lattice_points
+ * is the host twin, so caller and device agree on the transformation bit for bit, and verdicts equal jg_detect_multi on
+ * the composed (cos, sin, tx, ty) records. Items need jg_item_set_rotations. */
+typedef struct JgLattice {
+    float x0, y0, dx, dy;
+} JgLattice;
+int jg_detect_multi_lattice(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const JgLattice* lattice,
+                            const uint8_t* rot_idx, const uint16_t* ij, int filter_id, int mode, uint8_t* out);
+int jg_detect_multi_lattice_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const JgLattice* lattice,
+                                  const uint8_t* rot_idx, const uint16_t* ij, int filter_id, int mode, uint8_t* out);
+void jg_lattice_points(const JgLattice* lattice, const uint16_t* ij, int64_t n, float* txy);
+
 /* collect_surrogate_collisions + collect_poly_collisions into one collector per query
  * (cd_engine.rs:261-310; lbf/benches/ci_bench.rs:56-70). out_bits: n x words u32, bit = hazard slot
  * index (an order-normalised BasicHazardCollector). words*32 must cover the layout's slot capacity. */
@@ -133,6 +175,16 @@ int jg_collect_batch_async(JgEngine* e, int item_id, const float* transforms, in
                            uint32_t* out_bits, int words);
 int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int mode,
                             uint32_t* d_out_bits, int words);
+/* Multi-item collect batch (segments as in jg_detect_multi): ONE launch resolves all segments. seed_bits (n x words, or
+ * NULL for empty collectors) pre-seeds every query's collector: hazards already in a collector are skipped by the
+ * traversal (`collector.contains_key`, qt_node.rs:172; cd_engine.rs:279) and stay in the result, which is the reference's
+ * behaviour for a collector that is passed in non-empty. seed_bits may alias out_bits (in place). */
+int jg_collect_multi(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int mode,
+                     const uint32_t* seed_bits, uint32_t* out_bits, int words);
+int jg_collect_multi_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int mode,
+                           const uint32_t* seed_bits, uint32_t* out_bits, int words);
+int jg_collect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* d_transforms,
+                            int mode, const uint32_t* d_seed_bits, uint32_t* d_out_bits, int words);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Batched placement search rounds                                                             */
@@ -212,6 +264,9 @@ int jg_engine_detect_path(const JgEngine* e);
 
 /* Memory helpers (pinned host / device) so callers can keep the C ABI free of CUDA headers. */
 int jg_host_alloc(size_t bytes, void** out);
+/* write-combined pinned memory (cudaHostAllocWriteCombined): for buffers the host only writes and the device only reads
+ * (query records); not snooped on the way over PCIe. Reading it from the host is slow. */
+int jg_host_alloc_wc(size_t bytes, void** out);
 int jg_host_free(void* p);
 int jg_device_alloc(JgEngine* e, size_t bytes, void** out);
 int jg_device_free(JgEngine* e, void* p);
@@ -302,6 +357,47 @@ int jg_shape_offset(const float* pts_xy, int n_pts, int mode, float distance, fl
 int jg_shape_import(const float* pts_xy, int n_pts, float* verts_xy, int* n_verts, float poi_xyr[3]);
 
 /* ------------------------------------------------------------------------------------------ */
+/* In-process multi-device pool                                                                */
+/* ------------------------------------------------------------------------------------------ */
+
+/* One engine per CUDA device of this process (BASELINE north_star: "the query batch shards across
+ * the GPUs of one box ... results are gathered on the host"). Layout, items and filters are REPLICATED on every device;
+ * a host batch is cut into contiguous shards [g n/G, (g+1) n/G), device g copies its shard in, resolves it and copies the
+ * results into ITS slice of the caller's one result array; there is no collective on the query path. One host thread per
+ * device does that device's enqueueing. Batches smaller than min_shard queries per device use fewer devices. The *_async
+ * forms return at once (segment tables are copied; `transforms` / `out` must stay valid - pinned - until jg_pool_sync). */
+typedef struct JgPool JgPool;
+int jg_pool_create(const int* devices, int n_devices, const JgConfig* cfg, JgPool** out);
+void jg_pool_destroy(JgPool* p);
+int jg_pool_size(const JgPool* p);
+JgEngine* jg_pool_engine(JgPool* p, int k); /* the engine of the k-th device: knobs, stats, jg_layout_broadcast */
+const char* jg_pool_last_error(const JgPool* p);
+int jg_pool_set_min_shard(JgPool* p, int64_t min_queries_per_device);
+int jg_pool_item_upload(JgPool* p, int item_id, const float* verts_xy, int n_verts, const float* poi_xy, const float* poles_xyr,
+                        int n_poles, const float* piers, int n_piers);
+int jg_pool_item_set_rotations(JgPool* p, int item_id, const float* rot_cos_sin, int n_rot);
+int jg_pool_filter_upload(JgPool* p, int filter_id, const uint32_t* bits, int words);
+int jg_pool_layout_upload(JgPool* p, const void* blob, size_t bytes, uint64_t epoch);
+int jg_pool_cde_sync(JgCde* c, JgPool* p, uint64_t* epoch); /* flatten once, replicate */
+int jg_pool_detect_multi(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int filter_id,
+                         int mode, uint8_t* out);
+int jg_pool_detect_multi_async(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
+                               int filter_id, int mode, uint8_t* out);
+int jg_pool_detect_multi_indexed(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const uint8_t* rot_idx,
+                                 const float* txy, int filter_id, int mode, uint8_t* out);
+int jg_pool_detect_multi_indexed_async(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const uint8_t* rot_idx,
+                                       const float* txy, int filter_id, int mode, uint8_t* out);
+int jg_pool_detect_multi_lattice(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const JgLattice* lattice,
+                                 const uint8_t* rot_idx, const uint16_t* ij, int filter_id, int mode, uint8_t* out);
+int jg_pool_detect_multi_lattice_async(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const JgLattice* lattice,
+                                       const uint8_t* rot_idx, const uint16_t* ij, int filter_id, int mode, uint8_t* out);
+int jg_pool_collect_multi(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int mode,
+                          const uint32_t* seed_bits, uint32_t* out_bits, int words);
+int jg_pool_collect_multi_async(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int mode,
+                                const uint32_t* seed_bits, uint32_t* out_bits, int words);
+int jg_pool_sync(JgPool* p);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Host mirror of CDEngine's update path                                                       */
 /* ------------------------------------------------------------------------------------------ */
 
@@ -326,6 +422,17 @@ int jg_cde_place_item(JgCde* c, int64_t item_id, uint64_t pk, const float* item_
 int jg_cde_remove_item(JgCde* c, uint64_t pk);
 /* CDEngine::deregister_hazard_by_key (cd_engine.rs:87-96) */
 int jg_cde_deregister_hazard(JgCde* c, uint64_t hkey);
+/* CDEngine::deregister_hazard_by_entity (cd_engine.rs:72-85): the hazard whose HazardEntity equals (kind, id, quality,
+ * pk); JG_ERR_INVALID when there is none (the reference panics: "Cannot deregister hazard that is not registered") */
+int jg_cde_deregister_hazard_by_entity(JgCde* c, int kind, int64_t id, int64_t quality, uint64_t pk);
+/* Layout::swap_container (entities/layout.rs:40-50): `base` plays Container::base_cde of the new container (its bbox,
+ * config and static hazards); *c becomes a clone of it with every DYNAMIC hazard of the old *c re-registered in the
+ * order of the old CDE's snapshot (cd_engine.rs:98-106: slot order). Snapshots taken before the swap are dropped. */
+int jg_cde_swap_container(JgCde* c, const JgCde* base);
+/* CDEngine::clone (what Layout::new does with Container::base_cde, entities/layout.rs:24-31) */
+int jg_cde_clone(const JgCde* c, JgCde** out);
+/* counts register / deregister calls: the epoch jg_cde_sync_to_engine stamps on the upload */
+uint64_t jg_cde_epoch(const JgCde* c);
 /* CDEngine::haz_key_from_pi_key (cd_engine.rs:333-341); *hkey = 0 when absent */
 int jg_cde_hkey_from_pk(const JgCde* c, uint64_t pk, uint64_t* hkey);
 /* CDEngine::save / restore (cd_engine.rs:98-149); snapshots are owned by the JgCde */

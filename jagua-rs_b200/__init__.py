@@ -54,8 +54,45 @@ C_ABI = {
     "jg_layout_upload": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64]),
     "jg_layout_upload_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64]),
     "jg_engine_layout_epoch": (C.c_uint64, [_vp]),
+    "jg_nccl_unique_id": (C.c_int, [_u8p]),
+    "jg_engine_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int, C.c_size_t]),
+    "jg_engine_comm_destroy": (C.c_int, [_vp]),
+    "jg_layout_broadcast": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.c_uint64]),
+    "jg_cde_broadcast": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_uint64)]),
     "jg_item_upload": (C.c_int, [_vp, C.c_int, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int]),
     "jg_filter_upload": (C.c_int, [_vp, C.c_int, _u32p, C.c_int]),
+    "jg_filter_upload_keys": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
+    "jg_detect_multi_lattice": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_detect_multi_lattice_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_lattice_points": (None, [_vp, _vp, C.c_int64, _vp]),
+    "jg_collect_multi": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int]),
+    "jg_collect_multi_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int]),
+    "jg_collect_multi_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int]),
+    "jg_host_alloc_wc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "jg_cde_deregister_hazard_by_entity": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64]),
+    "jg_cde_swap_container": (C.c_int, [_vp, _vp]),
+    "jg_cde_clone": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "jg_cde_epoch": (C.c_uint64, [_vp]),
+    "jg_pool_create": (C.c_int, [_vp, C.c_int, C.POINTER(JgConfig), C.POINTER(_vp)]),
+    "jg_pool_destroy": (None, [_vp]),
+    "jg_pool_size": (C.c_int, [_vp]),
+    "jg_pool_engine": (_vp, [_vp, C.c_int]),
+    "jg_pool_last_error": (C.c_char_p, [_vp]),
+    "jg_pool_set_min_shard": (C.c_int, [_vp, C.c_int64]),
+    "jg_pool_item_upload": (C.c_int, [_vp, C.c_int, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int]),
+    "jg_pool_item_set_rotations": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
+    "jg_pool_filter_upload": (C.c_int, [_vp, C.c_int, _u32p, C.c_int]),
+    "jg_pool_layout_upload": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64]),
+    "jg_pool_cde_sync": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
+    "jg_pool_detect_multi": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_pool_detect_multi_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_pool_detect_multi_indexed": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_pool_detect_multi_indexed_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_pool_detect_multi_lattice": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_pool_detect_multi_lattice_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "jg_pool_collect_multi": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int]),
+    "jg_pool_collect_multi_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int]),
+    "jg_pool_sync": (C.c_int, [_vp]),
     "jg_detect_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "jg_detect_batch_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, C.c_int, _vp]),
     "jg_collect_batch_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
@@ -303,14 +340,34 @@ def import_shape(points):
     return verts[:nv.value].copy(), poi
 
 
-class PinnedBuffer:
-    """Page-locked host array (cudaHostAlloc) so that H2D/D2H copies overlap the kernels."""
+class JgLattice(C.Structure):
+    """Sampling lattice of the 5-byte query form: translation = (x0 + i * dx, y0 + j * dy), i, j in 0..65535."""
+    _fields_ = [("x0", C.c_float), ("y0", C.c_float), ("dx", C.c_float), ("dy", C.c_float)]
 
-    def __init__(self, shape, dtype):
+    @staticmethod
+    def over_box(box, steps: int = 65536) -> "JgLattice":
+        """`steps` points per axis over [x_min, x_max) x [y_min, y_max) (UniformRectSampler's box, quantised)."""
+        b = np.asarray(box, np.float32)
+        return JgLattice(float(b[0]), float(b[1]), float((b[2] - b[0]) / np.float32(steps)), float((b[3] - b[1]) / np.float32(steps)))
+
+
+def lattice_points(lattice: JgLattice, ij: np.ndarray) -> np.ndarray:
+    """The f32 translations the device derives from lattice coordinates (jg_lattice_points, the host twin)."""
+    ij = np.ascontiguousarray(ij, dtype=np.uint16).reshape(-1, 2)
+    out = np.empty((len(ij), 2), np.float32)
+    load_library().jg_lattice_points(C.addressof(lattice), ij.ctypes.data, len(ij), out.ctypes.data)
+    return out
+
+
+class PinnedBuffer:
+    """Page-locked host array (cudaHostAlloc) so that H2D/D2H copies overlap the kernels. write_combined=True: for
+    buffers the host only writes (query records)."""
+
+    def __init__(self, shape, dtype, write_combined: bool = False):
         self._lib = load_library()
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         p = _vp()
-        rc = self._lib.jg_host_alloc(max(self.nbytes, 1), C.byref(p))
+        rc = (self._lib.jg_host_alloc_wc if write_combined else self._lib.jg_host_alloc)(max(self.nbytes, 1), C.byref(p))
         if rc != JG_OK:
             raise JaguaCudaError(rc, "cudaHostAlloc failed (no GPU?)")
         self.ptr = p.value
@@ -417,9 +474,9 @@ class CDEngine:
         key = C.c_uint64(0)
         rc = self._lib.jg_cde_register_hazard(self._cde, int(kind), int(id), int(quality), int(pk), v, len(v),
                                               _f32(poi)[:2].copy(), 1 if dynamic else 0, C.byref(key))
+        self._dirty = True  # (also when the mirror reports a reference panic: the hazard is in the tree by then)
         if rc < 0:
             raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
-        self._dirty = True
         return int(key.value)
 
     def place_item(self, item_id: int, shape: "ItemShape", transform4, pk: int) -> int:
@@ -429,9 +486,9 @@ class CDEngine:
         key = C.c_uint64(0)
         rc = self._lib.jg_cde_place_item(self._cde, int(item_id), int(pk), v, len(v), _f32(shape.poi)[:2].copy(),
                                          _f32(transform4).reshape(4).copy(), C.byref(key))
+        self._dirty = True
         if rc < 0:
             raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
-        self._dirty = True
         return int(key.value)
 
     def remove_item(self, pk: int):
@@ -446,6 +503,24 @@ class CDEngine:
         if rc < 0:
             raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
         self._dirty = True
+
+    def deregister_hazard_by_entity(self, kind: int, *, id: int = 0, quality: int = 0, pk: int = 0):
+        """CDEngine::deregister_hazard_by_entity (cd_engine.rs:72-85)."""
+        rc = self._lib.jg_cde_deregister_hazard_by_entity(self._cde, int(kind), int(id), int(quality), int(pk))
+        if rc < 0:
+            raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
+        self._dirty = True
+
+    def swap_container(self, base: "CDEngine"):
+        """Layout::swap_container (entities/layout.rs:40-50): `base` is the new container's base CDE (bbox, config, static
+        hazards); this engine becomes a clone of it with its own dynamic hazards re-registered."""
+        rc = self._lib.jg_cde_swap_container(self._cde, base._cde)
+        self._dirty = True
+        if rc < 0:
+            raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
+
+    def epoch(self) -> int:
+        return int(self._lib.jg_cde_epoch(self._cde))
 
     def haz_key_from_pi_key(self, pk: int) -> Optional[int]:
         key = C.c_uint64(0)
@@ -519,6 +594,14 @@ class CDEngine:
         bits = np.ascontiguousarray(bits, dtype=np.uint32)
         self._chk(self._lib.jg_filter_upload(self._eng, int(filter_id), bits, len(bits)))
         self._filters[int(filter_id)] = len(bits)
+
+    def upload_filter_keys(self, filter_id: int, hkeys: Sequence[int]):
+        """HazKeyFilter by versioned HazKeys (jg_filter_upload_keys): survives layout changes - a key whose slot was freed
+        or reused matches nothing, as in the reference."""
+        self._need_engine()
+        k = np.ascontiguousarray(np.asarray(list(hkeys), dtype=np.uint64))
+        self._chk(self._lib.jg_filter_upload_keys(self._eng, int(filter_id), k.ctypes.data if len(k) else None, len(k)))
+        self._filters[int(filter_id)] = -1
 
     def sync_layout(self, force: bool = False) -> int:
         """Flatten the host quadtree and upload it if it changed since the last upload."""
@@ -604,6 +687,48 @@ class CDEngine:
         fn = self._lib.jg_detect_multi if wait else self._lib.jg_detect_multi_async
         self._chk(fn(self._eng, len(ids), ids.ctypes.data, offs.ctypes.data, t.ctypes.data, int(filter_id),
                      MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data))
+        return out
+
+    def collect_multi(self, item_ids, seg_offsets, transforms: np.ndarray, words: Optional[int] = None, poly_only: bool = False,
+                      seed: Optional[np.ndarray] = None, out: Optional[np.ndarray] = None, wait: bool = True) -> np.ndarray:
+        """collect for a batch of segments in ONE launch (jg_collect_multi). `seed` (n x words) pre-seeds the collectors:
+        hazards already present are skipped by the traversal and stay in the result (collector.contains_key)."""
+        self.sync_layout()
+        ids, offs = self._segments(item_ids, seg_offsets)
+        t = transforms if isinstance(transforms, np.ndarray) and transforms.dtype == np.float32 and transforms.flags.c_contiguous else _f32(transforms)
+        n = int(offs[-1])
+        assert t.size // 4 == n
+        words = int(words or self.collector_words())
+        if out is None:
+            out = np.empty((n, words), np.uint32)
+        if seed is not None:
+            seed = np.ascontiguousarray(seed, dtype=np.uint32)
+            assert seed.shape == (n, words)
+        fn = self._lib.jg_collect_multi if wait else self._lib.jg_collect_multi_async
+        self._chk(fn(self._eng, len(ids), ids.ctypes.data, offs.ctypes.data, t.ctypes.data, MODE_POLY_ONLY if poly_only else MODE_DEFAULT,
+                     seed.ctypes.data if seed is not None else None, out.ctypes.data, words))
+        return out
+
+    def collect_multi_device(self, item_ids, seg_offsets, d_transforms: int, d_out_bits: int, words: int, d_seed: int = 0,
+                             poly_only: bool = False):
+        self.sync_layout()
+        ids, offs = self._segments(item_ids, seg_offsets)
+        self._chk(self._lib.jg_collect_multi_device(self._eng, len(ids), ids.ctypes.data, offs.ctypes.data, int(d_transforms),
+                                                    MODE_POLY_ONLY if poly_only else MODE_DEFAULT, int(d_seed) or None, int(d_out_bits), int(words)))
+
+    def detect_multi_lattice(self, item_ids, seg_offsets, lattice: JgLattice, rot_idx: np.ndarray, ij: np.ndarray, filter_id: int = -1,
+                             poly_only: bool = False, out: Optional[np.ndarray] = None, wait: bool = True) -> np.ndarray:
+        """detect_multi with the queries as (rotation index u8, lattice coordinates 2 x u16) = 5 B/query."""
+        self.sync_layout()
+        ids, offs = self._segments(item_ids, seg_offsets)
+        assert rot_idx.dtype == np.uint8 and rot_idx.flags.c_contiguous and ij.dtype == np.uint16 and ij.flags.c_contiguous
+        assert rot_idx.size == int(offs[-1]) and ij.size == 2 * int(offs[-1])
+        if out is None:
+            out = np.empty(int(offs[-1]), np.uint8)
+        self._lat_keep = lattice
+        fn = self._lib.jg_detect_multi_lattice if wait else self._lib.jg_detect_multi_lattice_async
+        self._chk(fn(self._eng, len(ids), ids.ctypes.data, offs.ctypes.data, C.addressof(lattice), rot_idx.ctypes.data, ij.ctypes.data,
+                     int(filter_id), MODE_POLY_ONLY if poly_only else MODE_DEFAULT, out.ctypes.data))
         return out
 
     def set_item_rotations(self, item_id: int, rotations):
@@ -732,7 +857,9 @@ class CDEngine:
         self._chk(self._lib.jg_flush_l2(self._eng))
 
 
+from .pool import EnginePool  # noqa: E402
 from . import instance  # noqa: E402
 from . import export  # noqa: E402
 from . import workload  # noqa: E402
-from .workload import Workload, load_workload, build_engine, make_queries, make_queries_indexed, split_batch  # noqa: E402
+from .workload import (Workload, load_workload, build_engine, make_queries, make_queries_indexed, make_queries_lattice,  # noqa: E402
+                       compose_lattice_queries, split_batch)

@@ -251,6 +251,26 @@ uint64_t HostCDE::hkey_from_pk(uint64_t pk) const {  // cd_engine.rs:333-341
     return 0;
 }
 
+uint64_t HostCDE::hkey_from_entity(int kind, int64_t id, int64_t quality, uint64_t pk) const {  // cd_engine.rs:73-78: first match in slot order
+    HostHazard probe;
+    probe.kind = kind, probe.id = id, probe.quality = quality, probe.pk = pk;
+    for (uint32_t i = 0; i < slots_.size(); i++)
+        if (slots_[i].live && slots_[i].hz.same_entity(probe)) return make_key(i, slots_[i].version);
+    return 0;
+}
+
+void HostCDE::swap_container(const HostCDE& base) {  // entities/layout.rs:40-50
+    std::vector<HostHazard> dyn;  // self.cde.save(): dynamic hazards in slot order (cd_engine.rs:98-106)
+    for (const Slot& s : slots_)
+        if (s.live && s.hz.dynamic) dyn.push_back(s.hz);
+    const uint64_t ep = epoch;
+    *this = base;  // self.cde = container.base_cde.clone()
+    snapshots_.clear();
+    last_error.clear();
+    epoch = ep + 1;
+    for (HostHazard& h : dyn) register_hazard(std::move(h));
+}
+
 uint64_t HostCDE::hkey_exterior() const {  // cd_engine.rs:44-48: first Exterior in slot order
     for (uint32_t i = 0; i < slots_.size(); i++)
         if (slots_[i].live && slots_[i].hz.kind == JG_HAZ_EXTERIOR) return make_key(i, slots_[i].version);
@@ -412,6 +432,7 @@ std::vector<uint8_t> HostCDE::flatten() const {
     section(h.off_haz_bbox, n_slots * 16);
     section(h.off_haz_poi, n_slots * 16);
     section(h.off_haz_verts, n_haz_verts * 8);
+    section(h.off_haz_version, n_slots * 4);
     h.total_bytes = off;
 
     std::vector<uint8_t> blob(off, 0);
@@ -453,8 +474,10 @@ std::vector<uint8_t> HostCDE::flatten() const {
             ei++;
         }
     }
+    uint32_t* haz_version = (uint32_t*)(blob.data() + h.off_haz_version);
     uint32_t vi = 0;
     for (uint32_t s = 0; s < n_slots; s++) {
+        haz_version[s] = slots_[s].version;  // odd = occupied (slotmap); a dead slot keeps the even version it was freed with
         if (!slots_[s].live) continue;  // dead slot: vert_count 0
         const HostHazard& hz = slots_[s].hz;
         haz_meta[4 * s + 0] = hz.scope();

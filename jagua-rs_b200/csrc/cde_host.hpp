@@ -66,6 +66,9 @@ public:
 
     uint64_t register_hazard(HostHazard&& hz);
     bool deregister_hazard(uint64_t hkey);
+    uint64_t hkey_from_entity(int kind, int64_t id, int64_t quality, uint64_t pk) const;
+    // Layout::swap_container (entities/layout.rs:40-50): become a clone of `base` with this CDE's dynamic hazards re-registered
+    void swap_container(const HostCDE& base);
     uint64_t hkey_from_pk(uint64_t pk) const;
     int save();
     bool restore(int snapshot_id);

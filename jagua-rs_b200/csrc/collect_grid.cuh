@@ -134,31 +134,44 @@ __device__ __forceinline__ unsigned containment_mask_warp(const DevLayout& L, co
 #endif
 template <bool PIERS>
 __global__ void __launch_bounds__(S_THREADS, CG_MIN_BLOCKS)
-k_collect_grid(const DevLayout L, const DevItem it, const GridDev* __restrict__ ggrid, const GridCollect* __restrict__ cg,
-               const float4* __restrict__ xforms, int n, int mode, uint32_t* __restrict__ out_bits, int words, int* __restrict__ next) {
+k_collect_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid, const GridCollect* __restrict__ cg,
+               const float4* __restrict__ xforms, int mode, const uint32_t* __restrict__ seed_bits, uint32_t* __restrict__ out_bits, int words,
+               int* __restrict__ next, int GS, int n_groups) {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* p = smem;
+    SegTable* t = (SegTable*)smem;
+    for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
+    unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
     const GridDev& g = *stage_grid(p, ggrid);
     __syncthreads();
+    const SegTable& tab = *t;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     CGSlots& W = *(CGSlots*)(p + (size_t)warp * sizeof(CGSlots));
-    const int D = g.D, G = g.G, V = it.n_verts;
-    // queries per group: 16 when every warp has several groups to do (best lane use); fewer for small launches, where the
-    // length of a warp's dependent chain through one group, not the issue rate, sets the kernel's duration
-    const int per_warp = n / (int)(gridDim.x * S_WARPS * CG_GROUP);
-    const int GS = per_warp >= 4 ? CG_GROUP : per_warp >= 1 ? CG_GROUP / 2 : CG_GROUP / 4;
-    const float inv_v = 1.0f / (float)V;  // f / V for f < 16 V without the integer division: (f + 0.5) / V is >= 0.5 / V away
-                                          // from an integer, far beyond the rounding of two f32 operations on values < 2^17
+    const int D = g.D, G = g.G;
+    // GS = queries per group (chosen by the launcher): 16 when every warp has several groups to do (best lane use); fewer for
+    // small launches, where the length of a warp's dependent chain through one group, not the issue rate, sets the kernel's
+    // duration. A group never straddles two segments: segment k owns the groups [seg[k].gbeg, seg[k + 1].gbeg).
     const int quad = lane >> 2, sub = lane & 3;
+    int seg_hint = 0;
 
     for (;;) {
-        int qbase = 0;
-        if (lane == 0) qbase = atomicAdd(next, GS);
-        qbase = __shfl_sync(FULL, qbase, 0);
-        if (qbase >= n) break;
-        const int ng = (n - qbase) < GS ? (n - qbase) : GS;
+        int gi = 0;
+        if (lane == 0) gi = atomicAdd(next, 1);
+        gi = __shfl_sync(FULL, gi, 0);
+        if (gi >= n_groups) break;
+        while (seg_hint + 1 < tab.n_seg && gi >= tab.seg[seg_hint + 1].gbeg) seg_hint++;  // groups are claimed in increasing order
+        const SegDesc& it = tab.seg[seg_hint];
+        const int seg_end = seg_hint + 1 < tab.n_seg ? tab.seg[seg_hint + 1].begin : tab.n_queries;
+        const int qbase = it.begin + (gi - it.gbeg) * GS;
+        const int ng = (seg_end - qbase) < GS ? (seg_end - qbase) : GS;
+        const int V = it.n_verts;
+        const float inv_v = 1.0f / (float)V;  // f / V for f < 16 V without the integer division: (f + 0.5) / V is >= 0.5 / V away
+                                              // from an integer, far beyond the rounding of two f32 operations on values < 2^17
         if (lane < ng) W.xf[lane] = __ldg(&xforms[qbase + lane]);
-        for (int i = lane; i < GS * CG_MAX_WORDS; i += 32) (&W.bits[0][0])[i] = 0u;
+        // collectors start empty, or from the caller's seed: a hazard already present is skipped everywhere below and stays set
+        for (int i = lane; i < GS * CG_MAX_WORDS; i += 32) {
+            const int s = i / CG_MAX_WORDS, wd = i - s * CG_MAX_WORDS;
+            (&W.bits[0][0])[i] = (seed_bits && s < ng && wd < words) ? __ldg(&seed_bits[(size_t)(qbase + s) * words + wd]) : 0u;
+        }
         __syncwarp();
 
         // ---- surrogate poles from the root (cd_engine.rs:296-310); lane = (query, pole)

@@ -791,23 +791,37 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
 }
 
 // collect on the grid (k_collect_grid); d_kinds = the NoFilter summary buffer, d_next = a zeroed device int
-bool collect_grid_applicable(const DetectPlan& plan, const DevItem& it, int words) {
-    return plan.use_grid && words <= CG_MAX_WORDS && it.n_poles * CG_GROUP <= 4096 && it.n_piers * CG_GROUP <= 4096;
+bool collect_grid_applicable(const DetectPlan& plan, const SegTable& tab, int words) {
+    if (!plan.use_grid || words > CG_MAX_WORDS) return false;
+    for (int k = 0; k < tab.n_seg; k++)
+        if (tab.seg[k].n_poles * CG_GROUP > 4096 || tab.seg[k].n_piers * CG_GROUP > 4096) return false;
+    return true;
 }
-cudaError_t launch_collect_grid(const DevLayout& L, const DevItem& it, const uint8_t* d_kinds, const float4* d_xf, long long n, int mode,
-                                uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st, int* n_launches) {
+cudaError_t launch_collect_grid(const DevLayout& L, SegTable& tab, const uint8_t* d_kinds, const float4* d_xf, int mode,
+                                const uint32_t* d_seed, uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st,
+                                int* n_launches) {
     cudaMemsetAsync(d_next, 0, sizeof(int), st);
-    const size_t smem = ((sizeof(GridDev) + 15) & ~(size_t)15) + S_WARPS * sizeof(CGSlots);
-    const long long want = (n + S_WARPS * (CG_GROUP / 4) - 1) / (S_WARPS * (CG_GROUP / 4));  // (small launches use groups of 4)
-    if (it.n_piers > 0) {
-        const int g = persistent_grid(k_collect_grid<true>, 11, n_sms, smem);
-        k_collect_grid<true><<<(int)(want < g ? want : g), S_THREADS, smem, st>>>(L, it, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes),
-                                                                                  d_xf, (int)n, mode, d_out_bits, words, d_next);
-    } else {
-        const int g = persistent_grid(k_collect_grid<false>, 10, n_sms, smem);
-        k_collect_grid<false><<<(int)(want < g ? want : g), S_THREADS, smem, st>>>(L, it, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes),
-                                                                                   d_xf, (int)n, mode, d_out_bits, words, d_next);
+    const size_t smem = ((sizeof(SegTable) + 15) & ~(size_t)15) + ((sizeof(GridDev) + 15) & ~(size_t)15) + S_WARPS * sizeof(CGSlots);
+    bool piers = false;
+    for (int k = 0; k < tab.n_seg; k++) piers = piers || tab.seg[k].n_piers > 0;
+    const int g = piers ? persistent_grid(k_collect_grid<true>, 11, n_sms, smem) : persistent_grid(k_collect_grid<false>, 10, n_sms, smem);
+    // queries per group: 16 when every warp has several groups to do; 8 / 4 for small launches (see the kernel)
+    const long long per_warp = (long long)tab.n_queries / ((long long)g * S_WARPS * CG_GROUP);
+    const int GS = per_warp >= 4 ? CG_GROUP : per_warp >= 1 ? CG_GROUP / 2 : CG_GROUP / 4;
+    int n_groups = 0;
+    for (int k = 0; k < tab.n_seg; k++) {
+        const int len = (k + 1 < tab.n_seg ? tab.seg[k + 1].begin : tab.n_queries) - tab.seg[k].begin;
+        tab.seg[k].gbeg = n_groups;
+        n_groups += (len + GS - 1) / GS;
     }
+    const long long want = ((long long)n_groups + S_WARPS - 1) / S_WARPS;
+    const int blocks = (int)(want < g ? want : g);
+    if (piers)
+        k_collect_grid<true><<<blocks, S_THREADS, smem, st>>>(L, tab, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes), d_xf, mode, d_seed,
+                                                             d_out_bits, words, d_next, GS, n_groups);
+    else
+        k_collect_grid<false><<<blocks, S_THREADS, smem, st>>>(L, tab, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes), d_xf, mode, d_seed,
+                                                              d_out_bits, words, d_next, GS, n_groups);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

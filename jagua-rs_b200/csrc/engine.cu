@@ -40,6 +40,11 @@ struct FilterDev {
     uint8_t* kinds = nullptr;  // node summary under this filter (k_node_kinds), valid for kinds_version
     size_t kinds_cap = 0;
     uint64_t kinds_version = 0;
+    int grid_ok = 0;           // k_grid_build's verdict for this filter's summary (0: its batches take the walk kernels)
+    // jg_filter_upload_keys: versioned HazKeys; `bits` is re-derived from them for every layout (bits_version)
+    bool keyed = false;
+    std::vector<uint64_t> keys;
+    uint64_t bits_version = 0;
 };
 // One in-flight chunk of a host-pointer batch: its own stream and staging buffers.
 struct ChunkCtx {
@@ -84,6 +89,21 @@ struct JgEngine {
     bool has_layout = false;
     uint64_t epoch = 0;
     uint64_t layout_version = 0;  // bumped by every upload; per-filter node summaries are keyed on it
+    std::vector<uint32_t> slot_versions;  // SlotMap version per hazard slot of the current layout (blob section haz_version)
+    int* h_blob_bad = nullptr;    // pinned, [2]: k_blob_validate's count of violations in the last device-blob upload into each buffer
+    int* d_blob_bad = nullptr;
+    bool slot_versions_valid = false;
+    // layout broadcast over NCCL (jg_engine_comm_init / jg_layout_broadcast): communicator, its own stream, the fixed-capacity
+    // exchange buffer and the pinned read-back of {header, validation verdict}
+    void* nccl_comm = nullptr;
+    int comm_rank = -1, comm_world = 0;
+    cudaStream_t st_bc = nullptr;
+    void* d_bcast = nullptr;
+    size_t bcast_cap = 0;
+    void* h_bcast_stage = nullptr;  // pinned: root's copy of the blob on its way to d_bcast
+    JgLayoutHeader* h_bcast_hdr = nullptr;  // pinned: header of the received blob (+ one int: violations found by the device check)
+    cudaEvent_t ev_bc_consumed = nullptr;   // the last blob has been copied out of d_bcast
+    void* d_hdr_scratch = nullptr;          // device copy of the header k_bcast_check parsed
     DetectPlan plan{0, 0, 0, 0, 1 << 21};
     long long split_min = -1;  // jg_engine_set_split_min override (-1: the default of make_detect_plan)
     bool force_walk = false;  // jg_engine_set_detect_path: keep the quadtree-walk kernels even when the grid applies
@@ -212,17 +232,37 @@ static void free_ctx(ChunkCtx& c) {
     c = ChunkCtx{};
 }
 
-static DevItem dev_item(const JgEngine* e, const ItemDev& it) {
-    DevItem d;
-    d.verts = it.verts;
-    d.n_verts = it.n_verts;
-    d.poi_x = it.poi_x;
-    d.poi_y = it.poi_y;
-    d.poles = it.poles;
-    d.n_poles = it.n_poles < e->cfg.n_ff_poles ? it.n_poles : e->cfg.n_ff_poles;
-    d.piers = it.piers;
-    d.n_piers = it.n_piers;
-    return d;
+// Structural checks of a blob that arrived in device memory (jg_layout_upload_device, jg_layout_broadcast): the twin of the
+// host loop in upload_common. The kernels index with these fields unchecked, so a malformed blob must not be served.
+__global__ void k_blob_validate(const DevLayout L, int n_entries, int n_edges, int n_haz_verts, int* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool b = false;
+    if (i < L.n_nodes) {
+        const int4 m = L.node_meta[i];
+        const int n_ent = (m.z & 0xFFFF) + ((m.z >> 16) & 0xFFFF);
+        if (m.x >= 0 && ((m.x & 3) != 1 || m.x + 4 > L.n_nodes)) b = true;
+        if (m.y < 0 || m.y + n_ent > n_entries) b = true;
+        if (m.w >= L.n_nodes || (i > 0 && m.w < 0)) b = true;
+        const float4 r = L.node_bbox[i];
+        if (!(fabsf(r.x) < 1e30f && fabsf(r.y) < 1e30f && fabsf(r.z) < 1e30f && fabsf(r.w) < 1e30f && r.x <= r.z && r.y <= r.w)) b = true;
+    }
+    if (i < n_entries) {
+        const int4 em = L.entry_meta[i];
+        if (em.x < 0 || em.x >= L.n_slots || em.y < 0 || em.z < 0 || em.y + em.z > n_edges) b = true;
+    }
+    if (i < L.n_slots) {
+        const int4 hm = L.haz_meta[i];
+        if (hm.y < 0 || hm.z < 0 || hm.y + hm.z > n_haz_verts) b = true;
+    }
+    if (i == 0 && (L.exterior_slot < 0 || L.exterior_slot >= L.n_slots)) b = true;
+    if (b) atomicAdd(bad, 1);
+}
+static cudaError_t launch_blob_validate(const DevLayout& L, const JgLayoutHeader& h, int* d_bad, cudaStream_t st) {
+    cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    uint32_t n = h.n_nodes > h.n_entries ? h.n_nodes : h.n_entries;
+    if (h.n_slots > n) n = h.n_slots;
+    k_blob_validate<<<(n + 255) / 256, 256, 0, st>>>(L, (int)h.n_entries, (int)h.n_edges, (int)h.n_haz_verts, d_bad);
+    return cudaGetLastError();
 }
 
 extern "C" {
@@ -264,13 +304,19 @@ int jg_engine_create(int device, const JgConfig* cfg, JgEngine** out) {
     e->h_err = e->h_avail + JG_STREAM_MAX_CHUNKS;
     *e->h_err = 0;
     if (cudaStreamCreateWithFlags(&e->st_up, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaHostAlloc((void**)&e->h_grid_ok, 2 * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void**)&e->h_grid_ok, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->bufs[0].ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->bufs[1].ready, cudaEventDisableTiming) != cudaSuccess) {
         delete e;
         return JG_ERR_CUDA;
     }
     e->h_grid_ok[0] = e->h_grid_ok[1] = 0;
+    e->h_blob_bad = e->h_grid_ok + 2;
+    e->h_blob_bad[0] = e->h_blob_bad[1] = 0;
+    if (cudaMalloc((void**)&e->d_blob_bad, 2 * sizeof(int)) != cudaSuccess) {
+        delete e;
+        return JG_ERR_CUDA;
+    }
     e->chunks.resize(4);  // in-flight pieces of host batches (tools/pipeline_probe.py: 4 x 256 Ki is the best default)
     for (ChunkCtx& c : e->chunks)
         if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess) {
@@ -313,6 +359,9 @@ void jg_engine_destroy(JgEngine* e) {
     if (e->h_search) cudaFreeHost(e->h_search);
     if (e->st_up) cudaStreamDestroy(e->st_up);
     if (e->h_grid_ok) cudaFreeHost(e->h_grid_ok);
+    if (e->d_blob_bad) cudaFree(e->d_blob_bad);
+    jg_engine_comm_destroy(e);
+    if (e->d_hdr_scratch) cudaFree(e->d_hdr_scratch);
     for (ChunkCtx& c : e->chunks) {
         cudaStream_t st = c.st;
         free_ctx(c);
@@ -343,6 +392,7 @@ int jg_sync(JgEngine* e) {
             e->bufs[b].expect_grid = -1;
             if (e->h_grid_ok[b] != want) return fail(e, JG_ERR_INVALID, "layout upload: host and device disagree on the grid premise");
         }
+
     if (trace_on() && e->trace_used >= 5) {
         fprintf(stderr, "[jg trace] piece: queries | t(start) t(h2d done) t(kernels done) t(d2h done)  [us since first mark]\n");
         for (size_t i = 1; i + 3 < e->trace_used + 0 && (i - 1) / 4 < e->trace_m.size(); i += 4) {
@@ -377,40 +427,49 @@ static int validate_header(JgEngine* e, const JgLayoutHeader& h, size_t bytes) {
     } secs[] = {{h.off_node_meta, h.n_nodes, 16},  {h.off_node_bbox, h.n_nodes, 16},    {h.off_node_nactive, h.n_nodes, 4},
                 {h.off_entry_meta, h.n_entries, 16}, {h.off_entry_ffbbox, h.n_entries, 16}, {h.off_edges, h.n_edges, 16},
                 {h.off_haz_meta, h.n_slots, 16},   {h.off_haz_bbox, h.n_slots, 16},     {h.off_haz_poi, h.n_slots, 16},
-                {h.off_haz_verts, h.n_haz_verts, 8}};
+                {h.off_haz_verts, h.n_haz_verts, 8},  {h.off_haz_version, h.n_slots, 4}};
     for (auto& s : secs)
         if ((s.off & 15u) || (uint64_t)s.off + (uint64_t)s.n * s.sz > h.total_bytes)
             return fail(e, JG_ERR_INVALID, "layout blob: section out of bounds / misaligned");
     return JG_OK;
 }
 
+static DevLayout dev_layout_of(const void* d_blob, const JgLayoutHeader& h) {
+    const char* b = (const char*)d_blob;
+    DevLayout L;
+    L.node_meta = (const int4*)(b + h.off_node_meta);
+    L.node_bbox = (const float4*)(b + h.off_node_bbox);
+    L.node_nactive = (const uint32_t*)(b + h.off_node_nactive);
+    L.entry_meta = (const int4*)(b + h.off_entry_meta);
+    L.entry_ff = (const float4*)(b + h.off_entry_ffbbox);
+    L.edges = (const float4*)(b + h.off_edges);
+    L.haz_meta = (const int4*)(b + h.off_haz_meta);
+    L.haz_bbox = (const float4*)(b + h.off_haz_bbox);
+    L.haz_poi = (const float4*)(b + h.off_haz_poi);
+    L.haz_verts = (const float2*)(b + h.off_haz_verts);
+    L.cde_bbox = Rect{h.cde_bbox[0], h.cde_bbox[1], h.cde_bbox[2], h.cde_bbox[3]};
+    L.n_nodes = (int)h.n_nodes;
+    L.n_slots = (int)h.n_slots;
+    L.cd_threshold = (int)h.cd_threshold;
+    L.exterior_slot = (int)h.exterior_slot;
+    return L;
+}
 static void bind_layout(JgEngine* e, const JgLayoutHeader& h) {
-    const char* b = (const char*)e->d_blob;
     e->hdr = h;
-    e->L.node_meta = (const int4*)(b + h.off_node_meta);
-    e->L.node_bbox = (const float4*)(b + h.off_node_bbox);
-    e->L.node_nactive = (const uint32_t*)(b + h.off_node_nactive);
-    e->L.entry_meta = (const int4*)(b + h.off_entry_meta);
-    e->L.entry_ff = (const float4*)(b + h.off_entry_ffbbox);
-    e->L.edges = (const float4*)(b + h.off_edges);
-    e->L.haz_meta = (const int4*)(b + h.off_haz_meta);
-    e->L.haz_bbox = (const float4*)(b + h.off_haz_bbox);
-    e->L.haz_poi = (const float4*)(b + h.off_haz_poi);
-    e->L.haz_verts = (const float2*)(b + h.off_haz_verts);
-    e->L.cde_bbox = Rect{h.cde_bbox[0], h.cde_bbox[1], h.cde_bbox[2], h.cde_bbox[3]};
-    e->L.n_nodes = (int)h.n_nodes;
-    e->L.n_slots = (int)h.n_slots;
-    e->L.cd_threshold = (int)h.cd_threshold;
-    e->L.exterior_slot = (int)h.exterior_slot;
+    e->L = dev_layout_of(e->d_blob, h);
     e->has_layout = true;
 }
 
-static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t epoch, bool src_on_device) {
+// trusted_hdr != null: a device blob whose header is already on the host and whose structure the device has checked
+// (jg_layout_broadcast): no read-back, no second check, and the copy out of `src` is signalled by ev_bc_consumed
+// instead of a host wait.
+static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t epoch, bool src_on_device, const JgLayoutHeader* trusted_hdr = nullptr) {
     if (!e || !src) return JG_ERR_INVALID;
     JG_CUDA(e, cudaSetDevice(e->device));
     JgLayoutHeader h;
     if (bytes < sizeof(h)) return fail(e, JG_ERR_INVALID, "layout blob: truncated");
-    if (src_on_device) JG_CUDA(e, cudaMemcpy(&h, src, sizeof(h), cudaMemcpyDeviceToHost));
+    if (trusted_hdr) h = *trusted_hdr;
+    else if (src_on_device) JG_CUDA(e, cudaMemcpy(&h, src, sizeof(h), cudaMemcpyDeviceToHost));
     else std::memcpy(&h, src, sizeof(h));
     int rc = validate_header(e, h, bytes);
     if (rc != JG_OK) return rc;
@@ -437,6 +496,16 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
             if (em[4 * i + 1] < 0 || em[4 * i + 2] < 0 || (uint32_t)em[4 * i + 1] + (uint32_t)em[4 * i + 2] > h.n_edges)
                 return fail(e, JG_ERR_INVALID, "layout blob: bad edge range");
         }
+    }
+    if (src_on_device && !trusted_hdr) {
+        // A blob that arrived in device memory is checked there, BEFORE anything reads it: one small kernel on the upload
+        // stream and a 4-byte read-back (the engine keeps serving the previous layout meanwhile, and keeps it on failure).
+        JG_CUDA(e, launch_blob_validate(dev_layout_of(src, h), h, e->d_blob_bad, e->st_up));
+        JG_CUDA(e, cudaMemcpyAsync(e->h_blob_bad, e->d_blob_bad, sizeof(int), cudaMemcpyDeviceToHost, e->st_up));
+        JG_CUDA(e, cudaStreamSynchronize(e->st_up));
+        e->stat_launches += 1;
+        if (e->h_blob_bad[0])
+            return fail(e, JG_ERR_INVALID, "layout upload: malformed device blob (index out of range / bad child block / non-finite box)");
     }
     // Which kernels serve this layout (grid or walk) is decided on the host: by the producer (flags) or here.
     int host_grid = -1;  // -1 unknown (device blob of a foreign producer): read k_grid_build's verdict back
@@ -490,6 +559,7 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
             std::memcpy(B.h_stage, src, h.total_bytes);
             JG_CUDA(e, cudaMemcpyAsync(B.d_blob, B.h_stage, h.total_bytes, cudaMemcpyHostToDevice, e->st_up));
         } else {
+            // (a broadcast blob was read back and checked on st_bc, which the host has waited for: it is complete)
             JG_CUDA(e, cudaMemcpyAsync(B.d_blob, src, h.total_bytes, cudaMemcpyDeviceToDevice, e->st_up));
         }
         e->cur = nb;
@@ -517,11 +587,14 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
             JG_CUDA(e, cudaStreamWaitEvent(qs[i], B.ready, 0));
         }
         B.marks_valid = true;
-        if (src_on_device) JG_CUDA(e, cudaStreamSynchronize(e->st_up));  // the caller may reuse its buffer on return
+        if (trusted_hdr) JG_CUDA(e, cudaEventRecord(e->ev_bc_consumed, e->st_up));  // the next broadcast waits for this on the device
+        else if (src_on_device) JG_CUDA(e, cudaStreamSynchronize(e->st_up));         // the caller may reuse its buffer on return
     } else {
+        if (trusted_hdr) JG_CUDA(e, cudaStreamSynchronize(e->st_bc));  // (this path does not order `compute` behind the broadcast stream)
         JG_CUDA(e, cudaMemcpyAsync(B.d_blob, src, h.total_bytes,
                                    src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->compute));
         JG_CUDA(e, cudaStreamSynchronize(e->compute));
+        if (trusted_hdr) JG_CUDA(e, cudaEventRecord(e->ev_bc_consumed, e->compute));
         e->cur = nb;
         e->d_blob = B.d_blob;
         e->d_kinds = B.d_kinds;
@@ -542,7 +615,14 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
     e->stat_launches += 2;
     e->epoch = epoch;
     e->stat_uploads++;
-    if (!src_on_device) e->stat_h2d += h.total_bytes;
+    if (!src_on_device) {
+        e->stat_h2d += h.total_bytes;
+        const uint32_t* hv = (const uint32_t*)((const char*)src + h.off_haz_version);
+        e->slot_versions.assign(hv, hv + h.n_slots);
+        e->slot_versions_valid = true;
+    } else {
+        e->slot_versions_valid = false;  // fetched from the device when a keyed filter needs them (find_filter)
+    }
     return JG_OK;
 }
 
@@ -640,6 +720,20 @@ int jg_filter_upload(JgEngine* e, int filter_id, const uint32_t* bits, int words
     return JG_OK;
 }
 
+int jg_filter_upload_keys(JgEngine* e, int filter_id, const uint64_t* hkeys, int n_keys) {
+    if (!e || filter_id < 0 || n_keys < 0 || (n_keys > 0 && !hkeys)) return JG_ERR_INVALID;
+    JG_CUDA(e, cudaSetDevice(e->device));
+    int rc = jg_sync(e);
+    if (rc != JG_OK) return rc;
+    FilterDev& f = e->filters[filter_id];
+    cudaFree(f.bits);
+    cudaFree(f.kinds);
+    f = FilterDev{};
+    f.keyed = true;
+    f.keys.assign(hkeys, hkeys + n_keys);
+    return JG_OK;  // the bitset is derived against the layout in find_filter
+}
+
 // ---- queries ------------------------------------------------------------------------------------------
 static int check_ready(JgEngine* e) {
     if (!e) return JG_ERR_INVALID;
@@ -652,13 +746,45 @@ static int find_item(JgEngine* e, int item_id, const ItemDev** it) {
     *it = &f->second;
     return JG_OK;
 }
-static int find_filter(JgEngine* e, int filter_id, const uint32_t** d_filt, const uint8_t** d_kinds) {
+static int find_filter(JgEngine* e, int filter_id, const uint32_t** d_filt, const uint8_t** d_kinds, int* grid_ok) {
     *d_filt = nullptr;
     *d_kinds = e->d_kinds;
+    *grid_ok = 1;
     if (filter_id < 0) return JG_OK;
     auto g = e->filters.find(filter_id);
     if (g == e->filters.end()) return fail(e, JG_ERR_INVALID, "unknown filter id");
     FilterDev& f = g->second;
+    if (f.keyed && f.bits_version != e->layout_version) {
+        // HazKeyFilter semantics (filter.rs:12-58): a key hides its slot only while the slot still carries the key's version
+        JG_CUDA(e, cudaSetDevice(e->device));
+        if (!e->slot_versions_valid) {  // the layout came as a device blob: fetch the slot versions once
+            JG_CUDA(e, cudaStreamSynchronize(e->st_up));
+            e->slot_versions.resize(e->hdr.n_slots);
+            if (e->hdr.n_slots)
+                JG_CUDA(e, cudaMemcpy(e->slot_versions.data(), (const char*)e->d_blob + e->hdr.off_haz_version, (size_t)e->hdr.n_slots * 4,
+                                      cudaMemcpyDeviceToHost));
+            e->slot_versions_valid = true;
+        }
+        const int words = (int)((e->hdr.n_slots + 31) / 32) > 0 ? (int)((e->hdr.n_slots + 31) / 32) : 1;
+        std::vector<uint32_t> hb((size_t)words, 0u);
+        for (uint64_t k : f.keys) {
+            const uint32_t slot = (uint32_t)k, ver = (uint32_t)(k >> 32);
+            if (slot < e->hdr.n_slots && e->slot_versions[slot] == ver) hb[slot >> 5] |= 1u << (slot & 31);
+        }
+        JG_CUDA(e, cudaStreamSynchronize(e->compute));  // batches in flight may still read the old bitset
+        for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
+        if (f.words < words) {
+            cudaFree(f.bits);
+            f.bits = nullptr;
+            f.words = 0;
+            JG_CUDA(e, cudaMalloc(&f.bits, (size_t)words * 4 * 2));
+            f.words = words * 2;
+        }
+        JG_CUDA(e, cudaMemset(f.bits, 0, (size_t)f.words * 4));
+        JG_CUDA(e, cudaMemcpy(f.bits, hb.data(), (size_t)words * 4, cudaMemcpyHostToDevice));
+        f.bits_version = e->layout_version;
+        f.kinds_version = 0;  // the node summary depends on the bitset
+    }
     if ((size_t)f.words * 32 < e->hdr.n_slots)
         return fail(e, JG_ERR_CAPACITY, "filter bitset smaller than the hazard slot capacity");
     if (f.kinds_version != e->layout_version) {  // node summary of this filter for the current layout
@@ -672,12 +798,15 @@ static int find_filter(JgEngine* e, int filter_id, const uint32_t** d_filt, cons
             f.kinds_cap = need * 2;
         }
         JG_CUDA(e, launch_node_kinds(e->L, (int)e->hdr.root_level, f.bits, f.kinds, e->compute));
-        JG_CUDA(e, cudaStreamSynchronize(e->compute));
+        // Under a filter, nodes whose Entire entries are all hidden become leaves of the summary: k_grid_build may refuse
+        // what the NoFilter summary accepted (leaf record limits). Its verdict decides this filter's kernel path.
+        JG_CUDA(e, detect_grid_usable(f.kinds, (int)e->hdr.n_nodes, e->compute, &f.grid_ok));
         e->stat_launches += 2;
         f.kinds_version = e->layout_version;
     }
     *d_filt = f.bits;
     *d_kinds = f.kinds;
+    *grid_ok = f.grid_ok;
     return JG_OK;
 }
 
@@ -723,7 +852,7 @@ static bool next_piece(const JgEngine* e, int n_seg, const ItemDev* const* items
         sd.poi_y = it.poi_y;
         sd.rots = it.rots;
         sd.n_rots = it.n_rots;
-        sd.pad = 0;
+        sd.gbeg = 0;
         covered += len;
         edge_pairs += len * it.n_verts;
         if (b + len < seg_offsets[sgi + 1]) break;  // segment cut: the rest goes to the next piece
@@ -750,14 +879,20 @@ static int resolve_segments(JgEngine* e, int n_seg, const int* item_ids, const i
 #define JG_DEVICE_PIECE_MIN (1 << 16)
 
 // one piece on one stream: the fused kernel when the grid serves it, else the two-kernel sequence
-static cudaError_t launch_piece(JgEngine* e, const Piece& p, const XfSrc& src, const uint32_t* d_filt, const uint8_t* d_kinds, int mode,
-                                uint8_t* d_out, const DetectScratch& sc, cudaStream_t st, int* launches) {
-    if (e->use_fused && detect_fused_applicable(e->plan, p.tab, mode)) {
+static cudaError_t launch_piece(JgEngine* e, const DetectPlan& plan, const Piece& p, const XfSrc& src, const uint32_t* d_filt, const uint8_t* d_kinds,
+                                int mode, uint8_t* d_out, const DetectScratch& sc, cudaStream_t st, int* launches) {
+    if (e->use_fused && detect_fused_applicable(plan, p.tab, mode)) {
         cudaError_t err = cudaMemsetAsync(sc.ctl, 0, sizeof(DetectCtl), st);
         if (err != cudaSuccess) return err;
         return launch_detect_fused(e->L, p.tab, src, d_filt, d_kinds, d_out, sc, e->n_sms, 1, st, launches);
     }
-    return launch_detect(e->L, e->plan, p.tab, src, d_filt, d_kinds, mode, d_out, sc, e->n_sms, st, launches);
+    return launch_detect(e->L, plan, p.tab, src, d_filt, d_kinds, mode, d_out, sc, e->n_sms, st, launches);
+}
+// the launch plan of a batch: the engine's, minus the grid kernels when this filter's summary does not admit them
+static DetectPlan plan_for(const JgEngine* e, int filter_grid_ok) {
+    DetectPlan plan = e->plan;
+    if (!filter_grid_ok) plan.use_grid = 0;
+    return plan;
 }
 static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets,
                                const float* d_transforms, int filter_id, int mode, uint8_t* d_out) {
@@ -768,8 +903,10 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
     if (rc != JG_OK) return rc;
     const uint32_t* d_filt;
     const uint8_t* d_kinds;
-    rc = find_filter(e, filter_id, &d_filt, &d_kinds);
+    int fgrid = 1;
+    rc = find_filter(e, filter_id, &d_filt, &d_kinds, &fgrid);
     if (rc != JG_OK) return rc;
+    const DetectPlan plan = plan_for(e, fgrid);
     const int64_t n = seg_offsets[n_seg];
     if (n > 0 && (!d_transforms || !d_out)) return JG_ERR_INVALID;
     if (n == 0) return JG_OK;
@@ -794,7 +931,7 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
             ChunkCtx& c = e->chunks[k++ % e->chunks.size()];
             rc = ensure_ctx(e, c, (size_t)piece, 0, false);
             if (rc != JG_OK) return rc;
-            JG_CUDA(e, launch_piece(e, p, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off, c.sc,
+            JG_CUDA(e, launch_piece(e, plan, p, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off, c.sc,
                                     c.st, &launches));
         }
         for (ChunkCtx& c : e->chunks) {
@@ -806,7 +943,7 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
         rc = ensure_ctx(e, e->main_ctx, (size_t)(n < max_q ? n : max_q), 0, false);
         if (rc != JG_OK) return rc;
         while (next_piece(e, n_seg, items.data(), seg_offsets, max_q, cur, p))
-            JG_CUDA(e, launch_piece(e, p, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off,
+            JG_CUDA(e, launch_piece(e, plan, p, XfSrc{(const float4*)d_transforms + p.off, nullptr, nullptr}, d_filt, d_kinds, mode, d_out + p.off,
                                     e->main_ctx.sc, e->compute, &launches));
     }
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
@@ -820,7 +957,8 @@ static int detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, cons
 // the H2D copy of piece k+1 overlaps the kernels of piece k and the D2H copy of piece k-1.
 // `transforms` (16 B/query) or, when it is null, the compact form `rot_idx` + `txy` (9 B/query)
 static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms,
-                             const uint8_t* rot_idx, const float* txy, int filter_id, int mode, uint8_t* out, bool wait) {
+                             const uint8_t* rot_idx, const float* txy, int filter_id, int mode, uint8_t* out, bool wait,
+                             const JgLattice* lat = nullptr, const uint16_t* ij = nullptr) {
     int rc = check_ready(e);
     if (rc != JG_OK) return rc;
     std::vector<const ItemDev*> items;
@@ -828,23 +966,26 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
     if (rc != JG_OK) return rc;
     const uint32_t* d_filt;
     const uint8_t* d_kinds;
-    rc = find_filter(e, filter_id, &d_filt, &d_kinds);
+    int fgrid = 1;
+    rc = find_filter(e, filter_id, &d_filt, &d_kinds, &fgrid);
     if (rc != JG_OK) return rc;
+    const DetectPlan plan = plan_for(e, fgrid);
     const int64_t n = seg_offsets[n_seg];
     const bool indexed = transforms == nullptr;
-    if (n > 0 && (!out || (indexed && (!rot_idx || !txy)))) return JG_ERR_INVALID;
+    const bool lattice = indexed && ij != nullptr;
+    if (n > 0 && (!out || (indexed && (!rot_idx || (!txy && !lattice))) || (lattice && !lat))) return JG_ERR_INVALID;
     if (indexed)
         for (int k = 0; k < n_seg; k++)
             if (seg_offsets[k + 1] > seg_offsets[k] && items[k]->n_rots == 0)
                 return fail(e, JG_ERR_INVALID, "indexed queries need jg_item_set_rotations for every item of the batch");
     if (n == 0) return JG_OK;
     JG_CUDA(e, cudaSetDevice(e->device));
-    if (e->use_fused && n >= JG_STREAM_MIN_QUERIES && n <= JG_MAX_LAUNCH_QUERIES && n_seg <= JG_MAX_SEG) {
+    if (e->use_fused && !lattice && n >= JG_STREAM_MIN_QUERIES && n <= JG_MAX_LAUNCH_QUERIES && n_seg <= JG_MAX_SEG) {
         // Whole batch as ONE fused kernel that follows the copy front (see k_detect_fused).
         PieceCursor cur0;
         Piece whole;
         if (next_piece(e, n_seg, items.data(), seg_offsets, n, cur0, whole) && whole.m == n &&
-            detect_fused_applicable(e->plan, whole.tab, mode)) {
+            detect_fused_applicable(plan, whole.tab, mode)) {
             ChunkCtx& c = e->stream_ctx;
             JG_CUDA(e, cudaStreamSynchronize(e->compute));  // the previous streamed batch is done with the buffers
             JG_CUDA(e, cudaStreamSynchronize(e->st_copy));
@@ -920,6 +1061,13 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
         if (!indexed) {
             JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * p.off, (size_t)p.m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
             e->stat_h2d += (uint64_t)p.m * sizeof(float4);
+        } else if (lattice) {  // lattice coordinates (2 x u16) followed by the rotation indices
+            ushort2* d_ij = (ushort2*)c.d_xf;
+            uint8_t* d_ridx = (uint8_t*)(d_ij + p.m);
+            JG_CUDA(e, cudaMemcpyAsync(d_ij, ij + 2 * p.off, (size_t)p.m * sizeof(ushort2), cudaMemcpyHostToDevice, c.st));
+            JG_CUDA(e, cudaMemcpyAsync(d_ridx, rot_idx + p.off, (size_t)p.m, cudaMemcpyHostToDevice, c.st));
+            src = XfSrc{nullptr, d_ridx, nullptr, d_ij, make_float4(lat->x0, lat->y0, lat->dx, lat->dy)};
+            e->stat_h2d += (uint64_t)p.m * 5;
         } else {  // the staging buffer holds the translations followed by the rotation indices
             float2* d_txy = (float2*)c.d_xf;
             uint8_t* d_ridx = (uint8_t*)(d_txy + p.m);
@@ -930,7 +1078,7 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
         }
         int launches = 0;
         if (tr) trace_mark(e, c.st);
-        JG_CUDA(e, launch_piece(e, p, src, d_filt, d_kinds, mode, c.d_out, c.sc, c.st, &launches));
+        JG_CUDA(e, launch_piece(e, plan, p, src, d_filt, d_kinds, mode, c.d_out, c.sc, c.st, &launches));
         if (tr) trace_mark(e, c.st);
         JG_CUDA(e, cudaMemcpyAsync(out + p.off, c.d_out, (size_t)p.m, cudaMemcpyDeviceToHost, c.st));
         if (tr) trace_mark(e, c.st);
@@ -961,6 +1109,23 @@ int jg_detect_multi_indexed_async(JgEngine* e, int n_seg, const int* item_ids, c
     if (!rot_idx || !txy) return JG_ERR_INVALID;
     return detect_multi_host(e, n_seg, item_ids, seg_offsets, nullptr, rot_idx, txy, filter_id, mode, out, false);
 }
+int jg_detect_multi_lattice(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const JgLattice* lattice,
+                            const uint8_t* rot_idx, const uint16_t* ij, int filter_id, int mode, uint8_t* out) {
+    if (!lattice || !rot_idx || !ij) return JG_ERR_INVALID;
+    return detect_multi_host(e, n_seg, item_ids, seg_offsets, nullptr, rot_idx, nullptr, filter_id, mode, out, true, lattice, ij);
+}
+int jg_detect_multi_lattice_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const JgLattice* lattice,
+                                  const uint8_t* rot_idx, const uint16_t* ij, int filter_id, int mode, uint8_t* out) {
+    if (!lattice || !rot_idx || !ij) return JG_ERR_INVALID;
+    return detect_multi_host(e, n_seg, item_ids, seg_offsets, nullptr, rot_idx, nullptr, filter_id, mode, out, false, lattice, ij);
+}
+void jg_lattice_points(const JgLattice* lattice, const uint16_t* ij, int64_t n, float* txy) {
+    if (!lattice || !ij || !txy) return;
+    for (int64_t q = 0; q < n; q++) {
+        txy[2 * q] = lattice_coord(lattice->x0, lattice->dx, ij[2 * q]);
+        txy[2 * q + 1] = lattice_coord(lattice->y0, lattice->dy, ij[2 * q + 1]);
+    }
+}
 int jg_detect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* d_transforms,
                            int filter_id, int mode, uint8_t* d_out) {
     return detect_multi_device(e, n_seg, item_ids, seg_offsets, d_transforms, filter_id, mode, d_out);
@@ -983,35 +1148,55 @@ int jg_detect_batch_device(JgEngine* e, int item_id, const float* d_transforms, 
     return detect_multi_device(e, 1, &item_id, offs, d_transforms, filter_id, mode, d_out);
 }
 
-static int collect_checks(JgEngine* e, int item_id, int64_t n, const void* t, const void* out, int words, const ItemDev** it) {
+static int collect_checks(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const void* t, const void* out, int words,
+                          std::vector<const ItemDev*>& items) {
     int rc = check_ready(e);
     if (rc != JG_OK) return rc;
-    rc = find_item(e, item_id, it);
+    rc = resolve_segments(e, n_seg, item_ids, seg_offsets, items);
     if (rc != JG_OK) return rc;
-    if (n < 0 || words <= 0 || (n > 0 && (!t || !out))) return JG_ERR_INVALID;
+    if (words <= 0 || (seg_offsets[n_seg] > 0 && (!t || !out))) return JG_ERR_INVALID;
     if ((size_t)words * 32 < e->hdr.n_slots) return fail(e, JG_ERR_CAPACITY, "collector words do not cover the hazard slot capacity");
     if (words > 1024) return fail(e, JG_ERR_CAPACITY, "collector wider than 1024 words");
     return JG_OK;
 }
 
-int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int mode,
-                            uint32_t* d_out_bits, int words) {
-    const ItemDev* it;
-    int rc = collect_checks(e, item_id, n, d_transforms, d_out_bits, words, &it);
-    if (rc != JG_OK || n == 0) return rc;
+// one launch piece of a collect batch: ONE k_collect_grid launch for all of its segments where the grid serves it, else the
+// register-walk kernel segment by segment
+static cudaError_t launch_collect_piece(JgEngine* e, Piece& p, const float4* d_xf, int mode, const uint32_t* d_seed, uint32_t* d_out, int words,
+                                        int* d_next, cudaStream_t st, int* launches) {
+    if (!e->force_walk && collect_grid_applicable(e->plan, p.tab, words))
+        return launch_collect_grid(e->L, p.tab, e->d_kinds, d_xf, mode, d_seed, d_out, words, d_next, e->n_sms, st, launches);
+    for (int k = 0; k < p.tab.n_seg; k++) {
+        const SegDesc& sd = p.tab.seg[k];
+        const int end = k + 1 < p.tab.n_seg ? p.tab.seg[k + 1].begin : p.tab.n_queries;
+        DevItem di;
+        di.verts = sd.verts, di.n_verts = sd.n_verts, di.poi_x = sd.poi_x, di.poi_y = sd.poi_y;
+        di.poles = sd.poles, di.n_poles = sd.n_poles, di.piers = sd.piers, di.n_piers = sd.n_piers;
+        const int group = e->collect_group ? e->collect_group : auto_group(sd.n_verts);
+        cudaError_t err = launch_collect(e->L, di, d_xf + sd.begin, end - sd.begin, mode, d_seed ? d_seed + (size_t)sd.begin * words : nullptr,
+                                         d_out + (size_t)sd.begin * words, words, group, e->n_sms, st, launches);
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+
+static int collect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* d_transforms, int mode,
+                                const uint32_t* d_seed, uint32_t* d_out_bits, int words) {
+    std::vector<const ItemDev*> items;
+    int rc = collect_checks(e, n_seg, item_ids, seg_offsets, d_transforms, d_out_bits, words, items);
+    if (rc != JG_OK) return rc;
+    const int64_t n = seg_offsets[n_seg];
+    if (n == 0) return JG_OK;
     JG_CUDA(e, cudaSetDevice(e->device));
-    const int group = e->collect_group ? e->collect_group : auto_group(it->n_verts);
     int launches = 0;
     JG_CUDA(e, cudaEventRecord(e->ev0, e->compute));
-    const DevItem di = dev_item(e, *it);
-    if (!e->force_walk && n <= JG_MAX_LAUNCH_QUERIES && collect_grid_applicable(e->plan, di, words)) {
-        rc = ensure_ctx(e, e->main_ctx, 1, 0, false);  // the work counter lives in the scratch block
-        if (rc != JG_OK) return rc;
-        JG_CUDA(e, launch_collect_grid(e->L, di, e->d_kinds, (const float4*)d_transforms, n, mode, d_out_bits, words, &e->main_ctx.sc.ctl->s1_next,
-                                       e->n_sms, e->compute, &launches));
-    } else {
-        JG_CUDA(e, launch_collect(e->L, di, (const float4*)d_transforms, n, mode, d_out_bits, words, group, e->n_sms, e->compute, &launches));
-    }
+    rc = ensure_ctx(e, e->main_ctx, 1, 0, false);  // the work counter lives in the scratch block
+    if (rc != JG_OK) return rc;
+    PieceCursor cur;
+    Piece p;
+    while (next_piece(e, n_seg, items.data(), seg_offsets, JG_MAX_LAUNCH_QUERIES, cur, p))
+        JG_CUDA(e, launch_collect_piece(e, p, (const float4*)d_transforms + p.off, mode, d_seed ? d_seed + (size_t)p.off * words : nullptr,
+                                        d_out_bits + (size_t)p.off * words, words, &e->main_ctx.sc.ctl->s1_next, e->compute, &launches));
     JG_CUDA(e, cudaEventRecord(e->ev1, e->compute));
     e->timing_valid = true;
     e->stat_launches += launches;
@@ -1019,45 +1204,70 @@ int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms,
     return JG_OK;
 }
 
-static int collect_host(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words,
-                        bool wait) {
-    const ItemDev* it;
-    int rc = collect_checks(e, item_id, n, transforms, out_bits, words, &it);
-    if (rc != JG_OK || n == 0) return rc;
+static int collect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int mode,
+                              const uint32_t* seed_bits, uint32_t* out_bits, int words, bool wait) {
+    std::vector<const ItemDev*> items;
+    int rc = collect_checks(e, n_seg, item_ids, seg_offsets, transforms, out_bits, words, items);
+    if (rc != JG_OK) return rc;
+    const int64_t n = seg_offsets[n_seg];
+    if (n == 0) return JG_OK;
     JG_CUDA(e, cudaSetDevice(e->device));
     const size_t out_per_q = (size_t)words * 4;
     const int64_t chunk = e->chunk_queries;
-    const int group = e->collect_group ? e->collect_group : auto_group(it->n_verts);
-    const DevItem di = dev_item(e, *it);
-    for (int64_t off = 0; off < n; off += chunk) {
-        const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+    const size_t slot_q = (size_t)(chunk < n ? chunk : n);
+    PieceCursor cur;
+    Piece p;
+    while (next_piece(e, n_seg, items.data(), seg_offsets, chunk, cur, p)) {
         ChunkCtx& c = e->chunks[e->next_chunk++ % e->chunks.size()];
         JG_CUDA(e, cudaStreamSynchronize(c.st));
-        rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n) * out_per_q, true);
+        rc = ensure_ctx(e, c, slot_q, slot_q * out_per_q, true);
         if (rc != JG_OK) return rc;
-        JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * off, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
+        JG_CUDA(e, cudaMemcpyAsync(c.d_xf, transforms + 4 * p.off, (size_t)p.m * sizeof(float4), cudaMemcpyHostToDevice, c.st));
+        const uint32_t* d_seed = nullptr;
+        if (seed_bits) {  // seeded in place: a warp reads the seeds of its group before it writes that group's results
+            JG_CUDA(e, cudaMemcpyAsync(c.d_out, (const char*)seed_bits + (size_t)p.off * out_per_q, (size_t)p.m * out_per_q, cudaMemcpyHostToDevice, c.st));
+            d_seed = (const uint32_t*)c.d_out;
+            e->stat_h2d += (uint64_t)p.m * out_per_q;
+        }
         int launches = 0;
-        if (!e->force_walk && collect_grid_applicable(e->plan, di, words))
-            JG_CUDA(e, launch_collect_grid(e->L, di, e->d_kinds, c.d_xf, m, mode, (uint32_t*)c.d_out, words, &c.sc.ctl->s1_next, e->n_sms, c.st,
-                                           &launches));
-        else
-            JG_CUDA(e, launch_collect(e->L, di, c.d_xf, m, mode, (uint32_t*)c.d_out, words, group, e->n_sms, c.st, &launches));
-        JG_CUDA(e, cudaMemcpyAsync((char*)out_bits + (size_t)off * out_per_q, c.d_out, (size_t)m * out_per_q, cudaMemcpyDeviceToHost, c.st));
+        JG_CUDA(e, launch_collect_piece(e, p, c.d_xf, mode, d_seed, (uint32_t*)c.d_out, words, &c.sc.ctl->s1_next, c.st, &launches));
+        JG_CUDA(e, cudaMemcpyAsync((char*)out_bits + (size_t)p.off * out_per_q, c.d_out, (size_t)p.m * out_per_q, cudaMemcpyDeviceToHost, c.st));
         e->stat_launches += launches;
-        e->stat_h2d += (uint64_t)m * sizeof(float4);
-        e->stat_d2h += (uint64_t)m * out_per_q;
+        e->stat_h2d += (uint64_t)p.m * sizeof(float4);
+        e->stat_d2h += (uint64_t)p.m * out_per_q;
     }
     if (wait)
         for (ChunkCtx& c : e->chunks) JG_CUDA(e, cudaStreamSynchronize(c.st));
     e->stat_queries += (uint64_t)n;
     return JG_OK;
 }
-int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words) {
-    return collect_host(e, item_id, transforms, n, mode, out_bits, words, true);
+
+int jg_collect_multi(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int mode,
+                     const uint32_t* seed_bits, uint32_t* out_bits, int words) {
+    return collect_multi_host(e, n_seg, item_ids, seg_offsets, transforms, mode, seed_bits, out_bits, words, true);
 }
-int jg_collect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits,
-                           int words) {
-    return collect_host(e, item_id, transforms, n, mode, out_bits, words, false);
+int jg_collect_multi_async(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int mode,
+                           const uint32_t* seed_bits, uint32_t* out_bits, int words) {
+    return collect_multi_host(e, n_seg, item_ids, seg_offsets, transforms, mode, seed_bits, out_bits, words, false);
+}
+int jg_collect_multi_device(JgEngine* e, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* d_transforms, int mode,
+                            const uint32_t* d_seed_bits, uint32_t* d_out_bits, int words) {
+    return collect_multi_device(e, n_seg, item_ids, seg_offsets, d_transforms, mode, d_seed_bits, d_out_bits, words);
+}
+int jg_collect_batch_device(JgEngine* e, int item_id, const float* d_transforms, int64_t n, int mode, uint32_t* d_out_bits, int words) {
+    if (n < 0) return JG_ERR_INVALID;
+    const int64_t offs[2] = {0, n};
+    return collect_multi_device(e, 1, &item_id, offs, d_transforms, mode, nullptr, d_out_bits, words);
+}
+int jg_collect_batch(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words) {
+    if (n < 0) return JG_ERR_INVALID;
+    const int64_t offs[2] = {0, n};
+    return collect_multi_host(e, 1, &item_id, offs, transforms, mode, nullptr, out_bits, words, true);
+}
+int jg_collect_batch_async(JgEngine* e, int item_id, const float* transforms, int64_t n, int mode, uint32_t* out_bits, int words) {
+    if (n < 0) return JG_ERR_INVALID;
+    const int64_t offs[2] = {0, n};
+    return collect_multi_host(e, 1, &item_id, offs, transforms, mode, nullptr, out_bits, words, false);
 }
 
 int jg_engine_stats(const JgEngine* e, uint64_t out[8]) {
@@ -1127,8 +1337,10 @@ int jg_search_round(JgEngine* e, int item_id, const JgSearchRound* round, int64_
     if (round->rot_idx >= it.n_rots || (round->mode == 1 && round->rot_idx < 0)) return fail(e, JG_ERR_INVALID, "search round: bad rotation index");
     const uint32_t* d_filt;
     const uint8_t* d_kinds;
-    rc = find_filter(e, filter_id, &d_filt, &d_kinds);
+    int fgrid = 1;
+    rc = find_filter(e, filter_id, &d_filt, &d_kinds, &fgrid);
     if (rc != JG_OK) return rc;
+    const DetectPlan plan = plan_for(e, fgrid);
     JG_CUDA(e, cudaSetDevice(e->device));
     if (!e->d_search) {
         JG_CUDA(e, cudaMalloc(&e->d_search, 4 * sizeof(unsigned long long)));
@@ -1155,7 +1367,7 @@ int jg_search_round(JgEngine* e, int item_id, const JgSearchRound* round, int64_
     PieceCursor cur;
     Piece p;
     if (!next_piece(e, 1, items.data(), offs, JG_MAX_LAUNCH_QUERIES, cur, p) || p.m != n) return fail(e, JG_ERR_CAPACITY, "search round: batch does not fit one launch");
-    JG_CUDA(e, launch_piece(e, p, XfSrc{nullptr, d_ridx, d_txy}, d_filt, d_kinds, JG_MODE_DEFAULT, c.d_out, c.sc, st, &launches));
+    JG_CUDA(e, launch_piece(e, plan, p, XfSrc{nullptr, d_ridx, d_txy}, d_filt, d_kinds, JG_MODE_DEFAULT, c.d_out, c.sc, st, &launches));
     JG_CUDA(e, launch_search_reduce(n, c.d_out, d_ridx, d_txy, it.rot_ext, it.n_rots, e->d_search, e->n_sms, st));
     k_search_fetch<<<1, 1, 0, st>>>(e->d_search, d_ridx, d_txy);
     JG_CUDA(e, cudaMemcpyAsync(e->h_search, e->d_search, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1282,6 +1494,10 @@ int jg_engine_detect_path(const JgEngine* e) { return e && e->plan.use_grid ? (e
 int jg_host_alloc(size_t bytes, void** out) {
     if (!out) return JG_ERR_INVALID;
     return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? JG_OK : JG_ERR_CUDA;
+}
+int jg_host_alloc_wc(size_t bytes, void** out) {
+    if (!out) return JG_ERR_INVALID;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocWriteCombined) == cudaSuccess ? JG_OK : JG_ERR_CUDA;
 }
 int jg_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? JG_OK : JG_ERR_CUDA; }
 int jg_device_alloc(JgEngine* e, size_t bytes, void** out) {
@@ -1431,6 +1647,28 @@ int jg_cde_deregister_hazard(JgCde* c, uint64_t hkey) {
     if (!c) return JG_ERR_INVALID;
     return ((JgCdeBox*)c)->cde.deregister_hazard(hkey) ? JG_OK : JG_ERR_INVALID;
 }
+int jg_cde_deregister_hazard_by_entity(JgCde* c, int kind, int64_t id, int64_t quality, uint64_t pk) {
+    if (!c) return JG_ERR_INVALID;
+    HostCDE& cde = ((JgCdeBox*)c)->cde;
+    const uint64_t k = cde.hkey_from_entity(kind, id, quality, pk);
+    if (k == 0) {
+        cde.last_error = "Cannot deregister hazard that is not registered";  // cd_engine.rs:78
+        return JG_ERR_INVALID;
+    }
+    return cde.deregister_hazard(k) ? JG_OK : JG_ERR_INVALID;
+}
+int jg_cde_swap_container(JgCde* c, const JgCde* base) {
+    if (!c || !base || c == base) return JG_ERR_INVALID;
+    HostCDE& cde = ((JgCdeBox*)c)->cde;
+    cde.swap_container(((const JgCdeBox*)base)->cde);
+    return cde.last_error.empty() ? JG_OK : JG_ERR_REFERENCE_PANIC;
+}
+int jg_cde_clone(const JgCde* c, JgCde** out) {
+    if (!c || !out) return JG_ERR_INVALID;
+    *out = (JgCde*)new JgCdeBox(*(const JgCdeBox*)c);
+    return JG_OK;
+}
+uint64_t jg_cde_epoch(const JgCde* c) { return c ? ((const JgCdeBox*)c)->cde.epoch : 0; }
 int jg_cde_hkey_from_pk(const JgCde* c, uint64_t pk, uint64_t* hkey) {
     if (!c || !hkey) return JG_ERR_INVALID;
     *hkey = ((const JgCdeBox*)c)->cde.hkey_from_pk(pk);
@@ -1473,6 +1711,8 @@ int jg_cde_sync_to_engine(JgCde* c, JgEngine* e, uint64_t* epoch) {
     if (rc == JG_OK && epoch) *epoch = cde.epoch;
     return rc;
 }
+#include "engine_comm.inl"
+
 int64_t jg_cde_tree_dump(const JgCde* c, uint32_t* out, int64_t cap) {
     if (!c) return JG_ERR_INVALID;
     std::vector<uint32_t> v = ((const JgCdeBox*)c)->cde.tree_dump();

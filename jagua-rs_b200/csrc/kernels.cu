@@ -13,8 +13,8 @@ namespace jg {
 // ---------------------------------------------------------------------------------------------
 template <int G>
 __global__ void __launch_bounds__(256)
-k_collect(DevLayout L, DevItem it, const float4* __restrict__ xforms, long long n, int mode, uint32_t* __restrict__ out_bits,
-          int words) {
+k_collect(DevLayout L, DevItem it, const float4* __restrict__ xforms, long long n, int mode, const uint32_t* __restrict__ seed_bits,
+          uint32_t* __restrict__ out_bits, int words) {
     extern __shared__ float2 s_dyn[];
     float2* s_verts = s_dyn;
     uint32_t* s_bits = (uint32_t*)(s_dyn + it.n_verts);
@@ -29,7 +29,7 @@ k_collect(DevLayout L, DevItem it, const float4* __restrict__ xforms, long long 
     uint32_t* bits = s_bits + (threadIdx.x / G) * words;
     const int V = it.n_verts;
     for (long long q = (long long)blockIdx.x * groups_per_block + threadIdx.x / G; q < n; q += n_groups) {
-        for (int i = gl; i < words; i += G) bits[i] = 0;
+        for (int i = gl; i < words; i += G) bits[i] = seed_bits ? __ldg(&seed_bits[q * words + i]) : 0u;  // pre-seeded collector
         __syncwarp(gmask);
         const float4 t4 = __ldg(&xforms[q]);
         const Xf xf{t4.x, t4.y, t4.z, t4.w};
@@ -126,14 +126,14 @@ static int grid_for(K kernel, int slot, int n_sms, size_t smem) {
     return n_sms * g_blocks_per_sm_cache[slot];
 }
 
-cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,
+cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode, const uint32_t* d_seed,
                            uint32_t* d_out_bits, int words, int group, int n_sms, cudaStream_t st, int* n_launches) {
     const size_t smem = (size_t)it.n_verts * sizeof(float2) + (size_t)(256 / group) * words * sizeof(uint32_t);
 #define JG_COLLECT(G, SLOT)                                                                          \
     {                                                                                                \
         int g = grid_for(k_collect<G>, SLOT, n_sms, smem);                                           \
         long long w2 = (n * G + 255) / 256;                                                          \
-        k_collect<G><<<(int)(w2 < g ? w2 : g), 256, smem, st>>>(L, it, d_xf, n, mode, d_out_bits, words); \
+        k_collect<G><<<(int)(w2 < g ? w2 : g), 256, smem, st>>>(L, it, d_xf, n, mode, d_seed, d_out_bits, words); \
     }
     switch (group) {
         case 4: JG_COLLECT(4, 10) break;

@@ -21,7 +21,7 @@ struct SegDesc {
     float poi_x, poi_y;
     const float2* rots;  // (cos, sin) of the item's allowed rotations (jg_item_set_rotations), or null
     int n_rots;
-    int pad;
+    int gbeg;  // collect launches: first group of this segment (launch_collect_grid fills it); unused by detect
 };
 struct SegTable {
     int n_seg;
@@ -36,12 +36,27 @@ struct XfSrc {
     const float4* xf;
     const uint8_t* ridx;
     const float2* txy;
+    const ushort2* ij = nullptr;                   // lattice form (JgLattice): translation = (x0 + i * dx, y0 + j * dy)
+    float4 lat = {0.0f, 0.0f, 0.0f, 0.0f};         // x0, y0, dx, dy
 };
+// jg_lattice_points / the lattice query form: one rounding per product and per sum (no FMA on either side)
+__host__ __device__ __forceinline__ float lattice_coord(float o, float d, unsigned k) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(o, __fmul_rn((float)k, d));
+#else
+    volatile float prod = (float)k * d;  // (the host side is compiled -ffp-contract=off as well)
+    return o + prod;
+#endif
+}
 __device__ __forceinline__ float4 load_xf(const XfSrc& s, const SegDesc& sd, int q) {
     // L2 loads: in a streamed batch the queries land in device memory while the kernel is running
     if (s.xf) return __ldcg(&s.xf[q]);
     const int r = (int)__ldcg(&s.ridx[q]);
     const float2 cs = __ldg(&sd.rots[r < sd.n_rots ? r : sd.n_rots - 1]);  // out-of-range indices are clamped
+    if (s.ij) {
+        const ushort2 k = __ldcg(&s.ij[q]);
+        return make_float4(cs.x, cs.y, lattice_coord(s.lat.x, s.lat.z, k.x), lattice_coord(s.lat.y, s.lat.w, k.y));
+    }
     const float2 t = __ldcg(&s.txy[q]);
     return make_float4(cs.x, cs.y, t.x, t.y);
 }
@@ -102,10 +117,12 @@ bool detect_fused_applicable(const DetectPlan& plan, const SegTable& tab, int mo
 cudaError_t launch_detect_fused(const DevLayout& L, const SegTable& tab, const XfSrc& d_xf, const uint32_t* d_filt,
                                 const uint8_t* d_kinds, uint8_t* d_out, const DetectScratch& sc, int n_sms, int avail_all,
                                 cudaStream_t st, int* n_launches);
-bool collect_grid_applicable(const DetectPlan& plan, const DevItem& it, int words);
-cudaError_t launch_collect_grid(const DevLayout& L, const DevItem& it, const uint8_t* d_kinds, const float4* d_xf, long long n, int mode,
-                                uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st, int* n_launches);
-cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode,
+// collect on the grid: ONE launch for all segments of `tab` (fills tab.seg[k].gbeg); d_seed = pre-seeded collectors or null
+bool collect_grid_applicable(const DetectPlan& plan, const SegTable& tab, int words);
+cudaError_t launch_collect_grid(const DevLayout& L, SegTable& tab, const uint8_t* d_kinds, const float4* d_xf, int mode,
+                                const uint32_t* d_seed, uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st,
+                                int* n_launches);
+cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode, const uint32_t* d_seed,
                            uint32_t* d_out_bits, int words, int group, int n_sms, cudaStream_t st, int* n_launches);
 // one round of a batched placement search (search.cu)
 struct SearchRound {

@@ -9,11 +9,12 @@
 //   QTHazard      quadtree/qt_hazard.rs:13-33      -> entry_meta (+ entry_ffbbox for Partial)
 //   QTHazPartial  quadtree/qt_partial_hazard.rs:7-12 -> entry_ffbbox + a range of `edges`
 //   Hazard        hazards/hazard.rs:16-33          -> haz_meta, haz_bbox, haz_poi, haz_verts (by slot)
+//   HazKey        hazards/hazard.rs:8-12 (slotmap) -> slot index = position in the haz_* sections, version in haz_version
 #pragma once
 #include <stdint.h>
 
 #define JG_LAYOUT_MAGIC 0x4A47424Cu /* "JGBL" */
-#define JG_LAYOUT_VERSION 1u
+#define JG_LAYOUT_VERSION 2u
 /* flags: the producer evaluated the grid premise of csrc/detect_grid.cuh on the host (GRID_CHECKED) and it holds
  * (GRID_OK): depth <= 5, every node box equals the nested-midpoint grid bit for bit, leaf records fit. */
 #define JG_LAYOUT_FLAG_GRID_CHECKED 1u
@@ -43,5 +44,6 @@ typedef struct JgLayoutHeader {
     uint32_t off_haz_bbox;     // float4 shape bbox
     uint32_t off_haz_poi;      // float4 {poi.x, poi.y, 0, 0}
     uint32_t off_haz_verts;    // float2
-    uint32_t reserved1[2];
+    uint32_t off_haz_version;  // u32   SlotMap version of the slot (odd = occupied): what a HazKey must match (jg_filter_upload_keys)
+    uint32_t reserved1;
 } JgLayoutHeader;

@@ -86,8 +86,9 @@ class BatchedLBF:
 
     # -- container (probs/spp/entities/strip.rs:44-61: rectangle (0, 0, width, height); CDE bbox = its square hull) ----
     def _build_engine(self):
-        if self.cde is not None:
-            self.cde.close()
+        """The strip's CDE. First call: a new engine; afterwards (change_strip_width, fit_strip: problem.rs:27-57)
+        Layout::swap_container - the host mirror becomes a clone of the new strip's base CDE with the placed items
+        re-registered; the device engine, the uploaded items and their rotation tables stay as they are."""
         w, h = np.float32(self.width), self.height
         rect = np.array([[0, 0], [w, 0], [w, h], [0, h]], np.float32)
         dx = dy = np.float32(0.0)
@@ -95,16 +96,22 @@ class BatchedLBF:
             dy = np.float32((w - h) / np.float32(2.0))
         elif w < h:
             dx = np.float32((h - w) / np.float32(2.0))
-        self.bbox = np.array([-dx, -dy, w + dx, h + dy], np.float32)  # rect.rs:93-109 inflate_to_square
-        self.cde = CDEngine(self.bbox, device=self.device, **self.cfg)
+        self.bbox = np.array([np.float32(0.0) - dx, np.float32(0.0) - dy, w + dx, h + dy], np.float32)  # rect.rs:93-109 inflate_to_square
         verts, poi = polygon_poi(rect)
+        if self.cde is not None:
+            base = CDEngine(self.bbox, device=None, **self.cfg)  # Container::base_cde of the new strip
+            base.register_hazard(HAZ_EXTERIOR, verts, poi, dynamic=False)
+            self.cde.swap_container(base)
+            base.close()
+            return
+        self.cde = CDEngine(self.bbox, device=self.device, **self.cfg)
         self.cde.register_hazard(HAZ_EXTERIOR, verts, poi, dynamic=False)
         for it in self.items:
             self.cde.upload_item(it.id, it.shape)
             rots = self._device_rotations(it)
             if rots is not None:  # search rounds can run on the device
                 self.cde.set_item_rotations(it.id, rots)
-        for p in self.placements:  # Layout::swap_container re-registers every placed item
+        for p in self.placements:
             self.cde.place_item(p.item_id, self.items[p.item_id].shape, compose(p.d_transf.reshape(1, 3))[0], p.pk)
 
     def _device_rotations(self, item):

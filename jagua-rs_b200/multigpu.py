@@ -49,6 +49,50 @@ def broadcast_blob(blob: Optional[np.ndarray], dist, src: int = 0, device: Optio
     return buf
 
 
+class LayoutBroadcaster:
+    """Layout updates over NCCL inside the library (jg_engine_comm_init / jg_cde_broadcast): rank `root` flattens its host
+    mirror and every other rank binds the blob straight from the NCCL receive buffer - one collective and one host wait
+    per update on the receiving ranks, none on the root. torch.distributed only hands out the 128-byte NCCL id once."""
+
+    def __init__(self, cde, dist, rank: int, world: int, max_blob_bytes: int = 1 << 20):
+        import ctypes as C
+
+        import torch
+
+        from . import JG_OK, JaguaCudaError
+
+        self.cde, self.rank, self.world = cde, int(rank), int(world)
+        lib = cde._lib
+        nid = np.zeros(128, np.uint8)
+        if rank == 0:
+            rc = lib.jg_nccl_unique_id(nid)
+            if rc != JG_OK:
+                raise JaguaCudaError(rc, "jg_nccl_unique_id: libnccl.so.2 could not be loaded")
+        if world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            tid = torch.from_numpy(nid).to(dev)
+            dist.broadcast(tid, 0)
+            nid = np.ascontiguousarray(tid.cpu().numpy())
+        cde._chk(lib.jg_engine_comm_init(cde._eng, nid, self.rank, self.world, int(max_blob_bytes)))
+        self._C = C
+        self.info = {"transport": "ncclBroadcast inside libjagua_cuda.so (dlopen libnccl.so.2), fixed-capacity exchange buffer",
+                     "capacity_bytes": int(max_blob_bytes), "updates": 0, "last_ms": None}
+
+    def broadcast(self, root: int = 0) -> int:
+        """Collective: every rank calls it. Returns the layout epoch now bound on this rank."""
+        import time
+
+        C = self._C
+        ep = C.c_uint64(0)
+        t0 = time.perf_counter()
+        host = self.cde._cde if self.rank == root else None
+        self.cde._chk(self.cde._lib.jg_cde_broadcast(host, self.cde._eng, int(root), C.byref(ep)))
+        self.cde._dirty = False
+        self.info["updates"] += 1
+        self.info["last_ms"] = (time.perf_counter() - t0) * 1e3
+        return int(ep.value)
+
+
 def bind_to_gpu_numa_node(local_rank: int, lib=None) -> dict:
     """Pins this process to the CPU cores of the NUMA node the GPU hangs off, BEFORE any pinned host buffer is
     allocated (first touch puts the pages on the calling thread's node). With 8 ranks each streaming 53 GB/s of

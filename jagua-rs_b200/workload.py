@@ -128,12 +128,38 @@ def make_queries_indexed(w: Workload, item_id: int, n: int, seed: int = 0):
     return idx.astype(np.uint8), np.ascontiguousarray(np.stack([tx, ty], 1))
 
 
-def make_queries(w: Workload, item_id: int, n: int, seed: int = 0) -> np.ndarray:
+def make_queries_lattice(w: Workload, item_id: int, n: int, seed: int = 0, steps: int = 65536):
+    """n seeded queries of one item on the 65536 x 65536 sampling lattice over the CDE bbox (the 5-byte query form):
+    (lattice, rot_idx u8, ij (n, 2) u16). The same uniform distribution as make_queries, quantised; the translations
+    are lattice_points(lattice, ij)."""
+    from . import JgLattice
+
+    rng = np.random.Generator(np.random.Philox(key=[seed, item_id]))
+    it = w.items[item_id]
+    assert it.rotations is not None and len(it.rotations) > 0, "item has no discrete rotation set"
+    lat = JgLattice.over_box(w.cde_bbox, steps)
+    ij = rng.integers(0, steps, (n, 2)).astype(np.uint16)
+    idx = rng.integers(0, len(it.rotations), n)
+    return lat, idx.astype(np.uint8), np.ascontiguousarray(ij)
+
+
+def compose_lattice_queries(w: Workload, item_id: int, lattice, rot_idx: np.ndarray, ij: np.ndarray, compose_fn=None) -> np.ndarray:
+    """The (cos, sin, tx, ty) records a lattice batch stands for (checker side of the 5-byte form)."""
+    from . import compose, lattice_points
+
+    it = w.items[item_id]
+    txy = lattice_points(lattice, ij)
+    rot = np.asarray(it.rotations, np.float32)[np.minimum(rot_idx, len(it.rotations) - 1)]
+    return (compose_fn or compose)(np.stack([rot, txy[:, 0], txy[:, 1]], 1))
+
+
+def make_queries(w: Workload, item_id: int, n: int, seed: int = 0, compose_fn=None) -> np.ndarray:
     """n seeded (cos, sin, tx, ty) queries for one item: translation uniform over the CDE bbox
     (UniformRectSampler::new(cde.bbox(), item), lbf/src/samplers/uniform_rect_sampler.rs:18-36;
     lbf/benches/ci_bench.rs:55,106), rotation uniform over the item's allowed orientations
     (rotation_distr.rs:32-49). Counter-based PRNG (Philox), not the reference's SmallRng stream."""
-    from . import compose
+    if compose_fn is None:  # (bench.py's reference arm passes the oracle's compose: it must not load the product library)
+        from . import compose as compose_fn
 
     rng = np.random.Generator(np.random.Philox(key=[seed, item_id]))
     it = w.items[item_id]
@@ -147,7 +173,7 @@ def make_queries(w: Workload, item_id: int, n: int, seed: int = 0) -> np.ndarray
         rot = np.zeros(n, np.float32)
     else:
         rot = np.asarray(it.rotations, np.float32)[rng.integers(0, len(it.rotations), n)]
-    return compose(np.stack([rot, tx, ty], 1))
+    return compose_fn(np.stack([rot, tx, ty], 1))
 
 
 def split_batch(total: int, n_items: int) -> List[int]:

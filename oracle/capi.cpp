@@ -2,7 +2,9 @@
 // extern "C" surface over the oracle for ctypes (tests/, smoke(), bench.py's CPU legs).
 #include <atomic>
 #include <cstdio>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <thread>
 
 #include "entities.hpp"
@@ -552,80 +554,187 @@ int orc_lbf_fill_bin(World* w, int n_samples, float ls_frac, uint64_t seed, int 
 }
 
 // ---- batched queries (the CPU baseline loop; lbf/benches/ci_bench.rs:56-70,107-121) -------
+// The reference is single-threaded on the query path; "rayon-parallel over the same queries" (BASELINE north_star) is a
+// parallel-for over independent queries. Here: a persistent pool of worker threads (created once, like rayon's global
+// pool) that take chunks of ORC_CHUNK queries from an atomic counter (dynamic balancing: per-query cost varies a lot).
+#define ORC_CHUNK 2048
+namespace {
+struct ThreadPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    const std::function<void(int)>* job = nullptr;
+    uint64_t gen = 0;
+    int want = 0, running = 0;
+    bool stop = false;
+    void worker(int k) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_go.wait(lk, [&] { return stop || (gen != seen && k < want); });
+                if (stop) return;
+                seen = gen;
+                j = job;
+            }
+            (*j)(k);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--running == 0) cv_done.notify_all();
+            }
+        }
+    }
+    // runs fn(k) for k in [0, n) on n threads (the caller is thread 0) and waits
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 1) {
+            fn(0);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m);
+            while ((int)th.size() < n - 1) {
+                const int k = (int)th.size();
+                th.emplace_back([this, k] { worker(k); });
+            }
+            job = &fn;
+            want = n - 1;
+            running = n - 1;
+            gen++;
+        }
+        cv_go.notify_all();
+        fn(n - 1);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return running == 0; });
+        want = 0;
+    }
+    ~ThreadPool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv_go.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
+ThreadPool& pool() {
+    static ThreadPool* p = new ThreadPool();  // leaked on purpose: no destructor race at process exit
+    return *p;
+}
+// segment of query q (segments are contiguous, offsets non-decreasing)
+inline int seg_of(const int64_t* offs, int n_seg, int64_t q, int hint) {
+    int k = hint;
+    while (k + 1 < n_seg && q >= offs[k + 1]) k++;
+    while (k > 0 && q < offs[k]) k--;
+    return k;
+}
+}  // namespace
+
 // transforms: n x (cos, sin, tx, ty). mode bit0: poly only (surrogate disabled, quadtree_bench.rs:73-124)
 // out byte: bit0 surrogate hit, bit1 poly hit (only evaluated when bit0 == 0), bit7 reference panics
+// Multi-item batch: segment k = queries seg_offsets[k] .. seg_offsets[k+1] of item item_ids[k].
 // Returns algorithmic flops (ORC_COUNT builds) or 0.
-uint64_t orc_detect_batch(World* w, int item_id, const float* t4, int64_t n, const uint32_t* filter_bits,
-                          int filter_words, uint8_t* out, int nthreads, int mode) {
-    const Item& item = w->items[item_id];
+uint64_t orc_detect_multi(World* w, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* t4,
+                          const uint32_t* filter_bits, int filter_words, uint8_t* out, int nthreads, int mode) {
     const CDEngine& cde = w->layout->cde;
     HazardFilter filter;
     if (filter_bits) filter.bits.assign(filter_bits, filter_bits + filter_words);
+    const int64_t n = seg_offsets[n_seg];
     std::atomic<uint64_t> flops{0};
-    auto work = [&](int64_t lo, int64_t hi) {
-        SPolygon buffer = item.shape_cd;
-        buffer.has_surrogate = false;
+    std::atomic<int64_t> next{0};
+    auto work = [&](int) {
 #ifdef ORC_COUNT
         g_flops = 0;
 #endif
-        for (int64_t i = lo; i < hi; i++) {
-            Transformation t = from_cstt(t4[4 * i], t4[4 * i + 1], t4[4 * i + 2], t4[4 * i + 3]);
-            uint8_t v = 0;
-            if (!(mode & 1) && cde.detect_surrogate_collision(item.shape_cd.surrogate, t, filter)) v |= 1;
-            if (!(v & 1)) {
-                buffer.transform_from(item.shape_cd, t);
-                try {
-                    if (cde.detect_poly_collision(buffer, filter)) v |= 2;
-                } catch (const PanicInReference&) {
-                    v |= 0x80;
+        int k = 0, buf_item = -1;
+        SPolygon buffer;
+        for (;;) {
+            const int64_t lo = next.fetch_add(ORC_CHUNK);
+            if (lo >= n) break;
+            const int64_t hi = std::min<int64_t>(n, lo + ORC_CHUNK);
+            for (int64_t i = lo; i < hi; i++) {
+                k = seg_of(seg_offsets, n_seg, i, k);
+                const Item& item = w->items[item_ids[k]];
+                if (buf_item != item_ids[k]) {
+                    buffer = item.shape_cd;
+                    buffer.has_surrogate = false;
+                    buf_item = item_ids[k];
                 }
+                Transformation t = from_cstt(t4[4 * i], t4[4 * i + 1], t4[4 * i + 2], t4[4 * i + 3]);
+                uint8_t v = 0;
+                if (!(mode & 1) && cde.detect_surrogate_collision(item.shape_cd.surrogate, t, filter)) v |= 1;
+                if (!(v & 1)) {
+                    buffer.transform_from(item.shape_cd, t);
+                    try {
+                        if (cde.detect_poly_collision(buffer, filter)) v |= 2;
+                    } catch (const PanicInReference&) {
+                        v |= 0x80;
+                    }
+                }
+                out[i] = v;
             }
-            out[i] = v;
         }
 #ifdef ORC_COUNT
         flops += g_flops;
 #endif
     };
-    if (nthreads <= 1) work(0, n);
-    else {
-        std::vector<std::thread> th;
-        for (int k = 0; k < nthreads; k++) th.emplace_back(work, n * k / nthreads, n * (k + 1) / nthreads);
-        for (auto& t : th) t.join();
-    }
+    pool().run(nthreads < 1 ? 1 : nthreads, work);
     return flops.load();
 }
-// out_bits: n x words_per_query u32 (bit = hazard slot index). mode bit0: poly only.
-uint64_t orc_collect_batch(World* w, int item_id, const float* t4, int64_t n, uint32_t* out_bits,
-                           int words_per_query, int nthreads, int mode) {
-    const Item& item = w->items[item_id];
+uint64_t orc_detect_batch(World* w, int item_id, const float* t4, int64_t n, const uint32_t* filter_bits,
+                          int filter_words, uint8_t* out, int nthreads, int mode) {
+    const int64_t offs[2] = {0, n};
+    return orc_detect_multi(w, 1, &item_id, offs, t4, filter_bits, filter_words, out, nthreads, mode);
+}
+// out_bits: n x words_per_query u32 (bit = hazard slot index). mode bit0: poly only. seed_bits (or null): the collectors
+// start from these sets instead of empty ones (a collector passed in non-empty: its hazards are skipped by
+// `contains_key`, qt_node.rs:172 / cd_engine.rs:279, and stay in the result).
+uint64_t orc_collect_multi(World* w, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* t4,
+                           const uint32_t* seed_bits, uint32_t* out_bits, int words_per_query, int nthreads, int mode) {
     const CDEngine& cde = w->layout->cde;
+    const int64_t n = seg_offsets[n_seg];
     std::atomic<uint64_t> flops{0};
-    auto work = [&](int64_t lo, int64_t hi) {
-        SPolygon buffer = item.shape_cd;
-        buffer.has_surrogate = false;
+    std::atomic<int64_t> next{0};
+    auto work = [&](int) {
         HazardCollector col(std::max<size_t>(cde.hazards_map.capacity(), (size_t)words_per_query * 32));
 #ifdef ORC_COUNT
         g_flops = 0;
 #endif
-        for (int64_t i = lo; i < hi; i++) {
-            Transformation t = from_cstt(t4[4 * i], t4[4 * i + 1], t4[4 * i + 2], t4[4 * i + 3]);
-            col.clear();
-            if (!(mode & 1)) cde.collect_surrogate_collisions(item.shape_cd.surrogate, t, col);
-            buffer.transform_from(item.shape_cd, t);
-            cde.collect_poly_collisions(buffer, col);
-            for (int k = 0; k < words_per_query; k++) out_bits[i * words_per_query + k] = col.bits[k];
+        int k = 0, buf_item = -1;
+        SPolygon buffer;
+        for (;;) {
+            const int64_t lo = next.fetch_add(ORC_CHUNK);
+            if (lo >= n) break;
+            const int64_t hi = std::min<int64_t>(n, lo + ORC_CHUNK);
+            for (int64_t i = lo; i < hi; i++) {
+                k = seg_of(seg_offsets, n_seg, i, k);
+                const Item& item = w->items[item_ids[k]];
+                if (buf_item != item_ids[k]) {
+                    buffer = item.shape_cd;
+                    buffer.has_surrogate = false;
+                    buf_item = item_ids[k];
+                }
+                Transformation t = from_cstt(t4[4 * i], t4[4 * i + 1], t4[4 * i + 2], t4[4 * i + 3]);
+                col.clear();
+                if (seed_bits)
+                    for (int j = 0; j < words_per_query; j++) col.bits[j] = seed_bits[i * words_per_query + j];
+                if (!(mode & 1)) cde.collect_surrogate_collisions(item.shape_cd.surrogate, t, col);
+                buffer.transform_from(item.shape_cd, t);
+                cde.collect_poly_collisions(buffer, col);
+                for (int j = 0; j < words_per_query; j++) out_bits[i * words_per_query + j] = col.bits[j];
+            }
         }
 #ifdef ORC_COUNT
         flops += g_flops;
 #endif
     };
-    if (nthreads <= 1) work(0, n);
-    else {
-        std::vector<std::thread> th;
-        for (int k = 0; k < nthreads; k++) th.emplace_back(work, n * k / nthreads, n * (k + 1) / nthreads);
-        for (auto& t : th) t.join();
-    }
+    pool().run(nthreads < 1 ? 1 : nthreads, work);
     return flops.load();
+}
+uint64_t orc_collect_batch(World* w, int item_id, const float* t4, int64_t n, uint32_t* out_bits,
+                           int words_per_query, int nthreads, int mode) {
+    const int64_t offs[2] = {0, n};
+    return orc_collect_multi(w, 1, &item_id, offs, t4, nullptr, out_bits, words_per_query, nthreads, mode);
 }
 // DTransformation -> (cos, sin, tx, ty) on the host libm (transformation.rs:131-139)
 void orc_compose_batch(const float* rot_tx_ty, int64_t n, float* t4) {

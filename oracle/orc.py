@@ -23,23 +23,42 @@ i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
+def cpu_tag() -> str:
+    """Tag of this machine's CPU feature flags: the oracle is built -march=native (like the reference's CI,
+    -C target-cpu=native), so a library built on another CPU must not be loaded here."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("flags"):
+                    flags = " ".join(sorted(ln.split(":", 1)[1].split()))
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+def _paths():
+    tag = cpu_tag()
+    return tag, os.path.join(_HERE, "_build", f"liboracle.{tag}.so"), os.path.join(_HERE, "_build", f"liboracle_count.{tag}.so")
+
+
 def build(force: bool = False) -> None:
-    """Compile the oracle with g++ (-ffp-contract=off). Building the checker is not using it."""
-    out = os.path.join(_HERE, "_build", "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "geom.hpp", "spoly.hpp", "cde.hpp", "entities.hpp")]
-    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
-        if os.path.exists(os.path.join(_HERE, "_build", "liboracle_count.so")):
-            return
-    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    """Compile the oracle with g++ (-O3 -march=native -ffp-contract=off). Building the checker is not using it."""
+    tag, out, out_count = _paths()
+    srcs = [os.path.join(_HERE, f) for f in ("capi.cpp", "geom.hpp", "spoly.hpp", "cde.hpp", "entities.hpp", "Makefile")]
+    if not force and all(os.path.exists(o) and all(os.path.getmtime(o) >= os.path.getmtime(s) for s in srcs) for o in (out, out_count)):
+        return
+    subprocess.run(["make", "-C", _HERE, "-s", f"TAG={tag}"] + (["-B"] if force else []), check=True)
 
 
 def lib(count: bool = False):
     key = "count" if count else "plain"
     if key in _LIBS:
         return _LIBS[key]
-    path = os.path.join(_HERE, "_build", "liboracle_count.so" if count else "liboracle.so")
-    if not os.path.exists(path):
-        build()
+    build()
+    path = _paths()[2 if count else 1]
     L = C.CDLL(path)
     vp = C.c_void_p
     sig = {
@@ -91,6 +110,8 @@ def lib(count: bool = False):
         "orc_lbf_fill_bin": (C.c_int, [vp, C.c_int, C.c_float, C.c_uint64, C.c_int]),
         "orc_detect_batch": (C.c_uint64, [vp, C.c_int, f32p, C.c_int64, C.c_void_p, C.c_int, u8p, C.c_int, C.c_int]),
         "orc_collect_batch": (C.c_uint64, [vp, C.c_int, f32p, C.c_int64, u32p, C.c_int, C.c_int, C.c_int]),
+        "orc_detect_multi": (C.c_uint64, [vp, C.c_int, i32p, i64p, f32p, C.c_void_p, C.c_int, u8p, C.c_int, C.c_int]),
+        "orc_collect_multi": (C.c_uint64, [vp, C.c_int, i32p, i64p, f32p, C.c_void_p, u32p, C.c_int, C.c_int, C.c_int]),
         "orc_compose_batch": (None, [f32p, C.c_int64, f32p]),
         "orc_approx_eq": (C.c_int, [C.c_float, C.c_float]),
         "orc_edge_edge": (C.c_int, [f32p, f32p]),
@@ -318,6 +339,38 @@ class OracleWorld:
         out = np.zeros((len(t4), words), np.uint32)
         flops = self.L.orc_collect_batch(self.w, int(item_id), t4, len(t4), out, int(words), int(nthreads), 1 if poly_only else 0)
         self.last_flops = int(flops)
+        return out
+
+
+    def detect_multi(self, item_ids, seg_offsets, t4, filter_bits=None, nthreads=1, poly_only=False, out=None):
+        """One parallel pass over a segmented batch (segment k = queries seg_offsets[k]..seg_offsets[k+1] of item_ids[k])."""
+        t4 = _f32(t4).reshape(-1, 4)
+        ids = np.ascontiguousarray(item_ids, dtype=np.int32)
+        offs = np.ascontiguousarray(seg_offsets, dtype=np.int64)
+        assert len(offs) == len(ids) + 1 and int(offs[-1]) == len(t4)
+        if out is None:
+            out = np.zeros(len(t4), np.uint8)
+        if filter_bits is None:
+            fb, fw = None, 0
+        else:
+            filter_bits = np.ascontiguousarray(filter_bits, dtype=np.uint32)
+            fb, fw = filter_bits.ctypes.data_as(C.c_void_p), len(filter_bits)
+        self.last_flops = int(self.L.orc_detect_multi(self.w, len(ids), ids, offs, t4, fb, fw, out, int(nthreads), 1 if poly_only else 0))
+        return out
+
+    def collect_multi(self, item_ids, seg_offsets, t4, words, seed=None, nthreads=1, poly_only=False):
+        """Segmented collect batch; `seed` (n x words): collectors passed in non-empty."""
+        t4 = _f32(t4).reshape(-1, 4)
+        ids = np.ascontiguousarray(item_ids, dtype=np.int32)
+        offs = np.ascontiguousarray(seg_offsets, dtype=np.int64)
+        assert len(offs) == len(ids) + 1 and int(offs[-1]) == len(t4)
+        out = np.zeros((len(t4), words), np.uint32)
+        sp = None
+        if seed is not None:
+            seed = np.ascontiguousarray(seed, dtype=np.uint32)
+            assert seed.shape == out.shape
+            sp = seed.ctypes.data_as(C.c_void_p)
+        self.last_flops = int(self.L.orc_collect_multi(self.w, len(ids), ids, offs, t4, sp, out, int(words), int(nthreads), 1 if poly_only else 0))
         return out
 
 

@@ -1,0 +1,366 @@
+"""GPU parity tests of the round-2 additions, all through the C ABI and all against the CPU oracle:
+the in-process multi-device pool (jg_pool_*), the lattice query form, one-launch multi-item collect with
+pre-seeded collectors, HazKey-versioned filters, Layout::swap_container on a live engine and device-blob validation."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import oracle_world, place_remove_sequence
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        r = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True)
+        return sum(1 for ln in r.stdout.splitlines() if ln.startswith("GPU "))
+    except OSError:
+        return 0
+
+
+def _batch(jg, wl, total, seed):
+    sizes = jg.split_batch(total, len(wl.items))
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    t = np.concatenate([jg.make_queries(wl, i, m, seed=seed) for i, m in enumerate(sizes)]).astype(np.float32)
+    return list(range(len(wl.items))), offs, np.ascontiguousarray(t)
+
+
+@pytest.fixture(scope="module")
+def world(jg, orc):
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            wl = jg.load_workload(name)
+            cache[name] = (wl, jg.build_engine(wl, device=0), oracle_world(orc, wl))
+        return cache[name]
+
+    yield get
+    for _, cde, _ in cache.values():
+        cde.close()
+
+
+# ---- pool -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,total", [("swim_half", 300_007), ("shirts_full", 120_001), ("baldacci1_bin", 50_000)])
+def test_pool_detect_and_collect_match_oracle(jg, orc, name, total):
+    """ONE host batch through jg_pool_*: sharded over every GPU of the box (1 on the single-GPU box), gathered into one
+    result array; verdicts and hazard sets equal the oracle's on every query. The shard cuts fall inside segments."""
+    wl = jg.load_workload(name)
+    host = jg.build_engine(wl, device=None)
+    w = oracle_world(orc, wl)
+    devs = list(range(max(1, min(_n_gpus(), 8))))
+    pool = jg.EnginePool(host, devs)
+    try:
+        pool.set_min_shard(1 << 12)  # small test batches still use every device
+        pool.upload_items(wl.items)
+        ids, offs, t = _batch(jg, wl, total, seed=11)
+        exp = w.detect_multi(ids, offs, t, nthreads=8)
+        got = pool.detect_multi(ids, offs, t)
+        assert np.array_equal(got, exp), f"{(got != exp).sum()} verdict mismatches over {len(devs)} device(s)"
+        # async form + pinned buffers, two batches in flight
+        pin_t, pin_o = jg.PinnedBuffer(t.shape, np.float32), [jg.PinnedBuffer((len(t),), np.uint8) for _ in range(2)]
+        pin_t.array[:] = t
+        for o in pin_o:
+            pool.detect_multi(ids, offs, pin_t.array, out=o.array, wait=False)
+        pool.sync()
+        assert all(np.array_equal(o.array, exp) for o in pin_o)
+        words = host.collector_words()
+        m = min(total, 60_000)
+        ids2, offs2, t2 = _batch(jg, wl, m, seed=12)
+        expc = w.collect_multi(ids2, offs2, t2, words, nthreads=8)
+        gotc = pool.collect_multi(ids2, offs2, t2, words)
+        bad = np.nonzero((gotc != expc).any(axis=1))[0]
+        assert len(bad) == 0, f"{len(bad)} hazard-set mismatches, first {bad[:3]}"
+        st = [pool.engine_stats(k) for k in range(len(pool))]
+        assert all(s["queries"] > 0 and s["launches"] > 0 for s in st), st  # every device did part of the work
+        assert sum(s["queries"] for s in st) == 3 * total + m
+    finally:
+        pool.close()
+        host.close()
+
+
+def test_pool_follows_layout_updates_and_small_batches(jg, orc):
+    wl = jg.load_workload("swim_half")
+    host = jg.build_engine(wl, device=None)
+    w = oracle_world(orc, wl)
+    pool = jg.EnginePool(host, list(range(max(1, min(_n_gpus(), 8)))))
+    try:
+        pool.upload_items(wl.items)
+        ids, offs, t = _batch(jg, wl, 40_000, seed=13)
+
+        def check(op):
+            if op % 6 == 5:
+                assert np.array_equal(pool.detect_multi(ids, offs, t), w.detect_multi(ids, offs, t, nthreads=8)), f"after operation {op}"
+
+        place_remove_sequence(jg, wl, host, w, n_ops=24, seed=2, after_each=check)
+        # a batch below min_shard runs on one device; an empty batch is a no-op
+        small = pool.detect_multi(ids[:1], np.array([0, 100], np.int64), np.ascontiguousarray(t[:100]))
+        assert np.array_equal(small, w.detect_batch(0, t[:100]))
+        assert len(pool.detect_multi(ids[:1], np.array([0, 0], np.int64), np.zeros((0, 4), np.float32))) == 0
+        with pytest.raises(jg.JaguaCudaError):
+            pool.detect_multi([99], np.array([0, 10], np.int64), np.ascontiguousarray(t[:10]))  # unknown item on every device
+    finally:
+        pool.close()
+        host.close()
+
+
+# ---- lattice form -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["swim_half", "shirts_full"])
+def test_lattice_queries_match_composed_queries(jg, world, name):
+    """5-byte queries (rotation index + lattice coordinates): the device's translations are jg_lattice_points', so the
+    verdicts equal the oracle's on the composed (cos, sin, tx, ty) records - on the engine and through the pool."""
+    wl, cde, w = world(name)
+    sizes = jg.split_batch(100_003, len(wl.items))
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    ridx, ij, comp = [], [], []
+    lat = None
+    for i, m in enumerate(sizes):
+        cde.set_item_rotations(i, wl.items[i].rotations)
+        lat, r, k = jg.make_queries_lattice(wl, i, m, seed=21)
+        ridx.append(r), ij.append(k)
+        comp.append(jg.compose_lattice_queries(wl, i, lat, r, k))
+    ridx, ij, comp = np.concatenate(ridx), np.ascontiguousarray(np.concatenate(ij)), np.concatenate(comp)
+    ids = list(range(len(wl.items)))
+    exp = w.detect_multi(ids, offs, comp, nthreads=8)
+    got = cde.detect_multi_lattice(ids, offs, lat, ridx, ij)
+    assert np.array_equal(got, exp), f"{(got != exp).sum()} mismatches"
+    assert np.array_equal(cde.detect_multi(ids, offs, np.ascontiguousarray(comp)), exp)
+    assert (exp == 0).sum() > 0 and (exp == 2).sum() > 0
+    # corners of the lattice, async form
+    edge = np.array([[0, 0], [65535, 65535], [0, 65535], [65535, 0]], np.uint16)
+    r4 = np.zeros(4, np.uint8)
+    got4 = cde.detect_multi_lattice([0], np.array([0, 4], np.int64), lat, r4, edge)
+    assert np.array_equal(got4, w.detect_batch(0, jg.compose_lattice_queries(wl, 0, lat, r4, edge)))
+
+
+# ---- one-launch collect, seeded collectors ----------------------------------------------------------------
+@pytest.mark.parametrize("name", ["shirts_full", "trousers_full", "swim_half", "baldacci1_bin", "shirts_full_d10", "gardeyn1c_half"])
+def test_collect_multi_matches_oracle(jg, world, name):
+    """jg_collect_multi: all item types in one launch (grid path) or segment by segment (walk path: depth 10), against
+    the oracle's segmented pass; ragged segments, an empty segment in the middle."""
+    wl, cde, w = world(name)
+    words = cde.collector_words()
+    n_items = len(wl.items)
+    sizes = [(997 * (i + 3)) % 4000 + 1 for i in range(n_items)]
+    if n_items > 2:
+        sizes[1] = 0
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    t = np.ascontiguousarray(np.concatenate([jg.make_queries(wl, i, m, seed=31) for i, m in enumerate(sizes)]).astype(np.float32).reshape(-1, 4))
+    ids = list(range(n_items))
+    l0 = cde.stats()["launches"]
+    got = cde.collect_multi(ids, offs, t, words)
+    n_launch = cde.stats()["launches"] - l0
+    exp = w.collect_multi(ids, offs, t, words, nthreads=8)
+    bad = np.nonzero((got != exp).any(axis=1))[0]
+    assert len(bad) == 0, f"{name}: {len(bad)} hazard-set mismatches, first {bad[:3]} got {got[bad[:3]]} exp {exp[bad[:3]]}"
+    if cde.detect_path() == "grid" and words <= 8 and n_items <= 32:
+        assert n_launch == 1, f"{n_launch} launches for {n_items} item types"
+    # per-item calls give the same sets
+    k = n_items - 1
+    one = cde.collect_batch(k, t[offs[k]:offs[k + 1]], words)
+    assert np.array_equal(one, exp[offs[k]:offs[k + 1]])
+    gp = cde.collect_multi(ids, offs, t, words, poly_only=True)
+    assert np.array_equal(gp, w.collect_multi(ids, offs, t, words, nthreads=8, poly_only=True))
+
+
+@pytest.mark.parametrize("name", ["shirts_full", "swim_half", "baldacci1_bin", "shirts_full_d10"])
+def test_preseeded_collectors_match_oracle(jg, world, name):
+    """A collector passed in non-empty (hazards/collector.rs:7-42; `contains_key` in qt_node.rs:172, cd_engine.rs:279):
+    its hazards are skipped and stay in the set. Seeds: random subsets of the live slots, the query's own full answer,
+    and the empty set."""
+    wl, cde, w = world(name)
+    words = cde.collector_words()
+    rng = np.random.default_rng(7)
+    ids, offs, t = _batch(jg, wl, 30_000, seed=33)
+    n = len(t)
+    live = np.array([int(k) & 0xFFFFFFFF for k in cde.hazard_keys], np.int64)
+    plain = w.collect_multi(ids, offs, t, words, nthreads=8)
+    seed = np.zeros((n, words), np.uint32)
+    pick = rng.random((n, len(live))) < 0.15
+    for j, s in enumerate(live):
+        seed[pick[:, j], s >> 5] |= np.uint32(1 << (s & 31))
+    seed[: n // 10] = 0
+    seed[n // 10: n // 5] = plain[n // 10: n // 5]
+    exp = w.collect_multi(ids, offs, t, words, seed=seed, nthreads=8)
+    assert np.array_equal(exp, plain | seed)  # (the reference's semantics: the result is the union)
+    got = cde.collect_multi(ids, offs, t, words, seed=seed)
+    bad = np.nonzero((got != exp).any(axis=1))[0]
+    assert len(bad) == 0, f"{name}: {len(bad)} mismatches, first {bad[:3]}"
+    inplace = seed.copy()
+    cde.collect_multi(ids, offs, t, words, seed=inplace, out=inplace)  # seed_bits may alias out_bits
+    assert np.array_equal(inplace, exp)
+
+
+# ---- HazKey-versioned filters -----------------------------------------------------------------------------
+def test_keyed_filter_survives_slot_reuse(jg, orc):
+    """a slot-bitset filter silently hides the NEW hazard when the SlotMap reuses the slot of a removed,
+    filtered hazard. jg_filter_upload_keys compares versions like the reference's HazKeyFilter: the stale key matches
+    nothing after the slot was reused."""
+    wl = jg.load_workload("swim_half")
+    cde = jg.build_engine(wl, device=0)
+    w = oracle_world(orc, wl)
+    try:
+        dyn = [(k, h) for k, h in zip(cde.hazard_keys, wl.hazards) if h.dynamic]
+        key, haz = dyn[3]
+        okey = w.dynamic_keys[3]
+        cde.upload_filter_keys(0, [key])
+        bits = cde.filter_from_keys([key])
+        ids, offs, t = _batch(jg, wl, 60_000, seed=51)
+        exp_f = w.detect_multi(ids, offs, t, filter_bits=bits, nthreads=8)
+        assert np.array_equal(cde.detect_multi(ids, offs, t, filter_id=0), exp_f)
+        assert (exp_f != w.detect_multi(ids, offs, t, nthreads=8)).sum() > 0  # the filter matters
+        # remove the filtered hazard, register another one: it takes the same slot with a new version
+        cde.deregister_hazard_by_key(key)
+        w.deregister_hazard(okey)
+        other = dyn[5][1]
+        shifted = (other.verts + np.array([3.0, -2.0], np.float32)).astype(np.float32)
+        k_new = cde.register_hazard(jg.HAZ_PLACED_ITEM, shifted, other.poi + np.array([3.0, -2.0, 0], np.float32), id=other.id, pk=0xABC00000001)
+        k_orc = w.register_hazard_raw(jg.HAZ_PLACED_ITEM, shifted, other.poi + np.array([3.0, -2.0, 0], np.float32), other.id, 0, 0xABC00000001, True)
+        assert k_new == k_orc and (k_new & 0xFFFFFFFF) == (key & 0xFFFFFFFF) and k_new != key
+        exp_now = w.detect_multi(ids, offs, t, nthreads=8)  # reference: the stale key filters nothing
+        got = cde.detect_multi(ids, offs, t, filter_id=0)
+        assert np.array_equal(got, exp_now), f"{(got != exp_now).sum()} mismatches: the stale key still hides a hazard"
+        # the slot-bitset form of the same filter WOULD hide the new hazard (documented: re-upload after every update)
+        cde.upload_filter(1, bits)
+        hidden = w.detect_multi(ids, offs, t, filter_bits=bits, nthreads=8)
+        assert np.array_equal(cde.detect_multi(ids, offs, t, filter_id=1), hidden) and (hidden != exp_now).sum() > 0
+        # a key of the new hazard works, and an empty keyed filter is NoFilter
+        cde.upload_filter_keys(2, [k_new])
+        assert np.array_equal(cde.detect_multi(ids, offs, t, filter_id=2),
+                              w.detect_multi(ids, offs, t, filter_bits=cde.filter_from_keys([k_new]), nthreads=8))
+        cde.upload_filter_keys(3, [])
+        assert np.array_equal(cde.detect_multi(ids, offs, t, filter_id=3), exp_now)
+    finally:
+        cde.close()
+
+
+# ---- swap_container on a live engine ----------------------------------------------------------------------
+def test_swap_container_on_device(jg, orc):
+    """Layout::swap_container (entities/layout.rs:40-50) with the device engine kept: the strip is widened and narrowed
+    under placed items, queries after each swap equal the oracle's (change_strip_width)."""
+    from test_update_path import _strip_engine
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inst = orc.load_instance_json(os.path.join(root, "assets", "swim.json"))
+    w = orc.world_from_instance(inst)
+    height = float(np.float32(inst["strip_height"]))
+    width = float(np.float32(w.strip_width() * 1.5))
+    w.change_strip_width(width)
+    cde = _strip_engine(jg, width, height, device=0)
+    try:
+        items = [w.item(i) for i in range(w.n_items())]
+        for i, it in enumerate(items):
+            cde.upload_item(i, jg.ItemShape(it["verts"], it["poi"], it["poles"], it["piers"]))
+        rng = np.random.default_rng(9)
+        for k in range(12):
+            i = int(rng.integers(len(items)))
+            rots = items[i]["rotations"]
+            dt = np.array([[float(rots[int(rng.integers(len(rots)))]), rng.random() * width, rng.random() * height]], np.float32)
+            pk = w.place_item(i, float(dt[0, 0]), float(dt[0, 1]), float(dt[0, 2]))
+            cde.place_item(i, jg.ItemShape(items[i]["verts"], items[i]["poi"], items[i]["poles"], items[i]["piers"]), jg.compose(dt)[0], pk)
+
+        def queries(bw):  # uniform over the square hull of the current strip
+            side = max(bw, height)
+            n = 20_000
+            txy = (rng.random((n, 2)) * side).astype(np.float32) - np.array([(side - bw) / 2, (side - height) / 2], np.float32)
+            rot = np.asarray(items[2]["rotations"], np.float32)[rng.integers(0, len(items[2]["rotations"]), n)]
+            return jg.compose(np.concatenate([rot[:, None], txy], 1).astype(np.float32))
+
+        for new_w in (width, width * 1.25, width * 0.9):
+            if new_w != width:
+                w.change_strip_width(float(np.float32(new_w)))
+                base = _strip_engine(jg, np.float32(new_w), height)
+                cde.swap_container(base)
+                base.close()
+            t = queries(float(new_w))
+            assert np.array_equal(cde.detect_batch(2, t), w.detect_batch(2, t)), f"width {new_w}"
+            words = cde.collector_words()
+            assert np.array_equal(cde.collect_batch(2, t[:5000], words), w.collect_batch(2, t[:5000], words))
+    finally:
+        cde.close()
+
+
+# ---- device blobs are validated ----------------------------------------------------------------------------
+def test_malformed_device_blob_is_rejected(jg):
+    wl = jg.load_workload("swim_half")
+    cde = jg.build_engine(wl, device=0)
+    try:
+        cde.sync_layout()
+        blob = cde.flatten().copy()
+        d = jg.DeviceBuffer(cde, len(blob))
+        d.upload(blob)
+        cde.upload_layout_device(d.ptr, len(blob), epoch=7)  # a well-formed device blob is accepted
+        cde.sync()
+        t = jg.make_queries(wl, 0, 2048, seed=1)
+        ok = cde.detect_batch(0, t)
+        import struct
+        off_entry_meta = struct.unpack_from("<12I4f12I", blob.tobytes(), 0)[19]
+        bad = blob.copy()
+        bad.view(np.int32)[off_entry_meta // 4 + 2] = 1 << 28  # edge_count of entry 0 far beyond the edge section
+        d.upload(bad)
+        with pytest.raises(jg.JaguaCudaError):  # checked on the device before anything reads the blob
+            cde.upload_layout_device(d.ptr, len(bad), epoch=8)
+        assert np.array_equal(cde.detect_batch(0, t), ok)  # the engine keeps serving the previous layout
+        d.free()
+    finally:
+        cde.close()
+
+
+# ---- layout broadcast over NCCL inside the library ---------------------------------------------------------
+def _bcast_worker(jg, wl, nid, rank, world, blobs, results, errors):
+    try:
+        cde = jg.CDEngine(wl.cde_bbox, wl.quadtree_depth, wl.cd_threshold, wl.n_ff_poles, wl.n_ff_piers, device=rank)
+        for i, it in enumerate(wl.items):
+            cde.upload_item(i, jg.ItemShape(it.verts, it.poi, it.poles, it.piers))
+        lib = cde._lib
+        cde._chk(lib.jg_engine_comm_init(cde._eng, nid, rank, world, 1 << 20))
+        t = jg.make_queries(wl, 3, 20_000, seed=61)
+        got = []
+        for blob in blobs:  # every rank calls the collective, in the same order
+            if rank == 0:
+                cde._chk(lib.jg_layout_broadcast(cde._eng, 0, blob.ctypes.data, blob.nbytes, 5))
+            else:
+                cde._chk(lib.jg_layout_broadcast(cde._eng, 0, None, 0, 0))
+            cde._dirty = False
+            got.append(cde.detect_batch(3, t).copy())
+        results[rank] = got
+        cde.close()
+    except Exception as ex:  # noqa: BLE001 - reported by the test
+        errors.append((rank, repr(ex)))
+
+
+def test_layout_broadcast_over_nccl(jg, orc):
+    """jg_engine_comm_init + jg_layout_broadcast: rank 0 sends two successive layouts, every rank (one thread and one
+    engine per GPU of the box; a single rank on the 1-GPU box) binds them from the NCCL receive buffer and answers like
+    the oracle on each."""
+    import threading
+
+    wl = jg.load_workload("swim_half")
+    host = jg.build_engine(wl, device=None)
+    w = oracle_world(orc, wl)
+    t = jg.make_queries(wl, 3, 20_000, seed=61)
+    blobs, exps = [host.flatten().copy()], [w.detect_batch(3, t)]
+    dyn = [(k, ok) for k, ok, h in zip(host.hazard_keys, iter([None] * len(wl.hazards)), wl.hazards) if h.dynamic]
+    for (k, _), ok in list(zip(dyn, w.dynamic_keys))[:6]:
+        host.deregister_hazard_by_key(k)
+        w.deregister_hazard(ok)
+    blobs.append(host.flatten().copy())
+    exps.append(w.detect_batch(3, t))
+    assert (exps[0] != exps[1]).sum() > 0
+    world = max(1, min(_n_gpus(), 4))
+    nid = np.zeros(128, np.uint8)
+    assert jg.load_library().jg_nccl_unique_id(nid) == jg.JG_OK
+    results, errors = {}, []
+    th = [threading.Thread(target=_bcast_worker, args=(jg, wl, nid, r, world, blobs, results, errors)) for r in range(world)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join(timeout=300)
+    assert not errors, errors
+    for r in range(world):
+        for k in range(2):
+            assert np.array_equal(results[r][k], exps[k]), f"rank {r}, layout {k}: {(results[r][k] != exps[k]).sum()} mismatches"
+    host.close()

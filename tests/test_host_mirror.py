@@ -108,14 +108,16 @@ def test_blob_is_structurally_valid(jg, name):
     blob = cde.flatten()
     hdr = struct.unpack_from("<12I4f12I", blob.tobytes(), 0)
     magic, version, total, n_nodes, n_entries, n_edges, n_slots, n_hv, root_level, thr, ext_slot, _ = hdr[:12]
-    offs = hdr[16:26]
-    assert magic == 0x4A47424C and version == 1 and total == len(blob)
+    offs = hdr[16:27]  # ten sections + haz_version (layout version 2)
+    assert magic == 0x4A47424C and version == 2 and total == len(blob)
     assert root_level == wl.quadtree_depth and thr == wl.cd_threshold and n_slots == cde.slot_capacity()
     assert all(o % 16 == 0 and o < total for o in offs)
     nm = np.frombuffer(blob, np.int32, 4 * n_nodes, offs[0]).reshape(-1, 4)
     nb = np.frombuffer(blob, np.float32, 4 * n_nodes, offs[1]).reshape(-1, 4)
     na = np.frombuffer(blob, np.uint32, n_nodes, offs[2])
     em = np.frombuffer(blob, np.int32, 4 * n_entries, offs[3]).reshape(-1, 4)
+    hv = np.frombuffer(blob, np.uint32, n_slots, offs[10])
+    assert all(int(hv[int(k) & 0xFFFFFFFF]) == int(k) >> 32 for k in cde.hazard_keys)  # HazKey = slot | version << 32
     assert nm[0, 3] == -1 and np.array_equal(nb[0], wl.cde_bbox)
     kids = nm[nm[:, 0] >= 0, 0]
     assert np.all(kids % 4 == 1) and len(set(kids.tolist())) == len(kids)  # blocks at 1 + 4k, each used once

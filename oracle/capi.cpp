@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see geom.hpp header).
 // extern "C" surface over the oracle for ctypes (tests/, smoke(), bench.py's CPU legs).
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <condition_variable>
 #include <functional>
@@ -564,18 +565,31 @@ struct ThreadPool {
     std::mutex m;
     std::condition_variable cv_go, cv_done;
     const std::function<void(int)>* job = nullptr;
-    uint64_t gen = 0;
-    int want = 0, running = 0;
+    std::atomic<uint64_t> gen{0};
+    std::atomic<int> want{0};
+    int running = 0;
     bool stop = false;
     void worker(int k) {
         uint64_t seen = 0;
         for (;;) {
+            // back-to-back parallel regions (the benchmark loop) find the workers still spinning: a blocked thread can take
+            // tens of milliseconds to wake up in a container, longer than a small batch lasts
+            const auto t0 = std::chrono::steady_clock::now();
+            bool got = false;
+            while (std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(20)) {
+                if (gen.load(std::memory_order_acquire) != seen && k < want.load(std::memory_order_acquire)) {
+                    got = true;
+                    break;
+                }
+                std::this_thread::yield();
+            }
             const std::function<void(int)>* j;
             {
                 std::unique_lock<std::mutex> lk(m);
-                cv_go.wait(lk, [&] { return stop || (gen != seen && k < want); });
+                if (!got) cv_go.wait(lk, [&] { return stop || (gen.load() != seen && k < want.load()); });
                 if (stop) return;
-                seen = gen;
+                if (gen.load() == seen || k >= want.load()) continue;  // (the region ended while this thread was still spinning)
+                seen = gen.load();
                 j = job;
             }
             (*j)(k);
@@ -585,7 +599,7 @@ struct ThreadPool {
             }
         }
     }
-    // runs fn(k) for k in [0, n) on n threads (the caller is thread 0) and waits
+    // runs fn(k) for k in [0, n) on n threads (the caller is thread n - 1) and waits
     void run(int n, const std::function<void(int)>& fn) {
         if (n <= 1) {
             fn(0);
@@ -598,15 +612,15 @@ struct ThreadPool {
                 th.emplace_back([this, k] { worker(k); });
             }
             job = &fn;
-            want = n - 1;
             running = n - 1;
-            gen++;
+            want.store(n - 1, std::memory_order_release);
+            gen.fetch_add(1, std::memory_order_release);
         }
         cv_go.notify_all();
         fn(n - 1);
         std::unique_lock<std::mutex> lk(m);
         cv_done.wait(lk, [&] { return running == 0; });
-        want = 0;
+        want.store(0);
     }
     ~ThreadPool() {
         {

@@ -634,11 +634,11 @@ static int g_dependent_launch = [] { const char* v = getenv("JG_PDL"); return v 
 void set_dependent_launch(int on) { g_dependent_launch = on ? 1 : 0; }
 int dependent_launch() { return g_dependent_launch; }
 template <class K>
-static int persistent_grid(K kernel, int slot, int n_sms, size_t smem) {
+static int persistent_grid(K kernel, int slot, int n_sms, size_t smem, int threads = S_THREADS) {
     if (g_occ[slot] == 0 || g_occ_smem[slot] != smem) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int b = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, S_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, smem);
         g_occ[slot] = b < 1 ? 1 : b;
         g_occ_smem[slot] = smem;
     }
@@ -794,34 +794,57 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
 bool collect_grid_applicable(const DetectPlan& plan, const SegTable& tab, int words) {
     if (!plan.use_grid || words > CG_MAX_WORDS) return false;
     for (int k = 0; k < tab.n_seg; k++)
-        if (tab.seg[k].n_poles * CG_GROUP > 4096 || tab.seg[k].n_piers * CG_GROUP > 4096) return false;
+        if (tab.seg[k].n_poles > CG_MAX_POLES || tab.seg[k].n_piers > CG_MAX_PIERS || tab.seg[k].n_verts > CG_VERT_CAP) return false;
     return true;
 }
 cudaError_t launch_collect_grid(const DevLayout& L, SegTable& tab, const uint8_t* d_kinds, const float4* d_xf, int mode,
                                 const uint32_t* d_seed, uint32_t* d_out_bits, int words, int* d_next, int n_sms, cudaStream_t st,
                                 int* n_launches) {
-    cudaMemsetAsync(d_next, 0, sizeof(int), st);
-    const size_t smem = ((sizeof(SegTable) + 15) & ~(size_t)15) + ((sizeof(GridDev) + 15) & ~(size_t)15) + S_WARPS * sizeof(CGSlots);
+    cudaMemsetAsync(d_next, 0, 2 * sizeof(int), st);  // work counters of the two kernels (DetectCtl::s1_next, s2_next)
     bool piers = false;
-    for (int k = 0; k < tab.n_seg; k++) piers = piers || tab.seg[k].n_piers > 0;
-    const int g = piers ? persistent_grid(k_collect_grid<true>, 11, n_sms, smem) : persistent_grid(k_collect_grid<false>, 10, n_sms, smem);
-    // queries per group: 16 when every warp has several groups to do; 8 / 4 for small launches (see the kernel)
-    const long long per_warp = (long long)tab.n_queries / ((long long)g * S_WARPS * CG_GROUP);
-    const int GS = per_warp >= 4 ? CG_GROUP : per_warp >= 1 ? CG_GROUP / 2 : CG_GROUP / 4;
+    int max_v = 1;
+    for (int k = 0; k < tab.n_seg; k++) {
+        piers = piers || tab.seg[k].n_piers > 0;
+        if (tab.seg[k].n_verts > max_v) max_v = tab.seg[k].n_verts;
+    }
+    const size_t smem = ((sizeof(SegTable) + 15) & ~(size_t)15) + ((sizeof(GridDev) + 15) & ~(size_t)15) +
+                        CG_WARPS * (piers ? sizeof(CGWarp<true>) : sizeof(CGWarp<false>));
+    const int g = piers ? persistent_grid(k_collect_grid<true>, 11, n_sms, smem, CG_THREADS) : persistent_grid(k_collect_grid<false>, 10, n_sms, smem, CG_THREADS);
+    // queries per group: 8 when every warp has several groups to do; 4 / 2 for small launches (see the kernel)
+    const long long per_warp = (long long)tab.n_queries / ((long long)g * CG_WARPS * CG_GROUP);
+    int GS = per_warp >= 4 ? CG_GROUP : per_warp >= 1 ? CG_GROUP / 2 : CG_GROUP / 4;
+    if (GS > CG_VERT_CAP / max_v) GS = CG_VERT_CAP / max_v;  // the group's transformed vertices live in the warp's shared-memory slice
+    if (GS < 1) GS = 1;
+    int gshift = 0;
+    while ((1 << gshift) < GS) gshift++;
     int n_groups = 0;
     for (int k = 0; k < tab.n_seg; k++) {
         const int len = (k + 1 < tab.n_seg ? tab.seg[k + 1].begin : tab.n_queries) - tab.seg[k].begin;
         tab.seg[k].gbeg = n_groups;
         n_groups += (len + GS - 1) / GS;
     }
-    const long long want = ((long long)n_groups + S_WARPS - 1) / S_WARPS;
+    const long long want = ((long long)n_groups + CG_WARPS - 1) / CG_WARPS;
     const int blocks = (int)(want < g ? want : g);
     if (piers)
-        k_collect_grid<true><<<blocks, S_THREADS, smem, st>>>(L, tab, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes), d_xf, mode, d_seed,
-                                                             d_out_bits, words, d_next, GS, n_groups);
+        k_collect_grid<true><<<blocks, CG_THREADS, smem, st>>>(L, tab, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes), d_xf, mode, d_seed,
+                                                              d_out_bits, words, d_next, GS, gshift, n_groups);
     else
-        k_collect_grid<false><<<blocks, S_THREADS, smem, st>>>(L, tab, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes), d_xf, mode, d_seed,
-                                                              d_out_bits, words, d_next, GS, n_groups);
+        k_collect_grid<false><<<blocks, CG_THREADS, smem, st>>>(L, tab, grid_of(d_kinds, L.n_nodes), cgrid_of(d_kinds, L.n_nodes), d_xf, mode, d_seed,
+                                                               d_out_bits, words, d_next, GS, gshift, n_groups);
+    {   // cd_engine.rs:274-288 in a kernel of its own (see k_collect_contain): groups of CC_GROUP queries, collectors completed in place
+        int n2 = 0;
+        for (int k = 0; k < tab.n_seg; k++) {
+            const int len = (k + 1 < tab.n_seg ? tab.seg[k + 1].begin : tab.n_queries) - tab.seg[k].begin;
+            tab.seg[k].gbeg = n2;
+            n2 += (len + CC_GROUP - 1) / CC_GROUP;
+        }
+        const size_t smem2 = ((sizeof(SegTable) + 15) & ~(size_t)15) + ((sizeof(GridDev) + 15) & ~(size_t)15) + S_WARPS * sizeof(CCSlots);
+        const int g2 = persistent_grid(k_collect_contain, 18, n_sms, smem2);
+        const long long want2 = ((long long)n2 + S_WARPS - 1) / S_WARPS;
+        k_collect_contain<<<(int)(want2 < g2 ? want2 : g2), S_THREADS, smem2, st>>>(L, tab, grid_of(d_kinds, L.n_nodes), d_xf, d_out_bits, words,
+                                                                                 d_next + 1, n2);
+        if (n_launches) *n_launches += 1;
+    }
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -588,14 +588,21 @@ __device__ __forceinline__ int virtual_root_grid(const GridDev& g, const Rect& b
 // Is the terminal of finest cell (i, j), at level lt, reached by QTNode::collides from the virtual root
 // (level l0)? Every ancestor from the virtual root down must flag the quadrant towards the cell
 // (qt_node.rs:111-126 with qt_traits.rs:19-106).
+template <bool ROLLED = false>
 __device__ __forceinline__ bool path_reaches(const GridDev& g, const Seg& sg, int l0, int lt, int i, int j) {
     const int D = g.D;
     for (int l = l0; l < lt; l++) {
         const int s = D - l;
         const int ci = i >> s, cj = j >> s;
+        // the child towards the cell holds an endpoint: flagged for sure (qt_traits.rs:36-44: `contains` -> Some(true), and
+        // half_intersect only ever adds quadrants). The child's box is the grid's (k_grid_build checked every node box against
+        // the nested midpoints that Rect::quadrants computes, rect.rs:141-151), so this is the reference's own comparison.
+        const int s1 = s - 1, ki = i >> s1, kj = j >> s1;
+        const Rect kb{g.xs[ki << s1], g.ys[kj << s1], g.xs[(ki + 1) << s1], g.ys[(kj + 1) << s1]};
+        if (rect_point(kb, sg.sx, sg.sy) || rect_point(kb, sg.ex, sg.ey)) continue;
         const Rect nb{g.xs[ci << s], g.ys[cj << s], g.xs[(ci + 1) << s], g.ys[(cj + 1) << s]};
-        const unsigned mask = seg_quadrants(sg, nb);
-        const int qd = quad_of((i >> (s - 1)) & 1, (j >> (s - 1)) & 1);
+        const unsigned mask = ROLLED ? seg_quadrants_rolled(sg, nb) : seg_quadrants(sg, nb);
+        const int qd = quad_of(ki & 1, kj & 1);
         if (!((mask >> qd) & 1u)) return false;
     }
     return true;

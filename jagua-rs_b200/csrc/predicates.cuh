@@ -57,7 +57,12 @@ JG_HD void xf_point(const Xf& t, float x, float y, float& ox, float& oy) {
 // {epsilon: f32::EPSILON, ulps: 4} (third-party crate; restated from its published algorithm).
 JG_HD bool approx_eq(float a, float b) {
     if (a == b) return true;
-    if (fabsf(a - b) <= 1.1920929e-07f) return true;
+    const float diff = fabsf(a - b);
+    // Far apart: neither margin can hold. Exact, not a heuristic: the epsilon test needs diff <= 1.2e-7, and four ulps of
+    // same-signed values are at most 4 * 2^-23 = 4.8e-7 of the larger magnitude (opposite signs never pass the ulps test:
+    // their i32 views differ by more than 2^31 - 4). NaN and infinite differences fall through to the full test.
+    if (diff > 1e-6f * fmaxf(fabsf(a), fabsf(b)) + 1e-6f) return false;
+    if (diff <= 1.1920929e-07f) return true;
     int32_t d = (int32_t)(f32_bits(a) - f32_bits(b));  // wrapping_sub on the i32 views
     int32_t ad = d < 0 ? (d == INT32_MIN ? INT32_MAX : -d) : d;
     return ad <= 4;
@@ -238,6 +243,44 @@ JG_HD unsigned seg_quadrants(const Seg& e, const Rect& r) {
     JG_HALF(h_bisect, 2u | 4u, 1u | 8u)
     JG_HALF(v_bisect, 4u | 8u, 1u | 2u)
 #undef JG_HALF
+    return yes;
+}
+
+// The same function with its two unrolled parts as loops: a fifth of the instructions (one seg_seg_half body instead of
+// six), a few more executed. For kernels whose hot loop must stay inside the instruction cache and which verify paths
+// rarely (k_collect_grid). Same operations on the same values in the same order: bit-identical masks.
+JG_HD unsigned seg_quadrants_rolled(const Seg& e, const Rect& r) {
+    const float ex_min = fminf(e.sx, e.ex), ex_max = fmaxf(e.sx, e.ex);
+    const float ey_min = fminf(e.sy, e.ey), ey_max = fmaxf(e.sy, e.ey);
+    unsigned yes = 0, undet = 0;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        const Rect q = rect_quadrant(r, i);
+        const bool x_no = fmaxf(ex_min, q.x_min) > fminf(ex_max, q.x_max);
+        const bool y_no = fmaxf(ey_min, q.y_min) > fminf(ey_max, q.y_max);
+        if (x_no || y_no) continue;
+        if (rect_point(q, e.sx, e.sy) || rect_point(q, e.ex, e.ey)) yes |= 1u << i;
+        else undet |= 1u << i;
+    }
+    if (undet == 0) return yes;
+    const float cx = (r.x_min + r.x_max) / 2.0f, cy = (r.y_min + r.y_max) / 2.0f;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {  // left, right, top, bottom, horizontal bisector, vertical bisector (qt_traits.rs:60-84)
+        Seg side;
+        unsigned fst, sec;
+        switch (k) {
+            case 0: side = Seg{r.x_min, r.y_max, r.x_min, r.y_min}; fst = 2u; sec = 4u; break;
+            case 1: side = Seg{r.x_max, r.y_min, r.x_max, r.y_max}; fst = 8u; sec = 1u; break;
+            case 2: side = Seg{r.x_max, r.y_max, r.x_min, r.y_max}; fst = 1u; sec = 2u; break;
+            case 3: side = Seg{r.x_min, r.y_min, r.x_max, r.y_min}; fst = 4u; sec = 8u; break;
+            case 4: side = Seg{r.x_min, cy, r.x_max, cy}; fst = 2u | 4u; sec = 1u | 8u; break;
+            default: side = Seg{cx, r.y_min, cx, r.y_max}; fst = 4u | 8u; sec = 1u | 2u; break;
+        }
+        if (!(undet & (fst | sec))) continue;
+        const int h = seg_seg_half(e, side);
+        if (h & 1) { yes |= fst; undet &= ~fst; }
+        if (h & 2) { yes |= sec; undet &= ~sec; }
+    }
     return yes;
 }
 

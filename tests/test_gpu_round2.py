@@ -150,14 +150,15 @@ def test_collect_multi_matches_oracle(jg, world, name):
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     t = np.ascontiguousarray(np.concatenate([jg.make_queries(wl, i, m, seed=31) for i, m in enumerate(sizes)]).astype(np.float32).reshape(-1, 4))
     ids = list(range(n_items))
+    cde.sync_layout()  # (the first query on a fresh engine uploads the layout: two more launches)
     l0 = cde.stats()["launches"]
     got = cde.collect_multi(ids, offs, t, words)
     n_launch = cde.stats()["launches"] - l0
     exp = w.collect_multi(ids, offs, t, words, nthreads=8)
     bad = np.nonzero((got != exp).any(axis=1))[0]
     assert len(bad) == 0, f"{name}: {len(bad)} hazard-set mismatches, first {bad[:3]} got {got[bad[:3]]} exp {exp[bad[:3]]}"
-    if cde.detect_path() == "grid" and words <= 8 and n_items <= 32:
-        assert n_launch == 1, f"{n_launch} launches for {n_items} item types"
+    if cde.detect_path() == "grid" and words <= 8 and n_items <= 32 and max(len(it.verts) for it in wl.items) <= 96:
+        assert n_launch == 2, f"{n_launch} launches for {n_items} item types"  # k_collect_grid + k_collect_contain, once each
     # per-item calls give the same sets
     k = n_items - 1
     one = cde.collect_batch(k, t[offs[k]:offs[k + 1]], words)

@@ -30,9 +30,9 @@ def main():
     hist = np.zeros(256, np.int64)
     for i, n in enumerate(sizes):
         t = jg.make_queries(wl, i, n, seed)
-        v = w.detect_batch(i, t)
+        v = w.detect_batch(i, t, nthreads=os.cpu_count() or 1)  # (thread-local counters, summed)
         fd = w.last_flops
-        w.collect_batch(i, t, max(1, (w.haz_capacity() + 31) // 32))
+        w.collect_batch(i, t, max(1, (w.haz_capacity() + 31) // 32), nthreads=os.cpu_count() or 1)
         fc = w.last_flops
         hist += np.bincount(v, minlength=256)
         out["items"].append(dict(item=i, n_verts=len(wl.items[i].verts), queries=n, detect_flops=fd, collect_flops=fc))

@@ -469,14 +469,15 @@ def run_strong(jg, wl, args, n_dev, offs, t, ridx, txy):
         for form in ("indexed", "composed"):
             for pipelined in (False, True):
                 per_dev = (n + n_dev - 1) // n_dev
-                chunk = per_dev if pipelined else max(1 << 16, min(1 << 18, (per_dev + 3) // 4))
-                pool.set_batching(min(chunk, 1 << 20), 3 if pipelined else 4)
+                # batches in flight: a device's whole shard per stream; one at a time: pieces of 256 Ki queries (shards of up to
+                # 512 Ki go as one piece, see detect_multi_host) and the blocking call (enqueue + wait on the device's own thread)
+                pool.set_batching(min(per_dev, 1 << 20) if pipelined else 1 << 18, 3 if pipelined else 4)
 
                 def step(i):
                     if form == "indexed":
-                        pool.detect_multi_indexed(ids, offs, p_r.array, p_t.array, out=outs[i % 4].array, wait=False)
+                        pool.detect_multi_indexed(ids, offs, p_r.array, p_t.array, out=outs[i % 4].array, wait=not pipelined)
                     else:
-                        pool.detect_multi(ids, offs, p_c.array, out=outs[i % 4].array, wait=False)
+                        pool.detect_multi(ids, offs, p_c.array, out=outs[i % 4].array, wait=not pipelined)
 
                 for i in range(max(args.warmup, 3)):
                     step(i)
@@ -484,8 +485,6 @@ def run_strong(jg, wl, args, n_dev, offs, t, ridx, txy):
                 t0 = time.perf_counter()
                 for i in range(args.steps):
                     step(i)
-                    if not pipelined:
-                        pool.sync()
                 pool.sync()
                 dt = time.perf_counter() - t0
                 res[(form, pipelined)] = dt

@@ -734,7 +734,35 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
                                                                                      sc.ctl, sc.sv_entry, sc.ct_meta,          \
                                                                                      sc.ct_bb, sc.ct_xf);                      \
     }
-        if (d_filt && split) JG_LAUNCH_S2(true, true, 6)
+        // JG_STAGE_S2=1 (experiment, BASELINE north_star item 3): leaf entries + hazard edges staged into shared memory by TMA
+        // bulk copies, one 1024-thread CTA per SM. Measured against the L1 path in profiles/ (r2j): kept off unless it wins.
+        static const int stage_env = [] { const char* v = getenv("JG_STAGE_S2"); return v ? atoi(v) : 0; }();
+        const size_t stage_bytes = 16 + (size_t)L.n_entries * 32 + (size_t)L.n_edges * 16;
+        const size_t gs2s = gcommon + stage_bytes + (S2_STAGE_THREADS / 32) * sizeof(G2Slots);
+        if (stage_env && gs2s <= 220 * 1024) {
+            const int want2s = (n + (S2_STAGE_THREADS / 32) * S2_MAX_GROUP - 1) / ((S2_STAGE_THREADS / 32) * S2_MAX_GROUP);
+#define JG_LAUNCH_S2S(FILT_, SPLIT_, SLOT_)                                                                                    \
+    {                                                                                                                          \
+        const int g = persistent_grid(k_s2_grid<FILT_, SPLIT_, true>, SLOT_, n_sms, gs2s, S2_STAGE_THREADS);                   \
+        cudaLaunchConfig_t lc = {};                                                                                            \
+        lc.gridDim = dim3((unsigned)(want2s < g ? want2s : g));                                                                \
+        lc.blockDim = dim3(S2_STAGE_THREADS);                                                                                  \
+        lc.dynamicSmemBytes = gs2s;                                                                                            \
+        lc.stream = st;                                                                                                        \
+        cudaLaunchAttribute at[1];                                                                                             \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                         \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                                  \
+        lc.attrs = at;                                                                                                         \
+        lc.numAttrs = (g_dependent_launch && !(mode & JG_MODE_POLY_ONLY)) ? 1 : 0;                                             \
+        cudaLaunchKernelEx(&lc, k_s2_grid<FILT_, SPLIT_, true>, L, tab, gd, d_kinds, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry, \
+                           sc.ct_meta, sc.ct_bb, sc.ct_xf);                                                                    \
+    }
+            if (d_filt && split) JG_LAUNCH_S2S(true, true, 21)
+            else if (d_filt) JG_LAUNCH_S2S(true, false, 19)
+            else if (split) JG_LAUNCH_S2S(false, true, 22)
+            else JG_LAUNCH_S2S(false, false, 20)
+#undef JG_LAUNCH_S2S
+        } else if (d_filt && split) JG_LAUNCH_S2(true, true, 6)
         else if (d_filt) JG_LAUNCH_S2(true, false, 14)
         else if (split) JG_LAUNCH_S2(false, true, 7)
         else JG_LAUNCH_S2(false, false, 15)

@@ -173,17 +173,43 @@ __device__ __forceinline__ uint32_t col_mask(int lo, int hi) {  // bits lo..hi, 
 }
 
 // QTHazPartial::collides_with (qt_partial_hazard.rs:67-72) over the relevant Partial entries of a leaf cell
-template <class Ent, bool FILT>
+// SM: the entry and edge sections were staged into shared memory (k_s2_grid<.., STAGE>): plain loads instead of ld.global.nc
+template <class Ent, bool FILT, bool SM = false>
 __device__ __forceinline__ bool leaf_cell_collides(const DevLayout& L, uint32_t rec, const Ent& ent, const uint32_t* filt) {
     const int e0 = (int)(rec >> 8), n_partial = (int)(rec & 255u);
     for (int i = 0; i < n_partial; i++) {
-        const int4 em = __ldg(&L.entry_meta[e0 + i]);
+        const int4 em = SM ? L.entry_meta[e0 + i] : __ldg(&L.entry_meta[e0 + i]);
         if (FILT && filt_bit(filt, em.x)) continue;
-        if (!ent_rect(ent, ld_rect(&L.entry_ff[e0 + i]))) continue;
-        for (int k = 0; k < em.z; k++)
-            if (ent_seg(ent, ld_seg(&L.edges[em.y + k]))) return true;
+        if (!ent_rect(ent, SM ? ld_rect_any(&L.entry_ff[e0 + i]) : ld_rect(&L.entry_ff[e0 + i]))) continue;
+        for (int k = 0; k < em.z; k++) {
+            const float4 v = SM ? L.edges[em.y + k] : __ldg(&L.edges[em.y + k]);
+            if (ent_seg(ent, Seg{v.x, v.y, v.z, v.w})) return true;
+        }
     }
     return false;
+}
+
+// ---- TMA bulk staging (cp.async.bulk + mbarrier, sm_90+): one elected thread copies whole sections of the layout blob into
+// the CTA's shared memory; every thread waits on the barrier's phase. BASELINE north_star item (3) "hazard edges staged through
+// TMA or shared memory"; data shape: qt_partial_hazard.rs:7-12 (edges + ff_bbox per QTHazPartial).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
 }
 
 // Does the circle pass circ_rect (circle.rs:115-128) for some Entire-flagged finest cell? Rows of the
@@ -242,7 +268,7 @@ __device__ __forceinline__ PoleWin pole_window(const GridDev& g, const Circ& c) 
 
 // what every warp-level routine of the grid kernels needs
 struct GCtx {
-    const DevLayout& L;
+    const DevLayout& L;   // (k_s2_grid<.., STAGE>: entry_meta / entry_ff / edges point into shared memory - leaf tests only)
     const SegTable& tab;
     const GridDev& g;
     const XfSrc& xforms;
@@ -254,6 +280,7 @@ struct GCtx {
     int4* ct_meta = nullptr;   // containment list (k_s2_grid -> k_s2_contain): {query | segment, first entry, n_partial, -}
     float4* ct_bb = nullptr;   // ... the transformed shape's bbox
     float4* ct_xf = nullptr;   // ... and the query's transformation
+    const int4* g_entry_meta = nullptr;  // the entry section in global memory (for __ldg readers next to a staged L)
 };
 struct G1Warp {  // stage-1 state of a warp (shared memory + two counters)
     float4* s_circ;    // phase B: the current pole of each lane's query
@@ -631,7 +658,7 @@ __device__ bool seg_collides_from_root(const GCtx& c, const Seg& sg) {
             bits &= bits - 1;
             if (!(((er >> i) & 1u) || leaf_cell_collides<Seg, FILT>(c.L, g.cell_leaf[j * GRID_G + i], sg, c.filt))) continue;
             const Rect cb{g.xs[i], g.ys[j], g.xs[i + 1], g.ys[j + 1]};
-            if (rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) || path_reaches(g, sg, 0, g.cell_level[j * GRID_G + i], i, j))
+            if (rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) || path_reaches<true>(g, sg, 0, g.cell_level[j * GRID_G + i], i, j))
                 return true;
         }
     }
@@ -640,7 +667,7 @@ __device__ bool seg_collides_from_root(const GCtx& c, const Seg& sg) {
 
 // one group of `ng` survivors (ents[0 .. ng): survivor-list entries in global memory, or in the warp's own shared
 // memory when LOCAL) resolved by a warp; GS = slots in use (>= ng)
-template <bool FILT, bool LOCAL, bool SPLIT>
+template <bool FILT, bool LOCAL, bool SPLIT, bool STAGE = false>
 __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* ents, int ng, int GS, int lane) {
     const int D = c.g.D, G = c.g.G;
     if (lane < ng) {
@@ -817,7 +844,7 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
                 }
                 const int i = __ffs(bits) - 1;
                 bits &= bits - 1;
-                if (((er >> i) & 1u) || leaf_cell_collides<Seg, FILT>(c.L, c.g.cell_leaf[j * GRID_G + i], sg, c.filt)) { hi = i; break; }
+                if (((er >> i) & 1u) || leaf_cell_collides<Seg, FILT, STAGE>(c.L, c.g.cell_leaf[j * GRID_G + i], sg, c.filt)) { hi = i; break; }
             }
             if (!__any_sync(FULL, hi >= 0)) break;
             bool lanehit = false;
@@ -826,7 +853,7 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
                 // rejected, `contains` true, and half_intersect only ever adds quadrants)
                 const Rect cb{c.g.xs[hi], c.g.ys[j], c.g.xs[hi + 1], c.g.ys[j + 1]};
                 lanehit = rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) ||
-                          path_reaches(c.g, sg, l0, c.g.cell_level[j * GRID_G + hi], hi, j);
+                          path_reaches<true>(c.g, sg, l0, c.g.cell_level[j * GRID_G + hi], hi, j);
             }
             if (lanehit) atomicOr(&W.hit, 1u << slot);
             __syncwarp();
@@ -889,7 +916,7 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
                     const int j = j0 + lane;
                     int hs = -1;
                     if (j < n_partial) {
-                        hs = __ldg(&c.L.entry_meta[m.y + j]).x;
+                        hs = __ldg(&c.g_entry_meta[m.y + j]).x;
                         if (FILT && filt_bit(c.filt, hs)) hs = -1;
                     }
                     col = containment_collision_warp(c.L, sd.verts, sd.n_verts, sd.poi_x, sd.poi_y, Xf{t4.x, t4.y, t4.z, t4.w},
@@ -905,10 +932,11 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
     __syncwarp();
 }
 
-template <bool FILT, bool SPLIT>
+#define S2_STAGE_THREADS 1024  // STAGE: one CTA per SM, so that the SM holds ONE copy of the staged sections
+template <bool FILT, bool SPLIT, bool STAGE = false>
 // (the split variant, without the containment code, gains from a fifth CTA per SM at 48 registers - 4M queries 646 -> 637 us;
 // the inline variant loses: 1M queries 212 -> 222 us)
-__global__ void __launch_bounds__(S_THREADS, SPLIT ? G2_MIN_BLOCKS + 1 : G2_MIN_BLOCKS)
+__global__ void __launch_bounds__(STAGE ? S2_STAGE_THREADS : S_THREADS, STAGE ? 1 : (SPLIT ? G2_MIN_BLOCKS + 1 : G2_MIN_BLOCKS))
 k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDev* __restrict__ ggrid,
           const uint8_t* __restrict__ g_kinds, const XfSrc xforms, const uint32_t* __restrict__ filt,
           uint8_t* __restrict__ out, DetectCtl* __restrict__ ctl, int* __restrict__ sv_entry,
@@ -918,26 +946,49 @@ k_s2_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const GridDe
     for (int i = threadIdx.x; i < (int)(sizeof(SegTable) / 4); i += blockDim.x) ((int*)t)[i] = ((const int*)&gtab)[i];
     unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
     const GridDev& g = *stage_grid(p, ggrid);
+    DevLayout Ls = L;
+    if (STAGE) {
+        // the leaf entries and hazard edges of the whole layout (swim: 100 KB) by TMA bulk copies into this CTA's shared
+        // memory: issued by one thread, completion counted in bytes on an mbarrier (the layout belongs to an earlier upload,
+        // so this too runs ahead of griddepcontrol.wait)
+        uint64_t* bar = (uint64_t*)p;
+        p += 16;
+        const uint32_t b_em = (uint32_t)L.n_entries * 16u, b_ed = (uint32_t)L.n_edges * 16u;
+        int4* s_em = (int4*)p;
+        float4* s_ff = (float4*)(p + b_em);
+        float4* s_ed = (float4*)(p + 2 * (size_t)b_em);
+        p += 2 * (size_t)b_em + b_ed;
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, 2u * b_em + b_ed);
+            bulk_g2s(s_em, L.entry_meta, b_em, bar);
+            bulk_g2s(s_ff, L.entry_ff, b_em, bar);
+            bulk_g2s(s_ed, L.edges, b_ed, bar);
+        }
+        mbar_wait(bar, 0u);
+        Ls.entry_meta = s_em, Ls.entry_ff = s_ff, Ls.edges = s_ed;
+    }
     __syncthreads();
     // dependent launch: everything above reads launch parameters and the grid summary of an earlier upload; the survivor
     // list, its count and the verdict bytes belong to stage 1, complete and visible only after this wait
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // ... and k_s2_contain, when it follows as a dependent launch, may move in as this (fully resident) grid drains
     if (SPLIT) asm volatile("griddepcontrol.launch_dependents;");
-    const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry, ct_meta, ct_bb, ct_xf};
+    const GCtx c{STAGE ? Ls : L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry, ct_meta, ct_bb, ct_xf, L.entry_meta};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     G2Slots& W = *(G2Slots*)(p + (size_t)warp * sizeof(G2Slots));
     const int total = ctl->n_surv;
     // survivors per group: 8 when every warp has plenty to do (best lane use); fewer when the launch is small,
     // where the length of a warp's dependent chain, not the issue rate, sets the kernel's duration
-    const int per_warp = total / (int)(gridDim.x * S_WARPS);
+    const int per_warp = total / (int)(gridDim.x * (blockDim.x >> 5));
     const int GS = per_warp >= 16 ? 8 : per_warp >= 6 ? 4 : per_warp >= 2 ? 2 : 1;
     for (;;) {
         int gbase = 0;
         if (lane == 0) gbase = atomicAdd(&ctl->s2_next, GS);
         gbase = __shfl_sync(FULL, gbase, 0);
         if (gbase >= total) break;
-        g2_group<FILT, false, SPLIT>(c, W, sv_entry + gbase, (total - gbase) < GS ? (total - gbase) : GS, GS, lane);
+        g2_group<FILT, false, SPLIT, STAGE>(c, W, sv_entry + gbase, (total - gbase) < GS ? (total - gbase) : GS, GS, lane);
     }
 }
 
@@ -1079,7 +1130,7 @@ k_detect_fused(const DevLayout L, const __grid_constant__ SegTable gtab, const G
     unsigned char* p = smem + ((sizeof(SegTable) + 15) & ~(size_t)15);
     const GridDev& g = *stage_grid(p, ggrid);
     __syncthreads();
-    const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry};
+    const GCtx c{L, *t, g, xforms, filt, g_kinds, out, ctl, sv_entry, nullptr, nullptr, nullptr, L.entry_meta};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wp = p + (size_t)warp * GF_WARP_BYTES;
     G1Warp w;

@@ -452,6 +452,8 @@ static DevLayout dev_layout_of(const void* d_blob, const JgLayoutHeader& h) {
     L.n_slots = (int)h.n_slots;
     L.cd_threshold = (int)h.cd_threshold;
     L.exterior_slot = (int)h.exterior_slot;
+    L.n_entries = (int)h.n_entries;
+    L.n_edges = (int)h.n_edges;
     return L;
 }
 static void bind_layout(JgEngine* e, const JgLayoutHeader& h) {
@@ -1025,7 +1027,10 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
             return JG_OK;
         }
     }
-    const int64_t chunk = e->chunk_queries;
+    // Pieces of chunk_queries queries - but a batch of up to two chunks goes as ONE piece: the persistent kernels of
+    // consecutive pieces cannot overlap each other (each fills every SM slot), so two pieces pay two launch ramps and tails
+    // (262 Ki queries: 46 us of copy + 93 us of kernels in one piece, 23 + 70 + 70 us in two; tools/size_sweep.py).
+    const int64_t chunk = n <= 2 * e->chunk_queries ? n : e->chunk_queries;
     PieceCursor cur;
     Piece p;
     // The pipeline is bound by the H2D copies; what stays exposed is the kernels + D2H of the LAST piece, so

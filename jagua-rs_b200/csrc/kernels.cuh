@@ -23,6 +23,7 @@ struct DevLayout {
     const float2* haz_verts;
     Rect cde_bbox;
     int n_nodes, n_slots, cd_threshold, exterior_slot;
+    int n_entries, n_edges;
 };
 
 // One item's collision shape in device memory (SPolygon vertices + poi centre + ff surrogate).

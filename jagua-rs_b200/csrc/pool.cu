@@ -3,6 +3,8 @@
 // [g n/G, (g+1) n/G)), every device copying its shard's results straight into its own slice of the caller's result
 // array. No collective on the query path. One persistent host thread per device does that device's enqueueing, so the
 // per-launch driver work of the devices overlaps instead of queueing up in the caller's thread.
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -24,17 +26,24 @@ struct Worker {
     std::condition_variable cv, idle_cv;
     std::deque<std::function<int()>> q;
     bool stop = false;
+    std::atomic<int> pending{0};  // tasks queued (what a spinning worker polls)
     int busy = 0;      // tasks queued or running
     int first_rc = 0;  // first failure since the last jg_pool_sync
     void run() {
         for (;;) {
             std::function<int()> fn;
             {
+                // a short spin before blocking: batches usually follow each other within microseconds, and waking a blocked
+                // thread costs 10-50 us - a third of a small shard's device time
+                const auto t0 = std::chrono::steady_clock::now();
+                while (pending.load(std::memory_order_acquire) == 0 && std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200))
+                    std::this_thread::yield();
                 std::unique_lock<std::mutex> lk(m);
                 cv.wait(lk, [&] { return stop || !q.empty(); });
                 if (q.empty()) return;
                 fn = std::move(q.front());
                 q.pop_front();
+                pending.fetch_sub(1, std::memory_order_release);
             }
             const int rc = fn();
             {
@@ -50,6 +59,7 @@ struct Worker {
             std::lock_guard<std::mutex> lk(m);
             q.push_back(std::move(fn));
             busy++;
+            pending.fetch_add(1, std::memory_order_release);
         }
         cv.notify_one();
     }
@@ -119,6 +129,18 @@ static int pool_run_all(JgPool* p, int n_active, const std::function<int(int)>& 
     return rc;
 }
 
+// waits for the queued tasks of the first n_active workers; first failure wins
+static int pool_drain(JgPool* p, int n_active) {
+    int rc = JG_OK;
+    for (int k = 0; k < n_active; k++) {
+        const int r = p->workers[k]->drain();
+        if (r != JG_OK && rc == JG_OK) {
+            rc = r;
+            p->err = "device " + std::to_string(p->devices[k]) + ": " + jg_last_error(p->eng[k]);
+        }
+    }
+    return rc;
+}
 static int active_devices(const JgPool* p, int64_t n) {
     int64_t a = (n + p->min_shard - 1) / p->min_shard;
     if (a < 1) a = 1;
@@ -238,12 +260,16 @@ static int pool_detect(JgPool* p, int n_seg, const int* item_ids, const int64_t*
         p->workers[k]->push([=] {
             if (s.ids.empty()) return (int)JG_OK;
             const int ns = (int)s.ids.size();
-            if (transforms) return jg_detect_multi_async(e, ns, s.ids.data(), s.offs.data(), transforms + 4 * s.lo, filter_id, mode, out + s.lo);
-            if (ij) return jg_detect_multi_lattice_async(e, ns, s.ids.data(), s.offs.data(), &lat_copy, rot_idx + s.lo, ij + 2 * s.lo, filter_id, mode, out + s.lo);
-            return jg_detect_multi_indexed_async(e, ns, s.ids.data(), s.offs.data(), rot_idx + s.lo, txy + 2 * s.lo, filter_id, mode, out + s.lo);
+            int rc;
+            if (transforms) rc = jg_detect_multi_async(e, ns, s.ids.data(), s.offs.data(), transforms + 4 * s.lo, filter_id, mode, out + s.lo);
+            else if (ij) rc = jg_detect_multi_lattice_async(e, ns, s.ids.data(), s.offs.data(), &lat_copy, rot_idx + s.lo, ij + 2 * s.lo, filter_id, mode, out + s.lo);
+            else rc = jg_detect_multi_indexed_async(e, ns, s.ids.data(), s.offs.data(), rot_idx + s.lo, txy + 2 * s.lo, filter_id, mode, out + s.lo);
+            if (rc == JG_OK && wait) rc = jg_sync(e);  // the blocking form waits on the worker: one hand-over instead of two
+            return rc;
         });
     }
-    return wait ? jg_pool_sync(p) : (int)JG_OK;
+    if (!wait) return JG_OK;
+    return pool_drain(p, act);
 }
 
 int jg_pool_detect_multi(JgPool* p, int n_seg, const int* item_ids, const int64_t* seg_offsets, const float* transforms, int filter_id,

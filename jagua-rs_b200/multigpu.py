@@ -73,7 +73,19 @@ class LayoutBroadcaster:
             tid = torch.from_numpy(nid).to(dev)
             dist.broadcast(tid, 0)
             nid = np.ascontiguousarray(tid.cpu().numpy())
-        cde._chk(lib.jg_engine_comm_init(cde._eng, nid, self.rank, self.world, int(max_blob_bytes)))
+        # NCCL writes its version banner to stdout when the first communicator of a process is created (NCCL_DEBUG=VERSION
+        # and up): keep stdout clean for callers that print machine-readable lines (bench.py) - the banner goes to stderr
+        import os
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            rc = lib.jg_engine_comm_init(cde._eng, nid, self.rank, self.world, int(max_blob_bytes))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        cde._chk(rc)
         self._C = C
         self.info = {"transport": "ncclBroadcast inside libjagua_cuda.so (dlopen libnccl.so.2), fixed-capacity exchange buffer",
                      "capacity_bytes": int(max_blob_bytes), "updates": 0, "last_ms": None}

@@ -11,7 +11,8 @@ asset, optimizer or bench). Every rank owns one engine per strip (layouts are sm
 seeded slice of the sweep (weak scaling; no collective on the query path). Before every sub-batch rank 0
 applies one layout update to one strip - Layout::place_item of an item at a transform the previous sub-batch
 reported free, or Layout::remove_item of an earlier placement (entities/layout.rs:40-74) - flattens that
-strip's quadtree and broadcasts the blob over NCCL; every rank uploads it from the receive buffer. The reported
+strip's quadtree and broadcasts the blob over NCCL INSIDE the library (jg_cde_broadcast: one ncclBroadcast into a
+fixed-capacity exchange buffer and one host wait per update on the receiving ranks, none on rank 0). The reported
 queries/s include those stalls. After the timed sweep rank 0 replays the updates on the CPU oracle and compares
 the verdicts of every sub-batch it resolved (mismatches must be 0).
 """
@@ -61,21 +62,18 @@ S = len(strips)
 n_items = len(strips[0].items)
 shapes = [jg.ItemShape(it.verts, it.poi, it.poles, it.piers) for it in strips[0].items]
 
-# one engine per strip; rank 0 builds + flattens, the others receive the blob
-cdes = []
+# one engine per strip; rank 0 builds + flattens, the others receive the blob (one NCCL communicator per strip engine)
+cdes, bcs = [], []
 for s, wl in enumerate(strips):
     if rank == 0:
         cde = jg.build_engine(wl, device=local_rank)
-        blob = cde.flatten()
     else:
         cde = jg.CDEngine(wl.cde_bbox, wl.quadtree_depth, wl.cd_threshold, wl.n_ff_poles, wl.n_ff_piers, device=local_rank)
         for i, sh in enumerate(shapes):
             cde.upload_item(i, sh)
-        blob = None
     if world > 1:
-        d_blob = multigpu.broadcast_blob(blob, dist, src=0, device=f"cuda:{local_rank}")
-        torch.cuda.synchronize()
-        cde.upload_layout_device(d_blob.data_ptr(), d_blob.numel(), epoch=1)
+        bcs.append(multigpu.LayoutBroadcaster(cde, dist, rank, world))
+        bcs[-1].broadcast(root=0)
     else:
         cde.sync_layout()
     cdes.append(cde)
@@ -135,8 +133,7 @@ def apply_update(b):
         if src_b < 0:
             update_s += time.perf_counter() - t0
             if world > 1:  # nothing to decide yet, but every rank takes part in the broadcast
-                d_blob = multigpu.broadcast_blob(cde.flatten(), dist, src=0, device=f"cuda:{local_rank}")
-                cdes[s].upload_layout_device(d_blob.data_ptr(), d_blob.numel(), epoch=b + 2)
+                bcs[s].broadcast(root=0)
             return
         if args.lookahead:
             cde.wait_fence(fences.pop((src_b, s)))  # that sub-batch is done; the one in flight keeps running
@@ -164,14 +161,11 @@ def apply_update(b):
                 did = True
         if did:
             n_updates += 1
-        if world > 1:
-            blob = cde.flatten()
-        else:
+        if world == 1:
             cde.sync_layout()
     if world > 1:
-        d_blob = multigpu.broadcast_blob(blob, dist, src=0, device=f"cuda:{local_rank}")
-        # stream-ordered on the engine's upload stream; returns once the receive buffer has been copied
-        cdes[s].upload_layout_device(d_blob.data_ptr(), d_blob.numel(), epoch=b + 2)
+        # collective: rank 0 flattens + uploads its own copy stream-ordered and sends; the others bind the received blob
+        bcs[s].broadcast(root=0)
     update_s += time.perf_counter() - t0
 
 
@@ -188,10 +182,11 @@ for b in range(n_sub):
 barrier()
 dt = time.perf_counter() - t0
 launches = sum(c.stats()["launches"] for c in cdes) - launches0
+update_s_max = update_s
 if dist is not None:
-    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dt, update_s], dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt = float(tt[0])
+    dt, update_s_max = float(tt[0]), float(tt[1])
 
 if rank == 0:
     total = per_strip * S * n_sub * world
@@ -202,7 +197,9 @@ if rank == 0:
                                    f"{n_items} item types, host buffers (16 B in, 1 B out per query), one layout update + blob "
                                    "broadcast before every sub-batch", "hazards_per_strip": [len(w.hazards) for w in strips]},
             "lookahead": args.lookahead, "layout_updates": n_updates, "update_seconds_rank0": update_s,
-            "update_ms_each": update_s / max(n_sub - 1, 1) * 1e3}
+            "layout_broadcast": bcs[0].info if bcs else None,
+            "update_ms_each": update_s / max(n_sub - 1, 1) * 1e3,
+            "update_ms_each_slowest_rank": update_s_max / max(n_sub - 1, 1) * 1e3}
     if keep:
         for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
             sys.path.insert(0, p)

@@ -734,9 +734,12 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
                                                                                      sc.ctl, sc.sv_entry, sc.ct_meta,          \
                                                                                      sc.ct_bb, sc.ct_xf);                      \
     }
-        // JG_STAGE_S2=1 (experiment, BASELINE north_star item 3): leaf entries + hazard edges staged into shared memory by TMA
-        // bulk copies, one 1024-thread CTA per SM. Measured against the L1 path in profiles/ (r2j): kept off unless it wins.
-        static const int stage_env = [] { const char* v = getenv("JG_STAGE_S2"); return v ? atoi(v) : 0; }();
+        // BASELINE north_star item 3: the leaf entries + hazard edges of the layout staged into shared memory by TMA bulk copies
+        // (cp.async.bulk + mbarrier), one 1024-thread CTA per SM so that the SM holds one copy. On whenever the sections fit
+        // (swim: 100 KB); JG_STAGE_S2=0 restores the L1 path. Same-box A/B (profiles/r2k_size_sweep_stage*.txt): 64 Ki queries
+        // 54.7 -> 52.6 us, 256 Ki 93.2 -> 89.0, 1 Mi 214 -> 209, 4 Mi 643 -> 635; stage 2 alone 137 -> 131 us, long-scoreboard
+        // stalls 1.43 -> 1.00 per issue (profiles/r2j_ncu_key_metrics_s2_*.txt).
+        static const int stage_env = [] { const char* v = getenv("JG_STAGE_S2"); return v ? atoi(v) : 1; }();
         const size_t stage_bytes = 16 + (size_t)L.n_entries * 32 + (size_t)L.n_edges * 16;
         const size_t gs2s = gcommon + stage_bytes + (S2_STAGE_THREADS / 32) * sizeof(G2Slots);
         if (stage_env && gs2s <= 220 * 1024) {

@@ -190,6 +190,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly ONE line (the JSON record): libraries that write to fd 1 while this runs - NCCL prints its version
+    # banner there when the first communicator is created - are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import jagua_rs_b200 as jg
     from jagua_rs_b200 import multigpu
 
@@ -353,7 +359,10 @@ def main():
         if host_group is not None:
             dist.barrier(group=host_group)
         if rank == 0:
-            strong = run_strong(jg, wl, args, world, full_offs, full_t, full_ridx, full_txy)
+            try:  # (a failure here must not leave the other ranks waiting at the barrier below)
+                strong = run_strong(jg, wl, args, world, full_offs, full_t, full_ridx, full_txy)
+            except Exception as ex:  # noqa: BLE001 - reported in the line
+                strong = {"error": repr(ex)}
         if host_group is not None:
             dist.barrier(group=host_group)
 
@@ -440,7 +449,8 @@ def main():
                                     "sample": f"{reps} passes over the full {args.queries}-query batch ({dt:.1f} s), oracle/ C++ "
                                               "restatement built -O3 -march=native -ffp-contract=off, persistent thread pool, dynamic chunks",
                                     "mismatches_vs_gpu": mism}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     cde.close()
     if dist is not None:

@@ -619,8 +619,12 @@ k_s2_poly(const DevLayout L, const __grid_constant__ SegTable gtab, const uint8_
 namespace jg {
 
 // ---------------------------------------------------------------------------------------------------
-static int g_occ[24];
-static size_t g_occ_smem[24];
+// occupancy (and the opt-in to more than 48 KB of dynamic shared memory, a PER-DEVICE function attribute) per device and
+// kernel slot: an in-process pool launches the same kernels on every GPU of the box
+#define JG_OCC_DEVS 64
+#define JG_OCC_SLOTS 32
+static int g_occ[JG_OCC_DEVS][JG_OCC_SLOTS];
+static size_t g_occ_smem[JG_OCC_DEVS][JG_OCC_SLOTS];
 #ifdef JG_DIVCOUNT
 extern "C" int jg_debug_divcount(unsigned long long out[4], int reset) {
     cudaDeviceSynchronize();
@@ -635,15 +639,18 @@ void set_dependent_launch(int on) { g_dependent_launch = on ? 1 : 0; }
 int dependent_launch() { return g_dependent_launch; }
 template <class K>
 static int persistent_grid(K kernel, int slot, int n_sms, size_t smem, int threads = S_THREADS) {
-    if (g_occ[slot] == 0 || g_occ_smem[slot] != smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= JG_OCC_DEVS - 1;
+    if (g_occ[dev][slot] == 0 || g_occ_smem[dev][slot] != smem) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int b = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, smem);
-        g_occ[slot] = b < 1 ? 1 : b;
-        g_occ_smem[slot] = smem;
+        g_occ_smem[dev][slot] = smem;
+        g_occ[dev][slot] = b < 1 ? 1 : b;
     }
     static const int cap = [] { const char* v = getenv("JG_CTAS_PER_SM"); return v ? atoi(v) : 0; }();  // experiments
-    const int b = (cap > 0 && cap < g_occ[slot]) ? cap : g_occ[slot];
+    const int b = (cap > 0 && cap < g_occ[dev][slot]) ? cap : g_occ[dev][slot];
     return n_sms * b;
 }
 

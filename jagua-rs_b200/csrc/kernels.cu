@@ -114,16 +114,14 @@ __global__ void k_fill(uint32_t* p, size_t n, uint32_t v) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static int g_blocks_per_sm_cache[64];
-
 template <class K>
 static int grid_for(K kernel, int slot, int n_sms, size_t smem) {
-    if (g_blocks_per_sm_cache[slot] == 0) {
-        int b = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, 256, smem);
-        g_blocks_per_sm_cache[slot] = b < 1 ? 1 : b;
-    }
-    return n_sms * g_blocks_per_sm_cache[slot];
+    // (not cached: the shared-memory size varies with the item, and the >48 KB opt-in is a per-device attribute)
+    (void)slot;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int b = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, 256, smem);
+    return n_sms * (b < 1 ? 1 : b);
 }
 
 cudaError_t launch_collect(const DevLayout& L, const DevItem& it, const float4* d_xf, long long n, int mode, const uint32_t* d_seed,

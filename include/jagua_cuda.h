@@ -75,6 +75,14 @@ const char* jg_last_error(const JgEngine* e);
  * data the queries read. `epoch` is returned by jg_engine_layout_epoch; queries issued after this
  * call see the new layout, queries in flight finish on the old one. Host pointer. */
 int jg_layout_upload(JgEngine* e, const void* blob, size_t bytes, uint64_t epoch);
+/* Incremental update (BASELINE north_star item 1 "updated incrementally on register/deregister"):
+ * `image` is the CURRENT state of a position-stable blob (jg_cde_image_sync: node records at fixed indices, entry / edge /
+ * vertex blocks in section heaps) and ranges_off_len holds n_ranges (byte offset, byte length) pairs that changed since
+ * sequence number seq - 1 of the same lineage. The engine copies only what its target buffer is missing - as ONE patch
+ * buffer plus a scatter kernel - or the whole image when it does not hold this lineage (first use, a missed sync, a rebuilt
+ * image). Stream-ordered like jg_layout_upload. The image comes from this library's own host mirror and is not re-validated. */
+int jg_layout_patch(JgEngine* e, const void* image, size_t bytes, uint64_t lineage, uint64_t seq, const uint32_t* ranges_off_len, int n_ranges,
+                    uint64_t epoch);
 /* Same, blob already in this device's memory (e.g. the receive buffer of an NCCL broadcast). */
 int jg_layout_upload_device(JgEngine* e, const void* d_blob, size_t bytes, uint64_t epoch);
 uint64_t jg_engine_layout_epoch(const JgEngine* e);
@@ -225,7 +233,8 @@ int jg_fence_wait(JgEngine* e, uint64_t fence);
 
 /* Counters since engine creation: [0] kernel launches, [1] queries resolved, [2] H2D bytes,
  * [3] D2H bytes, [4] layout uploads, [5] survivors of the surrogate stage and [6] work items that
- * took the register-only fallback walk in the most recent *_device detect call. */
+ * took the register-only fallback walk in the most recent *_device detect call, [7] layout uploads
+ * that travelled as patches (jg_layout_patch). */
 int jg_engine_stats(const JgEngine* e, uint64_t out[8]);
 /* Device time (ms, CUDA events on the compute stream) of the kernels of the most recent
  * *_batch_device call; valid after jg_sync. */
@@ -449,7 +458,12 @@ int jg_cde_filter_qzones(const JgCde* c, int required_quality, uint32_t* bits, i
 /* Flattens quadtree + hazards into the SoA blob. Returns the byte size needed; writes it when
  * cap >= size. */
 int64_t jg_cde_flatten(JgCde* c, void* buf, int64_t cap);
-/* flatten + jg_layout_upload in one call; bumps and returns the epoch */
+/* Brings the host mirror's incremental device image up to date: only the quadtree nodes and hazard slots that register /
+ * deregister / restore touched since the previous call are re-serialised (what qt_node.rs:38-94 touches in the reference's
+ * pointer tree). Returns the image (owned by the JgCde, valid until the next call), its lineage and sequence number, and
+ * the byte ranges that changed (n_ranges = 0: a new lineage, take everything). Feed to jg_layout_patch. */
+int jg_cde_image_sync(JgCde* c, const void** image, size_t* bytes, uint64_t* lineage, uint64_t* seq, const uint32_t** ranges_off_len, int* n_ranges);
+/* jg_cde_image_sync + jg_layout_patch in one call (JG_INCREMENTAL=0: jg_cde_flatten + jg_layout_upload); returns the epoch */
 int jg_cde_sync_to_engine(JgCde* c, JgEngine* e, uint64_t* epoch);
 /* Canonical pre-order dump of the quadtree (u32 words) for tests: per node level, bbox bits,
  * has_children, n_hazards, n_active_edges, then entries sorted (presence desc, slot asc) with

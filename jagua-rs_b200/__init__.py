@@ -53,6 +53,9 @@ C_ABI = {
     "jg_last_error": (C.c_char_p, [_vp]),
     "jg_layout_upload": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64]),
     "jg_layout_upload_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64]),
+    "jg_layout_patch": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, C.c_uint64, _vp, C.c_int, C.c_uint64]),
+    "jg_cde_image_sync": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_vp),
+                                   C.POINTER(C.c_int)]),
     "jg_engine_layout_epoch": (C.c_uint64, [_vp]),
     "jg_nccl_unique_id": (C.c_int, [_u8p]),
     "jg_engine_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int, C.c_size_t]),
@@ -572,6 +575,17 @@ class CDEngine:
         self._lib.jg_cde_flatten(self._cde, buf.ctypes.data, n)
         return buf
 
+    def image_sync(self):
+        """jg_cde_image_sync: (image bytes as a uint8 array copy, lineage, seq, ranges as an (n, 2) uint32 array of (offset, length))."""
+        img, nbytes, lin, seq, rng, n = _vp(), C.c_size_t(0), C.c_uint64(0), C.c_uint64(0), _vp(), C.c_int(0)
+        rc = self._lib.jg_cde_image_sync(self._cde, C.byref(img), C.byref(nbytes), C.byref(lin), C.byref(seq), C.byref(rng), C.byref(n))
+        if rc < 0:
+            raise JaguaCudaError(rc, self._lib.jg_cde_last_error(self._cde).decode())
+        blob = np.frombuffer((C.c_char * nbytes.value).from_address(img.value), np.uint8).copy()
+        ranges = (np.frombuffer((C.c_uint32 * (2 * n.value)).from_address(rng.value), np.uint32).reshape(-1, 2).copy()
+                  if n.value else np.zeros((0, 2), np.uint32))
+        return blob, int(lin.value), int(seq.value), ranges
+
     def tree_dump(self) -> np.ndarray:
         n = self._lib.jg_cde_tree_dump(self._cde, None, 0)
         buf = np.zeros(n, np.uint32)
@@ -824,7 +838,7 @@ class CDEngine:
         a = (C.c_uint64 * 8)()
         self._lib.jg_engine_stats(self._eng, a)
         return dict(launches=int(a[0]), queries=int(a[1]), h2d_bytes=int(a[2]), d2h_bytes=int(a[3]),
-                    layout_uploads=int(a[4]), survivors=int(a[5]), fallbacks=int(a[6]))
+                    layout_uploads=int(a[4]), survivors=int(a[5]), fallbacks=int(a[6]), patched_uploads=int(a[7]))
 
     def set_batching(self, chunk_queries: int, n_streams: int):
         self._chk(self._lib.jg_engine_set_batching(self._eng, int(chunk_queries), int(n_streams)))

@@ -12,7 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjagua_cuda.so")
-SOURCES = ["kernels.cu", "detect.cu", "search.cu", "engine.cu", "pool.cu", "cde_host.cpp", "item_host.cpp"]
+SOURCES = ["kernels.cu", "detect.cu", "search.cu", "engine.cu", "pool.cu", "cde_host.cpp", "cde_image.cpp", "item_host.cpp"]
 HEADERS = ["kernels.cuh", "detect_grid.cuh", "collect_grid.cuh", "launch.hpp", "predicates.cuh", "layout_soa.h", "cde_host.hpp",
            os.path.join("..", "..", "include", "jagua_cuda.h")]
 

@@ -19,7 +19,16 @@ HostCDE::HostCDE(Rect bbox, JgConfig cfg) : cfg_(cfg) {
 }
 
 // ---- arena ----------------------------------------------------------------------------------
-int HostCDE::alloc_children(const Rect& bbox, uint8_t child_level) {
+void HostCDE::touch_node(int node) {
+    if ((size_t)node >= node_dirty_.size()) node_dirty_.resize(nodes_.size(), 0);
+    if (!node_dirty_[node]) {
+        node_dirty_[node] = 1;
+        dirty_nodes_.push_back(node);
+    }
+}
+void HostCDE::touch_slot(uint32_t slot) { dirty_slots_.push_back(slot); }
+
+int HostCDE::alloc_children(int parent, const Rect& bbox, uint8_t child_level) {
     int base;
     if (!free_blocks_.empty()) {
         base = free_blocks_.back();
@@ -33,8 +42,11 @@ int HostCDE::alloc_children(const Rect& bbox, uint8_t child_level) {
         c.level = child_level;
         c.bbox = rect_quadrant(bbox, i);
         c.child_base = -1;
+        c.parent = parent;
+        c.dead = false;
         c.entries.clear();
         c.n_active_edges = 0;
+        touch_node(base + i);
     }
     return base;
 }
@@ -44,9 +56,11 @@ void HostCDE::free_children(int child_base) {
         QNode& c = nodes_[child_base + i];
         if (c.child_base >= 0) free_children(c.child_base);
         c.child_base = -1;
+        c.dead = true;
         c.entries.clear();
         c.entries.shrink_to_fit();
         c.n_active_edges = 0;
+        touch_node(child_base + i);
     }
     free_blocks_.push_back(child_base);
 }
@@ -154,7 +168,7 @@ void HostCDE::constrict_into_children(int node, const QEntry& e) {
 // qt_node.rs:38-81
 void HostCDE::node_register(int node, QEntry&& e) {
     if (nodes_[node].child_base < 0 && nodes_[node].level > 0 && e.presence == PRES_PARTIAL) {
-        const int cb = alloc_children(nodes_[node].bbox, (uint8_t)(nodes_[node].level - 1));
+        const int cb = alloc_children(node, nodes_[node].bbox, (uint8_t)(nodes_[node].level - 1));
         nodes_[node].child_base = cb;
         // copy: registering into children never touches this node's entries, but keep it simple
         const size_t n_prev = nodes_[node].entries.size();
@@ -162,6 +176,7 @@ void HostCDE::node_register(int node, QEntry&& e) {
     }
     if (nodes_[node].child_base >= 0) constrict_into_children(node, e);
     entry_insert(nodes_[node], std::move(e));
+    touch_node(node);
 }
 
 // qt_node.rs:83-94
@@ -174,6 +189,7 @@ void HostCDE::node_deregister(int node, uint32_t slot, uint32_t version) {
             break;
         }
     if (pos == n.entries.size()) return;  // not modified
+    touch_node(node);
     n.n_active_edges -= (uint32_t)n.entries[pos].edges.size();
     n.entries.erase(n.entries.begin() + pos);
     bool any_partial = false;
@@ -223,6 +239,7 @@ uint64_t HostCDE::register_hazard(HostHazard&& hz) {  // cd_engine.rs:59-69
     e.edges.reserve(h.n_verts());
     for (int i = 0; i < h.n_verts(); i++) e.edges.push_back(h.edge(i));
     node_register(0, std::move(e));
+    touch_slot(idx);
     epoch++;
     return make_key(idx, slots_[idx].version);
 }
@@ -240,6 +257,7 @@ bool HostCDE::deregister_hazard(uint64_t hkey) {  // cd_engine.rs:87-96
     slots_[idx].next_free = free_head_;
     free_head_ = idx;
     n_live_--;
+    touch_slot(idx);
     epoch++;
     return true;
 }
@@ -265,6 +283,7 @@ void HostCDE::swap_container(const HostCDE& base) {  // entities/layout.rs:40-50
         if (s.live && s.hz.dynamic) dyn.push_back(s.hz);
     const uint64_t ep = epoch;
     *this = base;  // self.cde = container.base_cde.clone()
+    invalidate_image();
     snapshots_.clear();
     last_error.clear();
     epoch = ep + 1;
@@ -325,15 +344,13 @@ void HostCDE::filter_qzones(int required_quality, uint32_t* bits, int words) con
 // ---- flatten -------------------------------------------------------------------------------------
 static uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-bool blob_grid_ok(const uint8_t* blob) {
-    JgLayoutHeader h;
-    std::memcpy(&h, blob, sizeof(h));
-    const int D = (int)h.root_level;
-    if (D < 0 || D > 5 || h.n_nodes == 0 || h.n_nodes > 0xFFFEu) return false;
+// The grid premise of csrc/detect_grid.cuh in two parts: what depends on the root box alone (the nested midpoints and the
+// one-correction cell lookup), and what every node must satisfy (its box is the grid's, a leaf record fits). The incremental
+// image re-checks only the nodes it re-serialises.
+bool grid_axes_ok(const float root_bbox[4], int D, float xs[33], float ys[33]) {
+    if (D < 0 || D > 5) return false;
     const int G = 1 << D;
-    const int32_t* nm = (const int32_t*)(blob + h.off_node_meta);
-    const float* nb = (const float*)(blob + h.off_node_bbox);
-    float xs[33], ys[33];
+    const float* nb = root_bbox;
     xs[0] = nb[0], xs[G] = nb[2], ys[0] = nb[1], ys[G] = nb[3];
     if (!(nb[2] > nb[0] && nb[3] > nb[1])) return false;
     for (int step = G; step >= 2; step >>= 1)
@@ -347,32 +364,46 @@ bool blob_grid_ok(const uint8_t* blob) {
         if (!(fx >= (float)(k - 1) && fx <= (float)k && fy >= (float)(k - 1) && fy <= (float)k)) return false;
         if (k > 0 && !(xs[k] > xs[k - 1] && ys[k] > ys[k - 1])) return false;
     }
-    std::vector<uint8_t> level(h.n_nodes, 0);
-    for (uint32_t n = 0; n < h.n_nodes; n++) {
-        int lv = 0, ci = 0, cj = 0;
-        uint32_t cur = n;
-        while (cur > 0 && lv <= D) {
-            const int q = (int)((cur - 1) & 3u);
-            ci |= ((q == 0 || q == 3) ? 1 : 0) << lv;
-            cj |= ((q == 0 || q == 1) ? 1 : 0) << lv;
-            lv++;
-            const int32_t par = nm[4 * cur + 3];
-            if (par < 0 || (uint32_t)par >= h.n_nodes || nm[4 * par] != (int32_t)(((cur - 1) & ~3u) + 1)) return false;
-            cur = (uint32_t)par;
-        }
-        if (lv > D || cur != 0) return false;
-        const int s = D - lv;
-        if (!(nb[4 * n] == xs[ci << s] && nb[4 * n + 2] == xs[(ci + 1) << s] && nb[4 * n + 1] == ys[cj << s] &&
-              nb[4 * n + 3] == ys[(cj + 1) << s]))
-            return false;
-        level[n] = (uint8_t)lv;
-        const int n_entire = nm[4 * n + 2] & 0xFFFF, n_partial = (nm[4 * n + 2] >> 16) & 0xFFFF;
-        const bool has_children = nm[4 * n] >= 0;
-        if (n_entire == 0 && n_partial > 0) {
-            if (!has_children && (lv != D || n_partial > 255 || nm[4 * n + 1] + n_entire >= (1 << 24))) return false;  // leaf record
-            if (has_children && lv >= D) return false;
-        }
+    return true;
+}
+bool grid_node_ok(const int32_t* nm, const float* nb, uint32_t n, uint32_t n_nodes, int D, const float* xs, const float* ys) {
+    if (nm[4 * n + 3] == -2) return true;  // a record of a freed child block (incremental image): not part of the tree
+    int lv = 0, ci = 0, cj = 0;
+    uint32_t cur = n;
+    while (cur > 0 && lv <= D) {
+        const int q = (int)((cur - 1) & 3u);
+        ci |= ((q == 0 || q == 3) ? 1 : 0) << lv;
+        cj |= ((q == 0 || q == 1) ? 1 : 0) << lv;
+        lv++;
+        const int32_t par = nm[4 * cur + 3];
+        if (par < 0 || (uint32_t)par >= n_nodes || nm[4 * par] != (int32_t)(((cur - 1) & ~3u) + 1)) return false;
+        cur = (uint32_t)par;
     }
+    if (lv > D || cur != 0) return false;
+    const int s = D - lv;
+    if (!(nb[4 * n] == xs[ci << s] && nb[4 * n + 2] == xs[(ci + 1) << s] && nb[4 * n + 1] == ys[cj << s] &&
+          nb[4 * n + 3] == ys[(cj + 1) << s]))
+        return false;
+    const int n_entire = nm[4 * n + 2] & 0xFFFF, n_partial = (nm[4 * n + 2] >> 16) & 0xFFFF;
+    const bool has_children = nm[4 * n] >= 0;
+    if (n_entire == 0 && n_partial > 0) {
+        if (!has_children && (lv != D || n_partial > 255 || nm[4 * n + 1] + n_entire >= (1 << 24))) return false;  // leaf record
+        if (has_children && lv >= D) return false;
+    }
+    return true;
+}
+
+bool blob_grid_ok(const uint8_t* blob) {
+    JgLayoutHeader h;
+    std::memcpy(&h, blob, sizeof(h));
+    const int D = (int)h.root_level;
+    if (D < 0 || D > 5 || h.n_nodes == 0 || h.n_nodes > 0xFFFEu) return false;
+    const int32_t* nm = (const int32_t*)(blob + h.off_node_meta);
+    const float* nb = (const float*)(blob + h.off_node_bbox);
+    float xs[33], ys[33];
+    if (!grid_axes_ok(nb, D, xs, ys)) return false;
+    for (uint32_t n = 0; n < h.n_nodes; n++)
+        if (!grid_node_ok(nm, nb, n, h.n_nodes, D, xs, ys)) return false;
     return true;
 }
 

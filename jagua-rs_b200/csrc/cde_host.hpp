@@ -52,13 +52,22 @@ struct QNode {
     uint8_t level = 0;
     Rect bbox{0, 0, 0, 0};
     int child_base = -1;  // arena index of child 0; children are child_base .. child_base+3
+    int parent = -1;      // arena index of the parent (-1: root)
+    bool dead = false;    // lives in a freed child block
     std::vector<QEntry> entries;  // Entire entries first, then Partial
     uint32_t n_active_edges = 0;
+};
+
+// A byte range of the device image that changed (HostCDE::image_sync).
+struct ImageRange {
+    uint32_t off, len;
 };
 
 // The host twin of k_grid_build's validity verdict (csrc/detect_grid.cuh) for a NoFilter summary, evaluated on
 // a flattened blob: lets a layout upload choose the kernel path without reading anything back from the device.
 bool blob_grid_ok(const uint8_t* blob);
+bool grid_axes_ok(const float root_bbox[4], int D, float xs[33], float ys[33]);
+bool grid_node_ok(const int32_t* node_meta, const float* node_bbox, uint32_t n, uint32_t n_nodes, int D, const float* xs, const float* ys);
 
 class HostCDE {
 public:
@@ -81,6 +90,17 @@ public:
     std::vector<uint8_t> flatten() const;
     std::vector<uint32_t> tree_dump() const;
 
+    // ---- incremental device image (BASELINE north_star item 1: "flattened into SoA arrays in HBM and
+    // updated incrementally on register/deregister") ----
+    // A POSITION-STABLE form of the blob of layout_soa.h: node records at their arena index (freed child blocks stay as dead
+    // records, parent = -2), the entries / edges of a node in blocks of their own inside section-sized heaps, hazards by
+    // slot, hazard vertices in per-slot blocks. register_hazard / deregister_hazard (and everything built on them: restore,
+    // place_item, remove_item) record which nodes and slots they touched; image_sync re-serialises only those and reports the
+    // byte ranges that changed since the previous call. `lineage` changes whenever the image had to be rebuilt from scratch
+    // (first call, a section outgrew its capacity, fragmentation): the consumer must then take the whole blob.
+    const std::vector<uint8_t>& image_sync(std::vector<ImageRange>& ranges, uint64_t& lineage, uint64_t& seq);
+    void invalidate_image() { img_.valid = false; }  // (a copy of a CDE must not continue the original's image lineage)
+
     std::string last_error;
     uint64_t epoch = 0;
 
@@ -93,7 +113,9 @@ private:
     };
     static uint64_t make_key(uint32_t idx, uint32_t version) { return ((uint64_t)version << 32) | idx; }
 
-    int alloc_children(const Rect& bbox, uint8_t child_level);
+    int alloc_children(int parent, const Rect& bbox, uint8_t child_level);
+    void touch_node(int node);
+    void touch_slot(uint32_t slot);
     void free_children(int child_base);
     void node_register(int node, QEntry&& e);
     void node_deregister(int node, uint32_t slot, uint32_t version);
@@ -109,6 +131,42 @@ private:
     uint32_t free_head_ = UINT32_MAX;
     int n_live_ = 0;
     std::vector<std::vector<HostHazard>> snapshots_;
+
+    // image state (cde_image.cpp)
+    struct Block {
+        uint32_t off = 0, cap = 0;  // in elements of the section
+    };
+    struct Heap {  // element heap of one section: bump pointer + free lists by exact block size
+        uint32_t top = 0, cap = 0, live = 0;
+        std::vector<std::vector<uint32_t>> free_by_size;
+        bool alloc(uint32_t n, Block& b);
+        void release(Block& b);
+    };
+    struct Image {
+        std::vector<uint8_t> blob;
+        JgLayoutHeader hdr{};
+        uint32_t cap_nodes = 0, cap_slots = 0;
+        Heap entries, edges, verts;
+        std::vector<Block> node_entries, node_edges, slot_verts;
+        std::vector<ImageRange> dirty;
+        uint64_t lineage = 0, seq = 0;
+        bool valid = false;
+        // the grid premise, kept up to date node by node (the twin of k_grid_build's verdict, see blob_grid_ok)
+        bool axes_ok = false;
+        float xs[33], ys[33];
+        std::vector<uint8_t> node_bad;
+        int n_bad = 0;
+    } img_;
+    std::vector<int> dirty_nodes_;
+    std::vector<uint8_t> node_dirty_;
+    std::vector<uint32_t> dirty_slots_;
+    static uint64_t next_lineage_;
+    void image_rebuild();
+    bool image_write_node(int node);
+    void image_check_node(int node);
+    bool image_write_slot(uint32_t slot);
+    void image_mark(uint32_t off, uint32_t len);
+    void image_write_header();
 };
 
 }  // namespace jg

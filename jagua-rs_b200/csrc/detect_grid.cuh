@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(1024) k_grid_build(const DevLayout L, int dept
     }
     // every node: (level, column, row) from its chain of parents; its bbox must be the grid's
     for (int n = tid; n < L.n_nodes; n += blockDim.x) {
+        if (L.node_meta[n].w == -2) continue;  // a record of a freed child block (incremental image): not part of the tree
         int level = 0, ci = 0, cj = 0, cur = n;
         bool bad = n > 0xFFFE;
         while (cur > 0 && level <= D) {

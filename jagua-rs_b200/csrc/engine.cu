@@ -78,6 +78,12 @@ struct JgEngine {
         std::vector<cudaEvent_t> marks;  // recorded on every query stream when this buffer became current
         bool marks_valid = false;
         int expect_grid = -1;        // host verdict to be confirmed by k_grid_build's (-1: nothing pending)
+        // incremental images (jg_layout_patch): which image lineage this buffer holds (0: none) and the byte ranges that
+        // changed since it was last written
+        uint64_t img_lineage = 0;
+        std::vector<ImageRange> pending;
+        void* d_patch = nullptr;     // device copy of a patch buffer: {n, (off, len, data_off) x n, data}
+        size_t patch_cap = 0;
     } bufs[2];
     int cur = 0;
     cudaStream_t st_up = nullptr;
@@ -89,6 +95,8 @@ struct JgEngine {
     bool has_layout = false;
     uint64_t epoch = 0;
     uint64_t layout_version = 0;  // bumped by every upload; per-filter node summaries are keyed on it
+    uint64_t img_lineage = 0, img_seq = 0;  // the incremental image last received (jg_layout_patch)
+    uint64_t stat_patched = 0;
     std::vector<uint32_t> slot_versions;  // SlotMap version per hazard slot of the current layout (blob section haz_version)
     int* h_blob_bad = nullptr;    // pinned, [2]: k_blob_validate's count of violations in the last device-blob upload into each buffer
     int* d_blob_bad = nullptr;
@@ -242,7 +250,7 @@ __global__ void k_blob_validate(const DevLayout L, int n_entries, int n_edges, i
         const int n_ent = (m.z & 0xFFFF) + ((m.z >> 16) & 0xFFFF);
         if (m.x >= 0 && ((m.x & 3) != 1 || m.x + 4 > L.n_nodes)) b = true;
         if (m.y < 0 || m.y + n_ent > n_entries) b = true;
-        if (m.w >= L.n_nodes || (i > 0 && m.w < 0)) b = true;
+        if (m.w >= L.n_nodes || (i > 0 && m.w < 0 && m.w != -2)) b = true;
         const float4 r = L.node_bbox[i];
         if (!(fabsf(r.x) < 1e30f && fabsf(r.y) < 1e30f && fabsf(r.z) < 1e30f && fabsf(r.w) < 1e30f && r.x <= r.z && r.y <= r.w)) b = true;
     }
@@ -348,7 +356,7 @@ void jg_engine_destroy(JgEngine* e) {
     if (e->ev_reset) cudaEventDestroy(e->ev_reset);
     if (e->h_avail) cudaFreeHost(e->h_avail);
     for (JgEngine::LayoutBuf& B : e->bufs) {
-        cudaFree(B.d_blob), cudaFree(B.d_kinds);
+        cudaFree(B.d_blob), cudaFree(B.d_kinds), cudaFree(B.d_patch);
         if (B.h_stage) cudaFreeHost(B.h_stage);
         if (B.ready) cudaEventDestroy(B.ready);
         for (cudaEvent_t ev : B.marks) cudaEventDestroy(ev);
@@ -462,10 +470,27 @@ static void bind_layout(JgEngine* e, const JgLayoutHeader& h) {
     e->has_layout = true;
 }
 
+// Scatter of a patch buffer into a layout image: patch = {n, (byte offset, byte length, data offset) x n, data}; all
+// multiples of 4. One CTA per range.
+__global__ void k_apply_patch(const uint32_t* __restrict__ patch, unsigned char* __restrict__ blob) {
+    const uint32_t off = patch[1 + 3 * blockIdx.x], len = patch[2 + 3 * blockIdx.x], src = patch[3 + 3 * blockIdx.x];
+    const uint32_t* s = (const uint32_t*)((const unsigned char*)patch + src);
+    uint32_t* d = (uint32_t*)(blob + off);
+    for (uint32_t i = threadIdx.x; i < len / 4; i += blockDim.x) d[i] = s[i];
+}
+struct PatchInfo {
+    uint64_t lineage, seq;
+    const ImageRange* ranges;
+    int n_ranges;
+};
+
 // trusted_hdr != null: a device blob whose header is already on the host and whose structure the device has checked
 // (jg_layout_broadcast): no read-back, no second check, and the copy out of `src` is signalled by ev_bc_consumed
 // instead of a host wait.
-static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t epoch, bool src_on_device, const JgLayoutHeader* trusted_hdr = nullptr) {
+// patch != null: `src` is the current state of an incremental image of the library's own host mirror (position-stable, trusted:
+// no structural re-check); only the ranges that changed since the target buffer was last written are copied.
+static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t epoch, bool src_on_device, const JgLayoutHeader* trusted_hdr = nullptr,
+                         const PatchInfo* patch = nullptr) {
     if (!e || !src) return JG_ERR_INVALID;
     JG_CUDA(e, cudaSetDevice(e->device));
     JgLayoutHeader h;
@@ -475,7 +500,7 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
     else std::memcpy(&h, src, sizeof(h));
     int rc = validate_header(e, h, bytes);
     if (rc != JG_OK) return rc;
-    if (!src_on_device) {
+    if (!src_on_device && !patch) {
         // structural checks the kernels rely on: children blocks at 1 + 4k, indices in range
         const int32_t* nm = (const int32_t*)((const char*)src + h.off_node_meta);
         for (uint32_t i = 0; i < h.n_nodes; i++) {
@@ -483,7 +508,7 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
             const uint32_t n_ent = (uint32_t)(cnt & 0xFFFF) + (uint32_t)((cnt >> 16) & 0xFFFF);
             if (cb >= 0 && ((cb & 3) != 1 || (uint32_t)cb + 4 > h.n_nodes)) return fail(e, JG_ERR_INVALID, "layout blob: bad child block");
             if (eb < 0 || (uint32_t)eb + n_ent > h.n_entries) return fail(e, JG_ERR_INVALID, "layout blob: bad entry range");
-            if (par >= (int32_t)h.n_nodes || (i > 0 && par < 0)) return fail(e, JG_ERR_INVALID, "layout blob: bad parent");
+            if (par >= (int32_t)h.n_nodes || (i > 0 && par < 0 && par != -2)) return fail(e, JG_ERR_INVALID, "layout blob: bad parent");
         }
         // the shortcut descents of detect.cu assume finite, non-empty node boxes
         const float* nb = (const float*)((const char*)src + h.off_node_bbox);
@@ -513,6 +538,22 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
     int host_grid = -1;  // -1 unknown (device blob of a foreign producer): read k_grid_build's verdict back
     if (h.flags & JG_LAYOUT_FLAG_GRID_CHECKED) host_grid = (h.flags & JG_LAYOUT_FLAG_GRID_OK) ? 1 : 0;
     else if (!src_on_device) host_grid = blob_grid_ok((const uint8_t*)src) ? 1 : 0;
+    // incremental images: which buffers can be patched (they hold this lineage, and no sync was missed)
+    if (patch) {
+        const bool cont = e->img_lineage == patch->lineage && e->img_seq + 1 == patch->seq;
+        for (JgEngine::LayoutBuf& X : e->bufs) {
+            if (!cont || X.img_lineage != patch->lineage) {
+                X.img_lineage = 0;
+                X.pending.clear();
+            } else {
+                X.pending.insert(X.pending.end(), patch->ranges, patch->ranges + patch->n_ranges);
+            }
+        }
+        e->img_lineage = patch->lineage, e->img_seq = patch->seq;
+    } else {
+        e->img_lineage = 0;
+        for (JgEngine::LayoutBuf& X : e->bufs) X.img_lineage = 0, X.pending.clear();
+    }
     static const bool force_sync = getenv("JG_SYNC_UPLOAD") != nullptr;
     // stream-ordered path: needs a current layout to keep serving, a host verdict, and no per-filter summaries
     // (those are rebuilt lazily on the compute stream and are not double-buffered)
@@ -558,8 +599,42 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
                 B.stage_cap = (size_t)h.total_bytes * 2 + 4096;
             }
             JG_CUDA(e, cudaEventSynchronize(B.ready));  // the previous copy out of this staging buffer (two uploads ago)
-            std::memcpy(B.h_stage, src, h.total_bytes);
-            JG_CUDA(e, cudaMemcpyAsync(B.d_blob, B.h_stage, h.total_bytes, cudaMemcpyHostToDevice, e->st_up));
+            size_t patch_data = 0;
+            if (patch && B.img_lineage == patch->lineage)
+                for (const ImageRange& r : B.pending) patch_data += r.len;
+            const size_t patch_bytes = 4 + 12 * B.pending.size() + patch_data + 16;
+            if (patch && B.img_lineage == patch->lineage && !B.pending.empty() && patch_bytes < h.total_bytes / 2 && patch_bytes <= B.stage_cap) {
+                // ONE copy of {range table, range data} + a scatter kernel (a copy per range would cost more than the whole blob)
+                if (B.patch_cap < B.stage_cap) {
+                    cudaFree(B.d_patch);
+                    B.d_patch = nullptr;
+                    B.patch_cap = 0;
+                    JG_CUDA(e, cudaMalloc(&B.d_patch, B.stage_cap));
+                    B.patch_cap = B.stage_cap;
+                }
+                uint32_t* tab = (uint32_t*)B.h_stage;
+                const uint32_t n_r = (uint32_t)B.pending.size();
+                tab[0] = n_r;
+                uint32_t at = (4 + 12 * n_r + 15) & ~15u;
+                for (uint32_t k = 0; k < n_r; k++) {
+                    const ImageRange& r = B.pending[k];
+                    tab[1 + 3 * k] = r.off, tab[2 + 3 * k] = r.len, tab[3 + 3 * k] = at;
+                    std::memcpy((char*)B.h_stage + at, (const char*)src + r.off, r.len);
+                    at += r.len;
+                }
+                JG_CUDA(e, cudaMemcpyAsync(B.d_patch, B.h_stage, at, cudaMemcpyHostToDevice, e->st_up));
+                k_apply_patch<<<n_r, 128, 0, e->st_up>>>((const uint32_t*)B.d_patch, (unsigned char*)B.d_blob);
+                JG_CUDA(e, cudaGetLastError());
+                e->stat_h2d += at;
+                e->stat_patched++;
+                e->stat_launches++;
+            } else {
+                std::memcpy(B.h_stage, src, h.total_bytes);
+                JG_CUDA(e, cudaMemcpyAsync(B.d_blob, B.h_stage, h.total_bytes, cudaMemcpyHostToDevice, e->st_up));
+                e->stat_h2d += h.total_bytes;
+            }
+            B.img_lineage = patch ? patch->lineage : 0;
+            B.pending.clear();
         } else {
             // (a broadcast blob was read back and checked on st_bc, which the host has waited for: it is complete)
             JG_CUDA(e, cudaMemcpyAsync(B.d_blob, src, h.total_bytes, cudaMemcpyDeviceToDevice, e->st_up));
@@ -596,6 +671,9 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
         JG_CUDA(e, cudaMemcpyAsync(B.d_blob, src, h.total_bytes,
                                    src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->compute));
         JG_CUDA(e, cudaStreamSynchronize(e->compute));
+        if (!src_on_device) e->stat_h2d += h.total_bytes;
+        B.img_lineage = patch ? patch->lineage : 0;
+        B.pending.clear();
         if (trusted_hdr) JG_CUDA(e, cudaEventRecord(e->ev_bc_consumed, e->compute));
         e->cur = nb;
         e->d_blob = B.d_blob;
@@ -618,7 +696,6 @@ static int upload_common(JgEngine* e, const void* src, size_t bytes, uint64_t ep
     e->epoch = epoch;
     e->stat_uploads++;
     if (!src_on_device) {
-        e->stat_h2d += h.total_bytes;
         const uint32_t* hv = (const uint32_t*)((const char*)src + h.off_haz_version);
         e->slot_versions.assign(hv, hv + h.n_slots);
         e->slot_versions_valid = true;
@@ -633,6 +710,16 @@ int jg_layout_upload(JgEngine* e, const void* blob, size_t bytes, uint64_t epoch
 }
 int jg_layout_upload_device(JgEngine* e, const void* d_blob, size_t bytes, uint64_t epoch) {
     return upload_common(e, d_blob, bytes, epoch, true);
+}
+int jg_layout_patch(JgEngine* e, const void* image, size_t bytes, uint64_t lineage, uint64_t seq, const uint32_t* ranges_off_len, int n_ranges,
+                    uint64_t epoch) {
+    if (!e || !image || lineage == 0 || n_ranges < 0 || (n_ranges > 0 && !ranges_off_len)) return JG_ERR_INVALID;
+    static_assert(sizeof(ImageRange) == 8, "ranges cross the C ABI as (offset, length) pairs of u32");
+    const PatchInfo pi{lineage, seq, (const ImageRange*)ranges_off_len, n_ranges};
+    for (int k = 0; k < n_ranges; k++)
+        if ((pi.ranges[k].off & 3u) || (pi.ranges[k].len & 3u) || (uint64_t)pi.ranges[k].off + pi.ranges[k].len > bytes)
+            return fail(e, JG_ERR_INVALID, "jg_layout_patch: range out of bounds / not a multiple of 4");
+    return upload_common(e, image, bytes, epoch, false, nullptr, &pi);
 }
 uint64_t jg_engine_layout_epoch(const JgEngine* e) { return e ? e->epoch : 0; }
 
@@ -1283,6 +1370,7 @@ int jg_engine_stats(const JgEngine* e, uint64_t out[8]) {
     out[2] = e->stat_h2d;
     out[3] = e->stat_d2h;
     out[4] = e->stat_uploads;
+    out[7] = e->stat_patched;
     if (e->main_ctx.sc.ctl) {  // survivors of the last *_device detect launch sequence
         DetectCtl c;
         cudaSetDevice(e->device);
@@ -1590,6 +1678,7 @@ int jg_flush_l2(JgEngine* e) {
 // ---- host mirror of CDEngine's update path ------------------------------------------------------------
 struct JgCdeBox {
     HostCDE cde;
+    std::vector<ImageRange> ranges;  // of the last jg_cde_image_sync
     JgCdeBox(Rect r, JgConfig c) : cde(r, c) {}
 };
 
@@ -1670,7 +1759,9 @@ int jg_cde_swap_container(JgCde* c, const JgCde* base) {
 }
 int jg_cde_clone(const JgCde* c, JgCde** out) {
     if (!c || !out) return JG_ERR_INVALID;
-    *out = (JgCde*)new JgCdeBox(*(const JgCdeBox*)c);
+    JgCdeBox* b = new JgCdeBox(*(const JgCdeBox*)c);
+    b->cde.invalidate_image();
+    *out = (JgCde*)b;
     return JG_OK;
 }
 uint64_t jg_cde_epoch(const JgCde* c) { return c ? ((const JgCdeBox*)c)->cde.epoch : 0; }
@@ -1707,12 +1798,39 @@ int64_t jg_cde_flatten(JgCde* c, void* buf, int64_t cap) {
     if (buf && cap >= (int64_t)blob.size()) std::memcpy(buf, blob.data(), blob.size());
     return (int64_t)blob.size();
 }
+int jg_cde_image_sync(JgCde* c, const void** image, size_t* bytes, uint64_t* lineage, uint64_t* seq, const uint32_t** ranges_off_len, int* n_ranges) {
+    if (!c || !image || !bytes || !lineage || !seq || !ranges_off_len || !n_ranges) return JG_ERR_INVALID;
+    JgCdeBox* box = (JgCdeBox*)c;
+    if (box->cde.hkey_exterior() == 0) {
+        box->cde.last_error = "No exterior hazard registered in the CDE";  // cd_engine.rs:48
+        return JG_ERR_INVALID;
+    }
+    const std::vector<uint8_t>& blob = box->cde.image_sync(box->ranges, *lineage, *seq);
+    *image = blob.data();
+    *bytes = blob.size();
+    *ranges_off_len = box->ranges.empty() ? nullptr : (const uint32_t*)box->ranges.data();
+    *n_ranges = (int)box->ranges.size();
+    return JG_OK;
+}
 int jg_cde_sync_to_engine(JgCde* c, JgEngine* e, uint64_t* epoch) {
     if (!c || !e) return JG_ERR_INVALID;
     HostCDE& cde = ((JgCdeBox*)c)->cde;
     if (cde.hkey_exterior() == 0) return fail(e, JG_ERR_INVALID, "No exterior hazard registered in the CDE");
-    std::vector<uint8_t> blob = cde.flatten();
-    int rc = jg_layout_upload(e, blob.data(), blob.size(), cde.epoch);
+    static const bool incremental = [] { const char* v = getenv("JG_INCREMENTAL"); return !v || atoi(v) != 0; }();
+    int rc;
+    if (incremental) {  // only what register / deregister touched since the last sync travels
+        const void* image;
+        size_t bytes;
+        uint64_t lineage, seq;
+        const uint32_t* ranges;
+        int n_ranges;
+        rc = jg_cde_image_sync(c, &image, &bytes, &lineage, &seq, &ranges, &n_ranges);
+        if (rc != JG_OK) return fail(e, rc, cde.last_error.c_str());
+        rc = jg_layout_patch(e, image, bytes, lineage, seq, ranges, n_ranges, cde.epoch);
+    } else {
+        std::vector<uint8_t> blob = cde.flatten();
+        rc = jg_layout_upload(e, blob.data(), blob.size(), cde.epoch);
+    }
     if (rc == JG_OK && epoch) *epoch = cde.epoch;
     return rc;
 }

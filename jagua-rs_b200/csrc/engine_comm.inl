@@ -98,7 +98,7 @@ __global__ void k_bcast_check(const unsigned char* __restrict__ blob, size_t cap
             const int n_ent = (m.z & 0xFFFF) + ((m.z >> 16) & 0xFFFF);
             if (m.x >= 0 && ((m.x & 3) != 1 || m.x + 4 > n_nodes)) b = true;
             if (m.y < 0 || m.y + n_ent > n_entries) b = true;
-            if (m.w >= n_nodes || (i > 0 && m.w < 0)) b = true;
+            if (m.w >= n_nodes || (i > 0 && m.w < 0 && m.w != -2)) b = true;
             const float4 r = node_bbox[i];
             if (!(fabsf(r.x) < 1e30f && fabsf(r.y) < 1e30f && fabsf(r.z) < 1e30f && fabsf(r.w) < 1e30f && r.x <= r.z && r.y <= r.w)) b = true;
         }

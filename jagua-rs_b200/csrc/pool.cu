@@ -230,13 +230,16 @@ int jg_pool_layout_upload(JgPool* p, const void* blob, size_t bytes, uint64_t ep
 
 int jg_pool_cde_sync(JgCde* c, JgPool* p, uint64_t* epoch) {
     if (!c || !p) return JG_ERR_INVALID;
-    const int64_t need = jg_cde_flatten(c, nullptr, 0);
-    if (need < 0) return pool_fail(p, (int)need, jg_cde_last_error(c));
-    std::vector<uint8_t> blob((size_t)need);
-    const int64_t got = jg_cde_flatten(c, blob.data(), need);
-    if (got != need) return pool_fail(p, JG_ERR_INVALID, "jg_cde_flatten changed size between calls");
+    // the host mirror's incremental image: synced ONCE, the same ranges go to every device
+    const void* image;
+    size_t bytes;
+    uint64_t lineage, seq;
+    const uint32_t* ranges;
+    int n_ranges;
+    int rc = jg_cde_image_sync(c, &image, &bytes, &lineage, &seq, &ranges, &n_ranges);
+    if (rc != JG_OK) return pool_fail(p, rc, jg_cde_last_error(c));
     const uint64_t ep = jg_cde_epoch(c);
-    const int rc = jg_pool_layout_upload(p, blob.data(), blob.size(), ep);
+    rc = pool_run_all(p, (int)p->eng.size(), [=](int k) { return jg_layout_patch(p->eng[k], image, bytes, lineage, seq, ranges, n_ranges, ep); });
     if (rc == JG_OK && epoch) *epoch = ep;
     return rc;
 }

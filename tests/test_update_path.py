@@ -145,3 +145,99 @@ def test_lattice_points_are_plain_f32_arithmetic(jg):
     y = np.float32(lat.y0) + ij[:, 1].astype(np.float32) * np.float32(lat.dy)
     assert np.array_equal(got[:, 0], x.astype(np.float32)) and np.array_equal(got[:, 1], y.astype(np.float32))
     assert got[:, 0].max() < 5748.75 and got[:, 1].max() < 5762.5  # the lattice stays inside the half-open box
+
+
+# ---- incremental device image (jg_cde_image_sync) --------------------------------------------------------------
+def _decode_tree(blob):
+    """canonical pre-order dump (the format of jg_cde_tree_dump) of a layout blob, packed or position-stable"""
+    h = struct.unpack_from("<12I4f12I", blob.tobytes(), 0)
+    n_nodes, n_entries, n_edges, root_level = h[3], h[4], h[5], h[8]
+    o = h[16:27]
+    nm = np.frombuffer(blob, np.int32, 4 * n_nodes, o[0]).reshape(-1, 4)
+    nb = np.frombuffer(blob, np.uint32, 4 * n_nodes, o[1]).reshape(-1, 4)
+    na = np.frombuffer(blob, np.uint32, n_nodes, o[2])
+    em = np.frombuffer(blob, np.int32, 4 * n_entries, o[3]).reshape(-1, 4)
+    ef = np.frombuffer(blob, np.uint32, 4 * n_entries, o[4]).reshape(-1, 4)
+    ed = np.frombuffer(blob, np.uint32, 4 * n_edges, o[5]).reshape(-1, 4)
+    out = []
+
+    def rec(n, level):
+        cb, eb, cnt, _ = (int(v) for v in nm[n])
+        n_ent = (cnt & 0xFFFF) + ((cnt >> 16) & 0xFFFF)
+        out.extend([level, *[int(v) for v in nb[n]], 1 if cb >= 0 else 0, n_ent, int(na[n])])
+        ents = sorted(range(eb, eb + n_ent), key=lambda i: (-int(em[i, 3]), int(em[i, 0])))
+        for i in ents:
+            out.extend([int(em[i, 0]), int(em[i, 3])])
+            if em[i, 3] == 1:
+                out.extend(int(v) for v in ef[i])
+                out.append(int(em[i, 2]))
+                for k in range(int(em[i, 1]), int(em[i, 1]) + int(em[i, 2])):
+                    out.extend(int(v) for v in ed[k])
+            else:
+                out.extend([0] * 5)
+        if cb >= 0:
+            for q in range(4):
+                rec(cb + q, level - 1)
+
+    rec(0, root_level)
+    return np.array(out, np.uint32)
+
+
+@pytest.mark.parametrize("name", ["swim_half", "shirts_full", "baldacci1_bin", "swim_half_d0", "shirts_full_d10"])
+def test_incremental_image_tracks_the_tree(jg, orc, name):
+    """The position-stable image after every place / remove / restore: (1) it decodes to the same
+    quadtree as the host mirror and the oracle, word for word; (2) a consumer that applies only the reported byte ranges
+    to its previous copy holds exactly the image (nothing that changed goes unreported); (3) an update re-serialises a
+    fraction of the image, not all of it."""
+    from helpers import oracle_world, place_remove_sequence
+
+    wl = jg.load_workload(name)
+    cde = jg.build_engine(wl, device=None)
+    w = oracle_world(orc, wl)
+    shadow = {"blob": None, "lineage": 0, "seq": 0}
+    stats = {"patched": 0, "full": 0, "bytes": 0, "total": 0}
+
+    def sync(_op=None):
+        blob, lin, seq, ranges = cde.image_sync()
+        if lin != shadow["lineage"]:
+            assert len(ranges) == 0  # a new lineage is taken whole
+            shadow["blob"] = blob.copy()
+            stats["full"] += 1
+        else:
+            assert seq == shadow["seq"] + 1 and len(ranges) > 0
+            assert np.all(ranges[:, 0] % 4 == 0) and np.all(ranges[:, 1] % 4 == 0) and np.all(np.diff(ranges[:, 0]) > 0)
+            for off, ln in ranges:
+                shadow["blob"][off:off + ln] = blob[off:off + ln]
+            stats["patched"] += 1
+            stats["bytes"] += int(ranges[:, 1].sum())
+            stats["total"] += len(blob)
+        shadow["lineage"], shadow["seq"] = lin, seq
+        assert np.array_equal(shadow["blob"], blob), "a changed byte was not reported"
+        dump = cde.tree_dump()
+        assert np.array_equal(_decode_tree(blob), dump)
+        assert np.array_equal(dump, w.tree_dump())
+        # the grid premise, kept node by node for the image, equals the whole-tree check of the packed blob
+        assert blob.view(np.uint32)[11] == cde.flatten().view(np.uint32)[11]
+
+    sync()
+    place_remove_sequence(jg, wl, cde, w, n_ops=40, seed=11, after_each=sync)
+    snap_p, snap_o = cde.save(), w.cde_save()
+    rng = np.random.default_rng(12)
+    b = wl.cde_bbox
+    for k in range(5):  # a few more placements, then back to the snapshot
+        i = int(rng.integers(len(wl.items)))
+        it = wl.items[i]
+        rot = 0.0 if it.rotations is not None and len(it.rotations) == 0 else (
+            float(rng.random() * 6.28) if it.rotations is None else float(it.rotations[int(rng.integers(len(it.rotations)))]))
+        dt = np.array([[rot, b[0] + (b[2] - b[0]) * rng.random(), b[1] + (b[3] - b[1]) * rng.random()]], np.float32)
+        pk = w.place_item(i, float(dt[0, 0]), float(dt[0, 1]), float(dt[0, 2]))
+        cde.place_item(i, jg.ItemShape(it.verts, it.poi, it.poles, it.piers), jg.compose(dt)[0], pk)
+    sync()
+    cde.restore(snap_p)
+    w.cde_restore(snap_o)
+    sync()
+    assert np.array_equal(_decode_tree(cde.flatten()), cde.tree_dump())  # (the packed form decodes to the same tree)
+    assert stats["patched"] >= 30, stats
+    if wl.quadtree_depth >= 3:
+        assert stats["bytes"] < 0.35 * stats["total"], stats  # updates are local
+    cde.close()

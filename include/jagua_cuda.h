@@ -61,6 +61,25 @@ enum {
 };
 
 /* ------------------------------------------------------------------------------------------ */
+/* Limits (results never depend on which kernels serve a batch; speed does)                    */
+/* ------------------------------------------------------------------------------------------ */
+/* quadtree depth            <= 15 (JgConfig::quadtree_depth; the walk state keeps 4 pending bits per level)
+ * quadtree nodes            <= 2^20 (JG_ERR_CAPACITY beyond)
+ * item vertices             <= 4096
+ * queries per launch piece  <= 2^26 (larger batches are cut into pieces)
+ * collector words           <= 1024 (32768 hazard slots)
+ * GRID kernels (k_s1_grid / k_s2_grid / k_collect_grid: the fast path, 2-4x the walk kernels) serve a layout when
+ *   - the quadtree is at most 5 deep (the reference's default, lbf/src/config.rs:33-41) and has <= 0xFFFE nodes,
+ *   - every node box equals the nested-midpoint grid bit for bit (true for every tree built by CDEngine::new),
+ *   - no leaf holds more than 255 Partial hazards,
+ *   and, for hazard-set collection, when in addition
+ *   - the collector has <= 8 words (256 hazard slots),
+ *   - items carry <= 4 fail-fast poles, <= 4 piers and <= 96 vertices.
+ * Everything else runs on the quadtree-walk kernels (any depth <= 15, any item). jg_engine_detect_path reports which.
+ * Stage 2 stages the layout's entries + edges in shared memory by TMA when they fit 220 KB (swim: 100 KB), else reads
+ * them through L1. */
+
+/* ------------------------------------------------------------------------------------------ */
 /* Device engine                                                                               */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -52,10 +52,13 @@ void HostCDE::image_write_header() {
     std::memcpy(img_.blob.data(), &h, sizeof(h));
 }
 
-// block sizes: a little slack, so that a node whose hazard count changes by one usually keeps its blocks
-static uint32_t entry_block(uint32_t n) { return (n + 3u) & ~3u; }
-static uint32_t edge_block(uint32_t n) { return (n + 7u) & ~7u; }
-static uint32_t vert_block(uint32_t n) { return (n + 7u) & ~7u; }
+// Block sizes are exact: the kernels' working set (and what stage 2 stages into shared memory by TMA) is the sections up to
+// their high-water marks, and padding every block to 4 entries / 8 edges made the swim image 38 % larger and the detect
+// kernels 7 % slower (0.214 -> 0.228 ms per 1M queries). A node whose hazard count changes simply moves to a block of its new
+// size (exact-size free lists); the image is rebuilt - compacted - when turnover has grown a heap to 1.5x its live content.
+static uint32_t entry_block(uint32_t n) { return n; }
+static uint32_t edge_block(uint32_t n) { return n; }
+static uint32_t vert_block(uint32_t n) { return n; }
 
 // node record + its entry and edge blocks; false: a heap is full (the caller rebuilds with larger sections)
 bool HostCDE::image_write_node(int node) {
@@ -66,11 +69,11 @@ bool HostCDE::image_write_node(int node) {
     Block& gb = img_.node_edges[node];
     const uint32_t n_ent = n.dead ? 0u : (uint32_t)n.entries.size();
     const uint32_t n_edg = n.dead ? 0u : n.n_active_edges;
-    if (n_ent > eb.cap || (n_ent == 0 && eb.cap)) {
+    if (n_ent != eb.cap) {
         img_.entries.release(eb);
         if (n_ent && !img_.entries.alloc(entry_block(n_ent), eb)) return false;
     }
-    if (n_edg > gb.cap || (n_edg == 0 && gb.cap)) {
+    if (n_edg != gb.cap) {
         img_.edges.release(gb);
         if (n_edg && !img_.edges.alloc(edge_block(n_edg), gb)) return false;
     }
@@ -131,7 +134,7 @@ bool HostCDE::image_write_slot(uint32_t s) {
     Block& vb = img_.slot_verts[s];
     const Slot& sl = slots_[s];
     const uint32_t nv = sl.live ? (uint32_t)sl.hz.n_verts() : 0u;
-    if (nv > vb.cap || (nv == 0 && vb.cap)) {
+    if (nv != vb.cap) {
         img_.verts.release(vb);
         if (nv && !img_.verts.alloc(vert_block(nv), vb)) return false;
     }
@@ -226,7 +229,7 @@ const std::vector<uint8_t>& HostCDE::image_sync(std::vector<ImageRange>& ranges,
             for (int n : dirty_nodes_) image_check_node(n);
         for (uint32_t s : dirty_slots_) ok = ok && image_write_slot(s);
         // a full heap, or heaps grown to twice their live content by block turnover: start over (compacts)
-        if (!ok || img_.entries.top > 2 * img_.entries.live + 512 || img_.edges.top > 2 * img_.edges.live + 2048) {
+        if (!ok || img_.entries.top > img_.entries.live + img_.entries.live / 2 + 256 || img_.edges.top > img_.edges.live + img_.edges.live / 2 + 1024) {
             image_rebuild();
             rebuilt = true;
         }

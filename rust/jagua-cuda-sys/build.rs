@@ -4,7 +4,7 @@
 //! NOT COMPILED IN THE BUILD IMAGE OF THIS REPOSITORY (no Rust toolchain there).
 use std::{env, path::PathBuf, process::Command};
 
-const SOURCES: [&str; 7] = ["kernels.cu", "detect.cu", "search.cu", "engine.cu", "pool.cu", "cde_host.cpp", "item_host.cpp"];
+const SOURCES: [&str; 8] = ["kernels.cu", "detect.cu", "search.cu", "engine.cu", "pool.cu", "cde_host.cpp", "cde_image.cpp", "item_host.cpp"];
 const HEADERS: [&str; 9] = ["kernels.cuh", "detect_grid.cuh", "collect_grid.cuh", "launch.hpp", "predicates.cuh", "layout_soa.h",
                             "cde_host.hpp", "engine_comm.inl", "../../include/jagua_cuda.h"];
 

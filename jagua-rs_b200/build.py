@@ -11,7 +11,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libjagua_cuda.so")
+# JG_LIB_NAME (+ JG_EXTRA_NVCC): a second build of the library under another name, for same-box A/B runs of kernel variants
+LIB_NAME = os.environ.get("JG_LIB_NAME", "libjagua_cuda.so")
+LIB = os.path.join(HERE, LIB_NAME)
 SOURCES = ["kernels.cu", "detect.cu", "search.cu", "engine.cu", "pool.cu", "cde_host.cpp", "cde_image.cpp", "item_host.cpp"]
 HEADERS = ["kernels.cuh", "detect_grid.cuh", "collect_grid.cuh", "launch.hpp", "predicates.cuh", "layout_soa.h", "cde_host.hpp",
            os.path.join("..", "..", "include", "jagua_cuda.h")]
@@ -41,7 +43,7 @@ def is_fresh() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_fresh():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if LIB_NAME == "libjagua_cuda.so" else "build_" + os.path.splitext(LIB_NAME)[0])
     os.makedirs(objdir, exist_ok=True)
     objs = []
     for src in SOURCES:

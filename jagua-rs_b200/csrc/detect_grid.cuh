@@ -668,6 +668,9 @@ __device__ bool seg_collides_from_root(const GCtx& c, const Seg& sg) {
 
 // one group of `ng` survivors (ents[0 .. ng): survivor-list entries in global memory, or in the warp's own shared
 // memory when LOCAL) resolved by a warp; GS = slots in use (>= ng)
+#ifndef JG_S2_CONV
+#define JG_S2_CONV 1
+#endif
 template <bool FILT, bool LOCAL, bool SPLIT, bool STAGE = false>
 __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* ents, int ng, int GS, int lane) {
     const int D = c.g.D, G = c.g.G;
@@ -831,6 +834,62 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
                 }
             }
         }
+#if JG_S2_CONV
+        // Convergent rounds. Every lane is a small state machine over (candidate cell -> relevant Partial entry -> hazard
+        // edge); a round moves each lane on to its next PENDING EDGE TEST (cheap scanning: row words, entry boxes), then
+        // all lanes that have one run seg_seg together, and the lanes whose test (or Entire cell) produced a would-be hit
+        // verify that the reference's walk reaches the cell. The same tests in the same per-lane order as the nested loops
+        // (qt_partial_hazard.rs:67-72: first colliding edge of the first colliding entry), but the expensive body executes
+        // with the lanes of a round side by side instead of one divergent lane group after the other.
+        int hi = -1, ci = 0;   // would-be hit: column (the row is j); column of the cell being tested
+        int li = 0, ln = 0;    // entries of the current leaf cell still to look at
+        int hk = 0, hn = 0;    // hazard edges of the current entry still to test
+        for (;;) {
+            if (hk >= hn) {
+                while (scanning) {
+                    if (li < ln) {
+                        const int4 em = STAGE ? c.L.entry_meta[li] : __ldg(&c.L.entry_meta[li]);
+                        const Rect ff = STAGE ? ld_rect_any(&c.L.entry_ff[li]) : ld_rect(&c.L.entry_ff[li]);
+                        li++;
+                        if (FILT && filt_bit(c.filt, em.x)) continue;
+                        if (!rect_seg(ff, sg)) continue;
+                        hk = em.y, hn = em.y + em.z;
+                        if (hk < hn) break;
+                        continue;
+                    }
+                    if (!bits) {
+                        if (j >= j1) { scanning = false; break; }
+                        j++;
+                        er = c.g.ent_rows[j] & cm;
+                        bits = er | (c.g.leaf_rows[j] & cm);
+                        continue;
+                    }
+                    ci = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if ((er >> ci) & 1u) { hi = ci; break; }
+                    const uint32_t rec = c.g.cell_leaf[j * GRID_G + ci];
+                    li = (int)(rec >> 8), ln = li + (int)(rec & 255u);
+                }
+            }
+            const bool test = hi < 0 && hk < hn;
+            if (!__any_sync(FULL, test || hi >= 0)) break;  // every lane is through its cells
+            if (test) {
+                const float4 v = STAGE ? c.L.edges[hk] : __ldg(&c.L.edges[hk]);
+                hk++;
+                if (seg_seg(sg, Seg{v.x, v.y, v.z, v.w})) hi = ci, hk = hn, li = ln;  // the cell collides: leave it
+            }
+            if (!__any_sync(FULL, hi >= 0)) continue;
+            if (hi >= 0) {
+                const Rect cb{c.g.xs[hi], c.g.ys[j], c.g.xs[hi + 1], c.g.ys[j + 1]};
+                if (rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) ||
+                    path_reaches<!SPLIT>(c.g, sg, l0, c.g.cell_level[j * GRID_G + hi], hi, j))
+                    atomicOr(&W.hit, 1u << slot);
+                hi = -1;
+            }
+            __syncwarp();
+            if ((*(volatile unsigned*)&W.hit >> slot) & 1u) scanning = false, hk = hn, li = ln;
+        }
+#else
         // rounds: every lane scans on to its next would-be hit (an Entire cell, or a leaf cell whose edge
         // tests succeed), then the lanes that found one verify together that the reference reaches it
         for (;;) {
@@ -862,6 +921,7 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
             __syncwarp();
             if ((*(volatile unsigned*)&W.hit >> slot) & 1u) scanning = false;
         }
+#endif
         __syncwarp();
     }
     __syncwarp();

@@ -305,13 +305,13 @@ def main():
     gpu_launches = cde.stats()["launches"] - launches0 - args.steps  # minus the untimed L2 flush fills
 
     # ---- e2e: host buffers through the public API, copies inside the timed region
-    # (a) one batch at a time: enqueue + sync per step, pieces of 256 Ki queries on 4 streams
-    # (b) batches in flight: K steps enqueued back to back (whole batch per stream, 3 streams), one sync at the end
+    # (a) one batch at a time: enqueue + sync per step (the library cuts an idle engine's batch into pieces of 256 Ki queries)
+    # (b) batches in flight: K steps enqueued back to back (whole batch per piece stream), one sync at the end
     ring = {k: [jg.PinnedBuffer((n_q,), np.uint8) for _ in range(4)] for k in ("composed", "indexed", "lattice")}
     ring["composed"][0] = host_out
 
     def run_e2e(step_fn, pipelined):
-        cde.set_batching(1 << 20 if pipelined else 1 << 18, 3 if pipelined else 4)
+        cde.set_batching(0, 4)  # the library's per-batch piece schedule, 4 piece streams
         for i in range(max(args.warmup, 3)):
             step_fn(i)
             cde.sync()
@@ -409,7 +409,7 @@ def main():
             return {"value": total_q * args.steps / pip, "unit": UNIT, "ms_per_step": pip / args.steps * 1e3,
                     "h2d_bytes_per_step": bytes_in * n_q, "d2h_bytes_per_step": n_q, "input": desc, "same_verdicts_as_device_path": bool(same[k]),
                     "one_batch_at_a_time": {"value": total_q * args.steps / ser, "unit": UNIT, "ms_per_step": ser / args.steps * 1e3,
-                                            "mode": "sync after every batch; pieces of 256 Ki queries on 4 streams"}}
+                                            "mode": "sync after every batch; the library's piece schedule for an idle engine: pieces of 256 Ki queries on 4 streams (jg_engine_set_batching(0, 4))"}}
 
         composed = e2e_obj("composed", 16, "jg_detect_multi: composed (cos, sin, tx, ty) f32 records, 16 B/query, pinned host memory")
         head = composed
@@ -479,9 +479,9 @@ def run_strong(jg, wl, args, n_dev, offs, t, ridx, txy):
         for form in ("indexed", "composed"):
             for pipelined in (False, True):
                 per_dev = (n + n_dev - 1) // n_dev
-                # batches in flight: a device's whole shard per stream; one at a time: pieces of 256 Ki queries (shards of up to
-                # 512 Ki go as one piece, see detect_multi_host) and the blocking call (enqueue + wait on the device's own thread)
-                pool.set_batching(min(per_dev, 1 << 20) if pipelined else 1 << 18, 3 if pipelined else 4)
+                # every engine cuts its shard by the library's per-batch schedule (detect_multi_host); one at a time = the blocking
+                # call (enqueue + wait on the device's own thread)
+                pool.set_batching(0, 4)
 
                 def step(i):
                     if form == "indexed":

@@ -262,7 +262,11 @@ float jg_engine_last_kernel_ms(JgEngine* e);
  * start records an event, stop records another, waits for it and returns the elapsed ms. */
 int jg_timer_start(JgEngine* e);
 int jg_timer_stop(JgEngine* e, float* ms);
-/* Chunk size (queries) and number of in-flight chunks used by the host-pointer batch calls. */
+/* How the host-pointer batch calls cut a batch into pieces (piece k runs on stream k mod n_streams: H2D, kernels, D2H).
+ * chunk_queries == 0 (the default, with 4 streams): chosen per batch - one piece up to 512 Ki queries; engine idle (one batch
+ * at a time): pieces of 256 Ki, so that copies and kernels overlap; batches already in flight: whole pieces of up to 1 Mi
+ * (their copies hide behind the kernels of the previous batches, one launch pair per piece).
+ * chunk_queries > 0 pins fixed pieces of that size. */
 int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams);
 /* Lanes per query (0 = choose from the item's vertex count, else 4, 8, 16 or 32) of the detect
  * stage-2 and collect kernels. A tuning knob; results do not depend on it. */

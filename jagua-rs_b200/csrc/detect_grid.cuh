@@ -668,8 +668,8 @@ __device__ bool seg_collides_from_root(const GCtx& c, const Seg& sg) {
 
 // one group of `ng` survivors (ents[0 .. ng): survivor-list entries in global memory, or in the warp's own shared
 // memory when LOCAL) resolved by a warp; GS = slots in use (>= ng)
-#ifndef JG_S2_CONV
-#define JG_S2_CONV 1
+#ifndef JG_S2_REFILL
+#define JG_S2_REFILL 8
 #endif
 template <bool FILT, bool LOCAL, bool SPLIT, bool STAGE = false>
 __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* ents, int ng, int GS, int lane) {
@@ -798,53 +798,64 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
     const unsigned need = __ballot_sync(FULL, nE > 0);
     __syncwarp();
 
-    for (int f0 = 0; f0 < E; f0 += 32) {
-        const unsigned hm0 = *(volatile unsigned*)&W.hit;
-        if ((hm0 & need) == need) break;  // every survivor with edges already has a colliding one
-        const int f = f0 + lane;
+    // Convergent rounds WITH REFILL over the group's flat edge list. Every lane is a small state machine over (item edge ->
+    // candidate cell -> relevant Partial entry -> hazard edge). A round (1) hands the next edges of the list to the idle lanes
+    // - once at least JG_S2_REFILL lanes are idle, so that the edge set-up (transform, four cell look-ups) runs densely too -,
+    // (2) moves each lane on to its next PENDING EDGE TEST (cheap scanning: row words, entry boxes), (3) runs seg_seg for all
+    // lanes that have one, side by side, and (4) lets the lanes whose test (or Entire cell) produced a would-be hit verify
+    // that the reference's walk reaches the cell. Per edge the same tests in the same order as the nested loops
+    // (qt_partial_hazard.rs:67-72: first colliding edge of the first colliding entry); a survivor's remaining edges are
+    // skipped as soon as one of its edges collides (the verdict is an OR over the edges, cd_engine.rs:164-173).
+    {
+        int fnext = 0;  // next edge of the list to hand out (warp-uniform)
         int slot = 0;
         bool scanning = false;
         Seg sg{0.0f, 0.0f, 0.0f, 0.0f};
         int l0 = 0, j = 0, j1 = -1;
         uint32_t cm = 0u, bits = 0u, er = 0u;
-        if (f < E) {
-            // the last slot whose first edge is <= f: ebeg[0 .. 8] is non-decreasing (slots beyond ng hold E)
-            if (W.ebeg[4] <= f) slot = 4;
-            if (W.ebeg[slot + 2] <= f) slot += 2;
-            if (W.ebeg[slot + 1] <= f) slot += 1;
-            if (!((hm0 >> slot) & 1u)) {
-                const float4 t4 = W.xf[slot];
-                sg = item_edge(c.tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, f - W.ebeg[slot]);
-                const int vc = W.vcell[slot];
-                l0 = vc >> 16;
-                const int s0 = D - l0;
-                // candidate cells: the edge's bbox inflated by delta, clipped to the virtual root's cells
-                int i0 = cell_lo(c.g.xs, G, fminf(sg.sx, sg.ex) - c.g.delta, c.g.x0, c.g.inv_cw);
-                int i1 = cell_hi(c.g.xs, G, fmaxf(sg.sx, sg.ex) + c.g.delta, c.g.x0, c.g.inv_cw);
-                j = cell_lo(c.g.ys, G, fminf(sg.sy, sg.ey) - c.g.delta, c.g.y0, c.g.inv_ch);
-                j1 = cell_hi(c.g.ys, G, fmaxf(sg.sy, sg.ey) + c.g.delta, c.g.y0, c.g.inv_ch);
-                const int vi0 = (vc & 255) << s0, vj0 = ((vc >> 8) & 255) << s0;
-                i0 = max(i0, vi0), i1 = min(i1, vi0 + (1 << s0) - 1);
-                j = max(j, vj0), j1 = min(j1, vj0 + (1 << s0) - 1);
-                cm = col_mask(i0, i1);
-                scanning = j <= j1 && cm != 0u;
-                if (scanning) {
-                    er = c.g.ent_rows[j] & cm;
-                    bits = er | (c.g.leaf_rows[j] & cm);
-                }
-            }
-        }
-#if JG_S2_CONV
-        // Convergent rounds. Every lane is a small state machine over (candidate cell -> relevant Partial entry -> hazard
-        // edge); a round moves each lane on to its next PENDING EDGE TEST (cheap scanning: row words, entry boxes), then
-        // all lanes that have one run seg_seg together, and the lanes whose test (or Entire cell) produced a would-be hit
-        // verify that the reference's walk reaches the cell. The same tests in the same per-lane order as the nested loops
-        // (qt_partial_hazard.rs:67-72: first colliding edge of the first colliding entry), but the expensive body executes
-        // with the lanes of a round side by side instead of one divergent lane group after the other.
         int hi = -1, ci = 0;   // would-be hit: column (the row is j); column of the cell being tested
         int li = 0, ln = 0;    // entries of the current leaf cell still to look at
         int hk = 0, hn = 0;    // hazard edges of the current entry still to test
         for (;;) {
+            const unsigned hm0 = *(volatile unsigned*)&W.hit;
+            if ((hm0 & need) == need) break;  // every survivor with edges already has a colliding one
+            if ((hm0 >> slot) & 1u) scanning = false, hk = hn, li = ln;
+            const unsigned idle = __ballot_sync(FULL, !scanning);
+            if (fnext < E && (__popc(idle) >= JG_S2_REFILL || idle == FULL)) {
+                const int f = fnext + __popc(idle & lanemask_lt());
+                fnext += __popc(idle);
+                if (!scanning && f < E) {
+                    // the last slot whose first edge is <= f: ebeg[0 .. 8] is non-decreasing (slots beyond ng hold E)
+                    slot = 0;
+                    if (W.ebeg[4] <= f) slot = 4;
+                    if (W.ebeg[slot + 2] <= f) slot += 2;
+                    if (W.ebeg[slot + 1] <= f) slot += 1;
+                    if (!((hm0 >> slot) & 1u)) {
+                        const float4 t4 = W.xf[slot];
+                        sg = item_edge(c.tab.seg[W.seg[slot]], Xf{t4.x, t4.y, t4.z, t4.w}, f - W.ebeg[slot]);
+                        const int vc = W.vcell[slot];
+                        l0 = vc >> 16;
+                        const int s0 = D - l0;
+                        // candidate cells: the edge's bbox inflated by delta, clipped to the virtual root's cells
+                        int i0 = cell_lo(c.g.xs, G, fminf(sg.sx, sg.ex) - c.g.delta, c.g.x0, c.g.inv_cw);
+                        int i1 = cell_hi(c.g.xs, G, fmaxf(sg.sx, sg.ex) + c.g.delta, c.g.x0, c.g.inv_cw);
+                        j = cell_lo(c.g.ys, G, fminf(sg.sy, sg.ey) - c.g.delta, c.g.y0, c.g.inv_ch);
+                        j1 = cell_hi(c.g.ys, G, fmaxf(sg.sy, sg.ey) + c.g.delta, c.g.y0, c.g.inv_ch);
+                        const int vi0 = (vc & 255) << s0, vj0 = ((vc >> 8) & 255) << s0;
+                        i0 = max(i0, vi0), i1 = min(i1, vi0 + (1 << s0) - 1);
+                        j = max(j, vj0), j1 = min(j1, vj0 + (1 << s0) - 1);
+                        cm = col_mask(i0, i1);
+                        scanning = j <= j1 && cm != 0u;
+                        li = ln = hk = hn = 0;
+                        if (scanning) {
+                            er = c.g.ent_rows[j] & cm;
+                            bits = er | (c.g.leaf_rows[j] & cm);
+                        }
+                    }
+                }
+            } else if (idle == FULL) {
+                break;  // the list is handed out and every lane is through its edge
+            }
             if (hk >= hn) {
                 while (scanning) {
                     if (li < ln) {
@@ -871,9 +882,7 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
                     li = (int)(rec >> 8), ln = li + (int)(rec & 255u);
                 }
             }
-            const bool test = hi < 0 && hk < hn;
-            if (!__any_sync(FULL, test || hi >= 0)) break;  // every lane is through its cells
-            if (test) {
+            if (hi < 0 && scanning && hk < hn) {
                 const float4 v = STAGE ? c.L.edges[hk] : __ldg(&c.L.edges[hk]);
                 hk++;
                 if (seg_seg(sg, Seg{v.x, v.y, v.z, v.w})) hi = ci, hk = hn, li = ln;  // the cell collides: leave it
@@ -887,42 +896,7 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
                 hi = -1;
             }
             __syncwarp();
-            if ((*(volatile unsigned*)&W.hit >> slot) & 1u) scanning = false, hk = hn, li = ln;
         }
-#else
-        // rounds: every lane scans on to its next would-be hit (an Entire cell, or a leaf cell whose edge
-        // tests succeed), then the lanes that found one verify together that the reference reaches it
-        for (;;) {
-            int hi = -1;
-            while (scanning) {
-                if (!bits) {
-                    if (j >= j1) { scanning = false; break; }
-                    j++;
-                    er = c.g.ent_rows[j] & cm;
-                    bits = er | (c.g.leaf_rows[j] & cm);
-                    continue;
-                }
-                const int i = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (((er >> i) & 1u) || leaf_cell_collides<Seg, FILT, STAGE>(c.L, c.g.cell_leaf[j * GRID_G + i], sg, c.filt)) { hi = i; break; }
-            }
-            if (!__any_sync(FULL, hi >= 0)) break;
-            bool lanehit = false;
-            if (hi >= 0) {
-                // a finest cell that holds an endpoint is flagged at every level (qt_traits.rs:36-44: not range-
-                // rejected, `contains` true, and half_intersect only ever adds quadrants)
-                const Rect cb{c.g.xs[hi], c.g.ys[j], c.g.xs[hi + 1], c.g.ys[j + 1]};
-                // (the inline-containment variant is the larger kernel and bound by instruction fetch: it takes the rolled
-                // quadrant test - 1M queries 217.8 -> 214 us; the split variant, smaller, keeps the unrolled one - 4M: 620 vs 643 us)
-                lanehit = rect_point(cb, sg.sx, sg.sy) || rect_point(cb, sg.ex, sg.ey) ||
-                          path_reaches<!SPLIT>(c.g, sg, l0, c.g.cell_level[j * GRID_G + hi], hi, j);
-            }
-            if (lanehit) atomicOr(&W.hit, 1u << slot);
-            __syncwarp();
-            if ((*(volatile unsigned*)&W.hit >> slot) & 1u) scanning = false;
-        }
-#endif
-        __syncwarp();
     }
     __syncwarp();
     const unsigned hm = *(volatile unsigned*)&W.hit;

@@ -133,6 +133,7 @@ struct JgEngine {
     bool stream_pending = false;  // a streamed batch may still be in flight: check its error flag at the next sync
     int* h_err = nullptr;
     int64_t chunk_queries = 1 << 18;
+    bool auto_schedule = true;  // piece sizes chosen per batch (detect_multi_host); jg_engine_set_batching pins them
     uint64_t next_chunk = 0;
     int detect_group = 0, collect_group = 0;  // 0 = auto
 
@@ -1114,21 +1115,43 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
             return JG_OK;
         }
     }
-    // Pieces of chunk_queries queries - but a batch of up to two chunks goes as ONE piece: the persistent kernels of
-    // consecutive pieces cannot overlap each other (each fills every SM slot), so two pieces pay two launch ramps and tails
-    // (262 Ki queries: 46 us of copy + 93 us of kernels in one piece, 23 + 70 + 70 us in two; tools/size_sweep.py).
-    const int64_t chunk = n <= 2 * e->chunk_queries ? n : e->chunk_queries;
+    // Piece schedule. The persistent kernels of consecutive pieces cannot overlap each other (each fills every SM slot) and a
+    // launch pair has ~45 us of fixed latency (tools/size_sweep.py: 64 Ki queries 53 us, 256 Ki 87, 1 Mi 200), so:
+    //  * a batch of up to two chunks (512 Ki queries) goes as ONE piece (262 Ki queries: 46 us of copy + 93 us of kernels in
+    //    one piece, 23 + 70 + 70 us in two);
+    //  * engine idle (nothing in flight on the piece streams - the caller runs one batch at a time): pieces of one chunk.
+    //    With 9 B/query the copy (0.16 us per Ki queries) and the kernels (0.155) run at the same rate, so the step costs
+    //    about copy(first piece) + the kernel chain; 4 x 256 Ki = 0.384 ms per 1 Mi queries. Measured and not better
+    //    (tools/schedule_probe.py, tools/trace_e2e.py, profiles/r2u_*): a short first piece and the rest in one
+    //    (256 Ki + 768 Ki: 0.417 ms - all copies must land before the last piece's 173 us of kernels start), one piece
+    //    (0.43 ms), 512 Ki pieces;
+    //  * batches already in flight (the caller pipelines): the copies of this batch hide behind the kernels of the previous
+    //    ones, so whole pieces of up to four chunks - one launch pair per 1 Mi queries: 0.195 ms per 1 Mi batch instead of
+    //    0.259 ms in 256 Ki pieces.
+    // jg_engine_set_batching(chunk > 0) pins fixed pieces of that size in both situations.
+    std::vector<int64_t> sched;
+    {
+        const int64_t cq = e->chunk_queries;
+        int64_t piece = cq;
+        if (e->auto_schedule) {
+            bool busy = false;
+            for (ChunkCtx& c : e->chunks) busy = busy || cudaStreamQuery(c.st) == cudaErrorNotReady;
+            (void)cudaGetLastError();
+            if (busy) piece = 4 * cq;
+        }
+        if (n <= 2 * cq) piece = n;
+        for (int64_t done = 0; done < n; done += piece) sched.push_back(piece < n - done ? piece : n - done);
+    }
+    int64_t max_piece = 0;
+    for (int64_t m : sched) max_piece = m > max_piece ? m : max_piece;
+    // (the slots are sized for the larger of the two schedules: the same batch size must not re-allocate - a device-wide
+    // synchronisation - when the caller goes from one batch at a time to batches in flight)
+    if (e->auto_schedule && max_piece < (n < 4 * e->chunk_queries ? n : 4 * e->chunk_queries)) max_piece = n < 4 * e->chunk_queries ? n : 4 * e->chunk_queries;
+    size_t sched_k = 0;
     PieceCursor cur;
     Piece p;
-    // The pipeline is bound by the H2D copies; what stays exposed is the kernels + D2H of the LAST piece, so
-    // the pieces taper towards the end of the batch (halving down to JG_TAPER_MIN queries).
-    static const int64_t taper_min = [] { const char* v = getenv("JG_TAPER_MIN"); return v ? (int64_t)atoll(v) : (int64_t)0; }();
-    auto piece_size = [&](int64_t done) {
-        const int64_t rem = n - done;
-        if (taper_min <= 0 || rem > chunk + chunk / 2) return chunk;
-        if (rem > 2 * taper_min) return (rem / 2 + 31) & ~(int64_t)31;
-        return rem;
-    };
+    // (a piece can come out shorter than asked - segment table full -: what is left then goes in pieces of max_piece)
+    auto piece_size = [&](int64_t) { return sched_k < sched.size() ? sched[sched_k++] : max_piece; };
     const bool tr = trace_on();
     if (tr) {
         e->trace_used = 0;
@@ -1138,16 +1161,16 @@ static int detect_multi_host(JgEngine* e, int n_seg, const int* item_ids, const 
     // size every piece slot now (no-ops once they are): a slot that first grows in the middle of a run of batches would
     // stall that batch by several milliseconds of cudaMalloc
     for (ChunkCtx& c : e->chunks)
-        if (c.cap_q < (size_t)(chunk < n ? chunk : n) || c.cap_sv < (size_t)(chunk < n ? chunk : n) || c.cap_out < (size_t)(chunk < n ? chunk : n)) {
+        if (c.cap_q < (size_t)max_piece || c.cap_sv < (size_t)max_piece || c.cap_out < (size_t)max_piece) {
             JG_CUDA(e, cudaStreamSynchronize(c.st));
-            rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n), true);
+            rc = ensure_ctx(e, c, (size_t)max_piece, (size_t)max_piece, true);
             if (rc != JG_OK) return rc;
         }
     while (next_piece(e, n_seg, items.data(), seg_offsets, piece_size(cur.q), cur, p)) {
         ChunkCtx& c = e->chunks[e->next_chunk++ % e->chunks.size()];
         JG_CUDA(e, cudaStreamSynchronize(c.st));  // buffers of this slot are free again
         if (tr) trace_mark(e, c.st), e->trace_m.push_back(p.m);
-        rc = ensure_ctx(e, c, (size_t)(chunk < n ? chunk : n), (size_t)(chunk < n ? chunk : n), true);
+        rc = ensure_ctx(e, c, (size_t)max_piece, (size_t)max_piece, true);
         if (rc != JG_OK) return rc;
         XfSrc src{c.d_xf, nullptr, nullptr};
         if (!indexed) {
@@ -1499,10 +1522,11 @@ int jg_search_samples(JgEngine* e, int64_t n, uint8_t* rot_idx, float* txy, uint
 }
 
 int jg_engine_set_batching(JgEngine* e, int64_t chunk_queries, int n_streams) {
-    if (!e || chunk_queries < 1 || chunk_queries > JG_MAX_LAUNCH_QUERIES || n_streams < 1 || n_streams > 16) return JG_ERR_INVALID;
+    if (!e || chunk_queries < 0 || chunk_queries > JG_MAX_LAUNCH_QUERIES || n_streams < 1 || n_streams > 16) return JG_ERR_INVALID;
     int rc = jg_sync(e);
     if (rc != JG_OK) return rc;
-    e->chunk_queries = chunk_queries;
+    e->chunk_queries = chunk_queries > 0 ? chunk_queries : (int64_t)1 << 18;
+    e->auto_schedule = chunk_queries == 0;  // 0: the per-batch schedule of detect_multi_host (the default)
     e->bufs[0].marks_valid = e->bufs[1].marks_valid = false;  // the set of query streams changes
     while ((int)e->chunks.size() > n_streams) {
         cudaStream_t st = e->chunks.back().st;

@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(1024) k_cgrid_build(const DevLayout L, const G
 }
 
 #define CG_MAX_WORDS 8
+#ifndef CG_TRIPLES
+#define CG_TRIPLES 1  // lane = (query, terminal, entry) in the resolve step (0: lane = (query, terminal), for A/B)
+#endif
 #ifndef CG_GROUP
 #define CG_GROUP 8  // queries a warp resolves together
 #endif
@@ -84,6 +87,10 @@ struct CGSlots {  // per-warp state of the queries of the current group
     float4 pole[CG_GROUP][CG_MAX_POLES];  // transformed fail-fast poles (cx, cy, r, -)
     float2 tv[CG_VERT_CAP];               // transformed vertices, query s at s * V
     uint16_t list[CG_LIST_CAP];           // (query, terminal) pairs of the current pass
+#if CG_TRIPLES
+    int4 pp[32];        // per pair of the current 32: {first entry, candidate edges, edges ending inside, packed(query, vpair, poles, levels, cell)}
+    int pfx[36];        // prefix sums of the pairs' entry counts
+#endif
 };
 struct CGPierSlots {  // ... of the instantiation for items whose surrogate carries piers
     float4 pier[CG_GROUP][CG_MAX_PIERS];  // transformed fail-fast piers (sx, sy, ex, ey)
@@ -322,6 +329,7 @@ k_collect_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const G
             const bool more = __any_sync(FULL, alive);
             first = false;
             for (int p0 = 0; p0 < cnt; p0 += 32) {
+                if constexpr (PIERS || !CG_TRIPLES) {
                 if (p0 + lane < cnt) do {
                     const uint32_t pr = (uint32_t)W.list[p0 + lane];
                     const int s = (int)(pr & 15u);
@@ -446,6 +454,145 @@ k_collect_grid(const DevLayout L, const __grid_constant__ SegTable gtab, const G
                         }
                     }
                 } while (0);
+                } else {
+                // LANE = (QUERY, TERMINAL, ENTRY). Step a, lane = pair: the terminal's box, the poles that reach it, the
+                // candidate edges (once per pair), written to shared memory with a prefix sum of the pairs' entry counts. Step
+                // b, lane = entry of some pair (found by a search in the prefix sums): that entry against the pair's poles and
+                // candidate edges. The collector is a set: any order of the (entity, terminal, entry) triples gives the same
+                // result, `contains_key` only skips work. With lane = pair the per-entry work (ff_bbox pre-rejects per pole
+                // and candidate edge, hazard-edge loops) ran one entry after the other at 2 - 6 active lanes.
+                bool active = false, vpair = false, edge_ok = true;
+                int s = 0, my = 0, n_all = 0, lt = 0, l0 = 0, ci = 0, cj = 0;
+                unsigned pm = 0u;  // poles that reach this terminal
+                Rect tb{0.0f, 0.0f, 0.0f, 0.0f};
+                if (p0 + lane < cnt) {
+                    const uint32_t pr = (uint32_t)W.list[p0 + lane];
+                    s = (int)(pr & 15u);
+                    vpair = (pr & CG_PAIR_VNODE) != 0u;
+                    const int cell = (int)((pr >> 4) & 1023u);
+                    ci = cell & (GRID_G - 1), cj = cell >> 5;
+                    const int4 m = __ldg(&L.node_meta[vpair ? W.vnode[s] : cg->cell_node[cell]]);
+                    my = m.y;
+                    n_all = (m.z & 0xFFFF) + ((m.z >> 16) & 0xFFFF);
+                    // every hazard of this terminal collected already (through other terminals, or seeded)? nothing to do here
+#pragma unroll 1
+                    for (int i = 0; i < n_all && !active; i++) active = !cg_has(W.bits[s], __ldg(&L.entry_meta[my + i].x));
+                    if (active && !vpair) {
+                        lt = cg->cell_level[cell];
+                        const int sh = D - lt;
+                        const int ti = (ci >> sh) << sh, tj = (cj >> sh) << sh;  // first finest cell of the terminal
+                        tb = Rect{g.xs[ti], g.ys[tj], g.xs[ti + (1 << sh)], g.ys[tj + (1 << sh)]};
+                        // edges walk from the virtual root (cd_engine.rs:266-272): only terminals strictly below it, inside it
+                        const int vc = W.vcell[s];
+                        l0 = (vc >> 16) & 255;
+                        const int s0 = D - l0;
+                        edge_ok = lt > l0 && (ci >> s0) == (vc & 255) && (cj >> s0) == ((vc >> 8) & 255);
+#pragma unroll 1
+                        for (int pj = 0; pj < np; pj++) {  // circle.rs:115-128: a circle reaches a node iff its own box passes
+                            const float4 c4 = W.pole[s][pj];
+                            if (circ_rect(Circ{c4.x, c4.y, c4.z}, tb)) pm |= 1u << pj;
+                        }
+                    }
+                }
+                for (int e0 = 0; e0 < V; e0 += 32) {  // (one trip for polygons of up to 32 edges)
+                    const int ne32 = (V - e0) < 32 ? (V - e0) : 32;
+                    // candidate edges of this terminal: the edge's delta-inflated box meets the terminal's box (the candidate
+                    // superset of detect_grid.cuh); epm: edges with an end point inside the terminal's box - reached for sure
+                    unsigned cand = 0u, epm = 0u;
+                    if (active) {
+                        if (vpair) {
+                            cand = ne32 == 32 ? 0xFFFFFFFFu : ((1u << ne32) - 1u);
+                        } else if (edge_ok) {
+                            const float2* tv = W.tv + s * V;
+                            const float dq = W.dq[s];
+                            float2 a = tv[e0];
+                            bool a_in = rect_point(tb, a.x, a.y);
+#pragma unroll 2
+                            for (int k = 0; k < ne32; k++) {
+                                const int e = e0 + k;
+                                const float2 b = tv[e == V - 1 ? 0 : e + 1];
+                                const bool b_in = rect_point(tb, b.x, b.y);
+                                const bool out = fminf(a.x, b.x) - dq > tb.x_max || fmaxf(a.x, b.x) + dq < tb.x_min ||
+                                                 fminf(a.y, b.y) - dq > tb.y_max || fmaxf(a.y, b.y) + dq < tb.y_min;
+                                if (!out) cand |= 1u << k;
+                                if (a_in || b_in) epm |= 1u << k;
+                                a = b, a_in = b_in;
+                            }
+                        }
+                    }
+                    const unsigned pm_now = e0 == 0 ? pm : 0u;
+                    const int n_mine = (active && (cand != 0u || pm_now != 0u)) ? n_all : 0;
+                    int incl = n_mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int tt = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += tt;
+                    }
+                    const int T = __shfl_sync(FULL, incl, 31);
+                    __syncwarp();  // (the previous trip is done with pp / pfx)
+                    W.pp[lane] = make_int4(my, (int)cand, (int)epm,
+                                           s | (vpair ? 16 : 0) | ((int)pm_now << 5) | (lt << 9) | (l0 << 12) | (ci << 15) | (cj << 20));
+                    W.pfx[lane + 1] = incl;
+                    if (lane == 0) W.pfx[0] = 0;
+                    __syncwarp();
+                    for (int t0 = 0; t0 < T; t0 += 32) {
+                        const int t = t0 + lane;
+                        if (t < T) {
+                            int p = 0;  // the pair of triple t: the last one whose prefix is <= t
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1)
+                                if (W.pfx[p + o] <= t) p += o;
+                            const int4 q4 = W.pp[p];
+                            const int i = t - W.pfx[p];
+                            const int4 em = __ldg(&L.entry_meta[q4.x + i]);
+                            const int qs = q4.w & 15;
+                            uint32_t* bits = W.bits[qs];
+                            if (!cg_has(bits, em.x)) {  // collector.contains_key: skipping only saves work
+                                const bool vp = (q4.w & 16) != 0;
+                                const unsigned pmq = ((unsigned)q4.w >> 5) & 15u, cnd = (unsigned)q4.y, epq = (unsigned)q4.z;
+                                const float2* tv = W.tv + qs * V;
+                                const bool entire = em.w == 2;
+                                bool ins = false;
+                                Rect ff{0.0f, 0.0f, 0.0f, 0.0f};
+                                if (!entire) ff = ld_rect(&L.entry_ff[q4.x + i]);
+                                // poles (cd_engine.rs:296-304): Entire -> inserted by any pole that reaches the terminal
+                                if (entire) ins = pmq != 0u;
+                                else
+                                    for (unsigned pmm = pmq; pmm && !ins; pmm &= pmm - 1) {
+                                        const float4 c4 = W.pole[qs][__ffs(pmm) - 1];
+                                        const Circ c{c4.x, c4.y, c4.z};
+                                        if (!circ_rect(c, ff)) continue;  // QTHazPartial::collides_with (qt_partial_hazard.rs:67-72)
+#pragma unroll 1
+                                        for (int k = 0; k < em.z && !ins; k++) ins = circ_seg(c, ld_seg(&L.edges[em.y + k]));
+                                    }
+                                // edges: the bbox of the shape against ff_bbox first (exact: every edge lies inside the bbox)
+                                if (entire && !ins) ins = (cnd & epq) != 0u;  // some edge ends inside the terminal: reached, inserted
+                                if (!ins && cnd) {
+                                    const float4 b4 = W.bb[qs];
+                                    if (entire || rect_rect(Rect{b4.x, b4.y, b4.z, b4.w}, ff)) {
+                                        for (unsigned cc = cnd; cc && !ins; cc &= cc - 1) {
+                                            const int k = __ffs(cc) - 1, e = e0 + k;
+                                            const float2 a = tv[e], b = tv[e == V - 1 ? 0 : e + 1];
+                                            const Seg sg{a.x, a.y, b.x, b.y};
+                                            bool hit = entire;
+                                            if (!hit && rect_seg(ff, sg)) {
+#pragma unroll 1
+                                                for (int h = 0; h < em.z && !hit; h++) hit = seg_seg(sg, ld_seg(&L.edges[em.y + h]));
+                                            }
+                                            if (!hit) continue;
+                                            // would insert: is the terminal on the reference's walk of this edge?
+                                            ins = vp || ((epq >> k) & 1u) ||
+                                                  path_reaches<true>(g, sg, (q4.w >> 12) & 7, (q4.w >> 9) & 7, (q4.w >> 15) & 31, (q4.w >> 20) & 31);
+                                        }
+                                    }
+                                }
+                                if (ins) cg_set(bits, em.x);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                }
                 __syncwarp();
             }
             if (!more) break;

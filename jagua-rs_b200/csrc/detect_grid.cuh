@@ -668,6 +668,12 @@ __device__ bool seg_collides_from_root(const GCtx& c, const Seg& sg) {
 
 // one group of `ng` survivors (ents[0 .. ng): survivor-list entries in global memory, or in the warp's own shared
 // memory when LOCAL) resolved by a warp; GS = slots in use (>= ng)
+#ifndef JG_S2_BURST
+#define JG_S2_BURST 16
+#endif
+#ifndef JG_S2_BURST_MIN_RUN
+#define JG_S2_BURST_MIN_RUN 6  // mean hazard edges per leaf entry above which a round runs JG_S2_BURST tests
+#endif
 #ifndef JG_S2_REFILL
 #define JG_S2_REFILL 8
 #endif
@@ -808,6 +814,7 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
     // skipped as soon as one of its edges collides (the verdict is an OR over the edges, cd_engine.rs:164-173).
     {
         int fnext = 0;  // next edge of the list to hand out (warp-uniform)
+        const int burst = c.L.n_edges > JG_S2_BURST_MIN_RUN * c.L.n_entries ? JG_S2_BURST : 1;  // by the layout's mean edge run
         int slot = 0;
         bool scanning = false;
         Seg sg{0.0f, 0.0f, 0.0f, 0.0f};
@@ -883,9 +890,16 @@ __device__ __forceinline__ void g2_group(const GCtx& c, G2Slots& W, const int* e
                 }
             }
             if (hi < 0 && scanning && hk < hn) {
-                const float4 v = STAGE ? c.L.edges[hk] : __ldg(&c.L.edges[hk]);
-                hk++;
-                if (seg_seg(sg, Seg{v.x, v.y, v.z, v.w})) hi = ci, hk = hn, li = ln;  // the cell collides: leave it
+                // (up to `burst` tests per round: entries with long edge runs - hazards of a thousand vertices in depth-5
+                // leaves, 121 edges per entry - would otherwise pay the round's bookkeeping per edge; gardeyn4_c, 4.2 M queries:
+                // 0.86 G queries/s with one test per round, 1.05 G with 8, 1.12 G with 16; swim, 3.4 edges per entry, would lose
+                // 1.7 % to a burst of 4 and keeps one)
+#pragma unroll 1
+                for (int u = 0; u < burst && hk < hn; u++) {
+                    const float4 v = STAGE ? c.L.edges[hk] : __ldg(&c.L.edges[hk]);
+                    hk++;
+                    if (seg_seg(sg, Seg{v.x, v.y, v.z, v.w})) hi = ci, hk = hn, li = ln;  // the cell collides: leave it
+                }
             }
             if (!__any_sync(FULL, hi >= 0)) continue;
             if (hi >= 0) {

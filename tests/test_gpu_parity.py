@@ -117,7 +117,7 @@ def test_many_segments_and_small_chunks(jg, engines):
         one = jg.make_queries(wl, 3, 5000, seed=5)
         assert np.array_equal(cde.detect_batch(3, one), w.detect_batch(3, one))
     finally:
-        cde.set_batching(1 << 18, 3)
+        cde.set_batching(0, 4)  # back to the per-batch schedule (the default)
 
 
 def test_empty_batch(jg, engines):

@@ -365,3 +365,40 @@ def test_layout_broadcast_over_nccl(jg, orc):
         for k in range(2):
             assert np.array_equal(results[r][k], exps[k]), f"rank {r}, layout {k}: {(results[r][k] != exps[k]).sum()} mismatches"
     host.close()
+
+
+# ---- per-batch piece schedule of the host-buffer path -------------------------------------------------------
+def test_piece_schedule_idle_and_in_flight_agree(jg, world):
+    """jg_engine_set_batching(0, n): an idle engine cuts a large host batch into 256 Ki pieces, an engine with batches in
+    flight into whole pieces of up to 1 Mi, pinned chunk sizes cut it a third way - the verdicts must not depend on it
+    (and match the oracle on a sample)."""
+    wl, cde, w = world("swim_half")
+    ids, offs, t = _batch(jg, wl, 1_300_003, seed=11)
+    n = len(t)
+    hin = jg.PinnedBuffer((n, 4), np.float32)
+    hin.array[:] = t
+    outs = [jg.PinnedBuffer((n,), np.uint8) for _ in range(3)]
+    try:
+        cde.set_batching(0, 4)
+        cde.sync()
+        cde.detect_multi(ids, offs, hin.array, out=outs[0].array)  # idle: blocking call, nothing in flight
+        launches0 = cde.stats()["launches"]
+        for k in range(3):  # back to back: the second and third find the streams busy
+            cde.detect_multi(ids, offs, hin.array, out=outs[k].array, wait=False)
+        cde.sync()
+        in_flight_launches = cde.stats()["launches"] - launches0
+        assert np.array_equal(outs[0].array, outs[1].array) and np.array_equal(outs[0].array, outs[2].array)
+        cde.set_batching(100_000, 2)
+        fixed = cde.detect_multi(ids, offs, hin.array)
+        assert np.array_equal(fixed, outs[0].array)
+        # a sample against the oracle (the whole batch is compared in the bench)
+        m = 20_000
+        for k, i in enumerate(ids):
+            a = int(offs[k])
+            assert np.array_equal(outs[0].array[a:a + m], w.detect_batch(i, t[a:a + m]))
+        # idle: 5 pieces of <= 256 Ki (2 launches each); in flight: 2 pieces (1 Mi + the rest): fewer launches for batches 2, 3
+        assert in_flight_launches < 3 * 10
+    finally:
+        cde.set_batching(0, 4)
+        for b in outs + [hin]:
+            b.free()

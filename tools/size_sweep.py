@@ -1,6 +1,6 @@
 """Device-resident detect time vs batch size (CUDA events on the compute stream, warm L2).
 
-    python tools/size_sweep.py
+    [JG_SWEEP_WORKLOAD=gardeyn4c_half] python tools/size_sweep.py [n_queries ...]
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import jagua_rs_b200 as jg
 
-wl = jg.load_workload("swim_half")
+wl = jg.load_workload(os.environ.get("JG_SWEEP_WORKLOAD", "swim_half"))
 cde = jg.build_engine(wl, device=0)
 cde.sync_layout()
 ids = list(range(len(wl.items)))

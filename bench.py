@@ -71,6 +71,7 @@ def make_config(args, flops_info=None) -> dict:
                         "24 placed items + exterior, quadtree depth 5, cd_threshold 16, 2 ff poles",
             "queries_per_step": args.queries, "scaling": args.scaling,
             "l2": "flushed (256 MiB fill, untimed) before every timed step of `value`",
+            "timing": "`value`: CUDA events on the launching stream around each step; the step's launches are enqueued behind a gate kernel (jg_timer_start_gated), so the interval is device time and the host's enqueue time is not in it",
             "verdict_split": (flops_info or {}).get("verdicts")}
 
 
@@ -297,7 +298,7 @@ def main():
     dev_ms, step_ms = 0.0, []
     for _ in range(args.steps):
         cde.flush_l2()
-        cde.timer_start()
+        cde.timer_start(gated=True)
         step_device()
         step_ms.append(cde.timer_stop())
         dev_ms += step_ms[-1]

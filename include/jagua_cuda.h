@@ -261,6 +261,9 @@ float jg_engine_last_kernel_ms(JgEngine* e);
 /* CUDA-event stopwatch on the compute stream (the stream the *_device calls launch on):
  * start records an event, stop records another, waits for it and returns the elapsed ms. */
 int jg_timer_start(JgEngine* e);
+/* The same with a gate: the compute stream is held until jg_timer_stop has been called, so that everything enqueued in between
+ * runs back to back on the device and the host's enqueue time is outside the measured interval. */
+int jg_timer_start_gated(JgEngine* e);
 int jg_timer_stop(JgEngine* e, float* ms);
 /* How the host-pointer batch calls cut a batch into pieces (piece k runs on stream k mod n_streams: H2D, kernels, D2H).
  * chunk_queries == 0 (the default, with 4 streams): chosen per batch - one piece up to 512 Ki queries; engine idle (one batch

@@ -118,6 +118,7 @@ C_ABI = {
     "jg_timer_start": (C.c_int, [_vp]),
     "jg_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "jg_engine_set_batching": (C.c_int, [_vp, C.c_int64, C.c_int]),
+    "jg_timer_start_gated": (C.c_int, [_vp]),
     "jg_engine_set_groups": (C.c_int, [_vp, C.c_int, C.c_int]),
     "jg_engine_set_split_min": (C.c_int, [_vp, C.c_int64]),
     "jg_set_dependent_launch": (C.c_int, [C.c_int]),
@@ -826,8 +827,10 @@ class CDEngine:
     def last_kernel_ms(self) -> float:
         return float(self._lib.jg_engine_last_kernel_ms(self._eng))
 
-    def timer_start(self):
-        self._chk(self._lib.jg_timer_start(self._eng))
+    def timer_start(self, gated: bool = False):
+        """CUDA-event stopwatch on the compute stream; gated: the stream is held until timer_stop, so the launches enqueued in
+        between run back to back on the device (the host's enqueue time is not measured)."""
+        self._chk((self._lib.jg_timer_start_gated if gated else self._lib.jg_timer_start)(self._eng))
 
     def timer_stop(self) -> float:
         ms = C.c_float(0)

@@ -396,8 +396,9 @@ def test_piece_schedule_idle_and_in_flight_agree(jg, world):
         for k, i in enumerate(ids):
             a = int(offs[k])
             assert np.array_equal(outs[0].array[a:a + m], w.detect_batch(i, t[a:a + m]))
-        # idle: 5 pieces of <= 256 Ki (2 launches each); in flight: 2 pieces (1 Mi + the rest): fewer launches for batches 2, 3
-        assert in_flight_launches < 3 * 10
+        # idle: 5 pieces of <= 256 Ki (2 launches each); in flight: 2 pieces (1 Mi + the rest), i.e. fewer launches for batches
+        # 2 and 3 - whether they found the streams busy depends on host timing, so the count is bounded, not pinned
+        assert 3 * 4 <= in_flight_launches <= 3 * 10
     finally:
         cde.set_batching(0, 4)
         for b in outs + [hin]:

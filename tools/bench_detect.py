@@ -99,7 +99,21 @@ for name in args.workloads.split(","):
                 checked += m
         total += n
         ht.free(), ho.free(), d_t.free(), d_o.free()
+    roofline = None
+    try:  # algorithmic flops of exactly this batch (tools/count_flops_config4.py) against the non-FMA FP32 peak measured live
+        with open(os.path.join(ROOT, "workloads", f"{name}.detect_filtered.flops.json")) as f:
+            fl = json.load(f)
+        if fl["queries"] == total:
+            peak, _ = cde.fp32_nofma_peak()
+            ach = fl["detect_flops_total"] / (dev_ms * 1e-3) / 1e12
+            roofline = {"bound": "fp32_nofma", "achieved": ach, "peak": peak / 1e3, "unit": "TFLOP/s", "frac": ach / (peak / 1e3),
+                        "flops_per_query": fl["detect_flops_per_query"],
+                        "flops_source": f"workloads/{name}.detect_filtered.flops.json (instrumented oracle, this exact batch)",
+                        "peak_source": "measured live: jg_fp32_nofma_peak"}
+    except (OSError, KeyError):
+        pass
     print(json.dumps({"metric": "collision queries/sec (detect, per-item quality-zone filters)", "workload": name, "queries": total,
+                      "roofline": roofline,
                       "value": total / (dev_ms * 1e-3), "unit": "queries/s", "ms_total": dev_ms,
                       "e2e": {"value": total / e2e_s, "h2d_bytes": 16 * total, "d2h_bytes": total},
                       "filters": {str(q): int(np.unpackbits(b.view(np.uint8)).sum()) for q, (_, b) in fbits.items()},

@@ -381,11 +381,11 @@ def main():
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tr = json.load(f)
             if cde.detect_path() == "grid" and per_gpu_q == TOTAL_QUERIES:
-                traffic = {"bytes_per_step": tr["k_s1_grid"] + tr["k_s2_grid"], "algorithmic_bytes_per_step": ALG_BYTES_PER_QUERY * args.queries,
+                traffic = {"bytes_per_step": tr["k_s1_grid"] + tr["k_s2_grid"] + tr.get("k_s2_contain", 0), "algorithmic_bytes_per_step": ALG_BYTES_PER_QUERY * args.queries,
                            "measured": "static: read from profiles/ncu_traffic.json, not measured in this run", "source": tr["source"]}
                 wi = tr.get("warp_instructions")
                 if wi:  # what actually bounds these kernels: warp instructions issued vs the SMs' issue slots
-                    n_wi = wi["k_s1_grid"] + wi["k_s2_grid"]
+                    n_wi = wi["k_s1_grid"] + wi["k_s2_grid"] + wi.get("k_s2_contain", 0)
                     peak_issue = 148 * 4 * clocks_mhz_guess * 1e6
                     issue = {"warp_instructions_per_step": n_wi, "achieved": n_wi / (ms_per_step * 1e-3) / 1e9,
                              "peak": peak_issue / 1e9, "unit": "G warp-instructions/s", "frac": n_wi / (ms_per_step * 1e-3) / peak_issue,
@@ -400,7 +400,7 @@ def main():
                         "frac": ach / (peak_gflops / 1e3), "traffic": traffic["bytes_per_step"] if traffic else None,
                         "traffic_detail": traffic,
                         "peak_source": "measured live: jg_fp32_nofma_peak (independent FADD/FMUL chains)",
-                        "issue": issue, "flops_per_query": flops_per_q, "kernels": f"{cde.detect_path()} path: " + ("k_s1_grid + k_s2_grid" if cde.detect_path() == "grid" else "k_s1_surr + k_s2_poly") + ", one launch pair for the 10 item segments",
+                        "issue": issue, "flops_per_query": flops_per_q, "kernels": f"{cde.detect_path()} path: " + ("k_s1_grid + k_s2_grid + k_s2_contain (containment tests in their own kernel from 640 Ki queries per launch)" if cde.detect_path() == "grid" else "k_s1_surr + k_s2_poly") + ", one launch sequence for the 10 item segments",
                         "hbm": {"achieved": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9, "peak": 6554.2,
                                 "unit": "GB/s", "frac": ALG_BYTES_PER_QUERY * args.queries / (ms_per_step * 1e-3) / 1e9 / 6554.2,
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs"}}

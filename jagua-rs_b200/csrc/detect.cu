@@ -39,7 +39,8 @@ namespace jg {
 #define LEAF_CAP 160  // a leaf step runs as soon as 32 pairs wait; one inner step adds at most 128
 #define FULL 0xFFFFFFFFu
 #define S2_MAX_GROUP 8
-#define JG_SPLIT_MIN_QUERIES (3 << 19)  // launches from this size on (1.5 M; tools/split_probe.py) run the containment tests in k_s2_contain
+#define JG_SPLIT_MIN_QUERIES (5 << 17)  // launches from this size on (640 Ki; tools/split_probe.py, profiles/r2ai_split_probe.txt: the
+                                       // cross-over moved down from 1.5 M once stage 2 ran convergent rounds) run the containment tests in k_s2_contain
 
 enum : int { KIND_NONE = 0, KIND_INNER = 1, KIND_ENTIRE = 2, KIND_LEAF = 3 };
 enum : int { CH_DEAD = 0, CH_HIT = 1, CH_LEAF = 2, CH_INNER = 3 };

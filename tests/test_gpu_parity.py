@@ -513,7 +513,7 @@ def test_split_containment_kernel_matches_inline_path(jg, engines, name):
             n_contained += int((exp == 0).sum())
         assert n_contained > 0 or name == "baldacci1_bin"  # (uniform samples over that bin are almost never free)
     finally:
-        cde.set_split_min(3 << 19)
+        cde.set_split_min(5 << 17)  # back to the default
 
 
 @pytest.mark.parametrize("n", [3000, 200_000, 1_300_000])
@@ -609,7 +609,7 @@ def test_dependent_launch_matches_stream_order(jg, engines, name):
         cde.set_dependent_launch(False)
         assert np.array_equal(cde.detect_multi(ids, offs, tall), exp)
     finally:
-        cde.set_split_min(3 << 19)
+        cde.set_split_min(5 << 17)  # back to the default
         cde.set_dependent_launch(bool(was))
 
 

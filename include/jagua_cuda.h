@@ -243,6 +243,10 @@ int jg_search_round(JgEngine* e, int item_id, const JgSearchRound* round, int64_
 /* the samples and verdict bytes of the last jg_search_round (tests, debugging): n must match; null pointers are skipped */
 int jg_search_samples(JgEngine* e, int64_t n, uint8_t* rot_idx, float* txy, uint8_t* verdicts);
 
+/* Waits for everything enqueued on the engine. Deferred checks surface here: a device-side error of a streamed batch, and a
+ * disagreement between the producer's grid premise (JG_LAYOUT_FLAG_GRID_OK in the blob header) and k_grid_build's own verdict
+ * for a stream-ordered upload. When jg_sync returns an error, the results of every batch enqueued since the previous successful
+ * jg_sync are INVALID and must be discarded (jg_last_error says why); the engine itself stays usable. */
 int jg_sync(JgEngine* e);
 /* Finer than jg_sync: jg_fence_record marks everything enqueued on this engine so far, jg_fence_wait blocks until that
  * much has completed (later batches keep running). Fences are recycled after 32 newer ones (then a wait degrades to

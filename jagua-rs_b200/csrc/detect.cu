@@ -714,8 +714,10 @@ cudaError_t launch_detect(const DevLayout& L, const DetectPlan& plan, const SegT
             k_s1_grid<false><<<want1 < g ? want1 : g, S_THREADS, gs1, st>>>(L, tab, gd, d_xf, d_filt, d_out, sc.ctl, sc.sv_entry);
         }
         // Large launches hand the containment tests to their own kernel (k_s2_contain): stage 2 is bound by instruction
-        // fetch and runs 17 % faster without that code, which pays for the third launch (a dependent launch) from ~1.5 M queries on
-        // (4 M queries: 706 -> 670 us); smaller launches keep the containment tests inline.
+        // fetch and runs faster without that code (and the team code of k_s2_contain needs 8.7 M warp instructions per 1M
+        // queries where the inline, warp-cooperative form needs 22 M), which pays for the third launch (a dependent launch)
+        // from 640 Ki queries on (1 Mi: 198.3 -> 190.3 us, 4 Mi: 619.6 -> 564.0 us, profiles/r2ai_split_probe.txt); smaller
+        // launches keep the containment tests inline.
         const bool split = (long long)n >= plan.split_min && sc.ct_meta != nullptr;
         const size_t gs3 = ((sizeof(SegTable) + 15) & ~(size_t)15) + 16;
         const int want3 = (n + S_WARPS * CT_GROUP - 1) / (S_WARPS * CT_GROUP);

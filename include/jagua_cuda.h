@@ -412,6 +412,9 @@ int jg_pool_size(const JgPool* p);
 JgEngine* jg_pool_engine(JgPool* p, int k); /* the engine of the k-th device: knobs, stats, jg_layout_broadcast */
 const char* jg_pool_last_error(const JgPool* p);
 int jg_pool_set_min_shard(JgPool* p, int64_t min_queries_per_device);
+/* The sharding rule as a pure function (no device needed; what the CPU tests check): device k of n_devices resolves queries
+ * [lo, hi) of an n-query batch; devices the batch is not spread over get lo == hi == n. */
+int jg_pool_shard_bounds(int64_t n, int k, int n_devices, int64_t min_shard, int64_t* lo, int64_t* hi);
 int jg_pool_item_upload(JgPool* p, int item_id, const float* verts_xy, int n_verts, const float* poi_xy, const float* poles_xyr,
                         int n_poles, const float* piers, int n_piers);
 int jg_pool_item_set_rotations(JgPool* p, int item_id, const float* rot_cos_sin, int n_rot);

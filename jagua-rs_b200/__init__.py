@@ -119,6 +119,7 @@ C_ABI = {
     "jg_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "jg_engine_set_batching": (C.c_int, [_vp, C.c_int64, C.c_int]),
     "jg_timer_start_gated": (C.c_int, [_vp]),
+    "jg_pool_shard_bounds": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "jg_engine_set_groups": (C.c_int, [_vp, C.c_int, C.c_int]),
     "jg_engine_set_split_min": (C.c_int, [_vp, C.c_int64]),
     "jg_set_dependent_launch": (C.c_int, [C.c_int]),

@@ -141,13 +141,27 @@ static int pool_drain(JgPool* p, int n_active) {
     }
     return rc;
 }
-static int active_devices(const JgPool* p, int64_t n) {
-    int64_t a = (n + p->min_shard - 1) / p->min_shard;
+static int active_devices_of(int64_t n, int n_devices, int64_t min_shard) {
+    int64_t a = (n + min_shard - 1) / min_shard;
     if (a < 1) a = 1;
-    return a < (int64_t)p->eng.size() ? (int)a : (int)p->eng.size();
+    return a < (int64_t)n_devices ? (int)a : n_devices;
 }
+static int active_devices(const JgPool* p, int64_t n) { return active_devices_of(n, (int)p->eng.size(), p->min_shard); }
 
 extern "C" {
+
+// The pool's sharding rule as a pure function (no device needed): device k of n_devices resolves queries [lo, hi) of an
+// n-query batch; devices beyond the active ones (a batch is not cut below min_shard queries per device) get lo == hi.
+int jg_pool_shard_bounds(int64_t n, int k, int n_devices, int64_t min_shard, int64_t* lo, int64_t* hi) {
+    if (n < 0 || n_devices < 1 || k < 0 || k >= n_devices || min_shard < 1 || !lo || !hi) return JG_ERR_INVALID;
+    const int act = active_devices_of(n, n_devices, min_shard);
+    if (k >= act) {
+        *lo = *hi = n;
+        return JG_OK;
+    }
+    shard_bounds(n, k, act, *lo, *hi);
+    return JG_OK;
+}
 
 int jg_pool_create(const int* devices, int n_devices, const JgConfig* cfg, JgPool** out) {
     if (!devices || n_devices < 1 || n_devices > 64 || !cfg || !out) return JG_ERR_INVALID;

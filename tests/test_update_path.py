@@ -241,3 +241,25 @@ def test_incremental_image_tracks_the_tree(jg, orc, name):
     if wl.quadtree_depth >= 3:
         assert stats["bytes"] < 0.35 * stats["total"], stats  # updates are local
     cde.close()
+
+
+@pytest.mark.parametrize("n,n_dev,min_shard", [(0, 4, 32768), (1, 8, 32768), (32768, 8, 32768), (32769, 8, 32768), (1 << 20, 8, 32768),
+                                               (1_000_003, 3, 1), (100_000_007, 8, 1 << 15), (200_000, 8, 1 << 15)])
+def test_pool_sharding_rule(jg, n, n_dev, min_shard):
+    """jg_pool_shard_bounds (the rule jg_pool_* cut a host batch by): contiguous, disjoint, complete, sizes differ by at most one
+    among the active devices, and a batch is not spread thinner than min_shard queries per device."""
+    import ctypes as C
+
+    lib = jg.load_library()
+    cuts = []
+    for k in range(n_dev):
+        lo, hi = C.c_int64(-1), C.c_int64(-1)
+        assert lib.jg_pool_shard_bounds(n, k, n_dev, min_shard, C.byref(lo), C.byref(hi)) == 0
+        cuts.append((lo.value, hi.value))
+    assert cuts[0][0] == 0 and cuts[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    sizes = [b - a for a, b in cuts if b > a]
+    if n > 0:
+        assert max(sizes) - min(sizes) <= 1
+        assert len(sizes) == min(n_dev, max(1, -(-n // min_shard)))
+    assert lib.jg_pool_shard_bounds(10, n_dev, n_dev, min_shard, C.byref(C.c_int64()), C.byref(C.c_int64())) != 0  # k out of range
